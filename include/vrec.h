@@ -1,0 +1,216 @@
+/*
+ * vrec.h -- C ABI of libvrec.so, the B200-native engine for the two hot paths
+ * of the Visit Recommender (tashoyan/locations-recommender).
+ *
+ * The reference has NO native/FFI seam: the seam is the pair of Scala classes
+ *   recommender/src/main/scala/com/github/tashoyan/recommender/knn/KnnRecommender.scala:9-25
+ *   recommender/src/main/scala/com/github/tashoyan/recommender/stochastic/StochasticRecommender.scala:28-71
+ * and their only callers (knn/KnnRecommenderMain.scala:53-107,
+ * stochastic/StochasticRecommenderMain.scala:53-81).  A JVM-side drop-in
+ * `KnnRecommender` / `StochasticRecommender` with the same constructors binds
+ * exactly the entry points below through JNI.
+ *
+ * Conventions: plain C, opaque handles, caller-owned host buffers (may be freed
+ * as soon as a call returns), library-owned device memory.  Every call returns
+ * VREC_OK (0) or a negative VREC_E* code; vrec_last_error() gives the message
+ * of the last failure on the calling thread.  A context may be used by one
+ * thread at a time (the reference has one REPL thread).  There is NO CPU
+ * fallback: without an sm_100 device vrec_init fails with VREC_ENODEV.
+ *
+ * Paths cited below are relative to
+ * /root/reference/recommender/src/main/scala/com/github/tashoyan/recommender/.
+ */
+#ifndef VREC_H
+#define VREC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VREC_OK       0
+#define VREC_ENOENT  (-2)    /* "No such person: <id>" / "No such vertex in the graph: <id>"      */
+#define VREC_ENOMEM  (-12)
+#define VREC_ENODEV  (-19)   /* no sm_100 CUDA device                                              */
+#define VREC_EINVAL  (-22)   /* a Scala `require(...)` of the reference would have failed          */
+#define VREC_ECUDA   (-100)
+#define VREC_ENCCL   (-101)
+
+#define VREC_ABI_VERSION 1
+
+typedef struct vrec_ctx vrec_ctx;
+typedef struct vrec_knn vrec_knn;
+typedef struct vrec_sg  vrec_sg;
+
+/* ---------------------------------------------------------------- context */
+
+/* One context per process and GPU (one process per GPU).  device < 0 picks
+ * the current device.  Replaces `SparkSession.builder().getOrCreate()`
+ * (knn/KnnRecommenderMain.scala:20-21) as the owner of execution resources. */
+int vrec_init(int device, vrec_ctx **out);
+void vrec_shutdown(vrec_ctx *ctx);
+const char *vrec_last_error(void);
+int vrec_abi_version(void);
+
+/* cudaStream_t every kernel of this context is launched on (for CUDA-event
+ * timing by the caller), and the number of kernels launched so far.         */
+void *vrec_stream(vrec_ctx *ctx);
+int64_t vrec_launch_count(vrec_ctx *ctx);
+int vrec_synchronize(vrec_ctx *ctx);
+
+/* ---------------------------------------------------------------- KNN path */
+
+/*
+ * Loads one region-set: the three DataFrames handed to
+ * `new KnnRecommender(placeRatingVectors, categoryRatingVectors, placeRatings, ...)`
+ * (knn/KnnRecommender.scala:9-16; files of knn/KnnRecommenderMain.scala:69-88).
+ *
+ *  person_id[P]                    person ids (any order; sorted internally)
+ *  place_rowptr[P+1], place_col, place_val, place_dim
+ *                                  `place_rating_vectors`: row i is the SparseVector of
+ *                                  person i (indices ascending, < place_dim = SparseVector.size;
+ *                                  knn/RatingVectorsBuilder.scala:74-83).  An empty row means
+ *                                  "person has no row in this table".
+ *  cat_rowptr[P+1], cat_col, cat_val, cat_dim      `category_rating_vectors`, same layout
+ *  n_ratings, rating_person, rating_place, rating_value
+ *                                  `place_ratings` rows (person_id, place_id, rating)
+ *                                  (knn/RatingsBuilder.scala:32-48).  rating_person == NULL
+ *                                  derives them from the place vectors (they hold the same
+ *                                  non-zeros, knn/RatingVectorsBuilderMain.scala:41-73).
+ */
+int vrec_knn_load(vrec_ctx *ctx, int64_t P, const int64_t *person_id,
+                  const int64_t *place_rowptr, const int32_t *place_col, const double *place_val,
+                  int32_t place_dim,
+                  const int64_t *cat_rowptr, const int32_t *cat_col, const double *cat_val,
+                  int32_t cat_dim,
+                  int64_t n_ratings, const int64_t *rating_person, const int64_t *rating_place,
+                  const int64_t *rating_value,
+                  vrec_knn **out);
+void vrec_knn_free(vrec_knn *knn);
+
+/*
+ * KnnRecommender.makeRecommendations (knn/KnnRecommender.scala:22-25) for a batch of
+ * targets, followed by KnnRecommenderMain.printRecommendations' join with the target
+ * region's places and `orderBy(estimated_rating desc).limit(max_recs)`
+ * (knn/KnnRecommenderMain.scala:96-102).
+ *
+ *  place_weight, category_weight, k_nearest   ctor arguments; the `require`s of
+ *                                  knn/KnnRecommender.scala:17-20 give VREC_EINVAL
+ *  place_filter[n_filter]          ids of the places of the target region
+ *                                  (`places.where(region_id === target)`); NULL = all places
+ *  out_place_id / out_rating       [n_targets x max_recs], row t holds out_count[t] rows ordered
+ *                                  by (estimated_rating desc, place_id asc)
+ *  out_status[t]                   VREC_OK, or VREC_ENOENT = IllegalArgumentException
+ *                                  "No such person: <id>" (knn/KnnRecommender.scala:83)
+ */
+int vrec_knn_query(vrec_knn *knn, const int64_t *targets, int32_t n_targets,
+                   double place_weight, double category_weight, int32_t k_nearest,
+                   const int64_t *place_filter, int64_t n_filter, int32_t max_recs,
+                   int64_t *out_place_id, double *out_rating, int32_t *out_count,
+                   int32_t *out_status);
+
+/* Same, with targets and outputs already resident in device memory (the place filter
+ * is installed beforehand with vrec_knn_set_filter).  Asynchronous on vrec_stream(). */
+int vrec_knn_set_filter(vrec_knn *knn, const int64_t *place_filter, int64_t n_filter);
+int vrec_knn_query_device(vrec_knn *knn, const int64_t *d_targets, int32_t n_targets,
+                          double place_weight, double category_weight, int32_t k_nearest,
+                          int32_t max_recs,
+                          int64_t *d_out_place_id, double *d_out_rating, int32_t *d_out_count,
+                          int32_t *d_out_status);
+
+/* findSimilarPersons (knn/KnnRecommender.scala:27-49): the k_nearest most similar persons,
+ * ordered by (similarity desc, person_id asc).  capacity = size of the out arrays.          */
+int vrec_knn_neighbours(vrec_knn *knn, int64_t target, double place_weight, double category_weight,
+                        int32_t k_nearest, int64_t *out_person_id, double *out_similarity,
+                        int32_t capacity, int32_t *out_count);
+
+/* The raw DataFrame of makeRecommendations (place_id, estimated_rating), every place rated by
+ * at least one neighbour, sorted by place_id (knn/KnnRecommender.scala:51-70).              */
+int vrec_knn_estimates(vrec_knn *knn, int64_t target, double place_weight, double category_weight,
+                       int32_t k_nearest, int64_t *out_place_id, double *out_rating,
+                       int64_t capacity, int64_t *out_count);
+
+/* Person ids in the engine's (ascending) order: out[P]. */
+int vrec_knn_person_ids(vrec_knn *knn, int64_t *out);
+
+/* Dense similarity vector of one target after `orderBy(similarity desc).limit(k_nearest)`
+ * (knn/KnnRecommender.scala:38-48): out_sim[P] in vrec_knn_person_ids order, 0.0 for persons
+ * that are not among the k nearest.  Works for any k_nearest.                               */
+int vrec_knn_similarities(vrec_knn *knn, int64_t target, double place_weight, double category_weight,
+                          int32_t k_nearest, double *out_sim);
+
+/* Tuning / test knobs.  "rating_path": 0 = automatic, 1 = neighbour-row gather,
+ * 2 = column scan.  "tile": targets per pass; "splits": candidate ranges per target in the fused
+ * top-K kernel (0 = automatic).  Unknown names give VREC_EINVAL.                */
+int vrec_knn_set_option(vrec_knn *knn, const char *name, int64_t value);
+int64_t vrec_knn_resident_bytes(vrec_knn *knn);
+
+/* ---------------------------------------------------------------- SG path */
+
+/*
+ * Loads one stochastic graph: the DataFrame (source_id, target_id, balanced_weight) handed to
+ * `new StochasticRecommender(stochasticEdges, epsilon, maxIterations)`
+ * (stochastic/StochasticRecommender.scala:28-32; file of
+ * stochastic/StochasticRecommenderMain.scala:83-89).  Builds the vertex set
+ * distinct(source ∪ target) (:42-49) and the CSR of P^T on the device.
+ */
+int vrec_sg_load(vrec_ctx *ctx, int64_t nnz, const int64_t *source_id, const int64_t *target_id,
+                 const double *balanced_weight, vrec_sg **out);
+void vrec_sg_free(vrec_sg *sg);
+int64_t vrec_sg_vertex_count(vrec_sg *sg);
+int64_t vrec_sg_edge_count(vrec_sg *sg);
+int vrec_sg_vertex_ids(vrec_sg *sg, int64_t *out_ids);   /* [vertex_count], ascending */
+
+/*
+ * StochasticRecommender.makeRecommendations (stochastic/StochasticRecommender.scala:66-90) for a
+ * batch of vertices, followed by StochasticRecommenderMain.printRecommendations' join with the
+ * target region's places and `orderBy(probability desc).limit(max_recs)`
+ * (stochastic/StochasticRecommenderMain.scala:69-73).
+ *
+ *  epsilon, max_iterations         ctor arguments (`require`s of :33-34 give VREC_EINVAL)
+ *  place_filter[n_filter]          ids of the target region's places; NULL = every vertex
+ *  out_id / out_prob               [n x max_recs], ordered by (probability desc, id asc)
+ *  out_iterations[q]               the `iteration` printed by step() (:94,:100)
+ *  out_converged[q]                1 = "Converged in ...", 0 = "... reached the maximum ..."
+ *  out_status[q]                   VREC_OK or VREC_ENOENT ("No such vertex in the graph: <id>", :70)
+ */
+int vrec_sg_query(vrec_sg *sg, const int64_t *vertices, int32_t n,
+                  double epsilon, int32_t max_iterations,
+                  const int64_t *place_filter, int64_t n_filter, int32_t max_recs,
+                  int64_t *out_id, double *out_prob, int32_t *out_count,
+                  int32_t *out_iterations, int32_t *out_converged, int32_t *out_status);
+
+/* The full stationary vector of one vertex (the DataFrame step() returns, before the
+ * `id != vertex and probability > 0` filter): out_x[vertex_count], in vertex_ids order.   */
+int vrec_sg_stationary(vrec_sg *sg, int64_t vertex, double epsilon, int32_t max_iterations,
+                       double *out_x, int32_t *out_iterations, int32_t *out_converged,
+                       double *out_residual);
+
+/* Device-resident power iteration for throughput measurement: runs `iterations` SpMV
+ * passes x' = 0.15 u + 0.85 P^T x from x0 = 1/N for vertex index 0, no convergence stop,
+ * asynchronously on vrec_stream().                                                          */
+int vrec_sg_iterate_device(vrec_sg *sg, int32_t iterations);
+int64_t vrec_sg_resident_bytes(vrec_sg *sg);
+
+/* Synthetic graph built directly on the device (bench config "oversized graph"): n_vertices
+ * vertices, out_degree edges per vertex, row-stochastic weights; ids are 0..n_vertices-1.
+ * rank/world select the contiguous row range [lo, hi) of P^T this process owns.            */
+int vrec_sg_generate(vrec_ctx *ctx, int64_t n_vertices, int32_t out_degree, uint64_t seed,
+                     int32_t rank, int32_t world, vrec_sg **out);
+
+/* ---------------------------------------------------------------- host-only helpers (tests) */
+
+/* The vertex table and CSR of P^T exactly as vrec_sg_load builds them, on the host: out_ids
+ * [<= 2*nnz], out_rowptr [<= 2*nnz+1], out_src / out_w [nnz].  No device is touched.        */
+int vrec_host_sg_csr(int64_t nnz, const int64_t *source_id, const int64_t *target_id,
+                     const double *balanced_weight, int64_t *out_n, int64_t *out_ids,
+                     int32_t *out_rowptr, int32_t *out_src, double *out_w);
+/* Device CSR of P^T (rows owned by this process) copied back: out_rowptr [rows+1], out_src /
+ * out_w [edge_count].                                                                        */
+int vrec_sg_export_csr(vrec_sg *sg, int32_t *out_rowptr, int32_t *out_src, double *out_w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VREC_H */

@@ -1,0 +1,1113 @@
+// KNN path: cosine similarity of a batch of targets against every person of a region-set over
+// sparse place + category rating vectors (CSR, precomputed norms), weighted combine, top-K
+// neighbours, similarity-weighted estimated_rating per place, ranked top-N places.
+// Reference: knn/KnnRecommender.scala:22-96, knn/Distance.scala:7-16, knn/KnnRecommenderMain.scala:90-102.
+#include <algorithm>
+#include <numeric>
+#include <string.h>
+
+#include "vrec_internal.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ device views
+struct KnnVec {                 // one rating-vector table in CSR form
+    const int *rowptr;          // [P+1]
+    const int *col;             // ascending within a row
+    const double *val;
+    const double *len;          // vectorLength per row (knn/Distance.scala:11-16)
+};
+
+struct KnnDev {
+    long long P;
+    const long long *person;    // ascending person ids
+    KnnVec place, cat;
+};
+
+struct Nb {                     // one neighbour candidate
+    double sim;
+    int idx;                    // person index (== rank of person_id)
+    int pad;
+};
+
+constexpr int TOPK_THREADS = 256;
+constexpr int TOPK_PER_THREAD = 4;
+constexpr int TOPK_BUF = 2048;          // smem candidate buffer; requires K <= 1024
+constexpr int TOPK_MAX_K = 1024;
+constexpr int MERGE_THREADS = 256;
+constexpr int RATE_WARPS = 4;
+
+__device__ __forceinline__ bool nb_before(const Nb &a, const Nb &b) {
+    return a.sim > b.sim || (a.sim == b.sim && a.idx < b.idx);
+}
+
+// spark-mllib-local 3.1.2 BLAS.dot(sparse, sparse) ("y catching x"), called from knn/Distance.scala:8
+__device__ __forceinline__ double sparse_dot(const int *__restrict__ xi, const double *__restrict__ xv, int nx,
+                                             const int *__restrict__ yi, const double *__restrict__ yv, int ny) {
+    int kx = 0, ky = 0;
+    double sum = 0.0;
+    while (kx < nx && ky < ny) {
+        int ix = xi[kx];
+        while (ky < ny && yi[ky] < ix) ky++;
+        if (ky < ny && yi[ky] == ix) {
+            sum = xadd(sum, xmul(xv[kx], yv[ky]));
+            ky++;
+        }
+        kx++;
+    }
+    return sum;
+}
+
+// cosineSimilarity(row, target) of one table, or 0 when the row is absent / not kept.
+__device__ __forceinline__ double table_similarity(const KnnVec &v, long long i, int ts, int tn, double tlen,
+                                                   bool &keep) {
+    int s = v.rowptr[i], n = v.rowptr[i + 1] - s;
+    if (n == 0) return 0.0;
+    double d = sparse_dot(v.col + s, v.val + s, n, v.col + ts, v.val + ts, tn);
+    double den = xmul(v.len[i], tlen);                 // vectorLength(v1) * vectorLength(v2)
+    double c = xdiv(d, den);
+    if (c > 0) {                                       // knn/KnnRecommender.scala:91
+        keep = true;
+        return c;
+    }
+    return 0.0;
+}
+
+struct TargetRows {
+    int t;
+    int ps, pn, cs, cn;
+    double plen, clen;
+};
+
+__device__ __forceinline__ TargetRows load_target(const KnnDev &d, int t) {
+    TargetRows r;
+    r.t = t;
+    r.ps = d.place.rowptr[t];
+    r.pn = d.place.rowptr[t + 1] - r.ps;
+    r.cs = d.cat.rowptr[t];
+    r.cn = d.cat.rowptr[t + 1] - r.cs;
+    r.plen = d.place.len[t];
+    r.clen = d.cat.len[t];
+    return r;
+}
+
+// findSimilarPersons for one (candidate, target) pair: knn/KnnRecommender.scala:27-45.
+// 0.0 means "not a candidate" (the target itself, or neither similarity > 0).
+__device__ __forceinline__ double pair_similarity(const KnnDev &d, long long i, const TargetRows &t, double pw,
+                                                  double cw) {
+    if (i == t.t) return 0.0;                          // where(person_id =!= personId), :89
+    bool keep = false;
+    double ps = table_similarity(d.place, i, t.ps, t.pn, t.plen, keep);
+    double cs = table_similarity(d.cat, i, t.cs, t.cn, t.clen, keep);
+    if (!keep) return 0.0;
+    return xadd(xmul(ps, pw), xmul(cs, cw));           // :42-44
+}
+
+// ------------------------------------------------------------------ kernels: load time
+
+// vectorLength per row: values.map(v => v*v).sum left to right, sqrt (knn/Distance.scala:11-16)
+__global__ void knn_norms_kernel(const int *__restrict__ rowptr, const double *__restrict__ val, long long P,
+                                 double *__restrict__ len) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    double s = 0.0;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) s = xadd(s, xmul(val[k], val[k]));
+    len[i] = sqrt(s);
+}
+
+// ------------------------------------------------------------------ kernels: query
+
+// target id -> person index; status ENOENT when the person has no row in either table
+// ("No such person", knn/KnnRecommender.scala:77-83)
+__global__ void knn_lookup_kernel(KnnDev d, const long long *__restrict__ targets, int n, int *__restrict__ tidx,
+                                  int *__restrict__ status) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    long long id = targets[q];
+    long long lo = 0, hi = d.P;
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (d.person[mid] < id) lo = mid + 1; else hi = mid;
+    }
+    int t = -1;
+    if (lo < d.P && d.person[lo] == id) {
+        bool has_place = d.place.rowptr[lo + 1] > d.place.rowptr[lo];
+        bool has_cat = d.cat.rowptr[lo + 1] > d.cat.rowptr[lo];
+        if (has_place && has_cat) t = (int)lo;
+    }
+    tidx[q] = t;
+    status[q] = t >= 0 ? VREC_OK : VREC_ENOENT;
+}
+
+__device__ __forceinline__ void bitonic_sort_desc(Nb *buf, int n_pow2, int tid, int nthreads) {
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n_pow2; i += nthreads) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    Nb a = buf[i], b = buf[ixj];
+                    bool up = (i & k) == 0;            // "up" block: best first
+                    bool swap = up ? nb_before(b, a) : nb_before(a, b);
+                    if (swap) {
+                        buf[i] = b;
+                        buf[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int next_pow2(int n) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// Fused similarity + streaming top-K for K <= 1024.  Block (tt, sp) scans the candidate range
+// sp of target tt and emits its best K as part[tt][sp][*] in (similarity desc, index asc) order.
+__global__ void __launch_bounds__(TOPK_THREADS)
+knn_topk_kernel(KnnDev d, const int *__restrict__ tidx, int K, int S, double pw, double cw,
+                Nb *__restrict__ part, int *__restrict__ part_cnt) {
+    const int tt = blockIdx.x, sp = blockIdx.y, tid = threadIdx.x;
+    const int t = tidx[tt];
+    if (t < 0) {
+        if (tid == 0) part_cnt[tt * S + sp] = 0;
+        return;
+    }
+    __shared__ Nb buf[TOPK_BUF];
+    __shared__ int s_cnt;
+    __shared__ int s_have_thr;
+    __shared__ Nb s_thr;
+    if (tid == 0) {
+        s_cnt = 0;
+        s_have_thr = 0;
+    }
+    __syncthreads();
+    const TargetRows tr = load_target(d, t);
+    const long long lo = d.P * sp / S, hi = d.P * (sp + 1) / S;
+    for (long long base = lo; base < hi; base += TOPK_THREADS * TOPK_PER_THREAD) {
+        const bool have_thr = s_have_thr;
+        const Nb thr = s_thr;
+#pragma unroll
+        for (int c = 0; c < TOPK_PER_THREAD; ++c) {
+            long long i = base + (long long)c * TOPK_THREADS + tid;
+            if (i < hi) {
+                double s = pair_similarity(d, i, tr, pw, cw);
+                if (s > 0) {
+                    Nb e;
+                    e.sim = s;
+                    e.idx = (int)i;
+                    e.pad = 0;
+                    if (!have_thr || nb_before(e, thr)) {
+                        int slot = atomicAdd(&s_cnt, 1);
+                        buf[slot] = e;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        int cnt = s_cnt;
+        __syncthreads();                                           // nobody bumps s_cnt before all have read it
+        if (cnt > TOPK_BUF - TOPK_THREADS * TOPK_PER_THREAD) {     // uniform
+            int np2 = next_pow2(cnt);
+            for (int i = cnt + tid; i < np2; i += TOPK_THREADS) {
+                buf[i].sim = -1.0;
+                buf[i].idx = 0x7fffffff;
+            }
+            __syncthreads();
+            bitonic_sort_desc(buf, np2, tid, TOPK_THREADS);
+            if (tid == 0) {
+                if (cnt >= K) {
+                    s_cnt = K;
+                    s_thr = buf[K - 1];
+                    s_have_thr = 1;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // final sort and emit
+    int cnt = s_cnt;
+    int np2 = next_pow2(max(cnt, 1));
+    for (int i = cnt + tid; i < np2; i += TOPK_THREADS) {
+        buf[i].sim = -1.0;
+        buf[i].idx = 0x7fffffff;
+    }
+    __syncthreads();
+    bitonic_sort_desc(buf, np2, tid, TOPK_THREADS);
+    int keep = min(cnt, K);
+    Nb *out = part + ((size_t)tt * S + sp) * K;
+    for (int i = tid; i < keep; i += TOPK_THREADS) out[i] = buf[i];
+    if (tid == 0) part_cnt[tt * S + sp] = keep;
+}
+
+// Merges the S partial lists of a target (S*K <= TOPK_BUF): final neighbours in
+// (similarity desc, index asc) order -> nb_rank, and the same set in ascending index -> nb_idx.
+__global__ void __launch_bounds__(MERGE_THREADS)
+knn_merge_kernel(const Nb *__restrict__ part, const int *__restrict__ part_cnt, int K, int S,
+                 Nb *__restrict__ nb_rank, Nb *__restrict__ nb_idx, int *__restrict__ nb_cnt) {
+    const int tt = blockIdx.x, tid = threadIdx.x;
+    __shared__ Nb buf[TOPK_BUF];
+    __shared__ int s_off[33];
+    if (tid == 0) {
+        int o = 0;
+        for (int s = 0; s < S; ++s) {
+            s_off[s] = o;
+            o += part_cnt[tt * S + s];
+        }
+        s_off[S] = o;
+    }
+    __syncthreads();
+    const int total = s_off[S];
+    for (int s = 0; s < S; ++s) {
+        int c = s_off[s + 1] - s_off[s];
+        const Nb *src = part + ((size_t)tt * S + s) * K;
+        for (int i = tid; i < c; i += MERGE_THREADS) buf[s_off[s] + i] = src[i];
+    }
+    int np2 = next_pow2(max(total, 1));
+    for (int i = total + tid; i < np2; i += MERGE_THREADS) {
+        buf[i].sim = -1.0;
+        buf[i].idx = 0x7fffffff;
+    }
+    __syncthreads();
+    bitonic_sort_desc(buf, np2, tid, MERGE_THREADS);
+    const int keep = min(total, K);
+    for (int i = tid; i < keep; i += MERGE_THREADS) nb_rank[(size_t)tt * K + i] = buf[i];
+    if (tid == 0) nb_cnt[tt] = keep;
+    __syncthreads();
+    // re-sort the kept entries by ascending index: flip the key (sim := -idx) and reuse the sorter
+    int kp2 = next_pow2(max(keep, 1));
+    Nb mine[TOPK_BUF / MERGE_THREADS];
+    for (int i = tid, j = 0; i < kp2; i += MERGE_THREADS, ++j) {
+        Nb e = buf[i];
+        if (i >= keep) {
+            e.sim = -1.0;
+            e.idx = 0x7fffffff;
+        }
+        mine[j] = e;
+    }
+    __syncthreads();
+    // second array lives in registers while we sort (idx, original sim) pairs by idx:
+    // encode as sim' = -(double)idx (exact for idx < 2^31), keep the true sim in a side array
+    __shared__ double s_true[TOPK_MAX_K];
+    for (int i = tid, j = 0; i < kp2; i += MERGE_THREADS, ++j) {
+        Nb e = mine[j];
+        if (i < keep) s_true[i] = e.sim;
+        Nb f;
+        f.idx = i;                                       // remember the rank position
+        f.pad = e.idx;                                   // person index
+        f.sim = (i < keep) ? -(double)e.idx : -4.0e9;    // ascending idx == descending -idx
+        buf[i] = f;
+    }
+    __syncthreads();
+    bitonic_sort_desc(buf, kp2, tid, MERGE_THREADS);
+    for (int i = tid; i < keep; i += MERGE_THREADS) {
+        Nb f = buf[i];
+        Nb e;
+        e.sim = s_true[f.idx];
+        e.idx = f.pad;
+        e.pad = 0;
+        nb_idx[(size_t)tt * K + i] = e;
+    }
+}
+
+// makeRecommendations0 (knn/KnnRecommender.scala:51-70) by neighbour-row gather, one warp per
+// target: neighbours in ascending person index, num/den accumulated in the same pass in a
+// dense per-warp scratch row; then the region filter + ranked top-N
+// (knn/KnnRecommenderMain.scala:96-100).
+__global__ void __launch_bounds__(RATE_WARPS * 32)
+knn_rate_gather_kernel(const int *__restrict__ rrp, const int *__restrict__ rpl, const double *__restrict__ rv,
+                       const Nb *__restrict__ nb_idx, const int *__restrict__ nb_cnt, int T, int K, int rdim,
+                       const unsigned char *__restrict__ flag, double *__restrict__ num, double *__restrict__ den,
+                       int *__restrict__ touched, int touch_cap, int max_recs, long long *__restrict__ out_place,
+                       double *__restrict__ out_rating, int *__restrict__ out_count) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x * RATE_WARPS + warp, nslots = gridDim.x * RATE_WARPS;
+    double *mynum = num + (size_t)slot * rdim;
+    double *myden = den + (size_t)slot * rdim;
+    int *mytouched = touched + (size_t)slot * touch_cap;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int tt = slot; tt < T; tt += nslots) {
+        const int n = nb_cnt[tt];
+        int ntouched = 0;
+        for (int k = 0; k < n; ++k) {
+            Nb nb = nb_idx[(size_t)tt * K + k];
+            const int rs = rrp[nb.idx], rn = rrp[nb.idx + 1] - rs;
+            for (int e0 = 0; e0 < rn; e0 += 32) {
+                int e = e0 + lane;
+                bool valid = e < rn;
+                bool first = false;
+                int pl = 0;
+                if (valid) {
+                    pl = rpl[rs + e];
+                    double w = xmul(rv[rs + e], nb.sim);      // rating * similarity, :60
+                    double dold = myden[pl];
+                    first = dold == 0.0;
+                    mynum[pl] = xadd(mynum[pl], w);           // :63
+                    myden[pl] = xadd(dold, nb.sim);           // :64
+                }
+                unsigned m = __ballot_sync(0xffffffffu, first);
+                if (first) {
+                    int pos = ntouched + __popc(m & lt_mask);
+                    if (pos < touch_cap) mytouched[pos] = pl;
+                }
+                ntouched += __popc(m);
+            }
+            __syncwarp();
+        }
+        if (ntouched > touch_cap) ntouched = touch_cap;
+        __syncwarp();
+        for (int j = lane; j < ntouched; j += 32) {
+            int pl = mytouched[j];
+            double est = xdiv(mynum[pl], myden[pl]);          // :68
+            bool ok = !flag || flag[pl];
+            mynum[pl] = ok ? est : nan;
+        }
+        __syncwarp();
+        bool have_last = false;
+        double last_val = 0.0;
+        long long last_key = 0;
+        int count = 0;
+        for (int r = 0; r < max_recs; ++r) {
+            bool has = false;
+            double bv = 0.0;
+            long long bk = 0;
+            for (int j = lane; j < ntouched; j += 32) {
+                int pl = mytouched[j];
+                double x = mynum[pl];
+                if (x != x) continue;
+                if (have_last && !ranks_before(last_val, last_key, x, pl)) continue;
+                if (!has || ranks_before(x, pl, bv, bk)) {
+                    has = true;
+                    bv = x;
+                    bk = pl;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                int oh = __shfl_xor_sync(0xffffffffu, (int)has, off);
+                double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                long long ok2 = __shfl_xor_sync(0xffffffffu, bk, off);
+                if (oh && (!has || ranks_before(ov, ok2, bv, bk))) {
+                    has = true;
+                    bv = ov;
+                    bk = ok2;
+                }
+            }
+            if (!has) break;
+            have_last = true;
+            last_val = bv;
+            last_key = bk;
+            if (lane == 0) {
+                out_place[(size_t)tt * max_recs + r] = bk;
+                out_rating[(size_t)tt * max_recs + r] = bv;
+            }
+            count = r + 1;
+        }
+        if (lane == 0) out_count[tt] = count;
+        for (int j = lane; j < ntouched; j += 32) {
+            int pl = mytouched[j];
+            mynum[pl] = 0.0;
+            myden[pl] = 0.0;
+        }
+        __syncwarp();
+    }
+}
+
+// Dense similarity rows for the large-K path: sim[tt][i] for every person i.
+__global__ void __launch_bounds__(256)
+knn_sim_rows_kernel(KnnDev d, const int *__restrict__ tidx, double pw, double cw, double *__restrict__ sim) {
+    const int tt = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.P) return;
+    const int t = tidx[tt];
+    double s = 0.0;
+    if (t >= 0) {
+        const TargetRows tr = load_target(d, t);
+        s = pair_similarity(d, i, tr, pw, cw);
+    }
+    sim[(size_t)tt * d.P + i] = s;
+}
+
+// orderBy(similarity desc).limit(K) on a dense row (knn/KnnRecommender.scala:46-48): radix select
+// of the K-th largest positive similarity, ties taken in ascending index; everything else := 0.
+__global__ void __launch_bounds__(1024)
+knn_select_mask_kernel(double *__restrict__ sim, long long P, int K) {
+    double *row = sim + (size_t)blockIdx.x * P;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ unsigned hist[256];
+    __shared__ unsigned long long s_prefix, s_mask;
+    __shared__ long long s_remaining;
+    __shared__ long long s_count;
+    __shared__ long long s_wcnt[32];
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    long long c = 0;
+    for (long long i = tid; i < P; i += 1024) c += row[i] > 0;
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if (lane == 0) atomicAdd((unsigned long long *)&s_count, (unsigned long long)c);
+    __syncthreads();
+    if ((long long)K >= s_count) return;
+    if (tid == 0) {
+        s_prefix = 0;
+        s_mask = 0;
+        s_remaining = K;
+    }
+    for (int pass = 7; pass >= 0; --pass) {
+        const int shift = pass * 8;
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix, mask = s_mask;
+        for (long long i = tid; i < P; i += 1024) {
+            double v = row[i];
+            unsigned long long b = (unsigned long long)__double_as_longlong(v);
+            if (v > 0 && (b & mask) == prefix) atomicAdd(&hist[(b >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            long long cum = 0, rem = s_remaining;
+            int bin = 255;
+            for (; bin > 0; --bin) {
+                if (cum + (long long)hist[bin] >= rem) break;
+                cum += hist[bin];
+            }
+            s_remaining = rem - cum;
+            s_prefix = prefix | ((unsigned long long)bin << shift);
+            s_mask = mask | (0xffULL << shift);
+        }
+        __syncthreads();
+    }
+    const unsigned long long kth = s_prefix;
+    const long long need = s_remaining;
+    // ties in ascending index: warp w owns the contiguous range [P*w/32, P*(w+1)/32)
+    const long long lo = P * warp / 32, hi = P * (warp + 1) / 32;
+    long long eqc = 0;
+    for (long long i = lo + lane; i < hi; i += 32) {
+        double v = row[i];
+        eqc += (v > 0 && (unsigned long long)__double_as_longlong(v) == kth);
+    }
+    for (int off = 16; off > 0; off >>= 1) eqc += __shfl_xor_sync(0xffffffffu, eqc, off);
+    if (lane == 0) s_wcnt[warp] = eqc;
+    __syncthreads();
+    long long base = 0;
+    for (int w = 0; w < warp; ++w) base += s_wcnt[w];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (long long i0 = lo; i0 < hi; i0 += 32) {
+        long long i = i0 + lane;
+        double v = i < hi ? row[i] : 0.0;
+        unsigned long long b = (unsigned long long)__double_as_longlong(v);
+        bool eq = v > 0 && b == kth;
+        bool gt = v > 0 && b > kth;
+        unsigned m = __ballot_sync(0xffffffffu, eq);
+        long long rank = base + __popc(m & lt_mask);
+        bool keep = gt || (eq && rank < need);
+        if (i < hi && !keep && v != 0.0) row[i] = 0.0;
+        base += __popc(m);
+    }
+}
+
+// makeRecommendations0 by column scan (large K): one thread per place walks the persons that
+// rated it in ascending person index; a person contributes iff its masked similarity is > 0.
+__global__ void __launch_bounds__(128)
+knn_rate_cols_kernel(const int *__restrict__ colptr, const int *__restrict__ cper, const double *__restrict__ crv,
+                     int rdim, const double *__restrict__ simrow, double *__restrict__ est) {
+    int pl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pl >= rdim) return;
+    double num = 0.0, den = 0.0;
+    bool any = false;
+    for (int e = colptr[pl]; e < colptr[pl + 1]; ++e) {
+        double s = simrow[cper[e]];
+        if (s > 0) {
+            num = xadd(num, xmul(crv[e], s));
+            den = xadd(den, s);
+            any = true;
+        }
+    }
+    est[pl] = any ? xdiv(num, den) : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+__global__ void knn_fill_int_kernel(int *p, long long n, int v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host object
+struct vrec_knn {
+    vrec_ctx *ctx = nullptr;
+    int64_t P = 0;
+    int place_dim = 0, cat_dim = 0, rdim = 0;
+    int max_rating_row = 0;
+    int64_t nnz_place = 0, nnz_cat = 0, nnz_rat = 0;
+    std::vector<int64_t> h_person;
+    DevBuf<long long> d_person;
+    DevBuf<int> d_prp, d_pci, d_crp, d_cci;
+    DevBuf<double> d_pv, d_plen, d_cv, d_clen;
+    DevBuf<int> d_rrp, d_rpl;          // ratings by person
+    DevBuf<double> d_rv;
+    DevBuf<int> d_ccp, d_cper;         // ratings by place (CSC)
+    DevBuf<double> d_crv;
+    DevBuf<unsigned char> d_flag;
+    bool has_filter = false;
+    // options
+    int64_t opt_rating_path = 0, opt_tile = 0, opt_splits = 0;
+    // scratch
+    DevBuf<long long> d_targets;
+    DevBuf<int> d_tidx, d_status;
+    DevBuf<Nb> d_part, d_nb_rank, d_nb_idx;
+    DevBuf<int> d_part_cnt, d_nb_cnt;
+    DevBuf<double> d_num, d_den;
+    DevBuf<int> d_touched;
+    int rate_slots = 0, rate_touch_cap = 0;
+    DevBuf<double> d_sim, d_est;
+    DevBuf<long long> d_out_place;
+    DevBuf<double> d_out_rating;
+    DevBuf<int> d_out_count;
+
+    KnnDev dev() const {
+        KnnDev d;
+        d.P = P;
+        d.person = d_person.p;
+        d.place = KnnVec{d_prp.p, d_pci.p, d_pv.p, d_plen.p};
+        d.cat = KnnVec{d_crp.p, d_cci.p, d_cv.p, d_clen.p};
+        return d;
+    }
+};
+
+namespace {
+
+int check_csr(const char *what, int64_t P, const int64_t *rowptr, const int32_t *col, int32_t dim) {
+    if (rowptr[0] != 0) {
+        vrec_set_error("vrec_knn_load: %s rowptr[0] != 0", what);
+        return VREC_EINVAL;
+    }
+    for (int64_t i = 0; i < P; ++i) {
+        if (rowptr[i + 1] < rowptr[i]) {
+            vrec_set_error("vrec_knn_load: %s rowptr not monotone at row %lld", what, (long long)i);
+            return VREC_EINVAL;
+        }
+        for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            if (col[k] < 0 || col[k] >= dim || (k > rowptr[i] && col[k] <= col[k - 1])) {
+                vrec_set_error("vrec_knn_load: %s row %lld: indices must be strictly ascending in [0, %d)", what,
+                               (long long)i, dim);
+                return VREC_EINVAL;
+            }
+        }
+    }
+    if (rowptr[P] >= (int64_t)0x7fffffff) {
+        vrec_set_error("vrec_knn_load: %s has too many non-zeros", what);
+        return VREC_EINVAL;
+    }
+    return VREC_OK;
+}
+
+// permuted CSR copy (rows reordered by `order`), int32 row pointers
+void permute_csr(int64_t P, const std::vector<int64_t> &order, const int64_t *rowptr, const int32_t *col,
+                 const double *val, std::vector<int> &orp, std::vector<int> &oc, std::vector<double> &ov) {
+    orp.assign((size_t)P + 1, 0);
+    oc.resize((size_t)rowptr[P]);
+    ov.resize((size_t)rowptr[P]);
+    int pos = 0;
+    for (int64_t r = 0; r < P; ++r) {
+        int64_t src = order[r];
+        orp[r] = pos;
+        for (int64_t k = rowptr[src]; k < rowptr[src + 1]; ++k) {
+            oc[pos] = col[k];
+            ov[pos] = val[k];
+            ++pos;
+        }
+    }
+    orp[P] = pos;
+}
+
+}  // namespace
+
+extern "C" int vrec_knn_load(vrec_ctx *ctx, int64_t P, const int64_t *person_id, const int64_t *place_rowptr,
+                             const int32_t *place_col, const double *place_val, int32_t place_dim,
+                             const int64_t *cat_rowptr, const int32_t *cat_col, const double *cat_val,
+                             int32_t cat_dim, int64_t n_ratings, const int64_t *rating_person,
+                             const int64_t *rating_place, const int64_t *rating_value, vrec_knn **out) {
+    if (!ctx || !out || P < 0 || (P > 0 && !person_id) || !place_rowptr || !cat_rowptr || place_dim < 0 ||
+        cat_dim < 0 || P >= (int64_t)0x7fffffff) {
+        vrec_set_error("vrec_knn_load: bad argument");
+        return VREC_EINVAL;
+    }
+    *out = nullptr;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    VREC_TRY(check_csr("place_rating_vectors", P, place_rowptr, place_col, place_dim));
+    VREC_TRY(check_csr("category_rating_vectors", P, cat_rowptr, cat_col, cat_dim));
+    // persons in ascending id
+    std::vector<int64_t> order((size_t)P);
+    std::iota(order.begin(), order.end(), (int64_t)0);
+    bool sorted = true;
+    for (int64_t i = 1; i < P; ++i)
+        if (person_id[i] <= person_id[i - 1]) sorted = false;
+    if (!sorted) std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return person_id[a] < person_id[b]; });
+    vrec_knn *k = new vrec_knn();
+    k->ctx = ctx;
+    k->P = P;
+    k->place_dim = place_dim;
+    k->cat_dim = cat_dim;
+    k->h_person.resize((size_t)P);
+    for (int64_t i = 0; i < P; ++i) k->h_person[i] = person_id[order[i]];
+    for (int64_t i = 1; i < P; ++i)
+        if (k->h_person[i] == k->h_person[i - 1]) {
+            vrec_set_error("vrec_knn_load: duplicate person_id %lld", (long long)k->h_person[i]);
+            delete k;
+            return VREC_EINVAL;
+        }
+    std::vector<int> prp, pci, crp, cci;
+    std::vector<double> pv, cv;
+    permute_csr(P, order, place_rowptr, place_col, place_val, prp, pci, pv);
+    permute_csr(P, order, cat_rowptr, cat_col, cat_val, crp, cci, cv);
+    k->nnz_place = prp[P];
+    k->nnz_cat = crp[P];
+    // place_ratings grouped by person
+    std::vector<int> rrp, rpl;
+    std::vector<double> rv;
+    int rdim = place_dim;
+    if (!rating_person) {
+        rrp = prp;
+        rpl = pci;
+        rv = pv;
+    } else {
+        if (n_ratings < 0 || n_ratings >= (int64_t)0x7fffffff || !rating_place || !rating_value) {
+            vrec_set_error("vrec_knn_load: bad place_ratings arguments");
+            delete k;
+            return VREC_EINVAL;
+        }
+        std::vector<int> pidx((size_t)n_ratings);
+        rrp.assign((size_t)P + 1, 0);
+        for (int64_t e = 0; e < n_ratings; ++e) {
+            auto it = std::lower_bound(k->h_person.begin(), k->h_person.end(), rating_person[e]);
+            int idx = (it != k->h_person.end() && *it == rating_person[e]) ? (int)(it - k->h_person.begin()) : -1;
+            pidx[e] = idx;       // persons without rating vectors can never be neighbours: dropped
+            if (idx >= 0) {
+                if (rating_place[e] < 0 || rating_place[e] >= (int64_t)0x7ffffff0) {
+                    vrec_set_error("vrec_knn_load: place_id %lld out of Int range", (long long)rating_place[e]);
+                    delete k;
+                    return VREC_EINVAL;
+                }
+                rrp[idx + 1]++;
+                rdim = std::max<int64_t>(rdim, rating_place[e] + 1);
+            }
+        }
+        for (int64_t i = 0; i < P; ++i) rrp[i + 1] += rrp[i];
+        std::vector<int> pos(rrp.begin(), rrp.end() - 1);
+        rpl.resize((size_t)rrp[P]);
+        rv.resize((size_t)rrp[P]);
+        for (int64_t e = 0; e < n_ratings; ++e) {
+            if (pidx[e] < 0) continue;
+            int p = pos[pidx[e]]++;
+            rpl[p] = (int)rating_place[e];
+            rv[p] = (double)rating_value[e];           // long -> double, as `rating * similarity` does
+        }
+    }
+    k->rdim = std::max(rdim, 1);
+    k->nnz_rat = rrp[P];
+    // by place (CSC), persons ascending inside a column; reject duplicate (person, place) rows
+    std::vector<int> ccp((size_t)k->rdim + 1, 0), cper((size_t)k->nnz_rat);
+    std::vector<double> crv((size_t)k->nnz_rat);
+    for (int64_t e = 0; e < k->nnz_rat; ++e) ccp[rpl[e] + 1]++;
+    for (int64_t c = 0; c < k->rdim; ++c) ccp[c + 1] += ccp[c];
+    {
+        std::vector<int> pos(ccp.begin(), ccp.end() - 1);
+        for (int64_t i = 0; i < P; ++i) {
+            k->max_rating_row = std::max(k->max_rating_row, rrp[i + 1] - rrp[i]);
+            for (int e = rrp[i]; e < rrp[i + 1]; ++e) {
+                int c = rpl[e];
+                int p = pos[c]++;
+                if (p > ccp[c] && cper[p - 1] == (int)i) {
+                    vrec_set_error("vrec_knn_load: duplicate (person_id, place_id) = (%lld, %d) in place_ratings",
+                                   (long long)k->h_person[i], c);
+                    delete k;
+                    return VREC_EINVAL;
+                }
+                cper[p] = (int)i;
+                crv[p] = rv[e];
+            }
+        }
+    }
+    cudaStream_t s = ctx->stream;
+    int rc = k->d_person.upload((const long long *)k->h_person.data(), (size_t)P, s);
+    if (rc == VREC_OK) rc = k->d_prp.upload(prp.data(), prp.size(), s);
+    if (rc == VREC_OK) rc = k->d_pci.upload(pci.data(), pci.size(), s);
+    if (rc == VREC_OK) rc = k->d_pv.upload(pv.data(), pv.size(), s);
+    if (rc == VREC_OK) rc = k->d_crp.upload(crp.data(), crp.size(), s);
+    if (rc == VREC_OK) rc = k->d_cci.upload(cci.data(), cci.size(), s);
+    if (rc == VREC_OK) rc = k->d_cv.upload(cv.data(), cv.size(), s);
+    if (rc == VREC_OK) rc = k->d_rrp.upload(rrp.data(), rrp.size(), s);
+    if (rc == VREC_OK) rc = k->d_rpl.upload(rpl.data(), rpl.size(), s);
+    if (rc == VREC_OK) rc = k->d_rv.upload(rv.data(), rv.size(), s);
+    if (rc == VREC_OK) rc = k->d_ccp.upload(ccp.data(), ccp.size(), s);
+    if (rc == VREC_OK) rc = k->d_cper.upload(cper.data(), cper.size(), s);
+    if (rc == VREC_OK) rc = k->d_crv.upload(crv.data(), crv.size(), s);
+    if (rc == VREC_OK) rc = k->d_plen.alloc((size_t)P);
+    if (rc == VREC_OK) rc = k->d_clen.alloc((size_t)P);
+    if (rc == VREC_OK) rc = k->d_flag.alloc((size_t)k->rdim);
+    if (rc == VREC_OK && P > 0) {
+        int grid = (int)((P + 255) / 256);
+        knn_norms_kernel<<<grid, 256, 0, s>>>(k->d_prp.p, k->d_pv.p, P, k->d_plen.p);
+        knn_norms_kernel<<<grid, 256, 0, s>>>(k->d_crp.p, k->d_cv.p, P, k->d_clen.p);
+        ctx->launches += 2;
+        if (cudaGetLastError() != cudaSuccess) rc = VREC_ECUDA;
+    }
+    if (rc == VREC_OK && cudaStreamSynchronize(s) != cudaSuccess) {
+        vrec_set_error("vrec_knn_load: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = VREC_ECUDA;
+    }
+    if (rc != VREC_OK) {
+        delete k;
+        return rc;
+    }
+    *out = k;
+    return VREC_OK;
+}
+
+extern "C" void vrec_knn_free(vrec_knn *knn) {
+    if (!knn) return;
+    cudaSetDevice(knn->ctx->device);
+    cudaStreamSynchronize(knn->ctx->stream);
+    delete knn;
+}
+
+extern "C" int64_t vrec_knn_resident_bytes(vrec_knn *k) {
+    if (!k) return 0;
+    return (int64_t)(k->d_person.bytes() + k->d_prp.bytes() + k->d_pci.bytes() + k->d_pv.bytes() +
+                     k->d_plen.bytes() + k->d_crp.bytes() + k->d_cci.bytes() + k->d_cv.bytes() +
+                     k->d_clen.bytes());
+}
+
+extern "C" int vrec_knn_person_ids(vrec_knn *k, int64_t *out) {
+    if (!k || !out) return VREC_EINVAL;
+    std::copy(k->h_person.begin(), k->h_person.end(), out);
+    return VREC_OK;
+}
+
+extern "C" int vrec_knn_set_option(vrec_knn *k, const char *name, int64_t value) {
+    if (!k || !name) return VREC_EINVAL;
+    if (!strcmp(name, "rating_path") && value >= 0 && value <= 2) {
+        k->opt_rating_path = value;
+        return VREC_OK;
+    }
+    if (!strcmp(name, "tile") && value >= 0) {
+        k->opt_tile = value;
+        return VREC_OK;
+    }
+    if (!strcmp(name, "splits") && value >= 0 && value <= 32) {
+        k->opt_splits = value;
+        return VREC_OK;
+    }
+    vrec_set_error("vrec_knn_set_option: unknown option or bad value: %s=%lld", name, (long long)value);
+    return VREC_EINVAL;
+}
+
+extern "C" int vrec_knn_set_filter(vrec_knn *k, const int64_t *place_filter, int64_t n_filter) {
+    if (!k || n_filter < 0) return VREC_EINVAL;
+    VREC_CUDA(cudaSetDevice(k->ctx->device));
+    if (!place_filter) {
+        k->has_filter = false;
+        return VREC_OK;
+    }
+    std::vector<unsigned char> flag((size_t)k->rdim, 0);
+    for (int64_t i = 0; i < n_filter; ++i)
+        if (place_filter[i] >= 0 && place_filter[i] < k->rdim) flag[(size_t)place_filter[i]] = 1;
+    VREC_CUDA(cudaMemcpyAsync(k->d_flag.p, flag.data(), flag.size(), cudaMemcpyHostToDevice, k->ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(k->ctx->stream));
+    k->has_filter = true;
+    return VREC_OK;
+}
+
+namespace {
+
+int knn_check_params(double pw, double cw, int32_t K) {
+    // knn/KnnRecommender.scala:17-20
+    if (!(pw > 0 && pw < 1.0)) {
+        vrec_set_error("requirement failed: Place weight must be in the interval (0; 1): %g", pw);
+        return VREC_EINVAL;
+    }
+    if (!(cw > 0 && cw < 1.0)) {
+        vrec_set_error("requirement failed: Category weight must be in the interval (0; 1): %g", cw);
+        return VREC_EINVAL;
+    }
+    if (!(pw + cw == 1.0)) {
+        vrec_set_error("requirement failed: Sum of weights must be 1.0: place: %g, category: %g", pw, cw);
+        return VREC_EINVAL;
+    }
+    if (K <= 0) {
+        vrec_set_error("requirement failed: K nearest must be positive");
+        return VREC_EINVAL;
+    }
+    return VREC_OK;
+}
+
+bool use_gather_path(const vrec_knn *k, int K) {
+    if (K > TOPK_MAX_K) return false;
+    if (k->opt_rating_path == 1) return true;
+    if (k->opt_rating_path == 2) return false;
+    return (int64_t)K * std::max(1, k->max_rating_row) <= (int64_t)(1 << 20);
+}
+
+// neighbours of a tile of targets by the fused top-K kernels (K <= 1024)
+int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
+    vrec_ctx *ctx = k->ctx;
+    int smax = std::max(1, std::min(32, TOPK_BUF / K));
+    int S = (int)k->opt_splits;
+    if (S <= 0) {
+        S = 1;
+        int want_blocks = ctx->sm_count * 8;
+        while (S < smax && tn * S < want_blocks) S <<= 1;
+    }
+    S = std::min(S, smax);
+    if ((int64_t)S > std::max<int64_t>(1, k->P)) S = 1;
+    VREC_TRY(k->d_part.ensure((size_t)tn * S * K));
+    VREC_TRY(k->d_part_cnt.ensure((size_t)tn * S));
+    VREC_TRY(k->d_nb_rank.ensure((size_t)tn * K));
+    VREC_TRY(k->d_nb_idx.ensure((size_t)tn * K));
+    VREC_TRY(k->d_nb_cnt.ensure((size_t)tn));
+    dim3 grid(tn, S);
+    knn_topk_kernel<<<grid, TOPK_THREADS, 0, ctx->stream>>>(k->dev(), k->d_tidx.p, K, S, pw, cw, k->d_part.p,
+                                                           k->d_part_cnt.p);
+    VREC_LAUNCHED(ctx);
+    knn_merge_kernel<<<tn, MERGE_THREADS, 0, ctx->stream>>>(k->d_part.p, k->d_part_cnt.p, K, S, k->d_nb_rank.p,
+                                                           k->d_nb_idx.p, k->d_nb_cnt.p);
+    VREC_LAUNCHED(ctx);
+    return VREC_OK;
+}
+
+// dense masked similarity rows of a tile of targets (any K)
+int knn_run_dense(vrec_knn *k, int tn, double pw, double cw, int K) {
+    vrec_ctx *ctx = k->ctx;
+    VREC_TRY(k->d_sim.ensure((size_t)tn * (size_t)std::max<int64_t>(1, k->P)));
+    if (k->P == 0) return VREC_OK;
+    dim3 grid((unsigned)((k->P + 255) / 256), tn);
+    knn_sim_rows_kernel<<<grid, 256, 0, ctx->stream>>>(k->dev(), k->d_tidx.p, pw, cw, k->d_sim.p);
+    VREC_LAUNCHED(ctx);
+    knn_select_mask_kernel<<<tn, 1024, 0, ctx->stream>>>(k->d_sim.p, k->P, K);
+    VREC_LAUNCHED(ctx);
+    return VREC_OK;
+}
+
+int knn_lookup(vrec_knn *k, const long long *d_targets, int tn, int *d_status) {
+    VREC_TRY(k->d_tidx.ensure((size_t)tn));
+    knn_lookup_kernel<<<(tn + 127) / 128, 128, 0, k->ctx->stream>>>(k->dev(), d_targets, tn, k->d_tidx.p, d_status);
+    VREC_LAUNCHED(k->ctx);
+    return VREC_OK;
+}
+
+int knn_ensure_rate_scratch(vrec_knn *k, int K) {
+    int touch_cap = (int)std::min<int64_t>((int64_t)K * std::max(1, k->max_rating_row), k->rdim);
+    touch_cap = std::max(touch_cap, 1);
+    if (k->rate_slots > 0 && touch_cap <= k->rate_touch_cap) return VREC_OK;
+    int64_t per_slot = (int64_t)k->rdim * 16 + (int64_t)touch_cap * 4;
+    int64_t slots = std::min<int64_t>(k->ctx->sm_count * 16, ((int64_t)4 << 30) / std::max<int64_t>(1, per_slot));
+    slots = std::max<int64_t>(RATE_WARPS, slots / RATE_WARPS * RATE_WARPS);
+    VREC_TRY(k->d_num.alloc((size_t)slots * k->rdim));
+    VREC_TRY(k->d_den.alloc((size_t)slots * k->rdim));
+    VREC_TRY(k->d_touched.alloc((size_t)slots * touch_cap));
+    VREC_CUDA(cudaMemsetAsync(k->d_num.p, 0, k->d_num.bytes(), k->ctx->stream));
+    VREC_CUDA(cudaMemsetAsync(k->d_den.p, 0, k->d_den.bytes(), k->ctx->stream));
+    k->rate_slots = (int)slots;
+    k->rate_touch_cap = touch_cap;
+    return VREC_OK;
+}
+
+}  // namespace
+
+extern "C" int vrec_knn_query_device(vrec_knn *k, const int64_t *d_targets, int32_t n_targets, double pw,
+                                     double cw, int32_t K, int32_t max_recs, int64_t *d_out_place,
+                                     double *d_out_rating, int32_t *d_out_count, int32_t *d_out_status) {
+    if (!k || n_targets < 0 || (n_targets > 0 && (!d_targets || !d_out_count || !d_out_status))) {
+        vrec_set_error("vrec_knn_query: NULL argument");
+        return VREC_EINVAL;
+    }
+    VREC_TRY(knn_check_params(pw, cw, K));
+    if (max_recs < 0) {
+        vrec_set_error("Maximum recommendations number must be non-negative");
+        return VREC_EINVAL;
+    }
+    if (n_targets == 0) return VREC_OK;
+    vrec_ctx *ctx = k->ctx;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    const bool gather = use_gather_path(k, K);
+    int64_t tile = k->opt_tile;
+    if (tile <= 0) tile = gather ? 8192 : std::max<int64_t>(1, ((int64_t)1 << 30) / (8 * std::max<int64_t>(1, k->P)));
+    tile = std::min<int64_t>(tile, n_targets);
+    const unsigned char *flag = k->has_filter ? k->d_flag.p : nullptr;
+    if (gather) VREC_TRY(knn_ensure_rate_scratch(k, K));
+    if (!gather) VREC_TRY(k->d_est.ensure((size_t)k->rdim));
+    for (int64_t t0 = 0; t0 < n_targets; t0 += tile) {
+        const int tn = (int)std::min<int64_t>(tile, n_targets - t0);
+        VREC_TRY(knn_lookup(k, (const long long *)d_targets + t0, tn, d_out_status + t0));
+        if (max_recs == 0) {
+            knn_fill_int_kernel<<<(tn + 255) / 256, 256, 0, ctx->stream>>>(d_out_count + t0, tn, 0);
+            VREC_LAUNCHED(ctx);
+            continue;
+        }
+        if (gather) {
+            VREC_TRY(knn_run_topk(k, tn, pw, cw, K));
+            int blocks = std::min(k->rate_slots / RATE_WARPS, (tn + RATE_WARPS - 1) / RATE_WARPS);
+            knn_rate_gather_kernel<<<blocks, RATE_WARPS * 32, 0, ctx->stream>>>(
+                k->d_rrp.p, k->d_rpl.p, k->d_rv.p, k->d_nb_idx.p, k->d_nb_cnt.p, tn, K, k->rdim, flag, k->d_num.p,
+                k->d_den.p, k->d_touched.p, k->rate_touch_cap, max_recs, (long long *)d_out_place + t0 * max_recs,
+                d_out_rating + t0 * max_recs, d_out_count + t0);
+            VREC_LAUNCHED(ctx);
+        } else {
+            VREC_TRY(knn_run_dense(k, tn, pw, cw, K));
+            for (int tt = 0; tt < tn; ++tt) {
+                knn_rate_cols_kernel<<<(k->rdim + 127) / 128, 128, 0, ctx->stream>>>(
+                    k->d_ccp.p, k->d_cper.p, k->d_crv.p, k->rdim, k->d_sim.p + (size_t)tt * k->P, k->d_est.p);
+                VREC_LAUNCHED(ctx);
+                VREC_TRY(vrec_launch_select_topn(ctx, k->d_est.p, nullptr, flag, k->rdim, 0, 1, max_recs,
+                                                 (long long *)d_out_place + (t0 + tt) * max_recs,
+                                                 d_out_rating + (t0 + tt) * max_recs, d_out_count + t0 + tt));
+            }
+        }
+    }
+    return VREC_OK;
+}
+
+extern "C" int vrec_knn_query(vrec_knn *k, const int64_t *targets, int32_t n_targets, double pw, double cw,
+                              int32_t K, const int64_t *place_filter, int64_t n_filter, int32_t max_recs,
+                              int64_t *out_place_id, double *out_rating, int32_t *out_count, int32_t *out_status) {
+    if (!k || n_targets < 0 || (n_targets > 0 && (!targets || !out_count || !out_status))) {
+        vrec_set_error("vrec_knn_query: NULL argument");
+        return VREC_EINVAL;
+    }
+    VREC_TRY(knn_check_params(pw, cw, K));
+    if (max_recs < 0 || n_filter < 0) {
+        vrec_set_error("Maximum recommendations number must be non-negative");
+        return VREC_EINVAL;
+    }
+    if (n_targets == 0) return VREC_OK;
+    vrec_ctx *ctx = k->ctx;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    VREC_TRY(vrec_knn_set_filter(k, place_filter, n_filter));
+    const size_t m = (size_t)std::max(1, (int)max_recs);
+    VREC_TRY(k->d_targets.ensure((size_t)n_targets));
+    VREC_TRY(k->d_out_place.ensure((size_t)n_targets * m));
+    VREC_TRY(k->d_out_rating.ensure((size_t)n_targets * m));
+    VREC_TRY(k->d_out_count.ensure((size_t)n_targets));
+    VREC_TRY(k->d_status.ensure((size_t)n_targets));
+    VREC_CUDA(cudaMemcpyAsync(k->d_targets.p, targets, sizeof(int64_t) * (size_t)n_targets, cudaMemcpyHostToDevice,
+                              ctx->stream));
+    VREC_TRY(vrec_knn_query_device(k, (const int64_t *)k->d_targets.p, n_targets, pw, cw, K, max_recs,
+                                   (int64_t *)k->d_out_place.p, k->d_out_rating.p, k->d_out_count.p,
+                                   k->d_status.p));
+    if (max_recs > 0 && out_place_id && out_rating) {
+        VREC_CUDA(cudaMemcpyAsync(out_place_id, k->d_out_place.p, sizeof(int64_t) * (size_t)n_targets * max_recs,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+        VREC_CUDA(cudaMemcpyAsync(out_rating, k->d_out_rating.p, sizeof(double) * (size_t)n_targets * max_recs,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    VREC_CUDA(cudaMemcpyAsync(out_count, k->d_out_count.p, sizeof(int32_t) * (size_t)n_targets,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+    VREC_CUDA(cudaMemcpyAsync(out_status, k->d_status.p, sizeof(int32_t) * (size_t)n_targets,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int32_t t = 0; t < n_targets; ++t)
+        if (out_status[t] == VREC_ENOENT) {
+            vrec_set_error("No such person: %lld", (long long)targets[t]);     // knn/KnnRecommender.scala:83
+            break;
+        }
+    return VREC_OK;
+}
+
+namespace {
+
+// one target -> d_tidx / status on the host
+int knn_single_target(vrec_knn *k, int64_t target, int *status) {
+    vrec_ctx *ctx = k->ctx;
+    VREC_TRY(k->d_targets.ensure(1));
+    VREC_TRY(k->d_status.ensure(1));
+    VREC_CUDA(cudaMemcpyAsync(k->d_targets.p, &target, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    VREC_TRY(knn_lookup(k, k->d_targets.p, 1, k->d_status.p));
+    VREC_CUDA(cudaMemcpyAsync(status, k->d_status.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*status == VREC_ENOENT) vrec_set_error("No such person: %lld", (long long)target);
+    return VREC_OK;
+}
+
+}  // namespace
+
+extern "C" int vrec_knn_neighbours(vrec_knn *k, int64_t target, double pw, double cw, int32_t K,
+                                   int64_t *out_person_id, double *out_similarity, int32_t capacity,
+                                   int32_t *out_count) {
+    if (!k || !out_person_id || !out_similarity || !out_count || capacity < 0) return VREC_EINVAL;
+    VREC_TRY(knn_check_params(pw, cw, K));
+    if (K > TOPK_MAX_K) {
+        vrec_set_error("vrec_knn_neighbours supports k_nearest <= %d; use vrec_knn_similarities", TOPK_MAX_K);
+        return VREC_EINVAL;
+    }
+    VREC_CUDA(cudaSetDevice(k->ctx->device));
+    int status = 0;
+    VREC_TRY(knn_single_target(k, target, &status));
+    if (status != VREC_OK) return status;
+    VREC_TRY(knn_run_topk(k, 1, pw, cw, K));
+    int cnt = 0;
+    std::vector<Nb> h((size_t)K);
+    VREC_CUDA(cudaMemcpyAsync(&cnt, k->d_nb_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, k->ctx->stream));
+    VREC_CUDA(cudaMemcpyAsync(h.data(), k->d_nb_rank.p, sizeof(Nb) * (size_t)K, cudaMemcpyDeviceToHost,
+                              k->ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(k->ctx->stream));
+    cnt = std::min(cnt, (int)capacity);
+    for (int i = 0; i < cnt; ++i) {
+        out_person_id[i] = k->h_person[(size_t)h[i].idx];
+        out_similarity[i] = h[i].sim;
+    }
+    *out_count = cnt;
+    return VREC_OK;
+}
+
+// Dense similarity vector of one target after orderBy(similarity desc).limit(K): out_sim[P] in
+// ascending person_id order (vrec_knn_person_ids), 0.0 for persons that are not neighbours.
+extern "C" int vrec_knn_similarities(vrec_knn *k, int64_t target, double pw, double cw, int32_t K,
+                                     double *out_sim) {
+    if (!k || !out_sim) return VREC_EINVAL;
+    VREC_TRY(knn_check_params(pw, cw, K));
+    VREC_CUDA(cudaSetDevice(k->ctx->device));
+    int status = 0;
+    VREC_TRY(knn_single_target(k, target, &status));
+    if (status != VREC_OK) return status;
+    VREC_TRY(knn_run_dense(k, 1, pw, cw, K));
+    VREC_CUDA(cudaMemcpyAsync(out_sim, k->d_sim.p, sizeof(double) * (size_t)k->P, cudaMemcpyDeviceToHost,
+                              k->ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(k->ctx->stream));
+    return VREC_OK;
+}
+
+extern "C" int vrec_knn_estimates(vrec_knn *k, int64_t target, double pw, double cw, int32_t K,
+                                  int64_t *out_place_id, double *out_rating, int64_t capacity,
+                                  int64_t *out_count) {
+    if (!k || !out_place_id || !out_rating || !out_count || capacity < 0) return VREC_EINVAL;
+    VREC_TRY(knn_check_params(pw, cw, K));
+    vrec_ctx *ctx = k->ctx;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    int status = 0;
+    VREC_TRY(knn_single_target(k, target, &status));
+    if (status != VREC_OK) return status;
+    VREC_TRY(knn_run_dense(k, 1, pw, cw, K));
+    VREC_TRY(k->d_est.ensure((size_t)k->rdim));
+    knn_rate_cols_kernel<<<(k->rdim + 127) / 128, 128, 0, ctx->stream>>>(k->d_ccp.p, k->d_cper.p, k->d_crv.p,
+                                                                        k->rdim, k->d_sim.p, k->d_est.p);
+    VREC_LAUNCHED(ctx);
+    std::vector<double> est((size_t)k->rdim);
+    VREC_CUDA(cudaMemcpyAsync(est.data(), k->d_est.p, sizeof(double) * (size_t)k->rdim, cudaMemcpyDeviceToHost,
+                              ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(ctx->stream));
+    int64_t n = 0;
+    for (int pl = 0; pl < k->rdim; ++pl) {
+        if (est[pl] != est[pl]) continue;
+        if (n < capacity) {
+            out_place_id[n] = pl;
+            out_rating[n] = est[pl];
+        }
+        ++n;
+    }
+    *out_count = std::min(n, capacity);
+    return VREC_OK;
+}

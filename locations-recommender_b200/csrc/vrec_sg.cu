@@ -1,0 +1,689 @@
+// SG path: damped power iteration x' = alpha*u + (1-alpha) * P^T x over the CSR of P^T with a
+// fused residual / convergence check, then ranked top-N place extraction.
+// Reference: stochastic/StochasticRecommender.scala:38-141, stochastic/StochasticRecommenderMain.scala:64-76.
+#include <algorithm>
+#include <numeric>
+
+#include "vrec_internal.cuh"
+
+namespace {
+
+constexpr double kAlpha = 0.15;                 // stochastic/StochasticRecommender.scala:38
+constexpr int SPMV_THREADS = 256;
+constexpr int SPMV_WARPS = SPMV_THREADS / 32;
+
+// Device-side loop control (one per query slot).
+struct SgState {
+    int done;          // 1 once the iteration stopped
+    int iterations;    // the `iteration` of step()'s message (:94,:100)
+    int converged;     // 1 = "Converged in ...", 0 = "... reached the maximum ..."
+    unsigned int ticket;
+    double residual;   // last sum of squared differences (:131-139)
+};
+
+}  // namespace
+
+struct vrec_sg {
+    vrec_ctx *ctx = nullptr;
+    int64_t N = 0, nnz = 0;
+    int64_t row_lo = 0, row_hi = 0;           // rows of P^T owned by this process
+    std::vector<int64_t> h_ids;               // ascending vertex ids (host copy for lookups)
+    DevBuf<long long> d_ids;
+    DevBuf<int> d_rowptr;                     // [rows+1]
+    DevBuf<int> d_src;                        // source vertex index per in-edge
+    DevBuf<double> d_w;
+    // rows longer than VREC_CANON_SEG are summed segment-wise
+    int n_long = 0, n_seg = 0;
+    DevBuf<int> d_long_rows;                  // [n_long] ascending local row
+    DevBuf<int> d_long_segptr;                // [n_long+1] offsets into partials
+    DevBuf<int> d_seg_row;                    // [n_seg] index into long_rows
+    DevBuf<double> d_partials;                // [n_seg]
+    DevBuf<double> d_x[2];
+    DevBuf<double> d_block_partials;
+    DevBuf<SgState> d_state;
+    int grid = 0;
+    // top-N scratch
+    DevBuf<long long> d_filter_ids;
+    DevBuf<double> d_cand_val;
+    DevBuf<long long> d_cand_key;
+    DevBuf<long long> d_out_key;
+    DevBuf<double> d_out_val;
+    DevBuf<int> d_out_count;
+};
+
+namespace {
+
+__global__ void sg_fill_kernel(double *x, long long n, double v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) x[i] = v;
+}
+
+__global__ void sg_reset_state_kernel(SgState *st, int max_it) {
+    st->done = max_it <= 0 ? 1 : 0;          // maxIterations == 0 returns x0 (:93-95)
+    st->iterations = 0;
+    st->converged = 0;
+    st->ticket = 0;
+    st->residual = -1.0;
+}
+
+// lane-strided canonical sum of terms x[src[k]] * w[k], k in [s, s+n), n <= VREC_CANON_SEG
+__device__ __forceinline__ double canon_row_sum(const int *__restrict__ src, const double *__restrict__ w,
+                                                const double *__restrict__ x, int s, int n, int lane) {
+    double acc = 0.0;
+    // uniform trip count; up to 4 independent gathers in flight per lane, adds stay in index order
+    for (int kb = 0; kb < n; kb += 128) {
+        int k0 = kb + lane, k1 = k0 + 32, k2 = k0 + 64, k3 = k0 + 96;
+        bool v0 = k0 < n, v1 = k1 < n, v2 = k2 < n, v3 = k3 < n;
+        int c0 = v0 ? __ldg(src + s + k0) : 0, c1 = v1 ? __ldg(src + s + k1) : 0;
+        int c2 = v2 ? __ldg(src + s + k2) : 0, c3 = v3 ? __ldg(src + s + k3) : 0;
+        double w0 = v0 ? __ldg(w + s + k0) : 0.0, w1 = v1 ? __ldg(w + s + k1) : 0.0;
+        double w2 = v2 ? __ldg(w + s + k2) : 0.0, w3 = v3 ? __ldg(w + s + k3) : 0.0;
+        double x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
+        if (v0) acc = xadd(acc, xmul(x0, w0));
+        if (v1) acc = xadd(acc, xmul(x1, w1));
+        if (v2) acc = xadd(acc, xmul(x2, w2));
+        if (v3) acc = xadd(acc, xmul(x3, w3));
+    }
+    return canon_butterfly(acc);
+}
+
+// One warp per 1024-term segment of a long row.
+__global__ void __launch_bounds__(SPMV_THREADS)
+sg_long_partials_kernel(const int *__restrict__ rowptr, const int *__restrict__ src,
+                        const double *__restrict__ w, const double *__restrict__ x,
+                        const int *__restrict__ long_rows, const int *__restrict__ long_segptr,
+                        const int *__restrict__ seg_row, int n_seg, double *__restrict__ partials,
+                        const SgState *__restrict__ st) {
+    if (st->done) return;
+    const int lane = threadIdx.x & 31;
+    int seg = blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5);
+    if (seg >= n_seg) return;
+    int slot = seg_row[seg];
+    int row = long_rows[slot];
+    int j = seg - long_segptr[slot];
+    int s = rowptr[row] + j * VREC_CANON_SEG;
+    int n = min(VREC_CANON_SEG, rowptr[row + 1] - s);
+    double v = canon_row_sum(src, w, x, s, n, lane);
+    if (lane == 0) partials[seg] = v;
+}
+
+// Main pass: sigma per row in the canonical order, x' = u*alpha + sigma*(1-alpha)
+// (calcNextX, :108-128), squared-difference residual (isConverged, :130-141) reduced in a
+// fixed order, and the step() control (:92-106) updated by the last block.
+__global__ void __launch_bounds__(SPMV_THREADS)
+sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ rowptr, const int *__restrict__ src,
+               const double *__restrict__ w, const double *__restrict__ x, double *__restrict__ nx,
+               long long uidx, const int *__restrict__ long_rows, const int *__restrict__ long_segptr,
+               int n_long, const double *__restrict__ partials, SgState *st,
+               double *__restrict__ block_partials, int iteration, int max_it, double eps2,
+               int check_convergence) {
+    if (st->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long total_warps = (long long)gridDim.x * SPMV_WARPS;
+    const double one_minus = 1 - kAlpha;                     // :121, evaluates to 0.85
+    double dsum = 0.0;
+    for (long long base = ((long long)blockIdx.x * SPMV_WARPS + warp) * 32; base < n_rows;
+         base += total_warps * 32) {
+        long long r = base + lane;
+        int s = 0, e = 0;
+        if (r < n_rows) {
+            s = rowptr[r];
+            e = rowptr[r + 1];
+        }
+        int n = e - s;
+        double sigma = 0.0;
+        unsigned todo = __ballot_sync(0xffffffffu, n > 0);
+        while (todo) {
+            int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            int rs = __shfl_sync(0xffffffffu, s, l);
+            int rn = __shfl_sync(0xffffffffu, n, l);
+            double acc;
+            if (rn <= VREC_CANON_SEG) {
+                acc = canon_row_sum(src, w, x, rs, rn, lane);
+            } else {
+                // second level: lane-strided sum of the segment partials of this row
+                int row = (int)(base + l);
+                int lo = 0, hi = n_long;
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (long_rows[mid] < row) lo = mid + 1; else hi = mid;
+                }
+                int ps = long_segptr[lo], pn = long_segptr[lo + 1] - ps;
+                acc = 0.0;
+                for (int k = lane; k < pn; k += 32) acc = xadd(acc, partials[ps + k]);
+                acc = canon_butterfly(acc);
+            }
+            if (lane == l) sigma = acc;
+        }
+        if (r < n_rows) {
+            long long gi = row_lo + r;
+            double u = (gi == uidx) ? 1.0 : 0.0;
+            double v = xadd(xmul(u, kAlpha), xmul(sigma, one_minus));
+            nx[gi] = v;
+            double d = xsub(v, x[gi]);
+            dsum = xadd(dsum, xmul(d, d));
+        }
+    }
+    if (!check_convergence) return;
+    // fixed-order reduction of the residual
+    __shared__ double s_part[SPMV_WARPS];
+    __shared__ int s_last;
+    dsum = canon_butterfly(dsum);
+    if (lane == 0) s_part[warp] = dsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < SPMV_WARPS; ++i) t = xadd(t, s_part[i]);
+        block_partials[blockIdx.x] = t;
+        __threadfence();
+        unsigned tk = atomicInc(&st->ticket, gridDim.x - 1);
+        s_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {
+        __threadfence();
+        double acc = 0.0;
+        for (int k = lane; k < (int)gridDim.x; k += 32) acc = xadd(acc, __ldcg(block_partials + k));
+        acc = canon_butterfly(acc);
+        if (lane == 0) {
+            st->residual = acc;
+            if (acc <= eps2) {                   // :140 `diffSquared <= epsilonSquared`
+                st->converged = 1;
+                st->iterations = iteration;      // :100 "Converged in $iteration iterations"
+                st->done = 1;
+            } else if (iteration + 1 >= max_it) { // :93-95
+                st->converged = 0;
+                st->iterations = max_it;
+                st->done = 1;
+            }
+        }
+    }
+}
+
+// candidate values for the ranked top-N: filter ids -> vertex index by binary search
+__global__ void sg_candidates_kernel(const long long *__restrict__ ids, long long N,
+                                     const long long *__restrict__ filter, long long n_filter,
+                                     const double *__restrict__ x, long long target_id,
+                                     double *__restrict__ cand_val, long long *__restrict__ cand_key) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long n = filter ? n_filter : N;
+    if (i >= n) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    long long id;
+    long long idx;
+    if (filter) {
+        id = filter[i];
+        if (ids) {
+            long long lo = 0, hi = N;
+            while (lo < hi) {
+                long long mid = (lo + hi) >> 1;
+                if (ids[mid] < id) lo = mid + 1; else hi = mid;
+            }
+            idx = (lo < N && ids[lo] == id) ? lo : -1;
+        } else {
+            idx = (id >= 0 && id < N) ? id : -1;
+        }
+    } else {
+        idx = i;
+        id = ids ? ids[i] : i;                  // generated graphs: ids are 0..N-1
+    }
+    double v = nan;
+    if (idx >= 0 && id != target_id) {
+        double p = x[idx];
+        if (p > 0) v = p;                       // :85-88 id != vertex and probability > 0
+    }
+    cand_val[i] = v;
+    cand_key[i] = id;
+}
+
+int sg_setup_device(vrec_sg *g, const std::vector<int> &rowptr) {
+    vrec_ctx *ctx = g->ctx;
+    const int64_t rows = g->row_hi - g->row_lo;
+    // long rows and their segments
+    std::vector<int> long_rows, long_segptr(1, 0), seg_row;
+    for (int64_t r = 0; r < rows; ++r) {
+        int n = rowptr[r + 1] - rowptr[r];
+        if (n > VREC_CANON_SEG) {
+            int m = (n + VREC_CANON_SEG - 1) / VREC_CANON_SEG;
+            for (int j = 0; j < m; ++j) seg_row.push_back((int)long_rows.size());
+            long_rows.push_back((int)r);
+            long_segptr.push_back(long_segptr.back() + m);
+        }
+    }
+    g->n_long = (int)long_rows.size();
+    g->n_seg = (int)seg_row.size();
+    VREC_TRY(g->d_long_rows.upload(long_rows.data(), long_rows.size(), ctx->stream));
+    VREC_TRY(g->d_long_segptr.upload(long_segptr.data(), long_segptr.size(), ctx->stream));
+    VREC_TRY(g->d_seg_row.upload(seg_row.data(), seg_row.size(), ctx->stream));
+    VREC_TRY(g->d_partials.alloc(std::max(1, g->n_seg)));
+    VREC_TRY(g->d_x[0].alloc(g->N));
+    VREC_TRY(g->d_x[1].alloc(g->N));
+    // grid: a fixed function of the row count only, so the residual order is reproducible
+    int64_t want = (rows + 32 * SPMV_WARPS - 1) / (32 * SPMV_WARPS);
+    g->grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, 148 * 8));
+    VREC_TRY(g->d_block_partials.alloc(g->grid));
+    VREC_TRY(g->d_state.alloc(1));
+    VREC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VREC_OK;
+}
+
+// launches the whole step() loop for one vertex index; results stay on the device
+int sg_run_device(vrec_sg *g, long long uidx, double epsilon, int max_it, bool check_convergence) {
+    vrec_ctx *ctx = g->ctx;
+    const int rows = (int)(g->row_hi - g->row_lo);
+    const double x0 = 1.0 / (double)g->N;                   // :53-54
+    const double eps2 = epsilon * epsilon;                  // :40
+    sg_reset_state_kernel<<<1, 1, 0, ctx->stream>>>(g->d_state.p, max_it);
+    VREC_LAUNCHED(ctx);
+    int fill_grid = (int)std::min<int64_t>((g->N + 255) / 256, 148 * 16);
+    sg_fill_kernel<<<std::max(1, fill_grid), 256, 0, ctx->stream>>>(g->d_x[0].p, g->N, x0);
+    VREC_LAUNCHED(ctx);
+    for (int it = 0; it < max_it; ++it) {
+        const double *x = g->d_x[it & 1].p;
+        double *nx = g->d_x[(it + 1) & 1].p;
+        if (g->n_seg > 0) {
+            int pg = (g->n_seg + SPMV_WARPS - 1) / SPMV_WARPS;
+            sg_long_partials_kernel<<<pg, SPMV_THREADS, 0, ctx->stream>>>(
+                g->d_rowptr.p, g->d_src.p, g->d_w.p, x, g->d_long_rows.p, g->d_long_segptr.p,
+                g->d_seg_row.p, g->n_seg, g->d_partials.p, g->d_state.p);
+            VREC_LAUNCHED(ctx);
+        }
+        sg_spmv_kernel<<<g->grid, SPMV_THREADS, 0, ctx->stream>>>(
+            rows, g->row_lo, g->d_rowptr.p, g->d_src.p, g->d_w.p, x, nx, uidx, g->d_long_rows.p,
+            g->d_long_segptr.p, g->n_long, g->d_partials.p, g->d_state.p, g->d_block_partials.p, it,
+            max_it, eps2, check_convergence ? 1 : 0);
+        VREC_LAUNCHED(ctx);
+    }
+    return VREC_OK;
+}
+
+int sg_fetch_state(vrec_sg *g, int max_it, SgState *h, int *result_buf) {
+    VREC_CUDA(cudaMemcpyAsync(h, g->d_state.p, sizeof(SgState), cudaMemcpyDeviceToHost, g->ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    if (max_it <= 0) {
+        h->iterations = 0;
+        h->converged = 0;
+        *result_buf = 0;
+    } else if (h->converged) {
+        *result_buf = (h->iterations + 1) & 1;   // converged: step() returns nextX (:101)
+    } else {
+        *result_buf = max_it & 1;                // limit reached: returns x (:95)
+    }
+    return VREC_OK;
+}
+
+int64_t sg_lookup(const vrec_sg *g, int64_t id) {
+    auto it = std::lower_bound(g->h_ids.begin(), g->h_ids.end(), id);
+    if (it == g->h_ids.end() || *it != id) return -1;
+    return it - g->h_ids.begin();
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// Host-side construction of the vertex table and the CSR of P^T (exposed for CPU tests).
+//   ids      distinct(source ∪ target) ascending            (:42-49)
+//   rowptr   in-edge ranges per target vertex
+//   src/w    in-edges in ascending source index, stable for duplicate (s,t) pairs
+// ---------------------------------------------------------------------------------------
+int vrec_host_build_sg(int64_t nnz, const int64_t *source, const int64_t *target, const double *weight,
+                       std::vector<int64_t> &ids, std::vector<int> &rowptr, std::vector<int> &src,
+                       std::vector<double> &w) {
+    if (nnz < 0 || nnz >= (int64_t)0x7fffffff) {
+        vrec_set_error("vrec_sg_load: nnz %lld out of range [0, 2^31-1)", (long long)nnz);
+        return VREC_EINVAL;
+    }
+    ids.resize((size_t)(2 * nnz));
+    for (int64_t e = 0; e < nnz; ++e) {
+        ids[2 * e] = source[e];
+        ids[2 * e + 1] = target[e];
+    }
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    const int64_t N = (int64_t)ids.size();
+    std::vector<int> si((size_t)nnz), ti((size_t)nnz);
+    for (int64_t e = 0; e < nnz; ++e) {
+        si[e] = (int)(std::lower_bound(ids.begin(), ids.end(), source[e]) - ids.begin());
+        ti[e] = (int)(std::lower_bound(ids.begin(), ids.end(), target[e]) - ids.begin());
+    }
+    // stable counting sort by source, then by target
+    std::vector<int64_t> cnt((size_t)N + 1, 0);
+    for (int64_t e = 0; e < nnz; ++e) cnt[si[e] + 1]++;
+    for (int64_t i = 0; i < N; ++i) cnt[i + 1] += cnt[i];
+    std::vector<int> ord((size_t)nnz);
+    for (int64_t e = 0; e < nnz; ++e) ord[cnt[si[e]]++] = (int)e;
+    rowptr.assign((size_t)N + 1, 0);
+    for (int64_t e = 0; e < nnz; ++e) rowptr[ti[e] + 1]++;
+    for (int64_t i = 0; i < N; ++i) rowptr[i + 1] += rowptr[i];
+    std::vector<int> pos(rowptr.begin(), rowptr.end() - 1);
+    src.resize((size_t)nnz);
+    w.resize((size_t)nnz);
+    for (int64_t k = 0; k < nnz; ++k) {
+        int e = ord[k];
+        int p = pos[ti[e]]++;
+        src[p] = si[e];
+        w[p] = weight[e];
+    }
+    return VREC_OK;
+}
+
+extern "C" int vrec_host_sg_csr(int64_t nnz, const int64_t *source, const int64_t *target,
+                                const double *weight, int64_t *out_n, int64_t *out_ids /*[2*nnz]*/,
+                                int32_t *out_rowptr /*[2*nnz+1]*/, int32_t *out_src, double *out_w) {
+    std::vector<int64_t> ids;
+    std::vector<int> rowptr, src;
+    std::vector<double> w;
+    VREC_TRY(vrec_host_build_sg(nnz, source, target, weight, ids, rowptr, src, w));
+    *out_n = (int64_t)ids.size();
+    std::copy(ids.begin(), ids.end(), out_ids);
+    std::copy(rowptr.begin(), rowptr.end(), out_rowptr);
+    std::copy(src.begin(), src.end(), out_src);
+    std::copy(w.begin(), w.end(), out_w);
+    return VREC_OK;
+}
+
+extern "C" int vrec_sg_load(vrec_ctx *ctx, int64_t nnz, const int64_t *source_id, const int64_t *target_id,
+                            const double *balanced_weight, vrec_sg **out) {
+    if (!ctx || !out || (nnz > 0 && (!source_id || !target_id || !balanced_weight))) {
+        vrec_set_error("vrec_sg_load: NULL argument");
+        return VREC_EINVAL;
+    }
+    *out = nullptr;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    std::vector<int> rowptr, src;
+    std::vector<double> w;
+    vrec_sg *g = new vrec_sg();
+    g->ctx = ctx;
+    int rc = vrec_host_build_sg(nnz, source_id, target_id, balanced_weight, g->h_ids, rowptr, src, w);
+    if (rc == VREC_OK) {
+        g->N = (int64_t)g->h_ids.size();
+        g->nnz = nnz;
+        g->row_lo = 0;
+        g->row_hi = g->N;
+        rc = g->d_ids.upload((const long long *)g->h_ids.data(), g->h_ids.size(), ctx->stream);
+    }
+    if (rc == VREC_OK) rc = g->d_rowptr.upload(rowptr.data(), rowptr.size(), ctx->stream);
+    if (rc == VREC_OK) rc = g->d_src.upload(src.data(), src.size(), ctx->stream);
+    if (rc == VREC_OK) rc = g->d_w.upload(w.data(), w.size(), ctx->stream);
+    if (rc == VREC_OK) rc = sg_setup_device(g, rowptr);
+    if (rc != VREC_OK) {
+        delete g;
+        return rc;
+    }
+    *out = g;
+    return VREC_OK;
+}
+
+extern "C" void vrec_sg_free(vrec_sg *sg) {
+    if (!sg) return;
+    cudaSetDevice(sg->ctx->device);
+    cudaStreamSynchronize(sg->ctx->stream);
+    delete sg;
+}
+
+extern "C" int64_t vrec_sg_vertex_count(vrec_sg *sg) { return sg ? sg->N : 0; }
+extern "C" int64_t vrec_sg_edge_count(vrec_sg *sg) { return sg ? sg->nnz : 0; }
+
+extern "C" int vrec_sg_vertex_ids(vrec_sg *sg, int64_t *out_ids) {
+    if (!sg || !out_ids) return VREC_EINVAL;
+    if (!sg->h_ids.empty()) {
+        std::copy(sg->h_ids.begin(), sg->h_ids.end(), out_ids);
+    } else {
+        for (int64_t i = 0; i < sg->N; ++i) out_ids[i] = i;   // generated graphs: ids are 0..N-1
+    }
+    return VREC_OK;
+}
+
+extern "C" int64_t vrec_sg_resident_bytes(vrec_sg *sg) {
+    if (!sg) return 0;
+    return (int64_t)(sg->d_rowptr.bytes() + sg->d_src.bytes() + sg->d_w.bytes() + sg->d_x[0].bytes() +
+                     sg->d_x[1].bytes() + sg->d_ids.bytes());
+}
+
+static int sg_check_params(double epsilon, int32_t max_iterations) {
+    if (!(epsilon >= 0)) {          // :33
+        vrec_set_error("requirement failed: epsilon must be non-negative");
+        return VREC_EINVAL;
+    }
+    if (max_iterations < 0) {       // :34
+        vrec_set_error("requirement failed: max iterations number must be non-negative");
+        return VREC_EINVAL;
+    }
+    return VREC_OK;
+}
+
+extern "C" int vrec_sg_stationary(vrec_sg *sg, int64_t vertex, double epsilon, int32_t max_iterations,
+                                  double *out_x, int32_t *out_iterations, int32_t *out_converged,
+                                  double *out_residual) {
+    if (!sg || !out_x) return VREC_EINVAL;
+    VREC_TRY(sg_check_params(epsilon, max_iterations));
+    VREC_CUDA(cudaSetDevice(sg->ctx->device));
+    int64_t v = sg->h_ids.empty() ? ((vertex >= 0 && vertex < sg->N) ? vertex : -1) : sg_lookup(sg, vertex);
+    if (v < 0) {
+        vrec_set_error("No such vertex in the graph: %lld", (long long)vertex);   // :70
+        return VREC_ENOENT;
+    }
+    VREC_TRY(sg_run_device(sg, v, epsilon, max_iterations, true));
+    SgState st;
+    int buf = 0;
+    VREC_TRY(sg_fetch_state(sg, max_iterations, &st, &buf));
+    VREC_CUDA(cudaMemcpyAsync(out_x, sg->d_x[buf].p, sizeof(double) * (size_t)sg->N, cudaMemcpyDeviceToHost,
+                              sg->ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(sg->ctx->stream));
+    if (out_iterations) *out_iterations = st.iterations;
+    if (out_converged) *out_converged = st.converged;
+    if (out_residual) *out_residual = st.residual;
+    return VREC_OK;
+}
+
+extern "C" int vrec_sg_query(vrec_sg *sg, const int64_t *vertices, int32_t n, double epsilon,
+                             int32_t max_iterations, const int64_t *place_filter, int64_t n_filter,
+                             int32_t max_recs, int64_t *out_id, double *out_prob, int32_t *out_count,
+                             int32_t *out_iterations, int32_t *out_converged, int32_t *out_status) {
+    if (!sg || n < 0 || (n > 0 && (!vertices || !out_count || !out_status))) {
+        vrec_set_error("vrec_sg_query: NULL argument");
+        return VREC_EINVAL;
+    }
+    VREC_TRY(sg_check_params(epsilon, max_iterations));
+    if (max_recs < 0 || n_filter < 0) {
+        vrec_set_error("Maximum recommendations number must be non-negative");
+        return VREC_EINVAL;
+    }
+    vrec_ctx *ctx = sg->ctx;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    const bool use_filter = place_filter != nullptr;
+    const long long n_cand = use_filter ? n_filter : sg->N;
+    if (use_filter)
+        VREC_TRY(sg->d_filter_ids.upload((const long long *)place_filter, (size_t)n_filter, ctx->stream));
+    VREC_TRY(sg->d_cand_val.ensure((size_t)std::max<long long>(1, n_cand)));
+    VREC_TRY(sg->d_cand_key.ensure((size_t)std::max<long long>(1, n_cand)));
+    const int m = std::max(1, (int)max_recs);
+    VREC_TRY(sg->d_out_key.ensure(m));
+    VREC_TRY(sg->d_out_val.ensure(m));
+    VREC_TRY(sg->d_out_count.ensure(1));
+    std::vector<long long> h_key(m);
+    std::vector<double> h_val(m);
+    for (int q = 0; q < n; ++q) {
+        out_count[q] = 0;
+        if (out_iterations) out_iterations[q] = 0;
+        if (out_converged) out_converged[q] = 0;
+        int64_t v = sg->h_ids.empty() ? ((vertices[q] >= 0 && vertices[q] < sg->N) ? vertices[q] : -1)
+                                      : sg_lookup(sg, vertices[q]);
+        if (v < 0) {
+            vrec_set_error("No such vertex in the graph: %lld", (long long)vertices[q]);
+            out_status[q] = VREC_ENOENT;
+            continue;
+        }
+        out_status[q] = VREC_OK;
+        VREC_TRY(sg_run_device(sg, v, epsilon, max_iterations, true));
+        SgState st;
+        int buf = 0;
+        VREC_TRY(sg_fetch_state(sg, max_iterations, &st, &buf));
+        if (out_iterations) out_iterations[q] = st.iterations;
+        if (out_converged) out_converged[q] = st.converged;
+        if (max_recs == 0 || n_cand == 0) continue;
+        int cg = (int)((n_cand + 255) / 256);
+        sg_candidates_kernel<<<cg, 256, 0, ctx->stream>>>(
+            sg->h_ids.empty() ? nullptr : sg->d_ids.p, sg->N, use_filter ? sg->d_filter_ids.p : nullptr, n_filter,
+            sg->d_x[buf].p,
+            (long long)vertices[q], sg->d_cand_val.p, sg->d_cand_key.p);
+        VREC_LAUNCHED(ctx);
+        VREC_TRY(vrec_launch_select_topn(ctx, sg->d_cand_val.p, sg->d_cand_key.p, nullptr, n_cand, 0, 1,
+                                         max_recs, sg->d_out_key.p, sg->d_out_val.p, sg->d_out_count.p));
+        int cnt = 0;
+        VREC_CUDA(cudaMemcpyAsync(&cnt, sg->d_out_count.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        VREC_CUDA(cudaMemcpyAsync(h_key.data(), sg->d_out_key.p, sizeof(long long) * m, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+        VREC_CUDA(cudaMemcpyAsync(h_val.data(), sg->d_out_val.p, sizeof(double) * m, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+        VREC_CUDA(cudaStreamSynchronize(ctx->stream));
+        out_count[q] = cnt;
+        for (int k = 0; k < cnt; ++k) {
+            out_id[(size_t)q * max_recs + k] = h_key[k];
+            out_prob[(size_t)q * max_recs + k] = h_val[k];
+        }
+    }
+    return VREC_OK;
+}
+
+// Copies the device CSR of P^T (rows owned by this process) back to the host, for tests.
+extern "C" int vrec_sg_export_csr(vrec_sg *sg, int32_t *out_rowptr, int32_t *out_src, double *out_w) {
+    if (!sg || !out_rowptr || !out_src || !out_w) return VREC_EINVAL;
+    cudaStream_t s = sg->ctx->stream;
+    VREC_CUDA(cudaSetDevice(sg->ctx->device));
+    size_t rows = (size_t)(sg->row_hi - sg->row_lo);
+    VREC_CUDA(cudaMemcpyAsync(out_rowptr, sg->d_rowptr.p, sizeof(int) * (rows + 1), cudaMemcpyDeviceToHost, s));
+    VREC_CUDA(cudaMemcpyAsync(out_src, sg->d_src.p, sizeof(int) * (size_t)sg->nnz, cudaMemcpyDeviceToHost, s));
+    VREC_CUDA(cudaMemcpyAsync(out_w, sg->d_w.p, sizeof(double) * (size_t)sg->nnz, cudaMemcpyDeviceToHost, s));
+    VREC_CUDA(cudaStreamSynchronize(s));
+    return VREC_OK;
+}
+
+extern "C" int vrec_sg_iterate_device(vrec_sg *sg, int32_t iterations) {
+    if (!sg || iterations < 0) return VREC_EINVAL;
+    VREC_CUDA(cudaSetDevice(sg->ctx->device));
+    return sg_run_device(sg, 0, 0.0, iterations, false);
+}
+
+// ---------------------------------------------------------------------------------------
+// Synthetic graph generated on the device (bench config "oversized graph").
+// Row t of P^T gets its in-edges directly: in-degree = out_degree for every vertex, sources
+// 50 % uniform / 50 % skewed (u^3 * N) over a multiplicative permutation, ascending per row,
+// weight = 1/out_degree so that P is row-stochastic in expectation.
+// ---------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+    z += 0x9e3779b97f4a7c15ULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+__global__ void sg_gen_rows_kernel(long long N, int deg, unsigned long long seed, long long row_lo,
+                                   int n_rows, int *__restrict__ rowptr, int *__restrict__ src,
+                                   double *__restrict__ w) {
+    // one warp per row; deg <= 128: each lane draws deg/32 sources, then a bitonic-free
+    // insertion by rank keeps ascending order (rank = number of smaller (value, slot) pairs)
+    extern __shared__ int s_buf[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    int *buf = s_buf + warp * deg;
+    for (long long r = (long long)blockIdx.x * wpb + warp; r < n_rows; r += (long long)gridDim.x * wpb) {
+        long long gr = row_lo + r;
+        for (int k = lane; k < deg; k += 32) {
+            unsigned long long h = splitmix64(seed ^ (unsigned long long)(gr * 1024 + k) * 0x2545F4914F6CDD1DULL);
+            double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+            long long v;
+            if (k & 1) {
+                v = (long long)(u * (double)N);
+            } else {
+                long long z = (long long)(u * u * u * (double)N);
+                v = (long long)(((unsigned long long)z * 2654435761ULL + 12345ULL) % (unsigned long long)N);
+            }
+            if (v >= N) v = N - 1;
+            buf[k] = (int)v;
+        }
+        __syncwarp();
+        for (int k = lane; k < deg; k += 32) {
+            int v = buf[k], rank = 0;
+            for (int j = 0; j < deg; ++j) {
+                int o = buf[j];
+                rank += (o < v) || (o == v && j < k);
+            }
+            src[(size_t)r * deg + rank] = v;
+            w[(size_t)r * deg + rank] = 1.0 / (double)deg;
+        }
+        __syncwarp();
+        if (lane == 0) rowptr[r] = (int)(r * deg);
+        if (lane == 0 && r == n_rows - 1) rowptr[n_rows] = (int)((long long)n_rows * deg);
+    }
+}
+
+}  // namespace
+
+extern "C" int vrec_sg_generate(vrec_ctx *ctx, int64_t n_vertices, int32_t out_degree, uint64_t seed,
+                                int32_t rank, int32_t world, vrec_sg **out) {
+    if (!ctx || !out || n_vertices <= 0 || out_degree <= 0 || out_degree > 1024 || world <= 0 || rank < 0 ||
+        rank >= world) {
+        vrec_set_error("vrec_sg_generate: bad argument");
+        return VREC_EINVAL;
+    }
+    *out = nullptr;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    int64_t lo = n_vertices * rank / world, hi = n_vertices * (rank + 1) / world;
+    int64_t rows = hi - lo;
+    if (rows * out_degree >= (int64_t)0x7fffffff) {
+        vrec_set_error("vrec_sg_generate: %lld edges per process exceed 2^31-1", (long long)(rows * out_degree));
+        return VREC_EINVAL;
+    }
+    vrec_sg *g = new vrec_sg();
+    g->ctx = ctx;
+    g->N = n_vertices;
+    g->nnz = rows * out_degree;
+    g->row_lo = lo;
+    g->row_hi = hi;
+    int rc = g->d_rowptr.alloc((size_t)rows + 1);
+    if (rc == VREC_OK) rc = g->d_src.alloc((size_t)g->nnz);
+    if (rc == VREC_OK) rc = g->d_w.alloc((size_t)g->nnz);
+    if (rc == VREC_OK) rc = g->d_ids.alloc(1);
+    if (rc == VREC_OK) {
+        int wpb = 8;
+        size_t smem = (size_t)wpb * out_degree * sizeof(int);
+        int grid = (int)std::min<int64_t>((rows + wpb - 1) / wpb, 148 * 16);
+        sg_gen_rows_kernel<<<grid, wpb * 32, smem, ctx->stream>>>(n_vertices, out_degree, seed, lo, (int)rows,
+                                                                  g->d_rowptr.p, g->d_src.p, g->d_w.p);
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            vrec_set_error("sg_gen_rows_kernel -> %s", cudaGetErrorString(e));
+            rc = VREC_ECUDA;
+        }
+    }
+    if (rc == VREC_OK) {
+        // every row has out_degree <= 1024 terms: no long rows
+        std::vector<int> fake_rowptr(2, 0);
+        g->n_long = g->n_seg = 0;
+        rc = g->d_long_rows.alloc(1);
+        if (rc == VREC_OK) rc = g->d_long_segptr.alloc(2);
+        if (rc == VREC_OK) rc = g->d_seg_row.alloc(1);
+        if (rc == VREC_OK) rc = g->d_partials.alloc(1);
+        if (rc == VREC_OK) rc = g->d_x[0].alloc(g->N);
+        if (rc == VREC_OK) rc = g->d_x[1].alloc(g->N);
+        int64_t want = (rows + 32 * SPMV_WARPS - 1) / (32 * SPMV_WARPS);
+        g->grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, 148 * 8));
+        if (rc == VREC_OK) rc = g->d_block_partials.alloc(g->grid);
+        if (rc == VREC_OK) rc = g->d_state.alloc(1);
+    }
+    if (rc == VREC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        vrec_set_error("vrec_sg_generate: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = VREC_ECUDA;
+    }
+    if (rc != VREC_OK) {
+        delete g;
+        return rc;
+    }
+    *out = g;
+    return VREC_OK;
+}

@@ -1,0 +1,259 @@
+"""GPU parity: the CUDA engine, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  fp64 values are compared bit-for-bit (the engine shares the oracle's canonical
+summation orders); north_star's tolerance is 1e-6 relative, so exact equality is the stricter
+statement.  Integer / index outputs (ids, counts, order, status) are always exact."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "locations-recommender_b200"))
+
+from tests.golden import reference_kats as K  # noqa: E402
+from tests.helpers import oracle_knn_data  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vrec():
+    import vrec as v
+    return v
+
+
+@pytest.fixture(scope="module")
+def ctx(vrec):
+    c = vrec.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from vrec import synth as s
+    return s
+
+
+# ------------------------------------------------------------------ SG
+def _kat_graph(vrec, ctx):
+    s, t, w = zip(*K.SG_EDGES)
+    return vrec.StochasticGraph(s, t, w, ctx=ctx)
+
+
+def test_sg_reference_kats_exact(vrec, ctx):
+    g = _kat_graph(vrec, ctx)
+    assert g.vertex_ids().tolist() == [1, 2, 3, 4, 5]
+    for (vertex, eps, max_it), want in K.SG_CASES:
+        rec = vrec.StochasticRecommender(g, eps, max_it)
+        ids, pr = rec.makeRecommendations(vertex)
+        got = sorted(zip(ids.tolist(), pr.tolist()), key=lambda r: -r[1])
+        assert got == want                      # exact doubles, as StochasticRecommenderTest does
+        oi, op, cnt, its, conv, st = rec.recommend([vertex], None, 10)
+        assert list(zip(oi[0, :cnt[0]].tolist(), op[0, :cnt[0]].tolist())) == want
+    rec = vrec.StochasticRecommender(g, 0.05, 1000)
+    rec.stationary(1)
+    assert (rec.last_iterations, rec.last_converged) == (3, 1)
+    rec = vrec.StochasticRecommender(g, 0.01, 1)
+    rec.stationary(1)
+    assert (rec.last_iterations, rec.last_converged) == (1, 0)
+
+
+def test_sg_errors_and_corner_cases(vrec, ctx):
+    g = _kat_graph(vrec, ctx)
+    with pytest.raises(vrec.NoSuchElement, match="No such vertex in the graph: 100"):
+        vrec.StochasticRecommender(g, 0.05, 1000).makeRecommendations(K.SG_MISSING_VERTEX)
+    with pytest.raises(ValueError):
+        vrec.StochasticRecommender(g, -0.1, 10)
+    with pytest.raises(ValueError):
+        vrec.StochasticRecommender(g, 0.1, -1)
+    x = vrec.StochasticRecommender(g, 0.05, 0).stationary(1)        # maxIterations = 0 -> x0
+    assert np.all(x == 0.2)
+    rec = vrec.StochasticRecommender(g, 0.0, 7)                      # epsilon = 0 runs to the limit
+    rec.stationary(1)
+    assert (rec.last_iterations, rec.last_converged) == (7, 0)
+    oi, op, cnt, its, conv, st = vrec.StochasticRecommender(g, 0.01, 20).recommend([1, 100, 2], [2, 4, 99, 4], 10)
+    assert st.tolist() == [0, -2, 0]
+    assert sorted(oi[0, :cnt[0]].tolist()) == [2, 4] and cnt[1] == 0
+    oi, op, cnt, *_ = vrec.StochasticRecommender(g, 0.01, 20).recommend([1], None, 0)
+    assert cnt[0] == 0
+
+
+@pytest.mark.parametrize("n,deg,hub,seed", [(50, 3, 0.0, 1), (2000, 6, 0.0, 2), (5000, 5, 0.5, 3),
+                                            (30000, 40, 0.3, 4)])
+def test_sg_random_graphs_bit_exact(vrec, ctx, synth, oracle, n, deg, hub, seed):
+    s, t, w = synth.random_stochastic_graph(n, deg, seed=seed, hub_fraction=hub)
+    g = vrec.StochasticGraph(s, t, w, ctx=ctx)
+    og = oracle.SgGraph(s, t, w)
+    assert np.array_equal(g.vertex_ids(), og.ids)
+    flt = og.ids[::3]
+    for vertex, eps, max_it in [(int(og.ids[0]), 0.0, 5), (int(og.ids[n // 2]), 1e-3, 20),
+                                (int(og.ids[-1]), 1e-6, 12)]:
+        rec = vrec.StochasticRecommender(g, eps, max_it)
+        x = rec.stationary(vertex)
+        rc, ox, oit, oconv, ores = og.run(vertex, eps, max_it)
+        assert rc == 0
+        assert (rec.last_iterations, rec.last_converged) == (oit, oconv)
+        assert np.array_equal(x, ox)                                   # bit-exact
+        assert abs(rec.last_residual - ores) <= 1e-12 * max(ores, 1e-300)
+        oi, op, cnt, its, conv, st = rec.recommend([vertex], flt, 10)
+        rc, wi, wp, _, _ = og.query(vertex, eps, max_it, flt, 10)
+        assert oi[0, :cnt[0]].tolist() == wi.tolist() and op[0, :cnt[0]].tolist() == wp.tolist()
+
+
+def test_sg_default_sample_graph(vrec, ctx, synth, oracle):
+    # config 2 shape at reduced size: per-region graph of sample-generator data (giant place rows)
+    pl = synth.sample_places(30000, seed=0)
+    v = synth.sample_place_visits(pl, 0, persons_per_region=30000, person_count_total=3_000_000, seed=0)
+    s, t, w = synth.build_stochastic_graph(v)
+    g = vrec.StochasticGraph(s, t, w, ctx=ctx)
+    og = oracle.SgGraph(s, t, w)
+    person = int(v.person_id[0])
+    rec = vrec.StochasticRecommender(g, 0.01, 20)                     # bin/stochastic_recommender.sh:32-35
+    x = rec.stationary(person)
+    rc, ox, oit, oconv, _ = og.run(person, 0.01, 20)
+    assert (rec.last_iterations, rec.last_converged) == (oit, oconv)
+    assert np.array_equal(x, ox)
+    flt = pl.of_region(0)
+    oi, op, cnt, *_ = rec.recommend([person], flt, 10)
+    rc, wi, wp, _, _ = og.query(person, 0.01, 20, flt, 10)
+    assert oi[0, :cnt[0]].tolist() == wi.tolist() and op[0, :cnt[0]].tolist() == wp.tolist()
+
+
+def test_sg_generated_graph_matches_oracle(vrec, ctx, oracle):
+    g = vrec.StochasticGraph.generate(20000, 16, seed=5, ctx=ctx)
+    rowptr, src, w = g.export_csr()
+    assert rowptr[-1] == g.nnz == 20000 * 16
+    tgt = np.repeat(np.arange(g.N), np.diff(rowptr))
+    for r in (0, 1, 777):
+        assert np.all(np.diff(src[rowptr[r]:rowptr[r + 1]]) >= 0)
+    og = oracle.SgGraph(src.astype(np.int64), tgt.astype(np.int64), w)
+    if og.N == g.N:       # every vertex appears (overwhelmingly likely at this density)
+        x = vrec.StochasticRecommender(g, 0.0, 6).stationary(0)
+        rc, ox, *_ = og.run(0, 0.0, 6)
+        assert np.array_equal(x, ox)
+
+
+# ------------------------------------------------------------------ KNN
+def _check_knn(vrec, oracle, rs, inp, pw, cw, k, targets, flt, max_recs):
+    rec = vrec.KnnRecommender(rs, pw, cw, k)
+    d = oracle_knn_data(oracle, inp)
+    pl, rt, cnt, st = rec.recommend(targets, flt, max_recs)
+    rc, opl, ort, ocnt, ost = oracle.knn_query_batch(d, targets, pw, cw, k, flt, max_recs)
+    assert rc == 0
+    assert st.tolist() == ost.tolist()
+    assert cnt.tolist() == ocnt.tolist()
+    for q in range(len(targets)):
+        assert pl[q, :cnt[q]].tolist() == opl[q, :cnt[q]].tolist(), (q, targets[q])
+        assert rt[q, :cnt[q]].tolist() == ort[q, :cnt[q]].tolist(), (q, targets[q])
+    return rec, d
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("k", [1, 7, 50, 5000])
+@pytest.mark.parametrize("path", [0, 1, 2])
+def test_knn_random_bit_exact(vrec, ctx, synth, oracle, seed, k, path):
+    if path == 1 and k > 1024:
+        pytest.skip("gather path needs k <= 1024")
+    inp = synth.random_knn_inputs(700, 60, 9, seed=seed, separate_ratings=(seed == 2))
+    rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
+    rs.set_option("rating_path", path)
+    targets = np.concatenate([inp.person_id[:40], [1, 999999]])       # two unknown persons
+    flt = np.arange(0, 60, 2)
+    rec, d = _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, k, targets, flt, 10)
+    _check_knn(vrec, oracle, rs, inp, 0.25, 0.75, k, targets[:8], None, 60)
+    # neighbours and raw estimates of one target
+    t = int(inp.person_id[5])
+    rc, oids, osims = oracle.knn_neighbours(d, t, 0.5, 0.5, k)
+    if rc == 0:
+        sims = rec.similarities(t)
+        want = np.zeros(len(inp.person_id))
+        want[np.searchsorted(inp.person_id, oids)] = osims
+        assert np.array_equal(sims, want)
+        if k <= 1024:
+            ids, s2 = rec.findSimilarPersons(t)
+            assert ids.tolist() == oids.tolist() and s2.tolist() == osims.tolist()
+        epl, ert = rec.makeRecommendations(t)
+        rc, wpl, wrt = oracle.knn_estimates(d, t, 0.5, 0.5, k)
+        assert epl.tolist() == wpl.tolist() and ert.tolist() == wrt.tolist()
+    rs.close()
+
+
+def test_knn_errors(vrec, ctx, synth):
+    inp = synth.random_knn_inputs(50, 10, 4, seed=3)
+    rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
+    for pw, cw, k in [(0.0, 1.0, 5), (1.0, 0.0, 5), (0.6, 0.5, 5), (0.5, 0.5, 0)]:
+        with pytest.raises(ValueError, match="requirement failed"):
+            vrec.KnnRecommender(rs, pw, cw, k)
+    rec = vrec.KnnRecommender(rs, 0.5, 0.5, 5)
+    with pytest.raises(vrec.NoSuchElement, match="No such person: 12345678"):
+        rec.makeRecommendations(12345678)
+    pl, rt, cnt, st = rec.recommend([int(inp.person_id[0])], None, 0)
+    assert cnt[0] == 0
+    pl, rt, cnt, st = rec.recommend([], None, 5)
+    assert len(cnt) == 0
+    # unsorted persons are accepted (sorted internally)
+    perm = np.random.default_rng(0).permutation(len(inp.person_id))
+    rows = [(inp.place_col[inp.place_rowptr[i]:inp.place_rowptr[i + 1]],
+             inp.place_val[inp.place_rowptr[i]:inp.place_rowptr[i + 1]],
+             inp.cat_col[inp.cat_rowptr[i]:inp.cat_rowptr[i + 1]],
+             inp.cat_val[inp.cat_rowptr[i]:inp.cat_rowptr[i + 1]]) for i in perm]
+    prp = np.concatenate([[0], np.cumsum([len(r[0]) for r in rows])])
+    crp = np.concatenate([[0], np.cumsum([len(r[2]) for r in rows])])
+    rs2 = vrec.KnnRegionSet(inp.person_id[perm], prp, np.concatenate([r[0] for r in rows]),
+                            np.concatenate([r[1] for r in rows]), inp.place_dim, crp,
+                            np.concatenate([r[2] for r in rows]), np.concatenate([r[3] for r in rows]),
+                            inp.cat_dim, inp.rating_person, inp.rating_place, inp.rating_value, ctx=ctx)
+    t = inp.person_id[:10]
+    a = vrec.KnnRecommender(rs, 0.5, 0.5, 5).recommend(t, None, 5)
+    b = vrec.KnnRecommender(rs2, 0.5, 0.5, 5).recommend(t, None, 5)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    bad_col = inp.place_col.copy()
+    if len(bad_col) > 1:
+        bad_col[:] = 0
+        with pytest.raises(ValueError):
+            vrec.KnnRegionSet(inp.person_id, inp.place_rowptr, bad_col, inp.place_val, inp.place_dim,
+                              inp.cat_rowptr, inp.cat_col, inp.cat_val, inp.cat_dim, ctx=ctx)
+
+
+def test_knn_distance_kats(vrec, ctx):
+    # DistanceTest.scala:34-60 through the engine: target = person 1, candidate = person 2
+    for ((i1, v1), (i2, v2)), want in K.COSINE:
+        pid = [1, 2]
+        prp = [0, len(i1), len(i1) + len(i2)]
+        rs = vrec.KnnRegionSet(pid, prp, list(i1) + list(i2), list(v1) + list(v2), 2,
+                               [0, 1, 2], [0, 0], [1.0, 1.0], 1, ctx=ctx)
+        sims = vrec.KnnRecommender(rs, 0.5, 0.5, 10).similarities(1)
+        place_sim = want if want > 0 else 0.0
+        assert sims[1] == place_sim * 0.5 + 1.0 * 0.5
+        rs.close()
+
+
+def test_knn_g2_shape(vrec, ctx, synth, oracle):
+    # config 3 shape at reduced size (20k persons / 2k places), K = 50, both weights 0.5
+    v, places = synth.g2_place_visits(20000, 2000, seed=20181231)
+    inp = synth.build_rating_vectors(v)
+    rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
+    targets = inp.person_id[::400]
+    _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 50, targets, places.id, 10)
+    rs.set_option("splits", 1)
+    _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 50, targets[:10], places.id, 10)
+    rs.set_option("splits", 0)
+    # launcher configuration: K = 2 000 000 (every positive candidate), default sample data shape
+    _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 2_000_000, targets[:3], places.id, 10)
+    rs.close()
+
+
+def test_knn_default_sample_data(vrec, ctx, synth, oracle):
+    # config 1 shape at reduced size: degenerate diagonal data, huge tie groups
+    pl = synth.sample_places(30000, seed=0)
+    v = synth.sample_place_visits(pl, 0, persons_per_region=20000, person_count_total=3_000_000, seed=0)
+    inp = synth.build_rating_vectors(v)
+    rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
+    targets = inp.person_id[:3]
+    _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 2_000_000, targets, pl.of_region(0), 10)
+    _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 50, targets, pl.of_region(0), 10)
+    _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 3000, targets[:2], pl.of_region(0), 10)   # radix-select path
+    rs.close()

@@ -1,0 +1,71 @@
+"""The C oracle against an independent pure-Python restatement of the Scala source (small cases),
+and structural checks of the canonical summation order."""
+import sys
+
+import numpy as np
+import pytest
+
+from tests.helpers import oracle_knn_data, py_knn
+
+sys.path.insert(0, "locations-recommender_b200")
+from vrec import synth  # noqa: E402
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("k", [1, 5, 1000])
+def test_knn_oracle_vs_python(oracle, seed, k):
+    inp = synth.random_knn_inputs(60, 15, 6, seed=seed, separate_ratings=(seed % 2 == 0))
+    d = oracle_knn_data(oracle, inp)
+    flt = np.arange(0, 15, 2)
+    for target in list(inp.person_id[:12]) + [5]:
+        want = py_knn(inp, int(target), 0.3, 0.7, k, flt, 4)
+        rc, ids, sims = oracle.knn_neighbours(d, target, 0.3, 0.7, k)
+        if want is None:
+            assert rc == oracle.ENOENT
+            continue
+        nb, est, recs = want
+        assert rc == 0
+        got = sorted(zip(ids.tolist(), sims.tolist()))
+        assert got == sorted((int(inp.person_id[i]), s) for s, i in nb)
+        rc, pl, rt = oracle.knn_estimates(d, target, 0.3, 0.7, k)
+        assert rc == 0 and dict(zip(pl.tolist(), rt.tolist())) == est
+        rc, opl, ort, ocnt, ost = oracle.knn_query_batch(d, [target], 0.3, 0.7, k, flt, 4)
+        assert rc == 0 and ost[0] == 0
+        assert list(zip(ort[0, :ocnt[0]].tolist(), opl[0, :ocnt[0]].tolist())) == recs
+
+
+def test_knn_oracle_requires(oracle):
+    inp = synth.random_knn_inputs(10, 5, 3, seed=9)
+    d = oracle_knn_data(oracle, inp)
+    t = inp.person_id[0]
+    assert oracle.knn_neighbours(d, t, 0.0, 1.0, 3)[0] == oracle.EINVAL
+    assert oracle.knn_neighbours(d, t, 0.6, 0.5, 3)[0] == oracle.EINVAL
+    assert oracle.knn_neighbours(d, t, 0.5, 0.5, 0)[0] == oracle.EINVAL
+
+
+def test_sg_oracle_vs_sequential_python(oracle):
+    # rows with <= 3 in-edges: canonical order == left-to-right; longer rows: within 1e-12
+    s, t, w = synth.random_stochastic_graph(40, 3, seed=4)
+    g = oracle.SgGraph(s, t, w)
+    ids = g.ids
+    idx = {int(v): i for i, v in enumerate(ids)}
+    order = sorted(range(len(s)), key=lambda e: (idx[int(t[e])], idx[int(s[e])], e))
+    x = np.full(g.N, 1.0 / g.N)
+    v = idx[int(ids[3])]
+    for _ in range(5):
+        sig = np.zeros(g.N)
+        for e in order:
+            sig[idx[int(t[e])]] += x[idx[int(s[e])]] * w[e]
+        x = np.array([(1.0 if i == v else 0.0) * 0.15 + sig[i] * (1 - 0.15) for i in range(g.N)])
+    rc, ox, it, conv, res = g.run(int(ids[3]), 0.0, 5)
+    assert rc == 0 and it == 5 and conv == 0
+    np.testing.assert_allclose(ox, x, rtol=1e-12, atol=0)
+
+
+def test_sg_long_rows_segmenting(oracle):
+    # a hub row longer than the 1024-term segment; mass must be conserved up to rounding
+    s, t, w = synth.random_stochastic_graph(3000, 4, seed=5, hub_fraction=0.4)
+    g = oracle.SgGraph(s, t, w)
+    rc, x, it, conv, res = g.run(int(g.ids[10]), 1e-9, 50)
+    assert rc == 0
+    assert abs(x.sum() - 1.0) < 1e-9          # every vertex has out-edges: no mass is lost
