@@ -1,0 +1,471 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the two hot paths on B200, one JSON line on stdout.
+
+Headline (`metric`, `value`): KNN target persons/second on BASELINE.json config 3 (batch KNN,
+1 M persons / 100 K places, K = 50, place+category weights 0.5/0.5, top-10 places), data resident
+in HBM.  `e2e` is the same through the host-buffer C-ABI call (vrec_knn_query).  The `sg` object
+carries the second half of BASELINE.json's metric: SG power-iteration HBM GB/s on the oversized
+synthetic graph (config 5 shape at the size that fits one GPU), with its own roofline / e2e /
+cpu_baseline.  `--impl reference` times the CPU oracle port (the reference is Scala/Spark and
+cannot run here: no JVM) on bounded samples of the same workloads.
+
+A "step" = one batch of `--knn-batch` targets per GPU (KNN) / one 20-iteration power iteration (SG).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "locations-recommender_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons during the timed region (nvidia-smi, 200 ms)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- workloads
+def build_knn_inputs(args):
+    from vrec import synth
+    t0 = time.time()
+    v, places = synth.g2_place_visits(args.knn_persons, args.knn_places, seed=20181231, region=0)
+    inp = synth.build_rating_vectors(v)
+    log(f"[bench] G2 region-set: P={len(inp.person_id)} nnz_place={len(inp.place_col)} "
+        f"nnz_cat={len(inp.cat_col)} B_region={inp.algorithmic_bytes / 1e6:.1f} MB ({time.time() - t0:.1f}s)")
+    return inp, places
+
+
+def knn_workload_name(args):
+    return (f"knn_batch P={args.knn_persons} places={args.knn_places} K={args.k_nearest} pw=cw=0.5 "
+            f"top{args.max_recs}, {args.knn_batch} targets/step/GPU (BASELINE config 3, generator G2)")
+
+
+def sg_workload_name(args):
+    return (f"sg_power_iteration N={args.sg_vertices} in_degree={args.sg_degree} "
+            f"nnz={args.sg_vertices * args.sg_degree} eps=0 {args.sg_iterations} iterations/step "
+            f"(BASELINE config 5 shape, device generator)")
+
+
+def sg_bytes_per_iteration(n, nnz):
+    return 12 * nnz + 20 * n
+
+
+def oracle_knn_data(oracle, inp):
+    row = np.searchsorted(inp.person_id, inp.rating_person)
+    order = np.argsort(row, kind="stable")
+    rowptr = np.zeros(len(inp.person_id) + 1, dtype=np.int64)
+    np.add.at(rowptr, row + 1, 1)
+    return oracle.KnnData(inp.person_id, inp.place_rowptr, inp.place_col, inp.place_val,
+                          inp.cat_rowptr, inp.cat_col, inp.cat_val,
+                          np.cumsum(rowptr), inp.rating_place[order], inp.rating_value[order],
+                          place_dim=inp.place_dim)
+
+
+def cpu_knn(args, inp, places, n_targets, repeats=1):
+    """CPU oracle (port of the Scala path) on a bounded sample of the same workload."""
+    from oracle import oracle
+    oracle.build()
+    d = oracle_knn_data(oracle, inp)
+    threads = os.cpu_count() or 1
+    rng = np.random.default_rng(7)
+    targets = inp.person_id[rng.choice(len(inp.person_id), n_targets, replace=False)]
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        rc, *_ = oracle.knn_query_batch(d, targets, 0.5, 0.5, args.k_nearest, places.id, args.max_recs,
+                                        n_threads=threads)
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        best = dt if best is None else min(best, dt)
+    return {"value": n_targets / best, "unit": "persons/s", "cores": threads, "kind": "port",
+            "sample": f"{n_targets} random targets of the same region-set, {best:.2f}s, oracle/vrec_oracle.c "
+                      f"with OpenMP over targets"}, best
+
+
+def cpu_sg(args, n_vertices, iterations):
+    """CPU oracle SpMV on a smaller graph of the same generator (host RAM bound)."""
+    from oracle import oracle
+    oracle.build()
+    threads = os.cpu_count() or 1
+    rng = np.random.default_rng(5)
+    deg = args.sg_degree
+    tgt = np.repeat(np.arange(n_vertices, dtype=np.int64), deg)
+    u = rng.random(len(tgt))
+    skew = (np.arange(len(tgt)) % 2) == 0
+    src = np.where(skew, ((u ** 3 * n_vertices).astype(np.int64) * 2654435761 + 12345) % n_vertices,
+                   (u * n_vertices).astype(np.int64))
+    w = np.full(len(tgt), 1.0 / deg)
+    g = oracle.SgGraph(src, tgt, w)
+    oracle.set_threads(threads)
+    t0 = time.perf_counter()
+    rc, x, it, conv, res = g.run(int(g.ids[0]), 0.0, iterations)
+    dt = time.perf_counter() - t0
+    assert rc == 0 and it == iterations
+    gbs = sg_bytes_per_iteration(g.N, g.nnz) * iterations / dt / 1e9
+    return {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port",
+            "sample": f"N={g.N} nnz={g.nnz} same generator shape, {iterations} iterations, {dt:.2f}s, "
+                      f"oracle/vrec_oracle.c with OpenMP over rows"}, dt
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    inp, places = build_knn_inputs(args)
+    per_step = args.ref_knn_targets
+    times = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb, dt = cpu_knn(args, inp, places, per_step)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = per_step * len(times) / total
+    sg_cb, _ = cpu_sg(args, args.ref_sg_vertices, 3)
+    cb["value"] = value
+    line = {
+        "impl": "reference", "metric": "KNN target persons/sec (sim+top-K+rating)", "value": value,
+        "unit": "persons/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": knn_workload_name(args), "step": f"{per_step} targets on the host cores"},
+        "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": "persons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sg": {"metric": "SG power-iteration GB/s (algorithmic bytes)", "value": sg_cb["value"],
+               "unit": "GB/s", "cpu_baseline": sg_cb},
+        "note": "reference = Scala/Spark, not runnable here (no JVM); this arm is the C oracle port on all host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import vrec
+    from vrec import _lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = vrec.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    lib = ctx.lib
+    peak, peak_src = measured_peaks()
+
+    # ---------------- KNN (headline)
+    inp, places = build_knn_inputs(args)
+    t0 = time.time()
+    rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
+    load_s = time.time() - t0
+    rec = vrec.KnnRecommender(rs, 0.5, 0.5, args.k_nearest)
+    B = args.knn_batch
+    n_steps_total = args.warmup + args.steps
+    P = len(inp.person_id)
+    # each rank walks its own contiguous range of targets (weak scaling: B targets per GPU per step)
+    tgt_ids = np.stack([inp.person_id[(np.arange(B) + (s * world + rank) * B) % P] for s in range(n_steps_total)])
+    d_targets = torch.from_numpy(tgt_ids).cuda()
+    m = args.max_recs
+    d_place = torch.empty((B, m), dtype=torch.int64, device="cuda")
+    d_rating = torch.empty((B, m), dtype=torch.float64, device="cuda")
+    d_count = torch.empty(B, dtype=torch.int32, device="cuda")
+    d_status = torch.empty(B, dtype=torch.int32, device="cuda")
+    flt = np.ascontiguousarray(places.id, dtype=np.int64)
+    assert lib.vrec_knn_set_filter(rs._h, flt.ctypes.data_as(L.i64p), len(flt)) == 0
+    torch.cuda.synchronize()
+
+    def knn_step_device(s):
+        rc = lib.vrec_knn_query_device(rs._h, d_targets[s].data_ptr(), B, 0.5, 0.5, args.k_nearest, m,
+                                       d_place.data_ptr(), d_rating.data_ptr(), d_count.data_ptr(),
+                                       d_status.data_ptr())
+        if rc != 0:
+            raise RuntimeError(L.last_error())
+
+    for s in range(args.warmup):
+        knn_step_device(s)
+    ctx.synchronize()
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launch_count
+    barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        ev[i][0].record(stream)
+        knn_step_device(args.warmup + i)
+        ev[i][1].record(stream)
+    ctx.synchronize()
+    barrier()
+    knn_ms = [a.elapsed_time(b) for a, b in ev]
+    knn_total_ms = max_over_ranks(sum(knn_ms))
+    knn_launches = ctx.launch_count - launches0
+    clocks_knn = sampler.stop()
+    status_ok = int((d_status == 0).sum().item())
+    value = world * B * args.steps / (knn_total_ms / 1e3)
+    log(f"[bench] knn device: {value:,.0f} persons/s over {world} GPU(s); per-step ms {['%.1f' % x for x in knn_ms]}; "
+        f"status ok {status_ok}/{B}")
+
+    # end to end through the host-buffer ABI call, pinned host buffers
+    h_targets = torch.from_numpy(tgt_ids).pin_memory()
+    h_place = torch.empty((B, m), dtype=torch.int64).pin_memory()
+    h_rating = torch.empty((B, m), dtype=torch.float64).pin_memory()
+    h_count = torch.empty(B, dtype=torch.int32).pin_memory()
+    h_status = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def knn_step_host(s):
+        rc = lib.vrec_knn_query(rs._h, C_i64(h_targets[s].data_ptr()), B, 0.5, 0.5, args.k_nearest,
+                                flt.ctypes.data_as(L.i64p), len(flt), m, C_i64(h_place.data_ptr()),
+                                C_f64(h_rating.data_ptr()), C_i32(h_count.data_ptr()), C_i32(h_status.data_ptr()))
+        if rc != 0:
+            raise RuntimeError(L.last_error())
+
+    import ctypes as C
+
+    def C_i64(p):
+        return C.cast(p, L.i64p)
+
+    def C_f64(p):
+        return C.cast(p, L.f64p)
+
+    def C_i32(p):
+        return C.cast(p, L.i32p)
+
+    knn_step_host(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        knn_step_host(args.warmup + i)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * B * args.steps / e2e_s
+    h2d = B * 8 + len(flt) * 0 + int(rs.place_dim)      # target ids + the region filter flags
+    d2h = B * m * 16 + B * 8
+    log(f"[bench] knn e2e: {e2e_value:,.0f} persons/s")
+
+    # roofline of the dominant KNN kernel (knn_topk_kernel): algorithmic bytes of one launch = one
+    # pass over the region-set (bytes/target = B_region / T with T = targets per pass)
+    b_region = inp.algorithmic_bytes
+    knn_launch_ms = statistics.mean(knn_ms)
+    knn_roof = {"bound": "hbm", "kernel": "knn_topk_kernel", "achieved": b_region / (knn_launch_ms / 1e3) / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": b_region / (knn_launch_ms / 1e3) / 1e9 / peak,
+                "traffic": None, "peak_source": peak_src,
+                "note": f"one launch serves T={B} targets, so algorithmic bytes/launch = B_region = {b_region}; "
+                        "the batch kernel is issue-bound (10^6 exact fp64 pair evaluations per target), "
+                        "not HBM-bound: see DESIGN.md"}
+
+    cpu_knn_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu_knn_base, _ = cpu_knn(args, inp, places, args.cpu_knn_targets)
+        log(f"[bench] knn cpu baseline: {cpu_knn_base['value']:.1f} persons/s on {cpu_knn_base['cores']} threads")
+    rs.close()
+    del d_targets
+
+    # ---------------- SG (second half of the metric)
+    sg = None
+    if not args.no_sg:
+        sg = run_sg(args, vrec, ctx, stream, world, rank, barrier, max_over_ranks, peak, peak_src)
+
+    if rank == 0:
+        line = {
+            "metric": "KNN target persons/sec (sim+top-K+rating)", "value": value, "unit": "persons/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": knn_total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": knn_workload_name(args), "parallelism": f"targets sharded over {world} GPU(s), "
+                       "region-set replicated, no collective", "l2": "inputs larger than L2 "
+                       f"(region-set {b_region / 1e6:.0f} MB > 126 MB) and new targets every step",
+                       "load_seconds": round(load_s, 2)},
+            "e2e": {"value": e2e_value, "unit": "persons/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(knn_launches),
+            "roofline": knn_roof,
+            "cpu_baseline": cpu_knn_base,
+            "clocks": clocks_knn,
+            "sg": sg,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_sg(args, vrec, ctx, stream, world, rank, barrier, max_over_ranks, peak, peak_src):
+    import torch
+    if world > 1:
+        return {"skipped": "row-partitioned multi-GPU SpMV is not built yet; SG is measured at 1 GPU only"}
+    N, deg, iters = args.sg_vertices, args.sg_degree, args.sg_iterations
+    t0 = time.time()
+    g = vrec.StochasticGraph.generate(N, deg, seed=5, ctx=ctx)
+    log(f"[bench] sg graph generated on device: N={g.N} nnz={g.nnz} ({time.time() - t0:.1f}s, "
+        f"{g.resident_bytes / 1e9:.2f} GB resident)")
+    bytes_it = sg_bytes_per_iteration(g.N, g.nnz)
+    for _ in range(args.warmup):
+        g.iterate_device(iters)
+    ctx.synchronize()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    l0 = ctx.launch_count
+    barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        ev[i][0].record(stream)
+        g.iterate_device(iters)
+        ev[i][1].record(stream)
+    ctx.synchronize()
+    barrier()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = max_over_ranks(sum(ms))
+    clocks = sampler.stop()
+    launches = ctx.launch_count - l0
+    gbs = bytes_it * iters * args.steps / (total_ms / 1e3) / 1e9
+    per_launch_ms = statistics.mean(ms) / iters
+    log(f"[bench] sg device: {gbs:,.0f} GB/s algorithmic, {per_launch_ms * 1e3:.0f} us/iteration")
+    # end to end: one query through the host ABI (vertex id in, top-10 out), graph resident
+    rec = vrec.StochasticRecommender(g, 0.0, iters)
+    rec.recommend([0], None, 10)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        rec.recommend([i + 1], None, 10)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_gbs = bytes_it * iters * args.steps / e2e_s / 1e9
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu, _ = cpu_sg(args, args.cpu_sg_vertices, 5)
+        log(f"[bench] sg cpu baseline: {cpu['value']:.2f} GB/s on {cpu['cores']} threads")
+    out = {
+        "metric": "SG power-iteration HBM GB/s (algorithmic bytes 12*nnz + 20*N per iteration)",
+        "value": gbs, "unit": "GB/s", "ms_per_step": total_ms / args.steps, "us_per_iteration": per_launch_ms * 1e3,
+        "config": {"workload": sg_workload_name(args), "l2": f"inputs larger than L2 ({bytes_it / 1e9:.1f} GB/iteration)"},
+        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 10 * 16 + 24,
+                "note": "vrec_sg_query: vertex id in, ranked top-10 of all vertices out"},
+        "roofline": {"bound": "hbm", "kernel": "sg_spmv_kernel", "achieved": bytes_it / (per_launch_ms / 1e3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": bytes_it / (per_launch_ms / 1e3) / 1e9 / peak,
+                     "traffic": None, "peak_source": peak_src},
+        "cpu_baseline": cpu, "clocks": clocks,
+    }
+    g.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--knn-persons", type=int, default=1_000_000)
+    ap.add_argument("--knn-places", type=int, default=100_000)
+    ap.add_argument("--knn-batch", type=int, default=4096)
+    ap.add_argument("--k-nearest", type=int, default=50)
+    ap.add_argument("--max-recs", type=int, default=10)
+    ap.add_argument("--sg-vertices", type=int, default=10_000_000)
+    ap.add_argument("--sg-degree", type=int, default=100)
+    ap.add_argument("--sg-iterations", type=int, default=20)
+    ap.add_argument("--cpu-knn-targets", type=int, default=128)
+    ap.add_argument("--cpu-sg-vertices", type=int, default=500_000)
+    ap.add_argument("--ref-knn-targets", type=int, default=64)
+    ap.add_argument("--ref-sg-vertices", type=int, default=500_000)
+    ap.add_argument("--no-sg", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        log("[bench] note: W < 3 warm-up steps breaks the timing rules; use only for smoke runs")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
