@@ -95,6 +95,41 @@ __device__ __forceinline__ double canon_butterfly(double v) {
     return v;
 }
 
+// ---- L2 eviction-priority hints (createpolicy + ld/st .L2::cache_hint) ----
+// Streamed-once data (CSR columns / weights) is marked evict_first so that it does not push the
+// gathered vector (marked evict_last) out of the 126 MB L2.
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// `fraction` of the addresses (chosen by an address hash, so the same subset every time) get
+// evict_last; the rest keep the default priority.  Lets a vector somewhat larger than the L2
+// keep a stable resident subset instead of thrashing as a whole.
+__device__ __forceinline__ unsigned long long policy_evict_last(float fraction = 1.0f) {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, %1;" : "=l"(p) : "f"(fraction));
+    return p;
+}
+__device__ __forceinline__ int ld_stream_i32(const int *p, unsigned long long pol) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ld_stream_f64(const double *p, unsigned long long pol) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ld_keep_f64(const double *p, unsigned long long pol) {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f64(double *p, double v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+
 // (value desc, key asc) total order used for every ranked output.
 __device__ __forceinline__ bool ranks_before(double va, long long ka, double vb, long long kb) {
     return va > vb || (va == vb && ka < kb);

@@ -67,25 +67,52 @@ __global__ void sg_reset_state_kernel(SgState *st, int max_it) {
     st->residual = -1.0;
 }
 
-// lane-strided canonical sum of terms x[src[k]] * w[k], k in [s, s+n), n <= VREC_CANON_SEG
+// Canonical sum of terms x[src[k]] * w[k], k in [s, s+n), n <= VREC_CANON_SEG, computed by a
+// group of G physical lanes (G = 32 or 16).  Term k belongs to canonical lane k % 32; physical
+// lane p = k % G keeps the 32/G canonical lanes p, p+G, ... in separate accumulators, so the
+// per-lane order and the xor-butterfly 1,2,4,8,16 are exactly those of the oracle's warp_sum.
+// With G = 16 a warp sums two rows at once: twice the gathers in flight per warp.
+template <int G>
 __device__ __forceinline__ double canon_row_sum(const int *__restrict__ src, const double *__restrict__ w,
-                                                const double *__restrict__ x, int s, int n, int lane) {
-    double acc = 0.0;
-    // uniform trip count; up to 4 independent gathers in flight per lane, adds stay in index order
-    for (int kb = 0; kb < n; kb += 128) {
-        int k0 = kb + lane, k1 = k0 + 32, k2 = k0 + 64, k3 = k0 + 96;
-        bool v0 = k0 < n, v1 = k1 < n, v2 = k2 < n, v3 = k3 < n;
-        int c0 = v0 ? __ldg(src + s + k0) : 0, c1 = v1 ? __ldg(src + s + k1) : 0;
-        int c2 = v2 ? __ldg(src + s + k2) : 0, c3 = v3 ? __ldg(src + s + k3) : 0;
-        double w0 = v0 ? __ldg(w + s + k0) : 0.0, w1 = v1 ? __ldg(w + s + k1) : 0.0;
-        double w2 = v2 ? __ldg(w + s + k2) : 0.0, w3 = v3 ? __ldg(w + s + k3) : 0.0;
-        double x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
-        if (v0) acc = xadd(acc, xmul(x0, w0));
-        if (v1) acc = xadd(acc, xmul(x1, w1));
-        if (v2) acc = xadd(acc, xmul(x2, w2));
-        if (v3) acc = xadd(acc, xmul(x3, w3));
+                                                const double *__restrict__ x, int s, int n, int sublane,
+                                                unsigned long long pol_stream, unsigned long long pol_keep) {
+    constexpr int V = 32 / G;           // canonical lanes per physical lane
+    constexpr int U = 4 / V > 0 ? 4 / V : 1;   // unroll so that 4 gathers are in flight per lane
+    double acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.0;
+    for (int kb = 0; kb < n; kb += 32 * U) {    // uniform trip count within the group
+        int c[U * V];
+        double ww[U * V], xx[U * V];
+        bool ok[U * V];
+#pragma unroll
+        for (int q = 0; q < U * V; ++q) {
+            int k = kb + sublane + G * q;
+            ok[q] = k < n;
+            c[q] = ok[q] ? ld_stream_i32(src + s + k, pol_stream) : 0;
+            ww[q] = ok[q] ? ld_stream_f64(w + s + k, pol_stream) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < U * V; ++q) xx[q] = ld_keep_f64(x + c[q], pol_keep);
+#pragma unroll
+        for (int q = 0; q < U * V; ++q)
+            if (ok[q]) acc[q % V] = xadd(acc[q % V], xmul(xx[q], ww[q]));
     }
-    return canon_butterfly(acc);
+    // butterfly over canonical lanes: offsets < G are shuffles, offsets >= G stay in the thread
+#pragma unroll
+    for (int off = 1; off < G; off <<= 1) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = xadd(acc[j], __shfl_xor_sync(0xffffffffu, acc[j], off));
+    }
+#pragma unroll
+    for (int off = 1; off < V; off <<= 1) {
+        double t[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) t[j] = xadd(acc[j], acc[j ^ off]);
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = t[j];
+    }
+    return acc[0];
 }
 
 // One warp per 1024-term segment of a long row.
@@ -94,7 +121,7 @@ sg_long_partials_kernel(const int *__restrict__ rowptr, const int *__restrict__ 
                         const double *__restrict__ w, const double *__restrict__ x,
                         const int *__restrict__ long_rows, const int *__restrict__ long_segptr,
                         const int *__restrict__ seg_row, int n_seg, double *__restrict__ partials,
-                        const SgState *__restrict__ st) {
+                        const SgState *__restrict__ st, float keep_frac) {
     if (st->done) return;
     const int lane = threadIdx.x & 31;
     int seg = blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5);
@@ -104,24 +131,25 @@ sg_long_partials_kernel(const int *__restrict__ rowptr, const int *__restrict__ 
     int j = seg - long_segptr[slot];
     int s = rowptr[row] + j * VREC_CANON_SEG;
     int n = min(VREC_CANON_SEG, rowptr[row + 1] - s);
-    double v = canon_row_sum(src, w, x, s, n, lane);
+    double v = canon_row_sum<32>(src, w, x, s, n, lane, policy_evict_first(), policy_evict_last(keep_frac));
     if (lane == 0) partials[seg] = v;
 }
 
 // Main pass: sigma per row in the canonical order, x' = u*alpha + sigma*(1-alpha)
 // (calcNextX, :108-128), squared-difference residual (isConverged, :130-141) reduced in a
 // fixed order, and the step() control (:92-106) updated by the last block.
-__global__ void __launch_bounds__(SPMV_THREADS)
+__global__ void __launch_bounds__(SPMV_THREADS, 4)
 sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ rowptr, const int *__restrict__ src,
                const double *__restrict__ w, const double *__restrict__ x, double *__restrict__ nx,
                long long uidx, const int *__restrict__ long_rows, const int *__restrict__ long_segptr,
                int n_long, const double *__restrict__ partials, SgState *st,
                double *__restrict__ block_partials, int iteration, int max_it, double eps2,
-               int check_convergence) {
+               int check_convergence, float keep_frac) {
     if (st->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long total_warps = (long long)gridDim.x * SPMV_WARPS;
     const double one_minus = 1 - kAlpha;                     // :121, evaluates to 0.85
+    const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last(keep_frac);
     double dsum = 0.0;
     for (long long base = ((long long)blockIdx.x * SPMV_WARPS + warp) * 32; base < n_rows;
          base += total_warps * 32) {
@@ -133,36 +161,45 @@ sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ rowptr, con
         }
         int n = e - s;
         double sigma = 0.0;
-        unsigned todo = __ballot_sync(0xffffffffu, n > 0);
-        while (todo) {
-            int l = __ffs(todo) - 1;
-            todo &= todo - 1;
+        const unsigned nonempty = __ballot_sync(0xffffffffu, n > 0 && n <= VREC_CANON_SEG);
+        unsigned longrows = __ballot_sync(0xffffffffu, n > VREC_CANON_SEG);
+        // two rows at a time: half-warp h sums row 2j+h of this chunk
+        unsigned pairs = (nonempty | (nonempty >> 1)) & 0x55555555u;
+        const int half = lane >> 4, sub = lane & 15;
+        while (pairs) {
+            int l0 = __ffs(pairs) - 1;
+            pairs &= pairs - 1;
+            int l = l0 + half;
             int rs = __shfl_sync(0xffffffffu, s, l);
             int rn = __shfl_sync(0xffffffffu, n, l);
-            double acc;
-            if (rn <= VREC_CANON_SEG) {
-                acc = canon_row_sum(src, w, x, rs, rn, lane);
-            } else {
-                // second level: lane-strided sum of the segment partials of this row
-                int row = (int)(base + l);
-                int lo = 0, hi = n_long;
-                while (lo < hi) {
-                    int mid = (lo + hi) >> 1;
-                    if (long_rows[mid] < row) lo = mid + 1; else hi = mid;
-                }
-                int ps = long_segptr[lo], pn = long_segptr[lo + 1] - ps;
-                acc = 0.0;
-                for (int k = lane; k < pn; k += 32) acc = xadd(acc, partials[ps + k]);
-                acc = canon_butterfly(acc);
+            if (rn > VREC_CANON_SEG) rn = 0;               // long rows are handled below
+            double acc = canon_row_sum<16>(src, w, x, rs, rn, sub, pol_stream, pol_keep);
+            double other = __shfl_xor_sync(0xffffffffu, acc, 16);
+            if (lane == l0) sigma = half == 0 ? acc : other;
+            if (lane == l0 + 1) sigma = half == 1 ? acc : other;
+        }
+        while (longrows) {
+            // second level: lane-strided sum of the segment partials of this row
+            int l = __ffs(longrows) - 1;
+            longrows &= longrows - 1;
+            int row = (int)(base + l);
+            int lo = 0, hi = n_long;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (long_rows[mid] < row) lo = mid + 1; else hi = mid;
             }
+            int ps = long_segptr[lo], pn = long_segptr[lo + 1] - ps;
+            double acc = 0.0;
+            for (int k = lane; k < pn; k += 32) acc = xadd(acc, partials[ps + k]);
+            acc = canon_butterfly(acc);
             if (lane == l) sigma = acc;
         }
         if (r < n_rows) {
             long long gi = row_lo + r;
             double u = (gi == uidx) ? 1.0 : 0.0;
             double v = xadd(xmul(u, kAlpha), xmul(sigma, one_minus));
-            nx[gi] = v;
-            double d = xsub(v, x[gi]);
+            st_stream_f64(nx + gi, v, pol_stream);         // the written buffer is the old x: demote it
+            double d = xsub(v, ld_keep_f64(x + gi, pol_keep));
             dsum = xadd(dsum, xmul(d, d));
         }
     }
@@ -275,6 +312,10 @@ int sg_run_device(vrec_sg *g, long long uidx, double epsilon, int max_it, bool c
     const int rows = (int)(g->row_hi - g->row_lo);
     const double x0 = 1.0 / (double)g->N;                   // :53-54
     const double eps2 = epsilon * epsilon;                  // :40
+    // pin at most ~60 MiB of x in L2 (measured: 64 MB of evict_last data stays resident on B200
+    // next to the streamed matrix, 80 MB does not)
+    const double keep_bytes = 60.0 * 1024 * 1024;
+    const float keep_frac = (float)std::min(1.0, keep_bytes / (8.0 * (double)std::max<int64_t>(1, g->N)));
     sg_reset_state_kernel<<<1, 1, 0, ctx->stream>>>(g->d_state.p, max_it);
     VREC_LAUNCHED(ctx);
     int fill_grid = (int)std::min<int64_t>((g->N + 255) / 256, 148 * 16);
@@ -287,13 +328,13 @@ int sg_run_device(vrec_sg *g, long long uidx, double epsilon, int max_it, bool c
             int pg = (g->n_seg + SPMV_WARPS - 1) / SPMV_WARPS;
             sg_long_partials_kernel<<<pg, SPMV_THREADS, 0, ctx->stream>>>(
                 g->d_rowptr.p, g->d_src.p, g->d_w.p, x, g->d_long_rows.p, g->d_long_segptr.p,
-                g->d_seg_row.p, g->n_seg, g->d_partials.p, g->d_state.p);
+                g->d_seg_row.p, g->n_seg, g->d_partials.p, g->d_state.p, keep_frac);
             VREC_LAUNCHED(ctx);
         }
         sg_spmv_kernel<<<g->grid, SPMV_THREADS, 0, ctx->stream>>>(
             rows, g->row_lo, g->d_rowptr.p, g->d_src.p, g->d_w.p, x, nx, uidx, g->d_long_rows.p,
             g->d_long_segptr.p, g->n_long, g->d_partials.p, g->d_state.p, g->d_block_partials.p, it,
-            max_it, eps2, check_convergence ? 1 : 0);
+            max_it, eps2, check_convergence ? 1 : 0, keep_frac);
         VREC_LAUNCHED(ctx);
     }
     return VREC_OK;
