@@ -243,6 +243,313 @@ knn_topk_kernel(KnnDev d, const int *__restrict__ tidx, int K, int S, double pw,
     if (tid == 0) part_cnt[tt * S + sp] = keep;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Tiled batch kernel (K <= 1024, non-negative data, cat_dim <= 32).
+//
+// Every person carries a dense fp32 feature vector of TILE_D = 32 dims: its category vector
+// divided by its length, then the values of the `n_head` most popular ("head") places divided
+// by the place-vector length.  For a target t with the weights folded in,
+//     U(t, c) = sum_d tvec[t][d] * F[d][c]  =  cw * cos_cat + pw * (head part of cos_place)
+// equals the combined similarity of every pair that shares no non-head ("tail") place, up to
+// fp32 rounding (<= 2e-6, margin 3e-5).  The kernel
+//   1. enumerates the pairs that DO share a tail place through the place postings and
+//      evaluates them exactly (each pair once: at its smallest shared tail place);
+//   2. streams all candidates of its range, computes U for TILE_T targets per candidate from
+//      shared memory, and sends only pairs with U + margin >= current K-th best to the exact
+//      fp64 evaluation (pairs found to share a tail place are skipped: step 1 owns them).
+// Exact survivors go into per-target binary heaps in shared memory (worst neighbour at the
+// root).  Results are identical to knn_topk_kernel: the filter only prunes.
+// ---------------------------------------------------------------------------------------
+constexpr int TILE_D = 32;
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_QCAP = 2048;
+constexpr int TILE_TVEC_STRIDE = 36;            // 32 dims + threshold + pad (16-byte aligned rows)
+constexpr float TILE_MARGIN = 3e-5f;
+
+struct TileAux {
+    const float *feat;          // [TILE_D][fstride], dim-major
+    long long fstride;
+    const short *head_slot;     // per place: head slot or -1 (tail)
+    const int *pcp;             // place postings (CSC of the place vectors)
+    const int *pper;
+};
+
+// exact combined similarity + the smallest shared tail place (-1 if none)
+__device__ __forceinline__ double exact_pair(const KnnDev &d, const TileAux &aux, long long i, const TargetRows &t,
+                                             double pw, double cw, int &min_tail) {
+    min_tail = -1;
+    if (i == t.t) return 0.0;
+    bool keep = false;
+    double ps = 0.0;
+    {
+        const KnnVec &v = d.place;
+        int s = v.rowptr[i], n = v.rowptr[i + 1] - s;
+        if (n > 0) {
+            const int *xi = v.col + s, *yi = v.col + t.ps;
+            const double *xv = v.val + s, *yv = v.val + t.ps;
+            int kx = 0, ky = 0;
+            double sum = 0.0;
+            while (kx < n && ky < t.pn) {
+                int ix = xi[kx];
+                while (ky < t.pn && yi[ky] < ix) ky++;
+                if (ky < t.pn && yi[ky] == ix) {
+                    sum = xadd(sum, xmul(xv[kx], yv[ky]));
+                    if (min_tail < 0 && aux.head_slot[ix] < 0) min_tail = ix;
+                    ky++;
+                }
+                kx++;
+            }
+            double c = xdiv(sum, xmul(v.len[i], t.plen));
+            if (c > 0) {
+                keep = true;
+                ps = c;
+            }
+        }
+    }
+    double cs = table_similarity(d.cat, i, t.cs, t.cn, t.clen, keep);
+    if (!keep) return 0.0;
+    return xadd(xmul(ps, pw), xmul(cs, cw));
+}
+
+struct TileSmem {
+    float *tvec;                // [T][TILE_TVEC_STRIDE]; [32] = filter threshold
+    double *hsim;               // [T][K] heaps, worst at the root
+    int *hidx;                  // [T][K]
+    int *hcnt;                  // [T]
+    int *lock;                  // [T]
+    int *tid_of;                // [T] person index of the target or -1
+    unsigned long long *queue;  // [TILE_QCAP]  (t << 32 | candidate)
+    int *qn;
+};
+
+__device__ __forceinline__ bool nb_worse(double sa, int ia, double sb, int ib) {
+    return sa < sb || (sa == sb && ia > ib);
+}
+
+// insert (sim, idx) into the heap of target slot t (under its lock)
+__device__ __forceinline__ void tile_heap_insert(const TileSmem &sm, int t, int K, double sim, int idx) {
+    volatile double *hs = sm.hsim + (size_t)t * K;
+    volatile int *hi = sm.hidx + (size_t)t * K;
+    volatile int *cntp = sm.hcnt + t;
+    volatile float *thr = sm.tvec + (size_t)t * TILE_TVEC_STRIDE + TILE_D;
+    bool done = false;
+    while (!done) {
+        if (atomicCAS(sm.lock + t, 0, 1) == 0) {
+            __threadfence_block();
+            int n = *cntp;
+            if (n < K) {
+                int pos = n;
+                while (pos > 0) {                       // sift up: parents must be worse
+                    int par = (pos - 1) >> 1;
+                    double ps_ = hs[par];
+                    int pi_ = hi[par];
+                    if (nb_worse(sim, idx, ps_, pi_)) {
+                        hs[pos] = ps_;
+                        hi[pos] = pi_;
+                        pos = par;
+                    } else {
+                        break;
+                    }
+                }
+                hs[pos] = sim;
+                hi[pos] = idx;
+                *cntp = n + 1;
+                if (n + 1 == K) *thr = __double2float_rd(hs[0]);
+            } else if (nb_worse(hs[0], hi[0], sim, idx)) {
+                int pos = 0;
+                for (;;) {                              // sift down from the root
+                    int l = 2 * pos + 1, r = l + 1, w = -1;
+                    double ws = sim;
+                    int wi = idx;
+                    if (l < K && nb_worse(hs[l], hi[l], ws, wi)) {
+                        w = l;
+                        ws = hs[l];
+                        wi = hi[l];
+                    }
+                    if (r < K && nb_worse(hs[r], hi[r], ws, wi)) {
+                        w = r;
+                        ws = hs[r];
+                        wi = hi[r];
+                    }
+                    if (w < 0) break;
+                    hs[pos] = ws;
+                    hi[pos] = wi;
+                    pos = w;
+                }
+                hs[pos] = sim;
+                hi[pos] = idx;
+                *thr = __double2float_rd(hs[0]);
+            }
+            __threadfence_block();
+            atomicExch(sm.lock + t, 0);
+            done = true;
+        }
+    }
+}
+
+// exact evaluation of one filter survivor; from_postings = the place whose postings produced it
+__device__ __forceinline__ void tile_process(const KnnDev &d, const TileAux &aux, const TileSmem &sm, int t, int c,
+                                             int K, double pw, double cw, int from_postings) {
+    int tix = sm.tid_of[t];
+    if (tix < 0) return;
+    TargetRows tr = load_target(d, tix);
+    int min_tail;
+    double sim = exact_pair(d, aux, c, tr, pw, cw, min_tail);
+    if (!(sim > 0)) return;
+    if (from_postings >= 0) {
+        if (min_tail != from_postings) return;          // counted at its smallest shared tail place
+    } else if (min_tail >= 0) {
+        return;                                         // the postings pass owns this pair
+    }
+    // cheap pre-check without the lock: the root similarity is written once per update and only
+    // grows, so a stale read can only let too much through (the exact test is under the lock)
+    volatile double *hs = sm.hsim + (size_t)t * K;
+    if (*(volatile int *)(sm.hcnt + t) >= K && sim < hs[0]) return;
+    tile_heap_insert(sm, t, K, sim, c);
+}
+
+__global__ void __launch_bounds__(TILE_THREADS, 2)
+knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targets, int T, int K, int S,
+                int cat_dim, double pw, double cw, Nb *__restrict__ part, int *__restrict__ part_cnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x, sp = blockIdx.y;
+    const int t0 = tile * T;
+    const int nt = min(T, n_targets - t0);
+    TileSmem sm;
+    {
+        unsigned char *p = smem_raw;
+        sm.tvec = (float *)p;                       p += sizeof(float) * (size_t)T * TILE_TVEC_STRIDE;   // 144*T: 16-B aligned rows
+        sm.hsim = (double *)p;                      p += sizeof(double) * (size_t)T * K;
+        sm.queue = (unsigned long long *)p;         p += sizeof(unsigned long long) * TILE_QCAP;
+        sm.hidx = (int *)p;                         p += sizeof(int) * (size_t)T * K;
+        sm.hcnt = (int *)p;                         p += sizeof(int) * T;
+        sm.lock = (int *)p;                         p += sizeof(int) * T;
+        sm.tid_of = (int *)p;                       p += sizeof(int) * T;
+        sm.qn = (int *)p;
+    }
+    const long long lo = d.P * sp / S, hi = d.P * (sp + 1) / S;
+    // ---- target vectors (weights folded in), thresholds, empty heaps
+    for (int t = tid; t < T; t += TILE_THREADS) {
+        int tix = t < nt ? tidx[t0 + t] : -1;
+        sm.tid_of[t] = tix;
+        sm.hcnt[t] = 0;
+        sm.lock[t] = 0;
+        // invalid slots never pass the filter
+        sm.tvec[(size_t)t * TILE_TVEC_STRIDE + TILE_D] = tix >= 0 ? 0.0f : 3.0e38f;
+    }
+    if (tid == 0) *sm.qn = 0;
+    __syncthreads();
+    for (int e = tid; e < T * TILE_D; e += TILE_THREADS) {
+        int t = e / TILE_D, dd = e % TILE_D;
+        int tix = sm.tid_of[t];
+        float v = 0.0f;
+        if (tix >= 0) {
+            double f = (double)aux.feat[(size_t)dd * aux.fstride + tix];
+            v = (float)(f * (dd < cat_dim ? cw : pw));   // dims [0, cat_dim): category, rest: head places
+        }
+        sm.tvec[(size_t)t * TILE_TVEC_STRIDE + dd] = v;
+    }
+    __syncthreads();
+    // ---- 1. pairs sharing a tail place, through the postings
+    for (int t = warp; t < nt; t += TILE_THREADS / 32) {
+        int tix = sm.tid_of[t];
+        if (tix < 0) continue;
+        int ps = d.place.rowptr[tix], pn = d.place.rowptr[tix + 1] - ps;
+        for (int e = 0; e < pn; ++e) {
+            int pl = d.place.col[ps + e];
+            if (aux.head_slot[pl] >= 0) continue;
+            int b = aux.pcp[pl], en = aux.pcp[pl + 1];
+            // restrict the postings (ascending person index) to [lo, hi)
+            int l0 = b, h0 = en;
+            while (l0 < h0) {
+                int mid = (l0 + h0) >> 1;
+                if (aux.pper[mid] < lo) l0 = mid + 1; else h0 = mid;
+            }
+            int l1 = l0, h1 = en;
+            while (l1 < h1) {
+                int mid = (l1 + h1) >> 1;
+                if (aux.pper[mid] < hi) l1 = mid + 1; else h1 = mid;
+            }
+            for (int k = l0 + lane; k < l1; k += 32) tile_process(d, aux, sm, t, aux.pper[k], K, pw, cw, pl);
+        }
+    }
+    __syncthreads();
+    // ---- 2. dense filter over the candidate range
+    for (long long base = lo; base < hi; base += TILE_THREADS) {
+        long long c = base + tid;
+        if (c < hi) {
+            float f[TILE_D];
+#pragma unroll
+            for (int dd = 0; dd < TILE_D; ++dd) f[dd] = __ldg(aux.feat + (size_t)dd * aux.fstride + c);
+            for (int t = 0; t < nt; ++t) {
+                const float4 *tv = reinterpret_cast<const float4 *>(sm.tvec + (size_t)t * TILE_TVEC_STRIDE);
+                float u = 0.0f;
+#pragma unroll
+                for (int q = 0; q < TILE_D / 4; ++q) {
+                    float4 a = tv[q];
+                    u = __fmaf_rn(a.x, f[4 * q + 0], u);
+                    u = __fmaf_rn(a.y, f[4 * q + 1], u);
+                    u = __fmaf_rn(a.z, f[4 * q + 2], u);
+                    u = __fmaf_rn(a.w, f[4 * q + 3], u);
+                }
+                float thr = sm.tvec[(size_t)t * TILE_TVEC_STRIDE + TILE_D];
+                if (u + TILE_MARGIN >= thr) {
+                    int pos = atomicAdd(sm.qn, 1);
+                    if (pos < TILE_QCAP) {
+                        sm.queue[pos] = ((unsigned long long)t << 32) | (unsigned long long)(unsigned)c;
+                    } else {
+                        tile_process(d, aux, sm, t, (int)c, K, pw, cw, -1);   // queue full: evaluate now
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        int qn = *sm.qn;
+        __syncthreads();
+        if (qn >= TILE_QCAP / 2 || base + TILE_THREADS >= hi) {                 // block-uniform
+            int m = min(qn, TILE_QCAP);
+            for (int i = tid; i < m; i += TILE_THREADS) {
+                unsigned long long e = sm.queue[i];
+                tile_process(d, aux, sm, (int)(e >> 32), (int)(unsigned)(e & 0xffffffffu), K, pw, cw, -1);
+            }
+            __syncthreads();
+            if (tid == 0) *sm.qn = 0;
+            __syncthreads();
+        }
+    }
+    // ---- emit the heaps (unsorted; the merge kernel sorts)
+    for (int t = 0; t < nt; ++t) {
+        int cnt = sm.hcnt[t];
+        Nb *out = part + ((size_t)(t0 + t) * S + sp) * K;
+        for (int j = tid; j < cnt; j += TILE_THREADS) {
+            Nb e;
+            e.sim = sm.hsim[(size_t)t * K + j];
+            e.idx = sm.hidx[(size_t)t * K + j];
+            e.pad = 0;
+            out[j] = e;
+        }
+        if (tid == 0) part_cnt[(t0 + t) * S + sp] = cnt;
+    }
+}
+
+// Dense fp32 features, dim-major: F[d][i] = cat[i][d] / |cat_i| for d < cat_dim, then the head
+// places' values / |place_i|.  `wscale` (host) is applied per target in knn_tile_kernel.
+__global__ void knn_features_kernel(KnnDev d, const short *__restrict__ head_slot, int cat_dim, long long fstride,
+                                    float *__restrict__ feat) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.P) return;
+    for (int dd = 0; dd < TILE_D; ++dd) feat[(size_t)dd * fstride + i] = 0.0f;
+    double cl = d.cat.len[i], pl = d.place.len[i];
+    for (int k = d.cat.rowptr[i]; k < d.cat.rowptr[i + 1]; ++k)
+        feat[(size_t)d.cat.col[k] * fstride + i] = (float)(d.cat.val[k] / cl);
+    for (int k = d.place.rowptr[i]; k < d.place.rowptr[i + 1]; ++k) {
+        int slot = head_slot[d.place.col[k]];
+        if (slot >= 0) feat[(size_t)(cat_dim + slot) * fstride + i] = (float)(d.place.val[k] / pl);
+    }
+}
+
 // Merges the S partial lists of a target (S*K <= TOPK_BUF): final neighbours in
 // (similarity desc, index asc) order -> nb_rank, and the same set in ascending index -> nb_idx.
 __global__ void __launch_bounds__(MERGE_THREADS)
@@ -553,8 +860,15 @@ struct vrec_knn {
     DevBuf<double> d_crv;
     DevBuf<unsigned char> d_flag;
     bool has_filter = false;
+    // tiled batch kernel: dense fp32 features, head-place slots, place postings
+    bool tile_ok = false;
+    int n_head = 0;
+    long long fstride = 0;
+    DevBuf<float> d_feat;
+    DevBuf<short> d_head_slot;
+    DevBuf<int> d_pcp, d_pper;
     // options
-    int64_t opt_rating_path = 0, opt_tile = 0, opt_splits = 0;
+    int64_t opt_rating_path = 0, opt_tile = 0, opt_splits = 0, opt_kernel = 0;
     // scratch
     DevBuf<long long> d_targets;
     DevBuf<int> d_tidx, d_status;
@@ -756,6 +1070,42 @@ extern "C" int vrec_knn_load(vrec_ctx *ctx, int64_t P, const int64_t *person_id,
         ctx->launches += 2;
         if (cudaGetLastError() != cudaSuccess) rc = VREC_ECUDA;
     }
+    // ---- inputs of the tiled batch kernel
+    bool nonneg = true;
+    for (double v : pv) nonneg &= v >= 0;
+    for (double v : cv) nonneg &= v >= 0;
+    if (rc == VREC_OK && nonneg && cat_dim <= TILE_D && P > 0 && place_dim < (1 << 30)) {
+        // postings of the place vectors (persons ascending) and the n_head most visited places
+        std::vector<int> pcp((size_t)place_dim + 1, 0), pper((size_t)k->nnz_place);
+        for (int64_t e = 0; e < k->nnz_place; ++e) pcp[pci[e] + 1]++;
+        for (int64_t c = 0; c < place_dim; ++c) pcp[c + 1] += pcp[c];
+        {
+            std::vector<int> pos(pcp.begin(), pcp.end() - 1);
+            for (int64_t i = 0; i < P; ++i)
+                for (int e = prp[i]; e < prp[i + 1]; ++e) pper[pos[pci[e]]++] = (int)i;
+        }
+        k->n_head = std::min<int>(TILE_D - cat_dim, place_dim);
+        std::vector<int> byc((size_t)place_dim);
+        std::iota(byc.begin(), byc.end(), 0);
+        std::partial_sort(byc.begin(), byc.begin() + k->n_head, byc.end(), [&](int a, int b) {
+            int ca = pcp[a + 1] - pcp[a], cb = pcp[b + 1] - pcp[b];
+            return ca > cb || (ca == cb && a < b);
+        });
+        std::vector<short> head_slot((size_t)place_dim, (short)-1);
+        for (int h = 0; h < k->n_head; ++h) head_slot[byc[h]] = (short)h;
+        k->fstride = (P + 31) / 32 * 32;
+        rc = k->d_pcp.upload(pcp.data(), pcp.size(), s);
+        if (rc == VREC_OK) rc = k->d_pper.upload(pper.data(), pper.size(), s);
+        if (rc == VREC_OK) rc = k->d_head_slot.upload(head_slot.data(), head_slot.size(), s);
+        if (rc == VREC_OK) rc = k->d_feat.alloc((size_t)TILE_D * (size_t)k->fstride);
+        if (rc == VREC_OK) {
+            knn_features_kernel<<<(int)((P + 255) / 256), 256, 0, s>>>(k->dev(), k->d_head_slot.p, cat_dim,
+                                                                      k->fstride, k->d_feat.p);
+            ctx->launches++;
+            if (cudaGetLastError() != cudaSuccess) rc = VREC_ECUDA;
+        }
+        k->tile_ok = rc == VREC_OK;
+    }
     if (rc == VREC_OK && cudaStreamSynchronize(s) != cudaSuccess) {
         vrec_set_error("vrec_knn_load: %s", cudaGetErrorString(cudaGetLastError()));
         rc = VREC_ECUDA;
@@ -796,6 +1146,14 @@ extern "C" int vrec_knn_set_option(vrec_knn *k, const char *name, int64_t value)
     }
     if (!strcmp(name, "tile") && value >= 0) {
         k->opt_tile = value;
+        return VREC_OK;
+    }
+    if (!strcmp(name, "knn_kernel") && value >= 0 && value <= 2) {
+        if (value == 2 && !k->tile_ok) {
+            vrec_set_error("knn_kernel=2 (tiled) needs cat_dim <= 32 and non-negative rating values");
+            return VREC_EINVAL;
+        }
+        k->opt_kernel = value;
         return VREC_OK;
     }
     if (!strcmp(name, "splits") && value >= 0 && value <= 32) {
@@ -855,12 +1213,23 @@ bool use_gather_path(const vrec_knn *k, int K) {
 // neighbours of a tile of targets by the fused top-K kernels (K <= 1024)
 int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     vrec_ctx *ctx = k->ctx;
+    const bool tiled = k->tile_ok && k->opt_kernel != 1;
     int smax = std::max(1, std::min(32, TOPK_BUF / K));
     int S = (int)k->opt_splits;
+    int T = 1;
+    size_t smem = 0;
+    if (tiled) {
+        // targets per block: heaps must fit next to the queue and the target vectors
+        T = (int)std::max<int64_t>(1, std::min<int64_t>(64, (48 * 1024) / (12 * (int64_t)K)));
+        T = std::min(T, std::max(1, tn));
+        smem = sizeof(double) * (size_t)T * K + sizeof(unsigned long long) * TILE_QCAP +
+               sizeof(float) * (size_t)T * TILE_TVEC_STRIDE + sizeof(int) * (size_t)T * K + sizeof(int) * 3 * T + 16;
+    }
+    const int tiles = (tn + T - 1) / T;
     if (S <= 0) {
         S = 1;
-        int want_blocks = ctx->sm_count * 8;
-        while (S < smax && tn * S < want_blocks) S <<= 1;
+        int want_blocks = ctx->sm_count * (tiled ? 4 : 8);
+        while (S < smax && tiles * S < want_blocks) S <<= 1;
     }
     S = std::min(S, smax);
     if ((int64_t)S > std::max<int64_t>(1, k->P)) S = 1;
@@ -869,10 +1238,23 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     VREC_TRY(k->d_nb_rank.ensure((size_t)tn * K));
     VREC_TRY(k->d_nb_idx.ensure((size_t)tn * K));
     VREC_TRY(k->d_nb_cnt.ensure((size_t)tn));
-    dim3 grid(tn, S);
-    knn_topk_kernel<<<grid, TOPK_THREADS, 0, ctx->stream>>>(k->dev(), k->d_tidx.p, K, S, pw, cw, k->d_part.p,
-                                                           k->d_part_cnt.p);
-    VREC_LAUNCHED(ctx);
+    if (tiled) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            VREC_CUDA(cudaFuncSetAttribute(knn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        TileAux aux{k->d_feat.p, k->fstride, k->d_head_slot.p, k->d_pcp.p, k->d_pper.p};
+        dim3 grid(tiles, S);
+        knn_tile_kernel<<<grid, TILE_THREADS, smem, ctx->stream>>>(k->dev(), aux, k->d_tidx.p, tn, T, K, S,
+                                                                  k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p);
+        VREC_LAUNCHED(ctx);
+    } else {
+        dim3 grid(tn, S);
+        knn_topk_kernel<<<grid, TOPK_THREADS, 0, ctx->stream>>>(k->dev(), k->d_tidx.p, K, S, pw, cw, k->d_part.p,
+                                                               k->d_part_cnt.p);
+        VREC_LAUNCHED(ctx);
+    }
     knn_merge_kernel<<<tn, MERGE_THREADS, 0, ctx->stream>>>(k->d_part.p, k->d_part_cnt.p, K, S, k->d_nb_rank.p,
                                                            k->d_nb_idx.p, k->d_nb_cnt.p);
     VREC_LAUNCHED(ctx);

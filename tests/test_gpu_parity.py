@@ -152,13 +152,16 @@ def _check_knn(vrec, oracle, rs, inp, pw, cw, k, targets, flt, max_recs):
 
 @pytest.mark.parametrize("seed", [1, 2])
 @pytest.mark.parametrize("k", [1, 7, 50, 5000])
-@pytest.mark.parametrize("path", [0, 1, 2])
-def test_knn_random_bit_exact(vrec, ctx, synth, oracle, seed, k, path):
+@pytest.mark.parametrize("path,kernel", [(0, 0), (1, 1), (1, 2), (2, 0)])
+def test_knn_random_bit_exact(vrec, ctx, synth, oracle, seed, k, path, kernel):
+    # path: rating reduction (0 auto, 1 neighbour-row gather, 2 column scan)
+    # kernel: similarity + top-K (0 auto, 1 per-target exact scan, 2 tiled fp32 filter + exact survivors)
     if path == 1 and k > 1024:
         pytest.skip("gather path needs k <= 1024")
     inp = synth.random_knn_inputs(700, 60, 9, seed=seed, separate_ratings=(seed == 2))
     rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
     rs.set_option("rating_path", path)
+    rs.set_option("knn_kernel", kernel)
     targets = np.concatenate([inp.person_id[:40], [1, 999999]])       # two unknown persons
     flt = np.arange(0, 60, 2)
     rec, d = _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, k, targets, flt, 10)
@@ -241,6 +244,10 @@ def test_knn_g2_shape(vrec, ctx, synth, oracle):
     rs.set_option("splits", 1)
     _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 50, targets[:10], places.id, 10)
     rs.set_option("splits", 0)
+    rs.set_option("knn_kernel", 1)          # per-target exact scan must agree with the tiled kernel
+    _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 50, targets[:10], places.id, 10)
+    rs.set_option("knn_kernel", 0)
+    _check_knn(vrec, oracle, rs, inp, 0.3, 0.7, 200, targets[:20], places.id, 10)
     # launcher configuration: K = 2 000 000 (every positive candidate), default sample data shape
     _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 2_000_000, targets[:3], places.id, 10)
     rs.close()
