@@ -145,6 +145,9 @@ int vrec_knn_similarities(vrec_knn *knn, int64_t target, double place_weight, do
  * top-K kernel (0 = automatic).  Unknown names give VREC_EINVAL.                */
 int vrec_knn_set_option(vrec_knn *knn, const char *name, int64_t value);
 int64_t vrec_knn_resident_bytes(vrec_knn *knn);
+/* Debug counters of the tiled similarity kernel since the last call: out4 = {exact evaluations
+ * from the postings pass, exact evaluations of filter survivors, heap inserts, queue overflows}. */
+int vrec_knn_debug_stats(vrec_knn *knn, uint64_t *out4);
 
 /* ---------------------------------------------------------------- SG path */
 

@@ -312,6 +312,11 @@ __device__ __forceinline__ double exact_pair(const KnnDev &d, const TileAux &aux
     return xadd(xmul(ps, pw), xmul(cs, cw));
 }
 
+// event counters of the tiled kernel (rare events only): [0] exact evaluations from the
+// postings pass, [1] exact evaluations of dense-filter survivors, [2] heap insert attempts,
+// [3] survivors evaluated inline because the queue was full
+__device__ unsigned long long g_tile_stats[4];
+
 struct TileSmem {
     float *tvec;                // [T][TILE_TVEC_STRIDE]; [32] = filter threshold
     double *hsim;               // [T][K] heaps, worst at the root
@@ -355,7 +360,7 @@ __device__ __forceinline__ void tile_heap_insert(const TileSmem &sm, int t, int 
                 hs[pos] = sim;
                 hi[pos] = idx;
                 *cntp = n + 1;
-                if (n + 1 == K) *thr = __double2float_rd(hs[0]);
+                if (n + 1 == K) *thr = fmaxf(*thr, __double2float_rd(hs[0]));
             } else if (nb_worse(hs[0], hi[0], sim, idx)) {
                 int pos = 0;
                 for (;;) {                              // sift down from the root
@@ -379,7 +384,7 @@ __device__ __forceinline__ void tile_heap_insert(const TileSmem &sm, int t, int 
                 }
                 hs[pos] = sim;
                 hi[pos] = idx;
-                *thr = __double2float_rd(hs[0]);
+                *thr = fmaxf(*thr, __double2float_rd(hs[0]));
             }
             __threadfence_block();
             atomicExch(sm.lock + t, 0);
@@ -393,25 +398,28 @@ __device__ __forceinline__ void tile_process(const KnnDev &d, const TileAux &aux
                                              int K, double pw, double cw, int from_postings) {
     int tix = sm.tid_of[t];
     if (tix < 0) return;
+    atomicAdd(&g_tile_stats[from_postings >= 0 ? 0 : 1], 1ULL);
     TargetRows tr = load_target(d, tix);
     int min_tail;
     double sim = exact_pair(d, aux, c, tr, pw, cw, min_tail);
     if (!(sim > 0)) return;
     if (from_postings >= 0) {
         if (min_tail != from_postings) return;          // counted at its smallest shared tail place
-    } else if (min_tail >= 0) {
+    } else if (from_postings == -1 && min_tail >= 0) {
         return;                                         // the postings pass owns this pair
-    }
+    }                                                   // (-2: seed pass, every pair counts)
     // cheap pre-check without the lock: the root similarity is written once per update and only
     // grows, so a stale read can only let too much through (the exact test is under the lock)
     volatile double *hs = sm.hsim + (size_t)t * K;
     if (*(volatile int *)(sm.hcnt + t) >= K && sim < hs[0]) return;
+    atomicAdd(&g_tile_stats[2], 1ULL);
     tile_heap_insert(sm, t, K, sim, c);
 }
 
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targets, int T, int K, int S,
-                int cat_dim, double pw, double cw, Nb *__restrict__ part, int *__restrict__ part_cnt) {
+                int cat_dim, double pw, double cw, Nb *__restrict__ part, int *__restrict__ part_cnt,
+                long long cand_stride, long long cand_count, int seed_mode, double *__restrict__ seed_thr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x, sp = blockIdx.y;
@@ -429,7 +437,10 @@ knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targe
         sm.tid_of = (int *)p;                       p += sizeof(int) * T;
         sm.qn = (int *)p;
     }
-    const long long lo = d.P * sp / S, hi = d.P * (sp + 1) / S;
+    // candidates are j * cand_stride for j in [jlo, jhi); the main pass has stride 1 (all persons),
+    // the seed pass a strided sample.  [lo, hi) is the same range in person indices.
+    const long long jlo = cand_count * sp / S, jhi = cand_count * (sp + 1) / S;
+    const long long lo = jlo * cand_stride, hi = seed_mode == 1 ? d.P : jhi * cand_stride;
     // ---- target vectors (weights folded in), thresholds, empty heaps
     for (int t = tid; t < T; t += TILE_THREADS) {
         int tix = t < nt ? tidx[t0 + t] : -1;
@@ -437,7 +448,9 @@ knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targe
         sm.hcnt[t] = 0;
         sm.lock[t] = 0;
         // invalid slots never pass the filter
-        sm.tvec[(size_t)t * TILE_TVEC_STRIDE + TILE_D] = tix >= 0 ? 0.0f : 3.0e38f;
+        // the seed pass left a lower bound of the K-th best similarity (0 when it found < K)
+        float thr0 = (seed_mode != 1 && tix >= 0) ? __double2float_rd(seed_thr[t0 + t]) : 0.0f;
+        sm.tvec[(size_t)t * TILE_TVEC_STRIDE + TILE_D] = tix >= 0 ? thr0 : 3.0e38f;
     }
     if (tid == 0) *sm.qn = 0;
     __syncthreads();
@@ -452,55 +465,33 @@ knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targe
         sm.tvec[(size_t)t * TILE_TVEC_STRIDE + dd] = v;
     }
     __syncthreads();
-    // ---- 1. pairs sharing a tail place, through the postings
-    for (int t = warp; t < nt; t += TILE_THREADS / 32) {
-        int tix = sm.tid_of[t];
-        if (tix < 0) continue;
-        int ps = d.place.rowptr[tix], pn = d.place.rowptr[tix + 1] - ps;
-        for (int e = 0; e < pn; ++e) {
-            int pl = d.place.col[ps + e];
-            if (aux.head_slot[pl] >= 0) continue;
-            int b = aux.pcp[pl], en = aux.pcp[pl + 1];
-            // restrict the postings (ascending person index) to [lo, hi)
-            int l0 = b, h0 = en;
-            while (l0 < h0) {
-                int mid = (l0 + h0) >> 1;
-                if (aux.pper[mid] < lo) l0 = mid + 1; else h0 = mid;
-            }
-            int l1 = l0, h1 = en;
-            while (l1 < h1) {
-                int mid = (l1 + h1) >> 1;
-                if (aux.pper[mid] < hi) l1 = mid + 1; else h1 = mid;
-            }
-            for (int k = l0 + lane; k < l1; k += 32) tile_process(d, aux, sm, t, aux.pper[k], K, pw, cw, pl);
-        }
-    }
-    __syncthreads();
-    // ---- 2. dense filter over the candidate range
-    for (long long base = lo; base < hi; base += TILE_THREADS) {
-        long long c = base + tid;
-        if (c < hi) {
+    // ---- 1. dense filter over the candidate range (establishes strong thresholds first)
+    for (long long base = jlo; base < jhi; base += TILE_THREADS) {
+        long long c = (base + tid) * cand_stride;
+        if (base + tid < jhi) {
             float f[TILE_D];
 #pragma unroll
             for (int dd = 0; dd < TILE_D; ++dd) f[dd] = __ldg(aux.feat + (size_t)dd * aux.fstride + c);
             for (int t = 0; t < nt; ++t) {
                 const float4 *tv = reinterpret_cast<const float4 *>(sm.tvec + (size_t)t * TILE_TVEC_STRIDE);
-                float u = 0.0f;
+                float u0 = 0.0f, u1 = 0.0f, u2 = 0.0f, u3 = 0.0f;     // 4 independent FMA chains
 #pragma unroll
                 for (int q = 0; q < TILE_D / 4; ++q) {
                     float4 a = tv[q];
-                    u = __fmaf_rn(a.x, f[4 * q + 0], u);
-                    u = __fmaf_rn(a.y, f[4 * q + 1], u);
-                    u = __fmaf_rn(a.z, f[4 * q + 2], u);
-                    u = __fmaf_rn(a.w, f[4 * q + 3], u);
+                    u0 = __fmaf_rn(a.x, f[4 * q + 0], u0);
+                    u1 = __fmaf_rn(a.y, f[4 * q + 1], u1);
+                    u2 = __fmaf_rn(a.z, f[4 * q + 2], u2);
+                    u3 = __fmaf_rn(a.w, f[4 * q + 3], u3);
                 }
+                float u = (u0 + u1) + (u2 + u3);
                 float thr = sm.tvec[(size_t)t * TILE_TVEC_STRIDE + TILE_D];
                 if (u + TILE_MARGIN >= thr) {
                     int pos = atomicAdd(sm.qn, 1);
                     if (pos < TILE_QCAP) {
                         sm.queue[pos] = ((unsigned long long)t << 32) | (unsigned long long)(unsigned)c;
                     } else {
-                        tile_process(d, aux, sm, t, (int)c, K, pw, cw, -1);   // queue full: evaluate now
+                        atomicAdd(&g_tile_stats[3], 1ULL);
+                        tile_process(d, aux, sm, t, (int)c, K, pw, cw, seed_mode == 1 ? -2 : -1);   // queue full: now
                     }
                 }
             }
@@ -508,16 +499,73 @@ knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targe
         __syncthreads();
         int qn = *sm.qn;
         __syncthreads();
-        if (qn >= TILE_QCAP / 2 || base + TILE_THREADS >= hi) {                 // block-uniform
+        if (qn >= TILE_QCAP / 2 || base + TILE_THREADS >= jhi) {                // block-uniform
             int m = min(qn, TILE_QCAP);
             for (int i = tid; i < m; i += TILE_THREADS) {
                 unsigned long long e = sm.queue[i];
-                tile_process(d, aux, sm, (int)(e >> 32), (int)(unsigned)(e & 0xffffffffu), K, pw, cw, -1);
+                tile_process(d, aux, sm, (int)(e >> 32), (int)(unsigned)(e & 0xffffffffu), K, pw, cw,
+                             seed_mode == 1 ? -2 : -1);
             }
             __syncthreads();
             if (tid == 0) *sm.qn = 0;
             __syncthreads();
         }
+    }
+    // ---- 2. pairs sharing a tail place, through the postings.  One warp per target; the
+    // postings sub-ranges of 32 place entries at a time are flattened over the lanes.
+    for (int t = warp; t < nt && seed_mode == 0; t += TILE_THREADS / 32) {
+        int tix = sm.tid_of[t];
+        if (tix < 0) continue;                                                  // warp-uniform
+        int ps = d.place.rowptr[tix], pn = d.place.rowptr[tix + 1] - ps;
+        for (int e0 = 0; e0 < pn; e0 += 32) {
+            int e = e0 + lane, start = 0, len = 0, pl = -1;
+            if (e < pn) {
+                pl = d.place.col[ps + e];
+                if (aux.head_slot[pl] < 0) {
+                    int b = aux.pcp[pl], en = aux.pcp[pl + 1];
+                    int l0 = b, h0 = en;                 // postings (ascending person) within [lo, hi)
+                    while (l0 < h0) {
+                        int mid = (l0 + h0) >> 1;
+                        if (aux.pper[mid] < lo) l0 = mid + 1; else h0 = mid;
+                    }
+                    int l1 = l0, h1 = en;
+                    while (l1 < h1) {
+                        int mid = (l1 + h1) >> 1;
+                        if (aux.pper[mid] < hi) l1 = mid + 1; else h1 = mid;
+                    }
+                    start = l0;
+                    len = l1 - l0;
+                }
+            }
+            int incl = len;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int excl = incl - len;
+            for (int j0 = 0; j0 < total; j0 += 32) {
+                int j = j0 + lane;
+                int L = 0;                               // smallest lane whose inclusive prefix exceeds j
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    int probe = __shfl_sync(0xffffffffu, incl, L + step - 1);
+                    if (probe <= j) L += step;
+                }
+                L = min(L, 31);
+                int ex_l = __shfl_sync(0xffffffffu, excl, L);
+                int st_l = __shfl_sync(0xffffffffu, start, L);
+                int pl_l = __shfl_sync(0xffffffffu, pl, L);
+                if (j < total) tile_process(d, aux, sm, t, aux.pper[st_l + (j - ex_l)], K, pw, cw, pl_l);
+            }
+        }
+    }
+    __syncthreads();
+    if (seed_mode == 1) {
+        // K real candidates with similarity >= root exist, so the K-th best overall is >= root
+        for (int t = tid; t < nt; t += TILE_THREADS) seed_thr[t0 + t] = sm.hcnt[t] >= K ? sm.hsim[(size_t)t * K] : 0.0;
+        return;
     }
     // ---- emit the heaps (unsorted; the merge kernel sorts)
     for (int t = 0; t < nt; ++t) {
@@ -867,8 +915,10 @@ struct vrec_knn {
     DevBuf<float> d_feat;
     DevBuf<short> d_head_slot;
     DevBuf<int> d_pcp, d_pper;
+    DevBuf<double> d_seed_thr;
     // options
     int64_t opt_rating_path = 0, opt_tile = 0, opt_splits = 0, opt_kernel = 0;
+    int64_t opt_debug_skip_postings = 0;     // timing experiments only: results are then WRONG
     // scratch
     DevBuf<long long> d_targets;
     DevBuf<int> d_tidx, d_status;
@@ -1156,12 +1206,27 @@ extern "C" int vrec_knn_set_option(vrec_knn *k, const char *name, int64_t value)
         k->opt_kernel = value;
         return VREC_OK;
     }
+    if (!strcmp(name, "debug_skip_postings")) {
+        k->opt_debug_skip_postings = value;
+        return VREC_OK;
+    }
     if (!strcmp(name, "splits") && value >= 0 && value <= 32) {
         k->opt_splits = value;
         return VREC_OK;
     }
     vrec_set_error("vrec_knn_set_option: unknown option or bad value: %s=%lld", name, (long long)value);
     return VREC_EINVAL;
+}
+
+// Debug: reads and clears the event counters of the tiled kernel (see g_tile_stats).
+extern "C" int vrec_knn_debug_stats(vrec_knn *k, uint64_t *out4) {
+    if (!k || !out4) return VREC_EINVAL;
+    VREC_CUDA(cudaSetDevice(k->ctx->device));
+    VREC_CUDA(cudaStreamSynchronize(k->ctx->stream));
+    unsigned long long z[4] = {0, 0, 0, 0};
+    VREC_CUDA(cudaMemcpyFromSymbol(out4, g_tile_stats, sizeof(z)));
+    VREC_CUDA(cudaMemcpyToSymbol(g_tile_stats, z, sizeof(z)));
+    return VREC_OK;
 }
 
 extern "C" int vrec_knn_set_filter(vrec_knn *k, const int64_t *place_filter, int64_t n_filter) {
@@ -1245,9 +1310,20 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
             attr_set = true;
         }
         TileAux aux{k->d_feat.p, k->fstride, k->d_head_slot.p, k->d_pcp.p, k->d_pper.p};
+        VREC_TRY(k->d_seed_thr.ensure((size_t)tn));
+        // seed pass: exact top-K of a strided sample -> lower bound of every target's K-th best
+        long long sample = std::min<long long>(k->P, std::max<long long>(4096, std::min<long long>(65536, k->P / 16)));
+        long long stride = std::max<long long>(1, k->P / sample);
+        sample = (k->P + stride - 1) / stride;
+        knn_tile_kernel<<<dim3(tiles, 1), TILE_THREADS, smem, ctx->stream>>>(
+            k->dev(), aux, k->d_tidx.p, tn, T, K, 1, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p, stride, sample,
+            1, k->d_seed_thr.p);
+        VREC_LAUNCHED(ctx);
         dim3 grid(tiles, S);
         knn_tile_kernel<<<grid, TILE_THREADS, smem, ctx->stream>>>(k->dev(), aux, k->d_tidx.p, tn, T, K, S,
-                                                                  k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p);
+                                                                  k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p,
+                                                                  1, k->P, k->opt_debug_skip_postings ? 2 : 0,
+                                                                  k->d_seed_thr.p);
         VREC_LAUNCHED(ctx);
     } else {
         dim3 grid(tn, S);

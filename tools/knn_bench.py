@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the batch KNN query on G2 data (tuning + the short command profiled under ncu)."""
+import argparse
+import ctypes as C
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "locations-recommender_b200"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import vrec  # noqa: E402
+from vrec import _lib as L, synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--persons", type=int, default=1_000_000)
+ap.add_argument("--places", type=int, default=100_000)
+ap.add_argument("--batch", type=int, default=4096)
+ap.add_argument("--k", type=int, default=50)
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--warmup", type=int, default=1)
+ap.add_argument("--kernel", type=int, default=0)
+ap.add_argument("--splits", type=int, default=0)
+ap.add_argument("--skip-postings", type=int, default=0)
+a = ap.parse_args()
+v, places = synth.g2_place_visits(a.persons, a.places)
+inp = synth.build_rating_vectors(v)
+ctx = vrec.Context(0)
+stream = torch.cuda.ExternalStream(ctx.stream)
+rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
+rs.set_option("knn_kernel", a.kernel)
+rs.set_option("splits", a.splits)
+rs.set_option("debug_skip_postings", a.skip_postings)
+lib = ctx.lib
+flt = np.ascontiguousarray(places.id)
+lib.vrec_knn_set_filter(rs._h, flt.ctypes.data_as(L.i64p), len(flt))
+B, m = a.batch, 10
+P = len(inp.person_id)
+d_place = torch.empty((B, m), dtype=torch.int64, device="cuda")
+d_rating = torch.empty((B, m), dtype=torch.float64, device="cuda")
+d_count = torch.empty(B, dtype=torch.int32, device="cuda")
+d_status = torch.empty(B, dtype=torch.int32, device="cuda")
+stats = (C.c_uint64 * 4)()
+for s in range(a.warmup + a.steps):
+    t = torch.from_numpy(inp.person_id[(np.arange(B) + s * B) % P]).cuda()
+    lib.vrec_knn_debug_stats(rs._h, stats)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    rc = lib.vrec_knn_query_device(rs._h, t.data_ptr(), B, 0.5, 0.5, a.k, m, d_place.data_ptr(),
+                                   d_rating.data_ptr(), d_count.data_ptr(), d_status.data_ptr())
+    assert rc == 0, L.last_error()
+    e1.record(stream)
+    ctx.synchronize()
+    ms = e0.elapsed_time(e1)
+    lib.vrec_knn_debug_stats(rs._h, stats)
+    st = [int(x) for x in stats]
+    print(f"step {s}: {ms:.1f} ms  {B / ms * 1e3:,.0f} persons/s   per target: postings evals {st[0] / B:.0f}, "
+          f"filter survivors {st[1] / B:.0f}, heap inserts {st[2] / B:.0f}, queue overflow {st[3] / B:.0f}", flush=True)
