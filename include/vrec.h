@@ -59,6 +59,17 @@ void *vrec_stream(vrec_ctx *ctx);
 int64_t vrec_launch_count(vrec_ctx *ctx);
 int vrec_synchronize(vrec_ctx *ctx);
 
+/* ---------------------------------------------------------------- multi-GPU
+ * One process per GPU.  Rank 0 calls vrec_comm_unique_id and ships the 128 bytes to the other
+ * ranks by any means (bench.py uses torch.distributed); every rank then calls vrec_comm_init.
+ * Region-sharded work (independent region-sets / target ranges) needs no communicator; it is
+ * required only for the row-partitioned graph (vrec_sg_load_partitioned / vrec_sg_generate
+ * with world > 1), whose per-iteration all-gather of x' runs on NCCL over NVLink.            */
+int vrec_comm_unique_id(void *out128);
+int vrec_comm_init(vrec_ctx *ctx, int rank, int world, const void *unique_id128);
+int vrec_comm_rank(vrec_ctx *ctx);
+int vrec_comm_world(vrec_ctx *ctx);
+
 /* ---------------------------------------------------------------- KNN path */
 
 /*
@@ -160,6 +171,11 @@ int vrec_knn_debug_stats(vrec_knn *knn, uint64_t *out4);
  */
 int vrec_sg_load(vrec_ctx *ctx, int64_t nnz, const int64_t *source_id, const int64_t *target_id,
                  const double *balanced_weight, vrec_sg **out);
+/* Same, for ONE oversized graph on several GPUs: every rank passes the whole edge list and keeps a
+ * contiguous block of rows of P^T (vertex_count / world, rounded up); queries must then be issued
+ * by all ranks together (same arguments); every rank gets the full result.                      */
+int vrec_sg_load_partitioned(vrec_ctx *ctx, int64_t nnz, const int64_t *source_id, const int64_t *target_id,
+                             const double *balanced_weight, vrec_sg **out);
 void vrec_sg_free(vrec_sg *sg);
 int64_t vrec_sg_vertex_count(vrec_sg *sg);
 int64_t vrec_sg_edge_count(vrec_sg *sg);

@@ -61,6 +61,7 @@ extern "C" void vrec_shutdown(vrec_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
+        vrec_comm_destroy(ctx);
         cudaStreamDestroy(ctx->stream);
     }
     delete ctx;

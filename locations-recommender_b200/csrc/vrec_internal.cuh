@@ -19,7 +19,14 @@ struct vrec_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
+    // multi-GPU (vrec_comm.cu): NCCL communicator of the one-process-per-GPU job
+    void *comm = nullptr;
+    int rank = 0, world = 1;
 };
+
+void vrec_comm_destroy(vrec_ctx *ctx);
+int vrec_comm_allgather_f64(vrec_ctx *ctx, double *buf, size_t count);
+int vrec_comm_allreduce_sum_f64(vrec_ctx *ctx, double *buf, size_t count);
 
 #define VREC_CUDA(call)                                                                   \
     do {                                                                                  \

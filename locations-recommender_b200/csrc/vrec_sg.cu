@@ -19,6 +19,7 @@ struct SgState {
     int converged;     // 1 = "Converged in ...", 0 = "... reached the maximum ..."
     unsigned int ticket;
     double residual;   // last sum of squared differences (:131-139)
+    double residual_partial;   // this rank's share before the all-reduce (partitioned graphs)
 };
 
 }  // namespace
@@ -27,6 +28,8 @@ struct vrec_sg {
     vrec_ctx *ctx = nullptr;
     int64_t N = 0, nnz = 0;
     int64_t row_lo = 0, row_hi = 0;           // rows of P^T owned by this process
+    int64_t slice = 0;                        // rows per rank (equal, padded): x buffers hold slice * world values
+    bool partitioned = false;
     std::vector<int64_t> h_ids;               // ascending vertex ids (host copy for lookups)
     DevBuf<long long> d_ids;
     DevBuf<int> d_rowptr;                     // [rows+1]
@@ -224,7 +227,9 @@ sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ rowptr, con
         double acc = 0.0;
         for (int k = lane; k < (int)gridDim.x; k += 32) acc = xadd(acc, __ldcg(block_partials + k));
         acc = canon_butterfly(acc);
-        if (lane == 0) {
+        if (lane == 0 && check_convergence == 2) {
+            st->residual_partial = acc;          // partitioned: decided after the all-reduce
+        } else if (lane == 0) {
             st->residual = acc;
             if (acc <= eps2) {                   // :140 `diffSquared <= epsilonSquared`
                 st->converged = 1;
@@ -236,6 +241,22 @@ sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ rowptr, con
                 st->done = 1;
             }
         }
+    }
+}
+
+// step() control for a partitioned graph, after the residual partials were all-reduced
+__global__ void sg_control_kernel(SgState *st, int iteration, int max_it, double eps2) {
+    if (st->done) return;
+    double acc = st->residual_partial;
+    st->residual = acc;
+    if (acc <= eps2) {
+        st->converged = 1;
+        st->iterations = iteration;
+        st->done = 1;
+    } else if (iteration + 1 >= max_it) {
+        st->converged = 0;
+        st->iterations = max_it;
+        st->done = 1;
     }
 }
 
@@ -295,8 +316,11 @@ int sg_setup_device(vrec_sg *g, const std::vector<int> &rowptr) {
     VREC_TRY(g->d_long_segptr.upload(long_segptr.data(), long_segptr.size(), ctx->stream));
     VREC_TRY(g->d_seg_row.upload(seg_row.data(), seg_row.size(), ctx->stream));
     VREC_TRY(g->d_partials.alloc(std::max(1, g->n_seg)));
-    VREC_TRY(g->d_x[0].alloc(g->N));
-    VREC_TRY(g->d_x[1].alloc(g->N));
+    const int64_t xlen = g->partitioned ? g->slice * g->ctx->world : g->N;
+    VREC_TRY(g->d_x[0].alloc((size_t)xlen));
+    VREC_TRY(g->d_x[1].alloc((size_t)xlen));
+    VREC_CUDA(cudaMemsetAsync(g->d_x[0].p, 0, sizeof(double) * (size_t)xlen, ctx->stream));
+    VREC_CUDA(cudaMemsetAsync(g->d_x[1].p, 0, sizeof(double) * (size_t)xlen, ctx->stream));
     // grid: a fixed function of the row count only, so the residual order is reproducible
     int64_t want = (rows + 32 * SPMV_WARPS - 1) / (32 * SPMV_WARPS);
     g->grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, 148 * 8));
@@ -334,8 +358,17 @@ int sg_run_device(vrec_sg *g, long long uidx, double epsilon, int max_it, bool c
         sg_spmv_kernel<<<g->grid, SPMV_THREADS, 0, ctx->stream>>>(
             rows, g->row_lo, g->d_rowptr.p, g->d_src.p, g->d_w.p, x, nx, uidx, g->d_long_rows.p,
             g->d_long_segptr.p, g->n_long, g->d_partials.p, g->d_state.p, g->d_block_partials.p, it,
-            max_it, eps2, check_convergence ? 1 : 0, keep_frac);
+            max_it, eps2, check_convergence ? (g->partitioned ? 2 : 1) : 0, keep_frac);
         VREC_LAUNCHED(ctx);
+        if (g->partitioned) {
+            // the one exchange step of the path: every rank needs the whole x' for its gathers
+            VREC_TRY(vrec_comm_allgather_f64(ctx, nx, (size_t)g->slice));
+            if (check_convergence) {
+                VREC_TRY(vrec_comm_allreduce_sum_f64(ctx, &g->d_state.p->residual_partial, 1));
+                sg_control_kernel<<<1, 1, 0, ctx->stream>>>(g->d_state.p, it, max_it, eps2);
+                VREC_LAUNCHED(ctx);
+            }
+        }
     }
     return VREC_OK;
 }
@@ -443,11 +476,52 @@ extern "C" int vrec_sg_load(vrec_ctx *ctx, int64_t nnz, const int64_t *source_id
         g->nnz = nnz;
         g->row_lo = 0;
         g->row_hi = g->N;
+        g->slice = g->N;
         rc = g->d_ids.upload((const long long *)g->h_ids.data(), g->h_ids.size(), ctx->stream);
     }
     if (rc == VREC_OK) rc = g->d_rowptr.upload(rowptr.data(), rowptr.size(), ctx->stream);
     if (rc == VREC_OK) rc = g->d_src.upload(src.data(), src.size(), ctx->stream);
     if (rc == VREC_OK) rc = g->d_w.upload(w.data(), w.size(), ctx->stream);
+    if (rc == VREC_OK) rc = sg_setup_device(g, rowptr);
+    if (rc != VREC_OK) {
+        delete g;
+        return rc;
+    }
+    *out = g;
+    return VREC_OK;
+}
+
+// Row-partitioned load of one oversized graph: every rank passes the whole edge list and keeps
+// the rows [rank*slice, (rank+1)*slice) of P^T; x is all-gathered after every iteration.
+extern "C" int vrec_sg_load_partitioned(vrec_ctx *ctx, int64_t nnz, const int64_t *source_id,
+                                        const int64_t *target_id, const double *balanced_weight, vrec_sg **out) {
+    if (!ctx || !out || (nnz > 0 && (!source_id || !target_id || !balanced_weight))) {
+        vrec_set_error("vrec_sg_load_partitioned: NULL argument");
+        return VREC_EINVAL;
+    }
+    *out = nullptr;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    std::vector<int> rowptr, src;
+    std::vector<double> w;
+    vrec_sg *g = new vrec_sg();
+    g->ctx = ctx;
+    int rc = vrec_host_build_sg(nnz, source_id, target_id, balanced_weight, g->h_ids, rowptr, src, w);
+    if (rc == VREC_OK) {
+        g->N = (int64_t)g->h_ids.size();
+        g->slice = (g->N + ctx->world - 1) / ctx->world;
+        g->row_lo = std::min<int64_t>(g->N, g->slice * ctx->rank);
+        g->row_hi = std::min<int64_t>(g->N, g->row_lo + g->slice);
+        g->partitioned = ctx->world > 1;
+        const int e0 = rowptr[g->row_lo], e1 = rowptr[g->row_hi];
+        g->nnz = e1 - e0;
+        std::vector<int> lrp(rowptr.begin() + g->row_lo, rowptr.begin() + g->row_hi + 1);
+        for (int &v : lrp) v -= e0;
+        rowptr.swap(lrp);
+        rc = g->d_ids.upload((const long long *)g->h_ids.data(), g->h_ids.size(), ctx->stream);
+        if (rc == VREC_OK) rc = g->d_rowptr.upload(rowptr.data(), rowptr.size(), ctx->stream);
+        if (rc == VREC_OK) rc = g->d_src.upload(src.data() + e0, (size_t)g->nnz, ctx->stream);
+        if (rc == VREC_OK) rc = g->d_w.upload(w.data() + e0, (size_t)g->nnz, ctx->stream);
+    }
     if (rc == VREC_OK) rc = sg_setup_device(g, rowptr);
     if (rc != VREC_OK) {
         delete g;
@@ -673,7 +747,13 @@ extern "C" int vrec_sg_generate(vrec_ctx *ctx, int64_t n_vertices, int32_t out_d
     }
     *out = nullptr;
     VREC_CUDA(cudaSetDevice(ctx->device));
-    int64_t lo = n_vertices * rank / world, hi = n_vertices * (rank + 1) / world;
+    if (world > 1 && (ctx->world != world || ctx->rank != rank)) {
+        vrec_set_error("vrec_sg_generate: rank/world (%d/%d) do not match vrec_comm_init (%d/%d)", rank, world,
+                       ctx->rank, ctx->world);
+        return VREC_EINVAL;
+    }
+    const int64_t slice = (n_vertices + world - 1) / world;      // equal slices; the last may be short
+    int64_t lo = std::min<int64_t>(n_vertices, slice * rank), hi = std::min<int64_t>(n_vertices, lo + slice);
     int64_t rows = hi - lo;
     if (rows * out_degree >= (int64_t)0x7fffffff) {
         vrec_set_error("vrec_sg_generate: %lld edges per process exceed 2^31-1", (long long)(rows * out_degree));
@@ -685,6 +765,8 @@ extern "C" int vrec_sg_generate(vrec_ctx *ctx, int64_t n_vertices, int32_t out_d
     g->nnz = rows * out_degree;
     g->row_lo = lo;
     g->row_hi = hi;
+    g->slice = slice;
+    g->partitioned = world > 1;
     int rc = g->d_rowptr.alloc((size_t)rows + 1);
     if (rc == VREC_OK) rc = g->d_src.alloc((size_t)g->nnz);
     if (rc == VREC_OK) rc = g->d_w.alloc((size_t)g->nnz);
@@ -710,8 +792,13 @@ extern "C" int vrec_sg_generate(vrec_ctx *ctx, int64_t n_vertices, int32_t out_d
         if (rc == VREC_OK) rc = g->d_long_segptr.alloc(2);
         if (rc == VREC_OK) rc = g->d_seg_row.alloc(1);
         if (rc == VREC_OK) rc = g->d_partials.alloc(1);
-        if (rc == VREC_OK) rc = g->d_x[0].alloc(g->N);
-        if (rc == VREC_OK) rc = g->d_x[1].alloc(g->N);
+        const size_t xlen = (size_t)(g->partitioned ? slice * world : g->N);
+        if (rc == VREC_OK) rc = g->d_x[0].alloc(xlen);
+        if (rc == VREC_OK) rc = g->d_x[1].alloc(xlen);
+        if (rc == VREC_OK) {
+            cudaMemsetAsync(g->d_x[0].p, 0, sizeof(double) * xlen, ctx->stream);
+            cudaMemsetAsync(g->d_x[1].p, 0, sizeof(double) * xlen, ctx->stream);
+        }
         int64_t want = (rows + 32 * SPMV_WARPS - 1) / (32 * SPMV_WARPS);
         g->grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, 148 * 8));
         if (rc == VREC_OK) rc = g->d_block_partials.alloc(g->grid);

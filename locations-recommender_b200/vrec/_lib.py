@@ -24,6 +24,11 @@ SIGNATURES = {
     "vrec_stream": (vp, [vp]),
     "vrec_launch_count": (C.c_int64, [vp]),
     "vrec_synchronize": (C.c_int, [vp]),
+    "vrec_comm_unique_id": (C.c_int, [vp]),
+    "vrec_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "vrec_comm_rank": (C.c_int, [vp]),
+    "vrec_comm_world": (C.c_int, [vp]),
+    "vrec_sg_load_partitioned": (C.c_int, [vp, C.c_int64, i64p, i64p, f64p, C.POINTER(vp)]),
     "vrec_knn_load": (C.c_int, [vp, C.c_int64, i64p, i64p, i32p, f64p, C.c_int32, i64p, i32p, f64p, C.c_int32,
                                 C.c_int64, i64p, i64p, i64p, C.POINTER(vp)]),
     "vrec_knn_free": (None, [vp]),

@@ -77,6 +77,25 @@ class Context:
     def synchronize(self) -> None:
         _check(self.lib.vrec_synchronize(self._h))
 
+    # ---- multi-GPU: one process per GPU
+    def unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(self.lib.vrec_comm_unique_id(buf))
+        return buf.raw
+
+    def init_comm(self, rank: int, world: int, unique_id: bytes) -> None:
+        if len(unique_id) != 128:
+            raise ValueError("unique id must be 128 bytes")
+        _check(self.lib.vrec_comm_init(self._h, int(rank), int(world), C.create_string_buffer(unique_id, 128)))
+
+    @property
+    def rank(self) -> int:
+        return int(self.lib.vrec_comm_rank(self._h))
+
+    @property
+    def world(self) -> int:
+        return int(self.lib.vrec_comm_world(self._h))
+
 
 _default_ctx: Optional[Context] = None
 
@@ -209,7 +228,8 @@ class KnnRecommender:
 class StochasticGraph:
     """Device-resident stochastic graph (CSR of P^T) built from (source_id, target_id, balanced_weight)."""
 
-    def __init__(self, source_id, target_id, balanced_weight, ctx: Optional[Context] = None, _handle=None):
+    def __init__(self, source_id, target_id, balanced_weight, ctx: Optional[Context] = None, _handle=None,
+                 partitioned: bool = False):
         self.ctx = ctx or default_context()
         self._h = L.vp()
         if _handle is not None:
@@ -218,8 +238,9 @@ class StochasticGraph:
             s, t, w = _i64(source_id), _i64(target_id), _f64(balanced_weight)
             if not (len(s) == len(t) == len(w)):
                 raise ValueError("edge arrays differ in length")
-            _check(self.ctx.lib.vrec_sg_load(self.ctx._h, len(s), _ptr(s, L.i64p), _ptr(t, L.i64p),
-                                             _ptr(w, L.f64p), C.byref(self._h)))
+            load = self.ctx.lib.vrec_sg_load_partitioned if partitioned else self.ctx.lib.vrec_sg_load
+            _check(load(self.ctx._h, len(s), _ptr(s, L.i64p), _ptr(t, L.i64p), _ptr(w, L.f64p),
+                        C.byref(self._h)))
         self.N = int(self.ctx.lib.vrec_sg_vertex_count(self._h))
         self.nnz = int(self.ctx.lib.vrec_sg_edge_count(self._h))
 
