@@ -120,6 +120,11 @@ def sg_workload_name(args):
             f"(BASELINE config 5 shape, device generator)")
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one sg_spmv_kernel launch on the default SG workload,
+# from profiles/r1_sg_spmv_v1_ncu_raw.csv (ncu --set full)
+SG_NCU_TRAFFIC = 27_756_317_000 + 83_389_440
+
+
 def sg_bytes_per_iteration(n, nnz):
     return 12 * nnz + 20 * n
 
@@ -163,13 +168,16 @@ def cpu_sg(args, n_vertices, iterations):
     threads = os.cpu_count() or 1
     rng = np.random.default_rng(5)
     deg = args.sg_degree
-    tgt = np.repeat(np.arange(n_vertices, dtype=np.int64), deg)
-    u = rng.random(len(tgt))
-    skew = (np.arange(len(tgt)) % 2) == 0
-    src = np.where(skew, ((u ** 3 * n_vertices).astype(np.int64) * 2654435761 + 12345) % n_vertices,
-                   (u * n_vertices).astype(np.int64))
-    w = np.full(len(tgt), 1.0 / deg)
-    g = oracle.SgGraph(src, tgt, w)
+    # same shape as sg_gen_rows_kernel: every row has `deg` in-edges, half uniform / half skewed sources
+    u = rng.random((n_vertices, deg))
+    src = np.where((np.arange(deg) % 2 == 0)[None, :],
+                   ((u ** 3 * n_vertices).astype(np.int64) * 2654435761 + 12345) % n_vertices,
+                   (u * n_vertices).astype(np.int64)).astype(np.int32)
+    del u
+    src.sort(axis=1)
+    rowptr = np.arange(n_vertices + 1, dtype=np.int64) * deg
+    g = oracle.SgGraph.from_csr(rowptr, src.ravel(), np.full(n_vertices * deg, 1.0 / deg))
+    del src
     oracle.set_threads(threads)
     t0 = time.perf_counter()
     rc, x, it, conv, res = g.run(int(g.ids[0]), 0.0, iterations)
@@ -196,7 +204,7 @@ def run_reference(args):
             times.append(dt)
     total = sum(times)
     value = per_step * len(times) / total
-    sg_cb, _ = cpu_sg(args, args.ref_sg_vertices, 3)
+    sg_cb, _ = cpu_sg(args, args.ref_sg_vertices, 10)
     cb["value"] = value
     line = {
         "impl": "reference", "metric": "KNN target persons/sec (sim+top-K+rating)", "value": value,
@@ -242,6 +250,9 @@ def run_ours(args):
         return float(t.item())
 
     ctx = vrec.Context(local_rank)
+    if world > 1:
+        from vrec import dist as vdist
+        vdist.init_comm(ctx)          # NCCL communicator of the library (row-partitioned SG path)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
     lib = ctx.lib
     peak, peak_src = measured_peaks()
@@ -338,12 +349,12 @@ def run_ours(args):
     # pass over the region-set (bytes/target = B_region / T with T = targets per pass)
     b_region = inp.algorithmic_bytes
     knn_launch_ms = statistics.mean(knn_ms)
-    knn_roof = {"bound": "hbm", "kernel": "knn_topk_kernel", "achieved": b_region / (knn_launch_ms / 1e3) / 1e9,
+    knn_roof = {"bound": "hbm", "kernel": "knn_tile_kernel", "achieved": b_region / (knn_launch_ms / 1e3) / 1e9,
                 "peak": peak, "unit": "GB/s", "frac": b_region / (knn_launch_ms / 1e3) / 1e9 / peak,
                 "traffic": None, "peak_source": peak_src,
                 "note": f"one launch serves T={B} targets, so algorithmic bytes/launch = B_region = {b_region}; "
-                        "the batch kernel is issue-bound (10^6 exact fp64 pair evaluations per target), "
-                        "not HBM-bound: see DESIGN.md"}
+                        "the batch kernel is issue-bound (10^6 pair filters + ~12K exact fp64 evaluations "
+                        "per target), not HBM-bound: see DESIGN.md"}
 
     cpu_knn_base = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -381,14 +392,14 @@ def run_ours(args):
 
 def run_sg(args, vrec, ctx, stream, world, rank, barrier, max_over_ranks, peak, peak_src):
     import torch
-    if world > 1:
-        return {"skipped": "row-partitioned multi-GPU SpMV is not built yet; SG is measured at 1 GPU only"}
     N, deg, iters = args.sg_vertices, args.sg_degree, args.sg_iterations
     t0 = time.time()
-    g = vrec.StochasticGraph.generate(N, deg, seed=5, ctx=ctx)
+    # one oversized graph: rows of P^T partitioned over the ranks, x all-gathered every iteration
+    g = vrec.StochasticGraph.generate(N, deg, seed=5, rank=rank, world=world, ctx=ctx)
     log(f"[bench] sg graph generated on device: N={g.N} nnz={g.nnz} ({time.time() - t0:.1f}s, "
         f"{g.resident_bytes / 1e9:.2f} GB resident)")
-    bytes_it = sg_bytes_per_iteration(g.N, g.nnz)
+    bytes_it = sg_bytes_per_iteration(g.N, N * deg)          # whole graph, all ranks
+    bytes_rank = 12 * g.nnz + 4 * (g.nnz // deg) + 8 * g.N + 8 * (g.nnz // deg)   # this rank's rows + full x gather space
     for _ in range(args.warmup):
         g.iterate_device(iters)
     ctx.synchronize()
@@ -413,25 +424,34 @@ def run_sg(args, vrec, ctx, stream, world, rank, barrier, max_over_ranks, peak, 
     # end to end: one query through the host ABI (vertex id in, top-10 out), graph resident
     rec = vrec.StochasticRecommender(g, 0.0, iters)
     rec.recommend([0], None, 10)
+    barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         rec.recommend([i + 1], None, 10)
+    barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_gbs = bytes_it * iters * args.steps / e2e_s / 1e9
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu, _ = cpu_sg(args, args.cpu_sg_vertices, 5)
+        cpu, _ = cpu_sg(args, args.cpu_sg_vertices, 10)
         log(f"[bench] sg cpu baseline: {cpu['value']:.2f} GB/s on {cpu['cores']} threads")
     out = {
         "metric": "SG power-iteration HBM GB/s (algorithmic bytes 12*nnz + 20*N per iteration)",
         "value": gbs, "unit": "GB/s", "ms_per_step": total_ms / args.steps, "us_per_iteration": per_launch_ms * 1e3,
-        "config": {"workload": sg_workload_name(args), "l2": f"inputs larger than L2 ({bytes_it / 1e9:.1f} GB/iteration)"},
+        "n_gpus": world, "scaling": "strong",
+        "config": {"workload": sg_workload_name(args), "l2": f"inputs larger than L2 ({bytes_it / 1e9:.1f} GB/iteration)",
+                   "parallelism": "single GPU" if world == 1 else
+                   f"rows of P^T partitioned over {world} GPUs, ncclAllGather of x' ({8 * N / 1e6:.0f} MB) per iteration"},
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 10 * 16 + 24,
                 "note": "vrec_sg_query: vertex id in, ranked top-10 of all vertices out"},
-        "roofline": {"bound": "hbm", "kernel": "sg_spmv_kernel", "achieved": bytes_it / (per_launch_ms / 1e3) / 1e9,
-                     "peak": peak, "unit": "GB/s", "frac": bytes_it / (per_launch_ms / 1e3) / 1e9 / peak,
-                     "traffic": None, "peak_source": peak_src},
+        "roofline": {"bound": "hbm", "kernel": "sg_spmv_kernel",
+                     "achieved": bytes_rank / (per_launch_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": bytes_rank / (per_launch_ms / 1e3) / 1e9 / peak,
+                     "traffic": SG_NCU_TRAFFIC if world == 1 and N == 10_000_000 and deg == 100 else None,
+                     "peak_source": peak_src,
+                     "note": "per GPU: this rank's algorithmic bytes / (step time / iterations); at N > 1 the step "
+                             "time includes the all-gather"},
         "cpu_baseline": cpu, "clocks": clocks,
     }
     g.close()
@@ -446,16 +466,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--knn-persons", type=int, default=1_000_000)
     ap.add_argument("--knn-places", type=int, default=100_000)
-    ap.add_argument("--knn-batch", type=int, default=4096)
+    ap.add_argument("--knn-batch", type=int, default=16384)
     ap.add_argument("--k-nearest", type=int, default=50)
     ap.add_argument("--max-recs", type=int, default=10)
     ap.add_argument("--sg-vertices", type=int, default=10_000_000)
     ap.add_argument("--sg-degree", type=int, default=100)
     ap.add_argument("--sg-iterations", type=int, default=20)
-    ap.add_argument("--cpu-knn-targets", type=int, default=128)
-    ap.add_argument("--cpu-sg-vertices", type=int, default=500_000)
-    ap.add_argument("--ref-knn-targets", type=int, default=64)
-    ap.add_argument("--ref-sg-vertices", type=int, default=500_000)
+    ap.add_argument("--cpu-knn-targets", type=int, default=1024)
+    ap.add_argument("--cpu-sg-vertices", type=int, default=1_000_000)
+    ap.add_argument("--ref-knn-targets", type=int, default=512)
+    ap.add_argument("--ref-sg-vertices", type=int, default=1_000_000)
     ap.add_argument("--no-sg", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

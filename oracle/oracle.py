@@ -158,6 +158,21 @@ def knn_query_batch(d: KnnData, targets, pw, cw, k, place_filter, max_recs, n_th
 
 # ---------------------------------------------------------------- SG
 class SgGraph:
+    @classmethod
+    def from_csr(cls, rowptr, src, weight):
+        """CSR of P^T over vertex ids 0..N-1 (rows = targets, ascending sources)."""
+        rowptr, src, weight = _i64(rowptr), _i32(src), _f64(weight)
+        self = cls.__new__(cls)
+        self._h = C.c_void_p(0)
+        rc = lib().vro_sg_from_csr(C.c_int64(len(rowptr) - 1), _p(rowptr, C.c_int64), _p(src, C.c_int32),
+                                   _p(weight, C.c_double), C.byref(self._h))
+        if rc:
+            raise MemoryError(rc)
+        self.N = len(rowptr) - 1
+        self.ids = np.arange(self.N, dtype=np.int64)
+        self.nnz = len(src)
+        return self
+
     def __init__(self, source, target, weight):
         source, target, weight = _i64(source), _i64(target), _f64(weight)
         assert len(source) == len(target) == len(weight)
@@ -172,9 +187,12 @@ class SgGraph:
         self.nnz = len(source)
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().vro_sg_free(self._h)
-            self._h = C.c_void_p(0)
+        try:
+            if getattr(self, "_h", None) and self._h.value and _lib is not None:
+                _lib.vro_sg_free(self._h)
+                self._h = C.c_void_p(0)
+        except Exception:
+            pass
 
     def run(self, vertex, epsilon, max_iterations):
         """-> rc, x[N], iterations, converged, last_residual"""

@@ -538,6 +538,27 @@ int vro_sg_build(int64_t nnz, const int64_t *source, const int64_t *target, cons
     return VRO_OK;
 }
 
+/* Graph given directly as the CSR of P^T over vertex ids 0..N-1 (rows = targets, sources ascending
+ * per row): skips the id sort of vro_sg_build.  Used by bench.py's CPU baseline. */
+int vro_sg_from_csr(int64_t N, const int64_t *rowptr, const int32_t *src, const double *w, vro_sg **out)
+{
+    vro_sg *g = (vro_sg *)calloc(1, sizeof(vro_sg));
+    if (!g) return VRO_ENOMEM;
+    int64_t nnz = rowptr[N];
+    g->N = N; g->nnz = nnz;
+    g->ids = (int64_t *)malloc(sizeof(int64_t) * (size_t)(N + 1));
+    g->rowptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(N + 1));
+    g->src = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nnz + 1));
+    g->w = (double *)malloc(sizeof(double) * (size_t)(nnz + 1));
+    if (!g->ids || !g->rowptr || !g->src || !g->w) { vro_sg_free(g); return VRO_ENOMEM; }
+    for (int64_t i = 0; i < N; ++i) g->ids[i] = i;
+    memcpy(g->rowptr, rowptr, sizeof(int64_t) * (size_t)(N + 1));
+    memcpy(g->src, src, sizeof(int32_t) * (size_t)nnz);
+    memcpy(g->w, w, sizeof(double) * (size_t)nnz);
+    *out = g;
+    return VRO_OK;
+}
+
 int64_t vro_sg_vertex_count(const vro_sg *g) { return g->N; }
 void vro_sg_vertex_ids(const vro_sg *g, int64_t *out) { memcpy(out, g->ids, sizeof(int64_t) * (size_t)g->N); }
 
