@@ -34,6 +34,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Libraries (NCCL's version banner, ...) write to the process's stdout; the contract is ONE JSON
+# line there.  Keep the real stdout aside and point fd 1 at stderr for everything else.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -218,7 +228,7 @@ def run_reference(args):
                "unit": "GB/s", "cpu_baseline": sg_cb},
         "note": "reference = Scala/Spark, not runnable here (no JVM); this arm is the C oracle port on all host cores",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -385,7 +395,7 @@ def run_ours(args):
             "clocks": clocks_knn,
             "sg": sg,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
