@@ -229,6 +229,10 @@ int vrec_host_sg_csr(int64_t nnz, const int64_t *source_id, const int64_t *targe
  * out_w [edge_count].                                                                        */
 int vrec_sg_export_csr(vrec_sg *sg, int32_t *out_rowptr, int32_t *out_src, double *out_w);
 
+/* Debug: runs one 128x128x128 fp16 tile through tcgen05.mma + TMEM and returns the largest
+ * absolute deviation from a double-precision reference (validates the tensor-core plumbing).   */
+int vrec_debug_tc_selftest(vrec_ctx *ctx, double *out_max_abs_err);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,117 @@
+// Self-test of the tcgen05 path: one 128 x 128 x D fp16 tile through tcgen05.mma + TMEM against a
+// scalar reference.  Validates the shared-memory / instruction descriptors of vrec_tc.cuh.
+#include "vrec_internal.cuh"
+#include "vrec_tc.cuh"
+
+namespace {
+
+constexpr int ST_ROWS = 128;
+constexpr int ST_D = 128;
+
+__global__ void __launch_bounds__(128) tc_selftest_kernel(const __half *__restrict__ A, const __half *__restrict__ B,
+                                                           float *__restrict__ C) {
+    extern __shared__ unsigned char smem_raw[];
+    // operand tiles must start on a core-matrix (128 B) boundary: the low bits of the descriptor
+    // start address are ignored by the hardware.  Align the dynamic buffer by hand (1 KB).
+    unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *sA = smem, *sB = smem + ST_ROWS * ST_D * 2;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tc::tmem_alloc(&tmem_base, 128);
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_init_fence();
+    }
+    // row-major global (row r: D halves) -> chunk-major smem
+    for (int q = tid; q < ST_ROWS * (ST_D / 8); q += blockDim.x) {
+        int r = q % ST_ROWS, c = q / ST_ROWS;
+        uint4 va = *reinterpret_cast<const uint4 *>(A + (size_t)r * ST_D + c * 8);
+        uint4 vb = *reinterpret_cast<const uint4 *>(B + (size_t)r * ST_D + c * 8);
+        *reinterpret_cast<uint4 *>(sA + (size_t)c * (ST_ROWS * 16) + r * 16) = va;
+        *reinterpret_cast<uint4 *>(sB + (size_t)c * (ST_ROWS * 16) + r * 16) = vb;
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_base;
+    if (tid == 0) {
+        const uint32_t idesc = tc::make_idesc_f16(128, 128);
+        for (int k = 0; k < ST_D / 16; ++k) {
+            uint64_t da = tc::make_desc(tc::smem_u32(sA) + k * 2 * (ST_ROWS * 16), ST_ROWS * 16, 128);
+            uint64_t db = tc::make_desc(tc::smem_u32(sB) + k * 2 * (ST_ROWS * 16), ST_ROWS * 16, 128);
+            tc::mma_f16(tbase, da, db, idesc, k > 0);
+        }
+        tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    const int row = tid;                       // TMEM lane = row of A
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(tbase + ((uint32_t)(warp * 32) << 16) + c0, v);
+        for (int j = 0; j < 32; ++j) C[(size_t)row * 128 + c0 + j] = v[j];
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 128);
+}
+
+}  // namespace
+
+// Debug: C[128x128] = A[128x128] * B[128x128]^T for caller-supplied fp16 bit patterns (row-major).
+extern "C" int vrec_debug_tc_matmul(vrec_ctx *ctx, const uint16_t *A, const uint16_t *B, float *C) {
+    if (!ctx || !A || !B || !C) return VREC_EINVAL;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<__half> dA, dB;
+    DevBuf<float> dC;
+    VREC_TRY(dA.upload((const __half *)A, ST_ROWS * ST_D, ctx->stream));
+    VREC_TRY(dB.upload((const __half *)B, ST_ROWS * ST_D, ctx->stream));
+    VREC_TRY(dC.alloc(ST_ROWS * 128));
+    size_t smem = 2 * ST_ROWS * ST_D * 2 + 1024;
+    VREC_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_selftest_kernel<<<1, 128, smem, ctx->stream>>>(dA.p, dB.p, dC.p);
+    VREC_LAUNCHED(ctx);
+    VREC_CUDA(cudaMemcpyAsync(C, dC.p, ST_ROWS * 128 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VREC_OK;
+}
+
+// Debug: max |C_tc - C_ref| over a random 128x128x128 fp16 product (C_ref accumulated in double).
+extern "C" int vrec_debug_tc_selftest(vrec_ctx *ctx, double *out_max_abs_err) {
+    if (!ctx || !out_max_abs_err) return VREC_EINVAL;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    std::vector<__half> hA(ST_ROWS * ST_D), hB(ST_ROWS * ST_D);
+    uint64_t s = 88172645463325252ULL;
+    auto rnd = [&]() {
+        s ^= s << 13;
+        s ^= s >> 7;
+        s ^= s << 17;
+        return (float)((s >> 11) % 2001) / 2000.0f;       // [0, 1]
+    };
+    for (auto &v : hA) v = __float2half(rnd());
+    for (auto &v : hB) v = __float2half(rnd() * 0.5f);
+    DevBuf<__half> dA, dB;
+    DevBuf<float> dC;
+    VREC_TRY(dA.upload(hA.data(), hA.size(), ctx->stream));
+    VREC_TRY(dB.upload(hB.data(), hB.size(), ctx->stream));
+    VREC_TRY(dC.alloc(ST_ROWS * 128));
+    size_t smem = 2 * ST_ROWS * ST_D * 2 + 1024;
+    VREC_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_selftest_kernel<<<1, 128, smem, ctx->stream>>>(dA.p, dB.p, dC.p);
+    VREC_LAUNCHED(ctx);
+    std::vector<float> hC(ST_ROWS * 128);
+    VREC_CUDA(cudaMemcpyAsync(hC.data(), dC.p, hC.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(ctx->stream));
+    double worst = 0.0;
+    for (int i = 0; i < ST_ROWS; ++i)
+        for (int j = 0; j < 128; ++j) {
+            double ref = 0.0;
+            for (int k = 0; k < ST_D; ++k) ref += (double)__half2float(hA[i * ST_D + k]) * (double)__half2float(hB[j * ST_D + k]);
+            double e = fabs(ref - (double)hC[i * 128 + j]);
+            if (e > worst) worst = e;
+        }
+    *out_max_abs_err = worst;
+    return VREC_OK;
+}

@@ -36,6 +36,14 @@ def synth():
     return s
 
 
+def test_tcgen05_selftest(vrec, ctx):
+    import ctypes as C
+    err = C.c_double(-1.0)
+    assert ctx.lib.vrec_debug_tc_selftest(ctx._h, C.byref(err)) == 0
+    # fp16 inputs are exact, products exact in fp32, 128-term fp32 accumulation: error << 1e-3
+    assert 0.0 <= err.value < 1e-3, err.value
+
+
 # ------------------------------------------------------------------ SG
 def _kat_graph(vrec, ctx):
     s, t, w = zip(*K.SG_EDGES)
