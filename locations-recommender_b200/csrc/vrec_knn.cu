@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "vrec_internal.cuh"
+#include "vrec_tc.cuh"
 
 namespace {
 
@@ -318,6 +319,8 @@ __device__ __forceinline__ double exact_pair(const KnnDev &d, const TileAux &aux
 __device__ unsigned long long g_tile_stats[4];
 
 struct TileSmem {
+    float *thr;                 // filter threshold of target slot t at thr[t * thr_stride]
+    int thr_stride;
     float *tvec;                // [T][TILE_TVEC_STRIDE]; [32] = filter threshold
     double *hsim;               // [T][K] heaps, worst at the root
     int *hidx;                  // [T][K]
@@ -337,7 +340,7 @@ __device__ __forceinline__ void tile_heap_insert(const TileSmem &sm, int t, int 
     volatile double *hs = sm.hsim + (size_t)t * K;
     volatile int *hi = sm.hidx + (size_t)t * K;
     volatile int *cntp = sm.hcnt + t;
-    volatile float *thr = sm.tvec + (size_t)t * TILE_TVEC_STRIDE + TILE_D;
+    volatile float *thr = sm.thr + (size_t)t * sm.thr_stride;
     bool done = false;
     while (!done) {
         if (atomicCAS(sm.lock + t, 0, 1) == 0) {
@@ -436,6 +439,8 @@ knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targe
         sm.lock = (int *)p;                         p += sizeof(int) * T;
         sm.tid_of = (int *)p;                       p += sizeof(int) * T;
         sm.qn = (int *)p;
+        sm.thr = sm.tvec + TILE_D;
+        sm.thr_stride = TILE_TVEC_STRIDE;
     }
     // candidates are j * cand_stride for j in [jlo, jhi); the main pass has stride 1 (all persons),
     // the seed pass a strided sample.  [lo, hi) is the same range in person indices.
@@ -579,6 +584,250 @@ knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targe
             out[j] = e;
         }
         if (tid == 0) part_cnt[(t0 + t) * S + sp] = cnt;
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Tensor-core variant of the tiled batch kernel (tcgen05 / TMEM, fp16 features, D = 128).
+//
+// Same algorithm as knn_tile_kernel, but the dense bound U(t, c) of a 128-target x 128-candidate
+// tile is ONE tcgen05.mma chain (8 instructions of K = 16) into 128 TMEM columns, and the filter
+// `U * (1 + 2e-3) + 2e-5 >= K-th best` is applied to the accumulators as they come out of TMEM.
+// With 128 dims the head covers the 128 - cat_dim most visited places, so far fewer pairs are left
+// to the postings pass.  fp16 rounding (2 x 2^-11 relative) only loosens the filter; survivors
+// are evaluated in fp64 exactly as in the other kernels, so results stay bit-identical.
+// ---------------------------------------------------------------------------------------
+constexpr int TC_D = 128;
+constexpr int TC_M = 128;
+constexpr int TC_N = 128;
+constexpr int TC_THREADS = 256;
+constexpr int TC_TILE_BYTES = TC_M * TC_D * 2;          // 32 KB per operand tile
+constexpr int TC_LBO = TC_M * 16;                        // next k-chunk
+constexpr int TC_SBO = 128;                              // next 8 rows
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const int *__restrict__ tidx,
+              int n_targets, int K, int S, int cat_dim, double pw, double cw, Nb *__restrict__ part,
+              int *__restrict__ part_cnt, long long cand_stride, long long cand_count, int seed_mode,
+              double *__restrict__ seed_thr, double *__restrict__ heap_sim, int *__restrict__ heap_idx) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_m = blockIdx.x, sp = blockIdx.y;
+    const int t0 = tile_m * TC_M;
+    const int nt = min(TC_M, n_targets - t0);
+    // operand tiles on a 1 KB boundary (the descriptor start address ignores its low bits)
+    unsigned char *base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *sA = base, *sB = base + TC_TILE_BYTES;
+    TileSmem sm;
+    {
+        unsigned char *p = base + 2 * TC_TILE_BYTES;
+        sm.queue = (unsigned long long *)p;         p += sizeof(unsigned long long) * TILE_QCAP;
+        sm.thr = (float *)p;                        p += sizeof(float) * TC_M;
+        sm.thr_stride = 1;
+        sm.tvec = nullptr;
+        sm.hcnt = (int *)p;                         p += sizeof(int) * TC_M;
+        sm.lock = (int *)p;                         p += sizeof(int) * TC_M;
+        sm.tid_of = (int *)p;                       p += sizeof(int) * TC_M;
+        sm.qn = (int *)p;
+        const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        sm.hsim = heap_sim + blk * TC_M * K;        // heaps live in global memory (L2-resident)
+        sm.hidx = heap_idx + blk * TC_M * K;
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, TC_N);
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_init_fence();
+        *sm.qn = 0;
+    }
+    const long long jlo = cand_count * sp / S, jhi = cand_count * (sp + 1) / S;
+    const long long lo = jlo * cand_stride, hi = seed_mode == 1 ? d.P : jhi * cand_stride;
+    for (int t = tid; t < TC_M; t += TC_THREADS) {
+        int tix = t < nt ? tidx[t0 + t] : -1;
+        sm.tid_of[t] = tix;
+        sm.hcnt[t] = 0;
+        sm.lock[t] = 0;
+        float thr0 = (seed_mode != 1 && tix >= 0) ? __double2float_rd(seed_thr[t0 + t]) : 0.0f;
+        sm.thr[t] = tix >= 0 ? thr0 : 3.0e38f;
+    }
+    __syncthreads();
+    // ---- A tile: the targets' features with the weights folded in (chunk-major UMMA layout)
+    for (int q = tid; q < TC_M * (TC_D / 8); q += TC_THREADS) {
+        int r = q % TC_M, c = q / TC_M;
+        int tix = sm.tid_of[r];
+        __align__(16) __half h[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) h[e] = __float2half(0.0f);
+        if (tix >= 0) {
+            uint4 raw = *reinterpret_cast<const uint4 *>(feat16 + (size_t)tix * TC_D + c * 8);
+            const __half *src = reinterpret_cast<const __half *>(&raw);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                int dd = c * 8 + e;
+                h[e] = __float2half(__half2float(src[e]) * (float)(dd < cat_dim ? cw : pw));
+            }
+        }
+        *reinterpret_cast<uint4 *>(sA + (size_t)c * TC_LBO + r * 16) = *reinterpret_cast<const uint4 *>(h);
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t idesc = tc::make_idesc_f16(TC_M, TC_N);
+    const uint32_t a_addr = tc::smem_u32(sA), b_addr = tc::smem_u32(sB);
+    const int lq = warp & 3, ch = warp >> 2;                  // TMEM lane quarter, column half
+    const int my_t = lq * 32 + lane;
+    uint32_t phase = 0;
+    // ---- 1. dense filter on the tensor cores
+    for (long long tile = jlo; tile < jhi; tile += TC_N) {
+        for (int q = tid; q < TC_N * (TC_D / 8); q += TC_THREADS) {
+            int r = q % TC_N, c = q / TC_N;
+            long long j = tile + r;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (j < jhi) v = __ldg(reinterpret_cast<const uint4 *>(feat16 + (size_t)(j * cand_stride) * TC_D + c * 8));
+            *reinterpret_cast<uint4 *>(sB + (size_t)c * TC_LBO + r * 16) = v;
+        }
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+#pragma unroll
+            for (int k = 0; k < TC_D / 16; ++k) {
+                uint64_t da = tc::make_desc(a_addr + k * 2 * TC_LBO, TC_LBO, TC_SBO);
+                uint64_t db = tc::make_desc(b_addr + k * 2 * TC_LBO, TC_LBO, TC_SBO);
+                tc::mma_f16(tbase, da, db, idesc, k > 0);
+            }
+            tc::mma_commit(&bar);
+        }
+        tc::mbar_wait(&bar, phase);
+        phase ^= 1u;
+        tc::fence_after_sync();
+        const float thr = *(volatile float *)(sm.thr + my_t);
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c0 = ch * 64 + cc * 32;
+            float v[32];
+            tc::tmem_ld32(tbase + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+                if (v[jj] * 1.002f + 2e-5f >= thr) {
+                    long long j = tile + c0 + jj;
+                    if (j < jhi) {
+                        int c = (int)(j * cand_stride);
+                        int pos = atomicAdd(sm.qn, 1);
+                        if (pos < TILE_QCAP) {
+                            sm.queue[pos] = ((unsigned long long)my_t << 32) | (unsigned long long)(unsigned)c;
+                        } else {
+                            atomicAdd(&g_tile_stats[3], 1ULL);
+                            tile_process(d, aux, sm, my_t, c, K, pw, cw, seed_mode == 1 ? -2 : -1);
+                        }
+                    }
+                }
+            }
+        }
+        tc::fence_before_sync();
+        __syncthreads();                                           // TMEM drained, sB reusable
+        int qn = *sm.qn;
+        __syncthreads();
+        if (qn >= TILE_QCAP / 2 || tile + TC_N >= jhi) {           // block-uniform
+            int m = min(qn, TILE_QCAP);
+            for (int i = tid; i < m; i += TC_THREADS) {
+                unsigned long long e = sm.queue[i];
+                tile_process(d, aux, sm, (int)(e >> 32), (int)(unsigned)(e & 0xffffffffu), K, pw, cw,
+                             seed_mode == 1 ? -2 : -1);
+            }
+            __syncthreads();
+            if (tid == 0) *sm.qn = 0;
+            __syncthreads();
+        }
+    }
+    // ---- 2. pairs sharing a tail place, through the postings (as in knn_tile_kernel)
+    for (int t = warp; t < nt && seed_mode == 0; t += TC_THREADS / 32) {
+        int tix = sm.tid_of[t];
+        if (tix < 0) continue;
+        int ps = d.place.rowptr[tix], pn = d.place.rowptr[tix + 1] - ps;
+        for (int e0 = 0; e0 < pn; e0 += 32) {
+            int e = e0 + lane, start = 0, len = 0, pl = -1;
+            if (e < pn) {
+                pl = d.place.col[ps + e];
+                if (aux.head_slot[pl] < 0) {
+                    int b = aux.pcp[pl], en = aux.pcp[pl + 1];
+                    int l0 = b, h0 = en;
+                    while (l0 < h0) {
+                        int mid = (l0 + h0) >> 1;
+                        if (aux.pper[mid] < lo) l0 = mid + 1; else h0 = mid;
+                    }
+                    int l1 = l0, h1 = en;
+                    while (l1 < h1) {
+                        int mid = (l1 + h1) >> 1;
+                        if (aux.pper[mid] < hi) l1 = mid + 1; else h1 = mid;
+                    }
+                    start = l0;
+                    len = l1 - l0;
+                }
+            }
+            int incl = len;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int excl = incl - len;
+            for (int j0 = 0; j0 < total; j0 += 32) {
+                int j = j0 + lane;
+                int L = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    int probe = __shfl_sync(0xffffffffu, incl, L + step - 1);
+                    if (probe <= j) L += step;
+                }
+                L = min(L, 31);
+                int ex_l = __shfl_sync(0xffffffffu, excl, L);
+                int st_l = __shfl_sync(0xffffffffu, start, L);
+                int pl_l = __shfl_sync(0xffffffffu, pl, L);
+                if (j < total) tile_process(d, aux, sm, t, aux.pper[st_l + (j - ex_l)], K, pw, cw, pl_l);
+            }
+        }
+    }
+    __syncthreads();
+    if (seed_mode == 1) {
+        for (int t = tid; t < nt; t += TC_THREADS)
+            seed_thr[t0 + t] = sm.hcnt[t] >= K ? *(volatile double *)(sm.hsim + (size_t)t * K) : 0.0;
+    } else {
+        for (int t = 0; t < nt; ++t) {
+            int cnt = sm.hcnt[t];
+            Nb *out = part + ((size_t)(t0 + t) * S + sp) * K;
+            for (int j = tid; j < cnt; j += TC_THREADS) {
+                Nb e;
+                e.sim = *(volatile double *)(sm.hsim + (size_t)t * K + j);
+                e.idx = *(volatile int *)(sm.hidx + (size_t)t * K + j);
+                e.pad = 0;
+                out[j] = e;
+            }
+            if (tid == 0) part_cnt[(t0 + t) * S + sp] = cnt;
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, TC_N);
+}
+
+// fp16 features, row-major [P][TC_D]: category vector / length, then the head places' values / length
+__global__ void knn_features16_kernel(KnnDev d, const short *__restrict__ head_slot, int cat_dim,
+                                      __half *__restrict__ feat16) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.P) return;
+    __half *row = feat16 + (size_t)i * TC_D;
+    for (int dd = 0; dd < TC_D; ++dd) row[dd] = __float2half(0.0f);
+    double cl = d.cat.len[i], pl = d.place.len[i];
+    for (int k = d.cat.rowptr[i]; k < d.cat.rowptr[i + 1]; ++k) row[d.cat.col[k]] = __double2half(d.cat.val[k] / cl);
+    for (int k = d.place.rowptr[i]; k < d.place.rowptr[i + 1]; ++k) {
+        int slot = head_slot[d.place.col[k]];
+        if (slot >= 0) row[cat_dim + slot] = __double2half(d.place.val[k] / pl);
     }
 }
 
@@ -916,6 +1165,12 @@ struct vrec_knn {
     DevBuf<short> d_head_slot;
     DevBuf<int> d_pcp, d_pper;
     DevBuf<double> d_seed_thr;
+    // tensor-core variant: fp16 row-major features over TC_D dims, its own (larger) head set
+    bool tc_ok = false;
+    DevBuf<__half> d_feat16;
+    DevBuf<short> d_head_slot_tc;
+    DevBuf<double> d_tc_hsim;
+    DevBuf<int> d_tc_hidx;
     // options
     int64_t opt_rating_path = 0, opt_tile = 0, opt_splits = 0, opt_kernel = 0;
     int64_t opt_debug_skip_postings = 0;     // timing experiments only: results are then WRONG
@@ -1155,6 +1410,24 @@ extern "C" int vrec_knn_load(vrec_ctx *ctx, int64_t P, const int64_t *person_id,
             if (cudaGetLastError() != cudaSuccess) rc = VREC_ECUDA;
         }
         k->tile_ok = rc == VREC_OK;
+        if (rc == VREC_OK && cat_dim <= 64) {
+            int n_head_tc = std::min<int>(TC_D - cat_dim, place_dim);
+            std::partial_sort(byc.begin(), byc.begin() + n_head_tc, byc.end(), [&](int a, int b) {
+                int ca = pcp[a + 1] - pcp[a], cb = pcp[b + 1] - pcp[b];
+                return ca > cb || (ca == cb && a < b);
+            });
+            std::vector<short> hs((size_t)place_dim, (short)-1);
+            for (int h = 0; h < n_head_tc; ++h) hs[byc[h]] = (short)h;
+            rc = k->d_head_slot_tc.upload(hs.data(), hs.size(), s);
+            if (rc == VREC_OK) rc = k->d_feat16.alloc((size_t)TC_D * (size_t)P);
+            if (rc == VREC_OK) {
+                knn_features16_kernel<<<(int)((P + 127) / 128), 128, 0, s>>>(k->dev(), k->d_head_slot_tc.p, cat_dim,
+                                                                            k->d_feat16.p);
+                ctx->launches++;
+                if (cudaGetLastError() != cudaSuccess) rc = VREC_ECUDA;
+            }
+            k->tc_ok = rc == VREC_OK;
+        }
     }
     if (rc == VREC_OK && cudaStreamSynchronize(s) != cudaSuccess) {
         vrec_set_error("vrec_knn_load: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1198,7 +1471,11 @@ extern "C" int vrec_knn_set_option(vrec_knn *k, const char *name, int64_t value)
         k->opt_tile = value;
         return VREC_OK;
     }
-    if (!strcmp(name, "knn_kernel") && value >= 0 && value <= 2) {
+    if (!strcmp(name, "knn_kernel") && value >= 0 && value <= 3) {
+        if (value == 3 && !k->tc_ok) {
+            vrec_set_error("knn_kernel=3 (tensor cores) needs cat_dim <= 64 and non-negative rating values");
+            return VREC_EINVAL;
+        }
         if (value == 2 && !k->tile_ok) {
             vrec_set_error("knn_kernel=2 (tiled) needs cat_dim <= 32 and non-negative rating values");
             return VREC_EINVAL;
@@ -1278,12 +1555,18 @@ bool use_gather_path(const vrec_knn *k, int K) {
 // neighbours of a tile of targets by the fused top-K kernels (K <= 1024)
 int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     vrec_ctx *ctx = k->ctx;
-    const bool tiled = k->tile_ok && k->opt_kernel != 1;
+    // 0 = automatic (tensor cores > CUDA-core tile > exact scan), 1 = exact scan, 2 = tile, 3 = tensor cores
+    const bool use_tc = k->tc_ok && (k->opt_kernel == 0 || k->opt_kernel == 3);
+    const bool tiled = !use_tc && k->tile_ok && k->opt_kernel != 1;
     int smax = std::max(1, std::min(32, TOPK_BUF / K));
     int S = (int)k->opt_splits;
     int T = 1;
     size_t smem = 0;
-    if (tiled) {
+    if (use_tc) {
+        T = TC_M;
+        smem = 1024 + 2 * (size_t)TC_TILE_BYTES + sizeof(unsigned long long) * TILE_QCAP + sizeof(float) * TC_M +
+               sizeof(int) * 3 * TC_M + 16;
+    } else if (tiled) {
         // targets per block: heaps must fit next to the queue and the target vectors
         T = (int)std::max<int64_t>(1, std::min<int64_t>(64, (48 * 1024) / (12 * (int64_t)K)));
         T = std::min(T, std::max(1, tn));
@@ -1293,7 +1576,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     const int tiles = (tn + T - 1) / T;
     if (S <= 0) {
         S = 1;
-        int want_blocks = ctx->sm_count * (tiled ? 4 : 8);
+        int want_blocks = ctx->sm_count * (use_tc ? 2 : tiled ? 4 : 8);
         while (S < smax && tiles * S < want_blocks) S <<= 1;
     }
     S = std::min(S, smax);
@@ -1303,28 +1586,46 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     VREC_TRY(k->d_nb_rank.ensure((size_t)tn * K));
     VREC_TRY(k->d_nb_idx.ensure((size_t)tn * K));
     VREC_TRY(k->d_nb_cnt.ensure((size_t)tn));
-    if (tiled) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            VREC_CUDA(cudaFuncSetAttribute(knn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
-        TileAux aux{k->d_feat.p, k->fstride, k->d_head_slot.p, k->d_pcp.p, k->d_pper.p};
+    if (use_tc || tiled) {
         VREC_TRY(k->d_seed_thr.ensure((size_t)tn));
         // seed pass: exact top-K of a strided sample -> lower bound of every target's K-th best
         long long sample = std::min<long long>(k->P, std::max<long long>(4096, std::min<long long>(65536, k->P / 16)));
         long long stride = std::max<long long>(1, k->P / sample);
         sample = (k->P + stride - 1) / stride;
-        knn_tile_kernel<<<dim3(tiles, 1), TILE_THREADS, smem, ctx->stream>>>(
-            k->dev(), aux, k->d_tidx.p, tn, T, K, 1, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p, stride, sample,
-            1, k->d_seed_thr.p);
-        VREC_LAUNCHED(ctx);
-        dim3 grid(tiles, S);
-        knn_tile_kernel<<<grid, TILE_THREADS, smem, ctx->stream>>>(k->dev(), aux, k->d_tidx.p, tn, T, K, S,
-                                                                  k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p,
-                                                                  1, k->P, k->opt_debug_skip_postings ? 2 : 0,
-                                                                  k->d_seed_thr.p);
-        VREC_LAUNCHED(ctx);
+        const int main_mode = k->opt_debug_skip_postings ? 2 : 0;
+        if (use_tc) {
+            static bool attr_tc = false;
+            if (!attr_tc) {
+                VREC_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                attr_tc = true;
+            }
+            TileAux aux{nullptr, 0, k->d_head_slot_tc.p, k->d_pcp.p, k->d_pper.p};
+            VREC_TRY(k->d_tc_hsim.ensure((size_t)tiles * S * TC_M * K));
+            VREC_TRY(k->d_tc_hidx.ensure((size_t)tiles * S * TC_M * K));
+            knn_tc_kernel<<<dim3(tiles, 1), TC_THREADS, smem, ctx->stream>>>(
+                k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, 1, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p,
+                stride, sample, 1, k->d_seed_thr.p, k->d_tc_hsim.p, k->d_tc_hidx.p);
+            VREC_LAUNCHED(ctx);
+            knn_tc_kernel<<<dim3(tiles, S), TC_THREADS, smem, ctx->stream>>>(
+                k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, S, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p,
+                1, k->P, main_mode, k->d_seed_thr.p, k->d_tc_hsim.p, k->d_tc_hidx.p);
+            VREC_LAUNCHED(ctx);
+        } else {
+            static bool attr_set = false;
+            if (!attr_set) {
+                VREC_CUDA(cudaFuncSetAttribute(knn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_set = true;
+            }
+            TileAux aux{k->d_feat.p, k->fstride, k->d_head_slot.p, k->d_pcp.p, k->d_pper.p};
+            knn_tile_kernel<<<dim3(tiles, 1), TILE_THREADS, smem, ctx->stream>>>(
+                k->dev(), aux, k->d_tidx.p, tn, T, K, 1, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p, stride, sample,
+                1, k->d_seed_thr.p);
+            VREC_LAUNCHED(ctx);
+            knn_tile_kernel<<<dim3(tiles, S), TILE_THREADS, smem, ctx->stream>>>(
+                k->dev(), aux, k->d_tidx.p, tn, T, K, S, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p, 1, k->P,
+                main_mode, k->d_seed_thr.p);
+            VREC_LAUNCHED(ctx);
+        }
     } else {
         dim3 grid(tn, S);
         knn_topk_kernel<<<grid, TOPK_THREADS, 0, ctx->stream>>>(k->dev(), k->d_tidx.p, K, S, pw, cw, k->d_part.p,

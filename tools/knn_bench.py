@@ -56,5 +56,5 @@ for s in range(a.warmup + a.steps):
     ms = e0.elapsed_time(e1)
     lib.vrec_knn_debug_stats(rs._h, stats)
     st = [int(x) for x in stats]
-    print(f"step {s}: {ms:.1f} ms  {B / ms * 1e3:,.0f} persons/s   per target: postings evals {st[0] / B:.0f}, "
+    print(f"kernel={a.kernel} step {s}: {ms:.1f} ms  {B / ms * 1e3:,.0f} persons/s   per target: postings evals {st[0] / B:.0f}, "
           f"filter survivors {st[1] / B:.0f}, heap inserts {st[2] / B:.0f}, queue overflow {st[3] / B:.0f}", flush=True)
