@@ -159,6 +159,11 @@ int64_t vrec_knn_resident_bytes(vrec_knn *knn);
 /* Debug counters of the tiled similarity kernel since the last call: out4 = {exact evaluations
  * from the postings pass, exact evaluations of filter survivors, heap inserts, queue overflows}. */
 int vrec_knn_debug_stats(vrec_knn *knn, uint64_t *out4);
+/* Debug: SM cycles block 0 of the tensor-core kernel spent per phase since the last call: out8 =
+ * {B-tile wait, MMA, TMEM epilogue, barriers + queue drain, postings pass, tiles, -, -}.          */
+int vrec_knn_debug_tc_cycles(vrec_knn *knn, uint64_t *out8);
+/* Debug: cycles per block of the last tensor-core main pass: out[0..n) dense phase, out[n..2n) postings. */
+int vrec_knn_debug_tc_block_cycles(vrec_knn *knn, uint64_t *out, int n);
 
 /* ---------------------------------------------------------------- SG path */
 

@@ -276,47 +276,85 @@ struct TileAux {
     const int *pper;
 };
 
+// Sparse dot of candidate row [s, s+n) with the target row [ts, ts+tn) of one table, in the exact
+// order of the mllib merge (matches visited in ascending index), but with the candidate's entries
+// fetched 8 at a time by independent loads instead of one dependent load per merge step.  The
+// target row is shared by the whole block and stays L1-resident.
+template <bool TRACK_TAIL>
+__device__ __forceinline__ double bulk_dot(const KnnVec &v, int s, int n, int ts, int tn, const short *head_slot,
+                                           int &min_tail) {
+    const int *__restrict__ tcol = v.col + ts;
+    const double *__restrict__ tval = v.val + ts;
+    double sum = 0.0;
+    int ky = 0;
+    for (int k0 = 0; k0 < n && ky < tn; k0 += 8) {
+        int c[8];
+        double x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            bool ok = k0 + e < n;
+            c[e] = ok ? __ldg(v.col + s + k0 + e) : 0x7fffffff;
+            x[e] = ok ? __ldg(v.val + s + k0 + e) : 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int ix = c[e];
+            if (ix == 0x7fffffff) break;
+            while (ky < tn && tcol[ky] < ix) ky++;
+            if (ky < tn && tcol[ky] == ix) {
+                sum = xadd(sum, xmul(x[e], tval[ky]));
+                if (TRACK_TAIL) {
+                    if (min_tail < 0 && head_slot[ix] < 0) min_tail = ix;
+                }
+                ky++;
+            }
+        }
+    }
+    return sum;
+}
+
 // exact combined similarity + the smallest shared tail place (-1 if none)
 __device__ __forceinline__ double exact_pair(const KnnDev &d, const TileAux &aux, long long i, const TargetRows &t,
                                              double pw, double cw, int &min_tail) {
     min_tail = -1;
     if (i == t.t) return 0.0;
+    // round trip 1: row extents and lengths of both tables (independent loads)
+    const int ps = __ldg(d.place.rowptr + i), pe = __ldg(d.place.rowptr + i + 1);
+    const int cs0 = __ldg(d.cat.rowptr + i), ce = __ldg(d.cat.rowptr + i + 1);
+    const double plen = __ldg(d.place.len + i), clen = __ldg(d.cat.len + i);
     bool keep = false;
-    double ps = 0.0;
-    {
-        const KnnVec &v = d.place;
-        int s = v.rowptr[i], n = v.rowptr[i + 1] - s;
-        if (n > 0) {
-            const int *xi = v.col + s, *yi = v.col + t.ps;
-            const double *xv = v.val + s, *yv = v.val + t.ps;
-            int kx = 0, ky = 0;
-            double sum = 0.0;
-            while (kx < n && ky < t.pn) {
-                int ix = xi[kx];
-                while (ky < t.pn && yi[ky] < ix) ky++;
-                if (ky < t.pn && yi[ky] == ix) {
-                    sum = xadd(sum, xmul(xv[kx], yv[ky]));
-                    if (min_tail < 0 && aux.head_slot[ix] < 0) min_tail = ix;
-                    ky++;
-                }
-                kx++;
-            }
-            double c = xdiv(sum, xmul(v.len[i], t.plen));
-            if (c > 0) {
-                keep = true;
-                ps = c;
-            }
+    double ps_sim = 0.0, cs_sim = 0.0;
+    if (pe > ps) {
+        double sum = bulk_dot<true>(d.place, ps, pe - ps, t.ps, t.pn, aux.head_slot, min_tail);
+        double c = xdiv(sum, xmul(plen, t.plen));
+        if (c > 0) {
+            keep = true;
+            ps_sim = c;
         }
     }
-    double cs = table_similarity(d.cat, i, t.cs, t.cn, t.clen, keep);
+    if (ce > cs0) {
+        int dummy = 0;
+        double sum = bulk_dot<false>(d.cat, cs0, ce - cs0, t.cs, t.cn, nullptr, dummy);
+        double c = xdiv(sum, xmul(clen, t.clen));
+        if (c > 0) {
+            keep = true;
+            cs_sim = c;
+        }
+    }
     if (!keep) return 0.0;
-    return xadd(xmul(ps, pw), xmul(cs, cw));
+    return xadd(xmul(ps_sim, pw), xmul(cs_sim, cw));
 }
 
 // event counters of the tiled kernel (rare events only): [0] exact evaluations from the
 // postings pass, [1] exact evaluations of dense-filter survivors, [2] heap insert attempts,
 // [3] survivors evaluated inline because the queue was full
 __device__ unsigned long long g_tile_stats[4];
+// phase cycle counters of knn_tc_kernel, block (0,0) thread 0 of the main pass:
+// [0] wait for the B tile, [1] MMA issue + completion wait, [2] TMEM epilogue, [3] barriers + queue drain,
+// [4] postings pass, [5] tiles
+__device__ unsigned long long g_tc_cycles[8];
+// per-block cycles of the main pass: [0][b] dense phase, [1][b] postings phase
+__device__ unsigned long long g_tc_block_cycles[2][1024];
 
 struct TileSmem {
     float *thr;                 // filter threshold of target slot t at thr[t * thr_stride]
@@ -329,6 +367,7 @@ struct TileSmem {
     int *tid_of;                // [T] person index of the target or -1
     unsigned long long *queue;  // [TILE_QCAP]  (t << 32 | candidate)
     int *qn;
+    unsigned int *stats;        // [4] per-block event counters, flushed to g_tile_stats at the end
 };
 
 __device__ __forceinline__ bool nb_worse(double sa, int ia, double sb, int ib) {
@@ -401,7 +440,7 @@ __device__ __forceinline__ void tile_process(const KnnDev &d, const TileAux &aux
                                              int K, double pw, double cw, int from_postings) {
     int tix = sm.tid_of[t];
     if (tix < 0) return;
-    atomicAdd(&g_tile_stats[from_postings >= 0 ? 0 : 1], 1ULL);
+    atomicAdd(sm.stats + (from_postings >= 0 ? 0 : 1), 1u);
     TargetRows tr = load_target(d, tix);
     int min_tail;
     double sim = exact_pair(d, aux, c, tr, pw, cw, min_tail);
@@ -415,7 +454,7 @@ __device__ __forceinline__ void tile_process(const KnnDev &d, const TileAux &aux
     // grows, so a stale read can only let too much through (the exact test is under the lock)
     volatile double *hs = sm.hsim + (size_t)t * K;
     if (*(volatile int *)(sm.hcnt + t) >= K && sim < hs[0]) return;
-    atomicAdd(&g_tile_stats[2], 1ULL);
+    atomicAdd(sm.stats + 2, 1u);
     tile_heap_insert(sm, t, K, sim, c);
 }
 
@@ -442,6 +481,9 @@ knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targe
         sm.thr = sm.tvec + TILE_D;
         sm.thr_stride = TILE_TVEC_STRIDE;
     }
+    __shared__ unsigned int s_stats[4];
+    sm.stats = s_stats;
+    if (tid < 4) s_stats[tid] = 0;
     // candidates are j * cand_stride for j in [jlo, jhi); the main pass has stride 1 (all persons),
     // the seed pass a strided sample.  [lo, hi) is the same range in person indices.
     const long long jlo = cand_count * sp / S, jhi = cand_count * (sp + 1) / S;
@@ -495,7 +537,7 @@ knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targe
                     if (pos < TILE_QCAP) {
                         sm.queue[pos] = ((unsigned long long)t << 32) | (unsigned long long)(unsigned)c;
                     } else {
-                        atomicAdd(&g_tile_stats[3], 1ULL);
+                        atomicAdd(sm.stats + 3, 1u);
                         tile_process(d, aux, sm, t, (int)c, K, pw, cw, seed_mode == 1 ? -2 : -1);   // queue full: now
                     }
                 }
@@ -572,6 +614,7 @@ knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targe
         for (int t = tid; t < nt; t += TILE_THREADS) seed_thr[t0 + t] = sm.hcnt[t] >= K ? sm.hsim[(size_t)t * K] : 0.0;
         return;
     }
+    if (tid < 4) atomicAdd(&g_tile_stats[tid], (unsigned long long)s_stats[tid]);
     // ---- emit the heaps (unsorted; the merge kernel sorts)
     for (int t = 0; t < nt; ++t) {
         int cnt = sm.hcnt[t];
@@ -601,18 +644,30 @@ knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targe
 constexpr int TC_D = 128;
 constexpr int TC_M = 128;
 constexpr int TC_N = 128;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 512;                          // one CTA per SM
+constexpr int TC_MAX_K = 56;                             // heaps of 128 targets must fit shared memory
 constexpr int TC_TILE_BYTES = TC_M * TC_D * 2;          // 32 KB per operand tile
 constexpr int TC_LBO = TC_M * 16;                        // next k-chunk
 constexpr int TC_SBO = 128;                              // next 8 rows
+constexpr int TC_STAGES = 3;                             // B tiles in flight
+constexpr int TC_QCAP = 1024;                            // survivor queue entries (fits next to 3 B stages)
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool valid) {
+    unsigned bytes = valid ? 16u : 0u;                   // src-size 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const int *__restrict__ tidx,
               int n_targets, int K, int S, int cat_dim, double pw, double cw, Nb *__restrict__ part,
               int *__restrict__ part_cnt, long long cand_stride, long long cand_count, int seed_mode,
-              double *__restrict__ seed_thr, double *__restrict__ heap_sim, int *__restrict__ heap_idx) {
+              double *__restrict__ seed_thr) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_m = blockIdx.x, sp = blockIdx.y;
@@ -620,11 +675,13 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
     const int nt = min(TC_M, n_targets - t0);
     // operand tiles on a 1 KB boundary (the descriptor start address ignores its low bits)
     unsigned char *base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char *sA = base, *sB = base + TC_TILE_BYTES;
+    unsigned char *sA = base, *sB0 = base + TC_TILE_BYTES;            // sB: TC_STAGES stages
     TileSmem sm;
     {
-        unsigned char *p = base + 2 * TC_TILE_BYTES;
-        sm.queue = (unsigned long long *)p;         p += sizeof(unsigned long long) * TILE_QCAP;
+        unsigned char *p = base + (1 + TC_STAGES) * TC_TILE_BYTES;
+        sm.hsim = (double *)p;                      p += sizeof(double) * (size_t)TC_M * K;
+        sm.queue = (unsigned long long *)p;         p += sizeof(unsigned long long) * TC_QCAP;
+        sm.hidx = (int *)p;                         p += sizeof(int) * (size_t)TC_M * K;
         sm.thr = (float *)p;                        p += sizeof(float) * TC_M;
         sm.thr_stride = 1;
         sm.tvec = nullptr;
@@ -632,13 +689,14 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
         sm.lock = (int *)p;                         p += sizeof(int) * TC_M;
         sm.tid_of = (int *)p;                       p += sizeof(int) * TC_M;
         sm.qn = (int *)p;
-        const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-        sm.hsim = heap_sim + blk * TC_M * K;        // heaps live in global memory (L2-resident)
-        sm.hidx = heap_idx + blk * TC_M * K;
     }
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, TC_N);
+    __shared__ unsigned int s_stats[4];
+    sm.stats = s_stats;
+    if (tid < 4) s_stats[tid] = 0;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 2 * TC_N);        // two accumulators
     if (tid == 0) {
-        tc::mbar_init(&bar, 1);
+        tc::mbar_init(&bar[0], 1);
+        tc::mbar_init(&bar[1], 1);
         tc::mbar_init_fence();
         *sm.qn = 0;
     }
@@ -653,6 +711,28 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
         sm.thr[t] = tix >= 0 ? thr0 : 3.0e38f;
     }
     __syncthreads();
+    // candidate tiles are visited in a per-CTA rotated order, so that the CTAs do not all pull the
+    // same 32 KB out of L2 at the same moment
+    const long long ntiles = (jhi - jlo + TC_N - 1) / TC_N;
+    const long long rot = ntiles > 0 ? ((long long)blockIdx.x * 67 + (long long)blockIdx.y * 29) % ntiles : 0;
+    auto tile_start = [&](long long i) { return jlo + ((i + rot) % ntiles) * TC_N; };
+    // B tile loader: 16-byte chunk c of candidate row r -> chunk-major UMMA layout, zero fill past the end
+    auto load_b = [&](long long i) {
+        if (i < ntiles) {
+            const long long tile = tile_start(i);
+            unsigned char *sB = sB0 + (size_t)(i % TC_STAGES) * TC_TILE_BYTES;
+            for (int q = tid; q < TC_N * (TC_D / 8); q += TC_THREADS) {
+                int r = q % TC_N, c = q / TC_N;
+                long long j = tile + r;
+                bool ok = j < jhi;
+                const __half *src = feat16 + (size_t)((ok ? j : jlo) * cand_stride) * TC_D + c * 8;
+                cp_async16(sB + (size_t)c * TC_LBO + r * 16, src, ok);
+            }
+        }
+        cp_async_commit();                       // always commit: keeps the group count uniform
+    };
+    load_b(0);
+    load_b(1);
     // ---- A tile: the targets' features with the weights folded in (chunk-major UMMA layout)
     for (int q = tid; q < TC_M * (TC_D / 8); q += TC_THREADS) {
         int r = q % TC_M, c = q / TC_M;
@@ -671,71 +751,94 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
         }
         *reinterpret_cast<uint4 *>(sA + (size_t)c * TC_LBO + r * 16) = *reinterpret_cast<const uint4 *>(h);
     }
+    const uint32_t idesc = tc::make_idesc_f16(TC_M, TC_N);
+    const uint32_t a_addr = tc::smem_u32(sA), b_addr0 = tc::smem_u32(sB0);
+    // issue the MMA chain of tile i into accumulator i & 1 (one thread)
+    auto issue_mma = [&](long long i, uint32_t tbase_) {
+        tc::fence_after_sync();
+        const uint32_t b_addr = b_addr0 + (uint32_t)(i % TC_STAGES) * TC_TILE_BYTES;
+        const uint32_t acc = tbase_ + (uint32_t)(i & 1) * TC_N;
+#pragma unroll
+        for (int k = 0; k < TC_D / 16; ++k) {
+            uint64_t da = tc::make_desc(a_addr + k * 2 * TC_LBO, TC_LBO, TC_SBO);
+            uint64_t db = tc::make_desc(b_addr + k * 2 * TC_LBO, TC_LBO, TC_SBO);
+            tc::mma_f16(acc, da, db, idesc, k > 0);
+        }
+        tc::mma_commit(&bar[i & 1]);
+    };
+    cp_async_wait<1>();                          // tile 0 has landed
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tbase = tmem_base_s;
-    const uint32_t idesc = tc::make_idesc_f16(TC_M, TC_N);
-    const uint32_t a_addr = tc::smem_u32(sA), b_addr = tc::smem_u32(sB);
-    const int lq = warp & 3, ch = warp >> 2;                  // TMEM lane quarter, column half
+    if (tid == 0 && ntiles > 0) issue_mma(0, tbase);
+    const int lq = warp & 3, cq = warp >> 2;                  // TMEM lane quarter, column quarter (16 warps)
     const int my_t = lq * 32 + lane;
-    uint32_t phase = 0;
-    // ---- 1. dense filter on the tensor cores
-    for (long long tile = jlo; tile < jhi; tile += TC_N) {
-        for (int q = tid; q < TC_N * (TC_D / 8); q += TC_THREADS) {
-            int r = q % TC_N, c = q / TC_N;
-            long long j = tile + r;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (j < jhi) v = __ldg(reinterpret_cast<const uint4 *>(feat16 + (size_t)(j * cand_stride) * TC_D + c * 8));
-            *reinterpret_cast<uint4 *>(sB + (size_t)c * TC_LBO + r * 16) = v;
-        }
+    uint32_t phase0 = 0u, phase1 = 0u;
+    const bool prof = tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && seed_mode != 1;
+    long long tk0 = clock64(), tk1;
+    const long long blk_t0 = tk0;
+#define TC_TICK(slot)                                                  \
+    if (prof) {                                                        \
+        tk1 = clock64();                                               \
+        g_tc_cycles[slot] += (unsigned long long)(tk1 - tk0);          \
+        tk0 = tk1;                                                     \
+    }
+    // ---- 1. dense filter on the tensor cores.  Iteration i: B(i+1) has landed -> MMA(i+1) is issued
+    // into the other accumulator, B(i+2) starts streaming, then the epilogue of tile i runs under them.
+    for (long long i = 0; i < ntiles; ++i) {
+        const bool has_next = i + 1 < ntiles;
+        cp_async_wait<0>();                      // B(i+1) (issued one iteration ago) has landed
         tc::fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-#pragma unroll
-            for (int k = 0; k < TC_D / 16; ++k) {
-                uint64_t da = tc::make_desc(a_addr + k * 2 * TC_LBO, TC_LBO, TC_SBO);
-                uint64_t db = tc::make_desc(b_addr + k * 2 * TC_LBO, TC_LBO, TC_SBO);
-                tc::mma_f16(tbase, da, db, idesc, k > 0);
-            }
-            tc::mma_commit(&bar);
+        __syncthreads();                         // ... for every thread; also: epilogue(i-1) is finished
+        if (tid == 0 && has_next) issue_mma(i + 1, tbase);
+        load_b(i + 2);                           // stage (i+2)%3 was last read by MMA(i-1), long complete
+        TC_TICK(0)
+        if (prof) g_tc_cycles[5] += 1;
+        if (i & 1) {
+            tc::mbar_wait(&bar[1], phase1);
+            phase1 ^= 1u;
+        } else {
+            tc::mbar_wait(&bar[0], phase0);
+            phase0 ^= 1u;
         }
-        tc::mbar_wait(&bar, phase);
-        phase ^= 1u;
         tc::fence_after_sync();
+        TC_TICK(1)
         const float thr = *(volatile float *)(sm.thr + my_t);
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-            const int c0 = ch * 64 + cc * 32;
+        const long long tile = tile_start(i);
+        {
+            const int c0 = cq * 32;
             float v[32];
-            tc::tmem_ld32(tbase + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0, v);
+            tc::tmem_ld32(tbase + ((uint32_t)(lq * 32) << 16) + (uint32_t)((i & 1) * TC_N + c0), v);
+            unsigned pass = 0;
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-                if (v[jj] * 1.002f + 2e-5f >= thr) {
-                    long long j = tile + c0 + jj;
-                    if (j < jhi) {
-                        int c = (int)(j * cand_stride);
-                        int pos = atomicAdd(sm.qn, 1);
-                        if (pos < TILE_QCAP) {
-                            sm.queue[pos] = ((unsigned long long)my_t << 32) | (unsigned long long)(unsigned)c;
-                        } else {
-                            atomicAdd(&g_tile_stats[3], 1ULL);
-                            tile_process(d, aux, sm, my_t, c, K, pw, cw, seed_mode == 1 ? -2 : -1);
-                        }
+            for (int jj = 0; jj < 32; ++jj) pass |= (v[jj] * 1.002f + 2e-5f >= thr ? 1u : 0u) << jj;
+            while (pass) {                       // rare: a single copy of the survivor path
+                const int jj = __ffs(pass) - 1;
+                pass &= pass - 1;
+                const long long j = tile + c0 + jj;
+                if (j < jhi) {
+                    int c = (int)(j * cand_stride);
+                    int pos = atomicAdd(sm.qn, 1);
+                    if (pos < TC_QCAP) {
+                        sm.queue[pos] = ((unsigned long long)my_t << 32) | (unsigned long long)(unsigned)c;
+                    } else {
+                        atomicAdd(sm.stats + 3, 1u);
+                        tile_process(d, aux, sm, my_t, c, K, pw, cw, seed_mode == 1 ? -2 : -1);
                     }
                 }
             }
         }
+        TC_TICK(2)
         tc::fence_before_sync();
-        __syncthreads();                                           // TMEM drained, sB reusable
+        __syncthreads();                                           // accumulator i & 1 drained
         int qn = *sm.qn;
         __syncthreads();
-        if (qn >= TILE_QCAP / 2 || tile + TC_N >= jhi) {           // block-uniform
-            int m = min(qn, TILE_QCAP);
-            for (int i = tid; i < m; i += TC_THREADS) {
-                unsigned long long e = sm.queue[i];
+        if (qn >= TC_QCAP / 2 || !has_next) {                    // block-uniform
+            int m = min(qn, TC_QCAP);
+            for (int qi = tid; qi < m; qi += TC_THREADS) {
+                unsigned long long e = sm.queue[qi];
                 tile_process(d, aux, sm, (int)(e >> 32), (int)(unsigned)(e & 0xffffffffu), K, pw, cw,
                              seed_mode == 1 ? -2 : -1);
             }
@@ -743,7 +846,10 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
             if (tid == 0) *sm.qn = 0;
             __syncthreads();
         }
+        TC_TICK(3)
     }
+    cp_async_wait<0>();
+    const long long blk_t1 = clock64();
     // ---- 2. pairs sharing a tail place, through the postings (as in knn_tile_kernel)
     for (int t = warp; t < nt && seed_mode == 0; t += TC_THREADS / 32) {
         int tix = sm.tid_of[t];
@@ -794,6 +900,13 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
         }
     }
     __syncthreads();
+    TC_TICK(4)
+#undef TC_TICK
+    if (tid < 4) atomicAdd(&g_tile_stats[tid], (unsigned long long)s_stats[tid]);
+    if (tid == 0 && seed_mode != 1 && blockIdx.y == 0 && blockIdx.x < 1024) {
+        g_tc_block_cycles[0][blockIdx.x] = (unsigned long long)(blk_t1 - blk_t0);
+        g_tc_block_cycles[1][blockIdx.x] = (unsigned long long)(clock64() - blk_t1);
+    }
     if (seed_mode == 1) {
         for (int t = tid; t < nt; t += TC_THREADS)
             seed_thr[t0 + t] = sm.hcnt[t] >= K ? *(volatile double *)(sm.hsim + (size_t)t * K) : 0.0;
@@ -813,7 +926,7 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tbase, TC_N);
+    if (warp == 0) tc::tmem_dealloc(tbase, 2 * TC_N);
 }
 
 // fp16 features, row-major [P][TC_D]: category vector / length, then the head places' values / length
@@ -1169,8 +1282,6 @@ struct vrec_knn {
     bool tc_ok = false;
     DevBuf<__half> d_feat16;
     DevBuf<short> d_head_slot_tc;
-    DevBuf<double> d_tc_hsim;
-    DevBuf<int> d_tc_hidx;
     // options
     int64_t opt_rating_path = 0, opt_tile = 0, opt_splits = 0, opt_kernel = 0;
     int64_t opt_debug_skip_postings = 0;     // timing experiments only: results are then WRONG
@@ -1506,6 +1617,27 @@ extern "C" int vrec_knn_debug_stats(vrec_knn *k, uint64_t *out4) {
     return VREC_OK;
 }
 
+// Debug: per-block cycles of the last tensor-core main pass: out[0..n) dense phase, out[n..2n) postings phase.
+extern "C" int vrec_knn_debug_tc_block_cycles(vrec_knn *k, uint64_t *out, int n) {
+    if (!k || !out || n < 0 || n > 1024) return VREC_EINVAL;
+    VREC_CUDA(cudaSetDevice(k->ctx->device));
+    VREC_CUDA(cudaStreamSynchronize(k->ctx->stream));
+    VREC_CUDA(cudaMemcpyFromSymbol(out, g_tc_block_cycles, sizeof(uint64_t) * n, 0));
+    VREC_CUDA(cudaMemcpyFromSymbol(out + n, g_tc_block_cycles, sizeof(uint64_t) * n, sizeof(uint64_t) * 1024));
+    return VREC_OK;
+}
+
+// Debug: reads and clears the phase cycle counters of knn_tc_kernel (see g_tc_cycles).
+extern "C" int vrec_knn_debug_tc_cycles(vrec_knn *k, uint64_t *out8) {
+    if (!k || !out8) return VREC_EINVAL;
+    VREC_CUDA(cudaSetDevice(k->ctx->device));
+    VREC_CUDA(cudaStreamSynchronize(k->ctx->stream));
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    VREC_CUDA(cudaMemcpyFromSymbol(out8, g_tc_cycles, sizeof(z)));
+    VREC_CUDA(cudaMemcpyToSymbol(g_tc_cycles, z, sizeof(z)));
+    return VREC_OK;
+}
+
 extern "C" int vrec_knn_set_filter(vrec_knn *k, const int64_t *place_filter, int64_t n_filter) {
     if (!k || n_filter < 0) return VREC_EINVAL;
     VREC_CUDA(cudaSetDevice(k->ctx->device));
@@ -1556,7 +1688,7 @@ bool use_gather_path(const vrec_knn *k, int K) {
 int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     vrec_ctx *ctx = k->ctx;
     // 0 = automatic (tensor cores > CUDA-core tile > exact scan), 1 = exact scan, 2 = tile, 3 = tensor cores
-    const bool use_tc = k->tc_ok && (k->opt_kernel == 0 || k->opt_kernel == 3);
+    const bool use_tc = k->tc_ok && K <= TC_MAX_K && (k->opt_kernel == 0 || k->opt_kernel == 3);
     const bool tiled = !use_tc && k->tile_ok && k->opt_kernel != 1;
     int smax = std::max(1, std::min(32, TOPK_BUF / K));
     int S = (int)k->opt_splits;
@@ -1564,8 +1696,9 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     size_t smem = 0;
     if (use_tc) {
         T = TC_M;
-        smem = 1024 + 2 * (size_t)TC_TILE_BYTES + sizeof(unsigned long long) * TILE_QCAP + sizeof(float) * TC_M +
-               sizeof(int) * 3 * TC_M + 16;
+        smem = 1024 + (1 + TC_STAGES) * (size_t)TC_TILE_BYTES + 12 * (size_t)TC_M * K +
+               sizeof(unsigned long long) * TC_QCAP +
+               sizeof(float) * TC_M + sizeof(int) * 3 * TC_M + 16;
     } else if (tiled) {
         // targets per block: heaps must fit next to the queue and the target vectors
         T = (int)std::max<int64_t>(1, std::min<int64_t>(64, (48 * 1024) / (12 * (int64_t)K)));
@@ -1576,7 +1709,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     const int tiles = (tn + T - 1) / T;
     if (S <= 0) {
         S = 1;
-        int want_blocks = ctx->sm_count * (use_tc ? 2 : tiled ? 4 : 8);
+        int want_blocks = ctx->sm_count * (use_tc ? 1 : tiled ? 4 : 8);
         while (S < smax && tiles * S < want_blocks) S <<= 1;
     }
     S = std::min(S, smax);
@@ -1596,19 +1729,17 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
         if (use_tc) {
             static bool attr_tc = false;
             if (!attr_tc) {
-                VREC_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                VREC_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
                 attr_tc = true;
             }
             TileAux aux{nullptr, 0, k->d_head_slot_tc.p, k->d_pcp.p, k->d_pper.p};
-            VREC_TRY(k->d_tc_hsim.ensure((size_t)tiles * S * TC_M * K));
-            VREC_TRY(k->d_tc_hidx.ensure((size_t)tiles * S * TC_M * K));
             knn_tc_kernel<<<dim3(tiles, 1), TC_THREADS, smem, ctx->stream>>>(
                 k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, 1, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p,
-                stride, sample, 1, k->d_seed_thr.p, k->d_tc_hsim.p, k->d_tc_hidx.p);
+                stride, sample, 1, k->d_seed_thr.p);
             VREC_LAUNCHED(ctx);
             knn_tc_kernel<<<dim3(tiles, S), TC_THREADS, smem, ctx->stream>>>(
                 k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, S, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p,
-                1, k->P, main_mode, k->d_seed_thr.p, k->d_tc_hsim.p, k->d_tc_hidx.p);
+                1, k->P, main_mode, k->d_seed_thr.p);
             VREC_LAUNCHED(ctx);
         } else {
             static bool attr_set = false;
@@ -1694,7 +1825,8 @@ extern "C" int vrec_knn_query_device(vrec_knn *k, const int64_t *d_targets, int3
     VREC_CUDA(cudaSetDevice(ctx->device));
     const bool gather = use_gather_path(k, K);
     int64_t tile = k->opt_tile;
-    if (tile <= 0) tile = gather ? 8192 : std::max<int64_t>(1, ((int64_t)1 << 30) / (8 * std::max<int64_t>(1, k->P)));
+    // gather path: as many targets per pass as possible (more M-tiles -> no candidate splits, one wave)
+    if (tile <= 0) tile = gather ? 65536 : std::max<int64_t>(1, ((int64_t)1 << 30) / (8 * std::max<int64_t>(1, k->P)));
     tile = std::min<int64_t>(tile, n_targets);
     const unsigned char *flag = k->has_filter ? k->d_flag.p : nullptr;
     if (gather) VREC_TRY(knn_ensure_rate_scratch(k, K));
