@@ -78,6 +78,9 @@ struct TargetRows {
     int t;
     int ps, pn, cs, cn;
     double plen, clen;
+    // the target's rows (global memory, or a shared-memory copy staged by the caller)
+    const int *pcol, *ccol;
+    const double *pval, *cval;
 };
 
 __device__ __forceinline__ TargetRows load_target(const KnnDev &d, int t) {
@@ -89,6 +92,10 @@ __device__ __forceinline__ TargetRows load_target(const KnnDev &d, int t) {
     r.cn = d.cat.rowptr[t + 1] - r.cs;
     r.plen = d.place.len[t];
     r.clen = d.cat.len[t];
+    r.pcol = d.place.col + r.ps;
+    r.pval = d.place.val + r.ps;
+    r.ccol = d.cat.col + r.cs;
+    r.cval = d.cat.val + r.cs;
     return r;
 }
 
@@ -274,17 +281,24 @@ struct TileAux {
     const short *head_slot;     // per place: head slot or -1 (tail)
     const int *pcp;             // place postings (CSC of the place vectors)
     const int *pper;
+    // packed per-person records for the exact evaluation (nullptr: read the CSR arrays instead).
+    // meta[i] = offset (8-byte words, bits 0..39) | place count (bits 40..51) | category count (52..63)
+    // record  = { |place|, |cat|, place cols (int, padded to 8 B), place vals, cat cols (padded), cat vals }
+    // place cols carry "tail place" flags of the two head sets in bits 31 / 30.
+    const unsigned long long *meta;
+    const double *rec;
+    unsigned tail_bit;          // which flag applies to this kernel's head set
 };
+
+constexpr unsigned REC_TAIL_TC = 0x80000000u, REC_TAIL_TILE = 0x40000000u, REC_COL_MASK = 0x3fffffffu;
 
 // Sparse dot of candidate row [s, s+n) with the target row [ts, ts+tn) of one table, in the exact
 // order of the mllib merge (matches visited in ascending index), but with the candidate's entries
 // fetched 8 at a time by independent loads instead of one dependent load per merge step.  The
 // target row is shared by the whole block and stays L1-resident.
 template <bool TRACK_TAIL>
-__device__ __forceinline__ double bulk_dot(const KnnVec &v, int s, int n, int ts, int tn, const short *head_slot,
-                                           int &min_tail) {
-    const int *__restrict__ tcol = v.col + ts;
-    const double *__restrict__ tval = v.val + ts;
+__device__ __forceinline__ double bulk_dot(const KnnVec &v, int s, int n, const int *tcol, const double *tval, int tn,
+                                           const short *head_slot, int &min_tail) {
     double sum = 0.0;
     int ky = 0;
     for (int k0 = 0; k0 < n && ky < tn; k0 += 8) {
@@ -313,9 +327,78 @@ __device__ __forceinline__ double bulk_dot(const KnnVec &v, int s, int n, int ts
     return sum;
 }
 
+// bulk_dot over a packed record: same order of operations, one contiguous block of memory
+template <bool TRACK_TAIL>
+__device__ __forceinline__ double packed_dot(const int *__restrict__ pc, const double *__restrict__ pv, int n,
+                                             const int *tcol, const double *tval, int tn, unsigned tail_bit,
+                                             int &min_tail) {
+    double sum = 0.0;
+    int ky = 0;
+    for (int k0 = 0; k0 < n && ky < tn; k0 += 8) {
+        unsigned c[8];
+        double x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            bool ok = k0 + e < n;
+            c[e] = ok ? (unsigned)__ldg(pc + k0 + e) : 0xffffffffu;
+            x[e] = ok ? __ldg(pv + k0 + e) : 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (c[e] == 0xffffffffu) break;
+            int ix = (int)(c[e] & REC_COL_MASK);
+            while (ky < tn && tcol[ky] < ix) ky++;
+            if (ky < tn && tcol[ky] == ix) {
+                sum = xadd(sum, xmul(x[e], tval[ky]));
+                if (TRACK_TAIL) {
+                    if (min_tail < 0 && (c[e] & tail_bit)) min_tail = ix;
+                }
+                ky++;
+            }
+        }
+    }
+    return sum;
+}
+
+__device__ __forceinline__ double exact_pair_packed(const TileAux &aux, long long i, const TargetRows &t, double pw,
+                                                    double cw, int &min_tail) {
+    min_tail = -1;
+    if (i == t.t) return 0.0;
+    const unsigned long long m = __ldg(aux.meta + i);                   // round trip 1 (8 MB table: L2)
+    const int np = (int)((m >> 40) & 0xfffu), nc = (int)(m >> 52);
+    const double *r = aux.rec + (m & 0xffffffffffULL);                  // round trip 2: one contiguous record
+    const double plen = __ldg(r), clen = __ldg(r + 1);
+    const int *pc = reinterpret_cast<const int *>(r + 2);
+    const double *pv = r + 2 + ((np + 1) >> 1);
+    const int *cc = reinterpret_cast<const int *>(pv + np);
+    const double *cvp = pv + np + ((nc + 1) >> 1);
+    bool keep = false;
+    double ps_sim = 0.0, cs_sim = 0.0;
+    if (np > 0) {
+        double sum = packed_dot<true>(pc, pv, np, t.pcol, t.pval, t.pn, aux.tail_bit, min_tail);
+        double c = xdiv(sum, xmul(plen, t.plen));
+        if (c > 0) {
+            keep = true;
+            ps_sim = c;
+        }
+    }
+    if (nc > 0) {
+        int dummy = 0;
+        double sum = packed_dot<false>(cc, cvp, nc, t.ccol, t.cval, t.cn, 0u, dummy);
+        double c = xdiv(sum, xmul(clen, t.clen));
+        if (c > 0) {
+            keep = true;
+            cs_sim = c;
+        }
+    }
+    if (!keep) return 0.0;
+    return xadd(xmul(ps_sim, pw), xmul(cs_sim, cw));
+}
+
 // exact combined similarity + the smallest shared tail place (-1 if none)
 __device__ __forceinline__ double exact_pair(const KnnDev &d, const TileAux &aux, long long i, const TargetRows &t,
                                              double pw, double cw, int &min_tail) {
+    if (aux.meta) return exact_pair_packed(aux, i, t, pw, cw, min_tail);
     min_tail = -1;
     if (i == t.t) return 0.0;
     // round trip 1: row extents and lengths of both tables (independent loads)
@@ -325,7 +408,7 @@ __device__ __forceinline__ double exact_pair(const KnnDev &d, const TileAux &aux
     bool keep = false;
     double ps_sim = 0.0, cs_sim = 0.0;
     if (pe > ps) {
-        double sum = bulk_dot<true>(d.place, ps, pe - ps, t.ps, t.pn, aux.head_slot, min_tail);
+        double sum = bulk_dot<true>(d.place, ps, pe - ps, t.pcol, t.pval, t.pn, aux.head_slot, min_tail);
         double c = xdiv(sum, xmul(plen, t.plen));
         if (c > 0) {
             keep = true;
@@ -334,7 +417,7 @@ __device__ __forceinline__ double exact_pair(const KnnDev &d, const TileAux &aux
     }
     if (ce > cs0) {
         int dummy = 0;
-        double sum = bulk_dot<false>(d.cat, cs0, ce - cs0, t.cs, t.cn, nullptr, dummy);
+        double sum = bulk_dot<false>(d.cat, cs0, ce - cs0, t.ccol, t.cval, t.cn, nullptr, dummy);
         double c = xdiv(sum, xmul(clen, t.clen));
         if (c > 0) {
             keep = true;
@@ -436,12 +519,10 @@ __device__ __forceinline__ void tile_heap_insert(const TileSmem &sm, int t, int 
 }
 
 // exact evaluation of one filter survivor; from_postings = the place whose postings produced it
-__device__ __forceinline__ void tile_process(const KnnDev &d, const TileAux &aux, const TileSmem &sm, int t, int c,
-                                             int K, double pw, double cw, int from_postings) {
-    int tix = sm.tid_of[t];
-    if (tix < 0) return;
+__device__ __forceinline__ void tile_process_rows(const KnnDev &d, const TileAux &aux, const TileSmem &sm, int t, int c,
+                                                  int K, double pw, double cw, int from_postings,
+                                                  const TargetRows &tr) {
     atomicAdd(sm.stats + (from_postings >= 0 ? 0 : 1), 1u);
-    TargetRows tr = load_target(d, tix);
     int min_tail;
     double sim = exact_pair(d, aux, c, tr, pw, cw, min_tail);
     if (!(sim > 0)) return;
@@ -456,6 +537,14 @@ __device__ __forceinline__ void tile_process(const KnnDev &d, const TileAux &aux
     if (*(volatile int *)(sm.hcnt + t) >= K && sim < hs[0]) return;
     atomicAdd(sm.stats + 2, 1u);
     tile_heap_insert(sm, t, K, sim, c);
+}
+
+__device__ __forceinline__ void tile_process(const KnnDev &d, const TileAux &aux, const TileSmem &sm, int t, int c,
+                                             int K, double pw, double cw, int from_postings) {
+    int tix = sm.tid_of[t];
+    if (tix < 0) return;
+    TargetRows tr = load_target(d, tix);
+    tile_process_rows(d, aux, sm, t, c, K, pw, cw, from_postings, tr);
 }
 
 __global__ void __launch_bounds__(TILE_THREADS, 2)
@@ -713,11 +802,15 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
     __syncthreads();
     // candidate tiles are visited in a per-CTA rotated order, so that the CTAs do not all pull the
     // same 32 KB out of L2 at the same moment
-    const long long ntiles = (jhi - jlo + TC_N - 1) / TC_N;
-    const long long rot = ntiles > 0 ? ((long long)blockIdx.x * 67 + (long long)blockIdx.y * 29) % ntiles : 0;
-    auto tile_start = [&](long long i) { return jlo + ((i + rot) % ntiles) * TC_N; };
+    const int ntiles = (int)((jhi - jlo + TC_N - 1) / TC_N);
+    const int rot = ntiles > 0 ? (int)(((long long)blockIdx.x * 67 + (long long)blockIdx.y * 29) % ntiles) : 0;
+    auto tile_start = [&](int i) {
+        int w = i + rot;
+        if (w >= ntiles) w -= ntiles;
+        return jlo + (long long)w * TC_N;
+    };
     // B tile loader: 16-byte chunk c of candidate row r -> chunk-major UMMA layout, zero fill past the end
-    auto load_b = [&](long long i) {
+    auto load_b = [&](int i) {
         if (i < ntiles) {
             const long long tile = tile_start(i);
             unsigned char *sB = sB0 + (size_t)(i % TC_STAGES) * TC_TILE_BYTES;
@@ -754,7 +847,7 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
     const uint32_t idesc = tc::make_idesc_f16(TC_M, TC_N);
     const uint32_t a_addr = tc::smem_u32(sA), b_addr0 = tc::smem_u32(sB0);
     // issue the MMA chain of tile i into accumulator i & 1 (one thread)
-    auto issue_mma = [&](long long i, uint32_t tbase_) {
+    auto issue_mma = [&](int i, uint32_t tbase_) {
         tc::fence_after_sync();
         const uint32_t b_addr = b_addr0 + (uint32_t)(i % TC_STAGES) * TC_TILE_BYTES;
         const uint32_t acc = tbase_ + (uint32_t)(i & 1) * TC_N;
@@ -787,13 +880,28 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
     }
     // ---- 1. dense filter on the tensor cores.  Iteration i: B(i+1) has landed -> MMA(i+1) is issued
     // into the other accumulator, B(i+2) starts streaming, then the epilogue of tile i runs under them.
-    for (long long i = 0; i < ntiles; ++i) {
-        const bool has_next = i + 1 < ntiles;
+    for (int i = 0; i <= ntiles; ++i) {                           // one extra turn drains the last survivors
+        const bool live = i < ntiles, has_next = i + 1 < ntiles;
         cp_async_wait<0>();                      // B(i+1) (issued one iteration ago) has landed
         tc::fence_proxy_async();
-        __syncthreads();                         // ... for every thread; also: epilogue(i-1) is finished
+        tc::fence_before_sync();
+        // ONE barrier per tile: B(i+1) visible to all, epilogue(i-1) finished, and a block-uniform
+        // decision whether the survivor queue must be drained now
+        const int drain = __syncthreads_or((*(volatile int *)sm.qn >= TC_QCAP / 2) || !live);
         if (tid == 0 && has_next) issue_mma(i + 1, tbase);
-        load_b(i + 2);                           // stage (i+2)%3 was last read by MMA(i-1), long complete
+        if (live) load_b(i + 2);                 // stage (i+2)%3 was last read by MMA(i-1), long complete
+        if (drain) {
+            int m = min(*(volatile int *)sm.qn, TC_QCAP);
+            for (int qi = tid; qi < m; qi += TC_THREADS) {
+                unsigned long long e = sm.queue[qi];
+                tile_process(d, aux, sm, (int)(e >> 32), (int)(unsigned)(e & 0xffffffffu), K, pw, cw,
+                             seed_mode == 1 ? -2 : -1);
+            }
+            __syncthreads();
+            if (tid == 0) *sm.qn = 0;
+            __syncthreads();
+        }
+        if (!live) break;
         TC_TICK(0)
         if (prof) g_tc_cycles[5] += 1;
         if (i & 1) {
@@ -831,29 +939,37 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
             }
         }
         TC_TICK(2)
-        tc::fence_before_sync();
-        __syncthreads();                                           // accumulator i & 1 drained
-        int qn = *sm.qn;
-        __syncthreads();
-        if (qn >= TC_QCAP / 2 || !has_next) {                    // block-uniform
-            int m = min(qn, TC_QCAP);
-            for (int qi = tid; qi < m; qi += TC_THREADS) {
-                unsigned long long e = sm.queue[qi];
-                tile_process(d, aux, sm, (int)(e >> 32), (int)(unsigned)(e & 0xffffffffu), K, pw, cw,
-                             seed_mode == 1 ? -2 : -1);
-            }
-            __syncthreads();
-            if (tid == 0) *sm.qn = 0;
-            __syncthreads();
-        }
-        TC_TICK(3)
     }
     cp_async_wait<0>();
     const long long blk_t1 = clock64();
-    // ---- 2. pairs sharing a tail place, through the postings (as in knn_tile_kernel)
+    __syncthreads();                                               // every MMA and epilogue is done: B stages are free
+    // ---- 2. pairs sharing a tail place, through the postings (as in knn_tile_kernel).  The current
+    // target's rows are staged in shared memory (the idle B stages): with ~220 KB of shared memory
+    // carved out there is hardly any L1 left to keep them hot.
+    constexpr int STG_P = 64, STG_C = 32, STG_BYTES = STG_P * 12 + STG_C * 12;
+    unsigned char *wbuf = sB0 + (size_t)warp * STG_BYTES;
+    double *s_pval = (double *)wbuf, *s_cval = (double *)(wbuf + STG_P * 8);
+    int *s_pcol = (int *)(wbuf + STG_P * 8 + STG_C * 8), *s_ccol = s_pcol + STG_P;
     for (int t = warp; t < nt && seed_mode == 0; t += TC_THREADS / 32) {
         int tix = sm.tid_of[t];
         if (tix < 0) continue;
+        TargetRows tr = load_target(d, tix);
+        __syncwarp();
+        if (tr.pn <= STG_P && tr.cn <= STG_C) {
+            for (int e = lane; e < tr.pn; e += 32) {
+                s_pcol[e] = tr.pcol[e];
+                s_pval[e] = tr.pval[e];
+            }
+            for (int e = lane; e < tr.cn; e += 32) {
+                s_ccol[e] = tr.ccol[e];
+                s_cval[e] = tr.cval[e];
+            }
+            tr.pcol = s_pcol;
+            tr.pval = s_pval;
+            tr.ccol = s_ccol;
+            tr.cval = s_cval;
+        }
+        __syncwarp();
         int ps = d.place.rowptr[tix], pn = d.place.rowptr[tix + 1] - ps;
         for (int e0 = 0; e0 < pn; e0 += 32) {
             int e = e0 + lane, start = 0, len = 0, pl = -1;
@@ -895,7 +1011,7 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
                 int ex_l = __shfl_sync(0xffffffffu, excl, L);
                 int st_l = __shfl_sync(0xffffffffu, start, L);
                 int pl_l = __shfl_sync(0xffffffffu, pl, L);
-                if (j < total) tile_process(d, aux, sm, t, aux.pper[st_l + (j - ex_l)], K, pw, cw, pl_l);
+                if (j < total) tile_process_rows(d, aux, sm, t, aux.pper[st_l + (j - ex_l)], K, pw, cw, pl_l, tr);
             }
         }
     }
@@ -1278,6 +1394,8 @@ struct vrec_knn {
     DevBuf<short> d_head_slot;
     DevBuf<int> d_pcp, d_pper;
     DevBuf<double> d_seed_thr;
+    DevBuf<unsigned long long> d_meta;     // packed records for the exact evaluation
+    DevBuf<double> d_rec;
     // tensor-core variant: fp16 row-major features over TC_D dims, its own (larger) head set
     bool tc_ok = false;
     DevBuf<__half> d_feat16;
@@ -1521,13 +1639,14 @@ extern "C" int vrec_knn_load(vrec_ctx *ctx, int64_t P, const int64_t *person_id,
             if (cudaGetLastError() != cudaSuccess) rc = VREC_ECUDA;
         }
         k->tile_ok = rc == VREC_OK;
+        std::vector<short> hs_tc((size_t)place_dim, (short)-1);
         if (rc == VREC_OK && cat_dim <= 64) {
             int n_head_tc = std::min<int>(TC_D - cat_dim, place_dim);
             std::partial_sort(byc.begin(), byc.begin() + n_head_tc, byc.end(), [&](int a, int b) {
                 int ca = pcp[a + 1] - pcp[a], cb = pcp[b + 1] - pcp[b];
                 return ca > cb || (ca == cb && a < b);
             });
-            std::vector<short> hs((size_t)place_dim, (short)-1);
+            std::vector<short> &hs = hs_tc;
             for (int h = 0; h < n_head_tc; ++h) hs[byc[h]] = (short)h;
             rc = k->d_head_slot_tc.upload(hs.data(), hs.size(), s);
             if (rc == VREC_OK) rc = k->d_feat16.alloc((size_t)TC_D * (size_t)P);
@@ -1538,6 +1657,48 @@ extern "C" int vrec_knn_load(vrec_ctx *ctx, int64_t P, const int64_t *person_id,
                 if (cudaGetLastError() != cudaSuccess) rc = VREC_ECUDA;
             }
             k->tc_ok = rc == VREC_OK;
+        }
+        // packed records (needs the device-computed lengths): one contiguous block per person
+        bool small_rows = true;
+        for (int64_t i = 0; i < P && small_rows; ++i)
+            small_rows = prp[i + 1] - prp[i] < 4096 && crp[i + 1] - crp[i] < 4096;
+        if (rc == VREC_OK && small_rows) {
+            std::vector<double> hpl((size_t)P), hcl((size_t)P);
+            if (cudaMemcpyAsync(hpl.data(), k->d_plen.p, sizeof(double) * (size_t)P, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaMemcpyAsync(hcl.data(), k->d_clen.p, sizeof(double) * (size_t)P, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaStreamSynchronize(s) != cudaSuccess) {
+                vrec_set_error("vrec_knn_load: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = VREC_ECUDA;
+            }
+            std::vector<unsigned long long> meta((size_t)P);
+            std::vector<double> rec;
+            rec.reserve((size_t)(2 * P + 2 * (k->nnz_place + k->nnz_cat)));
+            for (int64_t i = 0; i < P && rc == VREC_OK; ++i) {
+                const int np = prp[i + 1] - prp[i], nc = crp[i + 1] - crp[i];
+                meta[i] = (unsigned long long)rec.size() | ((unsigned long long)np << 40) | ((unsigned long long)nc << 52);
+                rec.push_back(hpl[i]);
+                rec.push_back(hcl[i]);
+                size_t at = rec.size();
+                rec.resize(at + (size_t)((np + 1) / 2), 0.0);
+                unsigned *pc = reinterpret_cast<unsigned *>(rec.data() + at);
+                for (int e = 0; e < np; ++e) {
+                    int col = pci[prp[i] + e];
+                    pc[e] = (unsigned)col | (hs_tc[col] < 0 ? REC_TAIL_TC : 0u) | (head_slot[col] < 0 ? REC_TAIL_TILE : 0u);
+                }
+                for (int e = 0; e < np; ++e) rec.push_back(pv[prp[i] + e]);
+                at = rec.size();
+                rec.resize(at + (size_t)((nc + 1) / 2), 0.0);
+                unsigned *cc = reinterpret_cast<unsigned *>(rec.data() + at);
+                for (int e = 0; e < nc; ++e) cc[e] = (unsigned)cci[crp[i] + e];
+                for (int e = 0; e < nc; ++e) rec.push_back(cv[crp[i] + e]);
+            }
+            if (rc == VREC_OK) rc = k->d_meta.upload(meta.data(), meta.size(), s);
+            if (rc == VREC_OK) rc = k->d_rec.upload(rec.data(), rec.size(), s);
+            if (rc == VREC_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = VREC_ECUDA;
+            if (rc != VREC_OK) {
+                k->d_meta.release();
+                k->d_rec.release();
+            }
         }
     }
     if (rc == VREC_OK && cudaStreamSynchronize(s) != cudaSuccess) {
@@ -1732,7 +1893,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                 VREC_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
                 attr_tc = true;
             }
-            TileAux aux{nullptr, 0, k->d_head_slot_tc.p, k->d_pcp.p, k->d_pper.p};
+            TileAux aux{nullptr, 0, k->d_head_slot_tc.p, k->d_pcp.p, k->d_pper.p, k->d_meta.p, k->d_rec.p, REC_TAIL_TC};
             knn_tc_kernel<<<dim3(tiles, 1), TC_THREADS, smem, ctx->stream>>>(
                 k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, 1, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p,
                 stride, sample, 1, k->d_seed_thr.p);
@@ -1747,7 +1908,8 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                 VREC_CUDA(cudaFuncSetAttribute(knn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 attr_set = true;
             }
-            TileAux aux{k->d_feat.p, k->fstride, k->d_head_slot.p, k->d_pcp.p, k->d_pper.p};
+            TileAux aux{k->d_feat.p, k->fstride, k->d_head_slot.p, k->d_pcp.p, k->d_pper.p, k->d_meta.p, k->d_rec.p,
+                        REC_TAIL_TILE};
             knn_tile_kernel<<<dim3(tiles, 1), TILE_THREADS, smem, ctx->stream>>>(
                 k->dev(), aux, k->d_tidx.p, tn, T, K, 1, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p, stride, sample,
                 1, k->d_seed_thr.p);
