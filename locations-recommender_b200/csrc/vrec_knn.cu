@@ -435,7 +435,7 @@ __device__ unsigned long long g_tile_stats[4];
 // phase cycle counters of knn_tc_kernel, block (0,0) thread 0 of the main pass:
 // [0] wait for the B tile, [1] MMA issue + completion wait, [2] TMEM epilogue, [3] barriers + queue drain,
 // [4] postings pass, [5] tiles
-__device__ unsigned long long g_tc_cycles[8];
+__device__ unsigned long long g_tc_cycles[12];
 // per-block cycles of the main pass: [0][b] dense phase, [1][b] postings phase
 __device__ unsigned long long g_tc_block_cycles[2][1024];
 
@@ -723,6 +723,8 @@ knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targe
 // ---------------------------------------------------------------------------------------
 // Tensor-core variant of the tiled batch kernel (tcgen05 / TMEM, fp16 features, D = 128).
 //
+// Operand tiles use the SWIZZLE_128B K-major layout of vrec_tc.cuh (un-swizzled tiles made the
+// tensor core's shared-memory reads ~6x slower).
 // Same algorithm as knn_tile_kernel, but the dense bound U(t, c) of a 128-target x 128-candidate
 // tile is ONE tcgen05.mma chain (8 instructions of K = 16) into 128 TMEM columns, and the filter
 // `U * (1 + 2e-3) + 2e-5 >= K-th best` is applied to the accumulators as they come out of TMEM.
@@ -815,11 +817,13 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
             const long long tile = tile_start(i);
             unsigned char *sB = sB0 + (size_t)(i % TC_STAGES) * TC_TILE_BYTES;
             for (int q = tid; q < TC_N * (TC_D / 8); q += TC_THREADS) {
-                int r = q % TC_N, c = q / TC_N;
+                // 16 consecutive lanes fetch one 256-byte feature row (coalesced); the swizzle keeps the
+                // shared-memory side conflict-free
+                int r = q >> 4, c = q & 15;
                 long long j = tile + r;
                 bool ok = j < jhi;
                 const __half *src = feat16 + (size_t)((ok ? j : jlo) * cand_stride) * TC_D + c * 8;
-                cp_async16(sB + (size_t)c * TC_LBO + r * 16, src, ok);
+                cp_async16(sB + tc::sw128_offset(TC_N, r, c), src, ok);
             }
         }
         cp_async_commit();                       // always commit: keeps the group count uniform
@@ -842,7 +846,7 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
                 h[e] = __float2half(__half2float(src[e]) * (float)(dd < cat_dim ? cw : pw));
             }
         }
-        *reinterpret_cast<uint4 *>(sA + (size_t)c * TC_LBO + r * 16) = *reinterpret_cast<const uint4 *>(h);
+        *reinterpret_cast<uint4 *>(sA + tc::sw128_offset(TC_M, r, c)) = *reinterpret_cast<const uint4 *>(h);
     }
     const uint32_t idesc = tc::make_idesc_f16(TC_M, TC_N);
     const uint32_t a_addr = tc::smem_u32(sA), b_addr0 = tc::smem_u32(sB0);
@@ -853,8 +857,8 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
         const uint32_t acc = tbase_ + (uint32_t)(i & 1) * TC_N;
 #pragma unroll
         for (int k = 0; k < TC_D / 16; ++k) {
-            uint64_t da = tc::make_desc(a_addr + k * 2 * TC_LBO, TC_LBO, TC_SBO);
-            uint64_t db = tc::make_desc(b_addr + k * 2 * TC_LBO, TC_LBO, TC_SBO);
+            uint64_t da = tc::make_desc_sw128(tc::sw128_kstep_addr(a_addr, TC_M, k));
+            uint64_t db = tc::make_desc_sw128(tc::sw128_kstep_addr(b_addr, TC_N, k));
             tc::mma_f16(acc, da, db, idesc, k > 0);
         }
         tc::mma_commit(&bar[i & 1]);
@@ -883,13 +887,17 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
     for (int i = 0; i <= ntiles; ++i) {                           // one extra turn drains the last survivors
         const bool live = i < ntiles, has_next = i + 1 < ntiles;
         cp_async_wait<0>();                      // B(i+1) (issued one iteration ago) has landed
+        TC_TICK(6)
         tc::fence_proxy_async();
         tc::fence_before_sync();
         // ONE barrier per tile: B(i+1) visible to all, epilogue(i-1) finished, and a block-uniform
         // decision whether the survivor queue must be drained now
         const int drain = __syncthreads_or((*(volatile int *)sm.qn >= TC_QCAP / 2) || !live);
+        TC_TICK(7)
         if (tid == 0 && has_next) issue_mma(i + 1, tbase);
+        TC_TICK(8)
         if (live) load_b(i + 2);                 // stage (i+2)%3 was last read by MMA(i-1), long complete
+        TC_TICK(3)
         if (drain) {
             int m = min(*(volatile int *)sm.qn, TC_QCAP);
             for (int qi = tid; qi < m; qi += TC_THREADS) {
@@ -1793,8 +1801,8 @@ extern "C" int vrec_knn_debug_tc_cycles(vrec_knn *k, uint64_t *out8) {
     if (!k || !out8) return VREC_EINVAL;
     VREC_CUDA(cudaSetDevice(k->ctx->device));
     VREC_CUDA(cudaStreamSynchronize(k->ctx->stream));
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    VREC_CUDA(cudaMemcpyFromSymbol(out8, g_tc_cycles, sizeof(z)));
+    unsigned long long z[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    VREC_CUDA(cudaMemcpyFromSymbol(out8, g_tc_cycles, sizeof(z)));       // out8 holds 12 values
     VREC_CUDA(cudaMemcpyToSymbol(g_tc_cycles, z, sizeof(z)));
     return VREC_OK;
 }

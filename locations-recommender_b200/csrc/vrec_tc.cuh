@@ -23,6 +23,30 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
     return d;                         // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
 }
 
+// SWIZZLE_128B K-major operand tile of ROWS rows x D fp16 (D a multiple of 64): the tile is split in
+// K-blocks of 64 halves (128 B per row); inside K-block kb, row r occupies the 128 bytes at
+//     kb * (ROWS * 128) + r * 128
+// and its 16-byte chunk q (0..7) sits at position q ^ (r & 7)  (Swizzle<3,4,3>; tile base 1 KB aligned).
+// SBO (next 8 rows) = 1024 B; LBO is not used by swizzled K-major layouts (encoded as 1).
+// The k-th MMA (K = 16 halves = 32 B) of a K-block starts 32 * k bytes into the row.
+__device__ __forceinline__ uint32_t sw128_offset(int rows, int r, int chunk /* 16-byte chunk of the row */) {
+    const int kb = chunk >> 3, q = chunk & 7;
+    return (uint32_t)(kb * rows * 128 + r * 128 + ((q ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                       // LBO (ignored)
+    d |= (uint64_t)(1024 >> 4) << 32;             // SBO: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                       // descriptor version for Blackwell
+    d |= (uint64_t)2 << 61;                       // layout_type = SWIZZLE_128B
+    return d;
+}
+// start address of the k-th K=16 step (k = 0 .. D/16-1) of a swizzled tile
+__device__ __forceinline__ uint32_t sw128_kstep_addr(uint32_t tile_addr, int rows, int k) {
+    return tile_addr + (uint32_t)((k >> 2) * rows * 128 + (k & 3) * 32);
+}
+
 // 32-bit instruction descriptor (cute::UMMA::InstrDescriptor): F16 x F16 -> F32, both K-major
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4)                      // c_format = F32

@@ -9,7 +9,7 @@ constexpr int ST_ROWS = 128;
 constexpr int ST_D = 128;
 
 __global__ void __launch_bounds__(128) tc_selftest_kernel(const __half *__restrict__ A, const __half *__restrict__ B,
-                                                           float *__restrict__ C) {
+                                                           float *__restrict__ C, int swizzled) {
     extern __shared__ unsigned char smem_raw[];
     // operand tiles must start on a core-matrix (128 B) boundary: the low bits of the descriptor
     // start address are ignored by the hardware.  Align the dynamic buffer by hand (1 KB).
@@ -28,8 +28,9 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __half *__restri
         int r = q % ST_ROWS, c = q / ST_ROWS;
         uint4 va = *reinterpret_cast<const uint4 *>(A + (size_t)r * ST_D + c * 8);
         uint4 vb = *reinterpret_cast<const uint4 *>(B + (size_t)r * ST_D + c * 8);
-        *reinterpret_cast<uint4 *>(sA + (size_t)c * (ST_ROWS * 16) + r * 16) = va;
-        *reinterpret_cast<uint4 *>(sB + (size_t)c * (ST_ROWS * 16) + r * 16) = vb;
+        uint32_t off = swizzled ? tc::sw128_offset(ST_ROWS, r, c) : (uint32_t)(c * (ST_ROWS * 16) + r * 16);
+        *reinterpret_cast<uint4 *>(sA + off) = va;
+        *reinterpret_cast<uint4 *>(sB + off) = vb;
     }
     tc::fence_proxy_async();
     tc::fence_before_sync();
@@ -39,8 +40,14 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __half *__restri
     if (tid == 0) {
         const uint32_t idesc = tc::make_idesc_f16(128, 128);
         for (int k = 0; k < ST_D / 16; ++k) {
-            uint64_t da = tc::make_desc(tc::smem_u32(sA) + k * 2 * (ST_ROWS * 16), ST_ROWS * 16, 128);
-            uint64_t db = tc::make_desc(tc::smem_u32(sB) + k * 2 * (ST_ROWS * 16), ST_ROWS * 16, 128);
+            uint64_t da, db;
+            if (swizzled) {
+                da = tc::make_desc_sw128(tc::sw128_kstep_addr(tc::smem_u32(sA), ST_ROWS, k));
+                db = tc::make_desc_sw128(tc::sw128_kstep_addr(tc::smem_u32(sB), ST_ROWS, k));
+            } else {
+                da = tc::make_desc(tc::smem_u32(sA) + k * 2 * (ST_ROWS * 16), ST_ROWS * 16, 128);
+                db = tc::make_desc(tc::smem_u32(sB) + k * 2 * (ST_ROWS * 16), ST_ROWS * 16, 128);
+            }
             tc::mma_f16(tbase, da, db, idesc, k > 0);
         }
         tc::mma_commit(&bar);
@@ -58,10 +65,71 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __half *__restri
     if (warp == 0) tc::tmem_dealloc(tbase, 128);
 }
 
+// issue `reps` chains of 8 MMAs (128x128x128) back to back and time them with clock64
+__global__ void __launch_bounds__(128) tc_rate_kernel(int swizzled, int reps, long long *out_cycles) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *sA = smem, *sB = smem + ST_ROWS * ST_D * 2;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tc::tmem_alloc(&tmem_base, 256);
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_init_fence();
+    }
+    for (int q = tid; q < 2 * ST_ROWS * ST_D * 2 / 16; q += blockDim.x) reinterpret_cast<uint4 *>(smem)[q] = make_uint4(0, 0, 0, 0);
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_base;
+    if (tid == 0) {
+        const uint32_t idesc = tc::make_idesc_f16(128, 128);
+        long long t0 = clock64();
+        for (int rep = 0; rep < reps; ++rep) {
+            for (int k = 0; k < ST_D / 16; ++k) {
+                uint64_t da, db;
+                if (swizzled) {
+                    da = tc::make_desc_sw128(tc::sw128_kstep_addr(tc::smem_u32(sA), ST_ROWS, k));
+                    db = tc::make_desc_sw128(tc::sw128_kstep_addr(tc::smem_u32(sB), ST_ROWS, k));
+                } else {
+                    da = tc::make_desc(tc::smem_u32(sA) + k * 2 * (ST_ROWS * 16), ST_ROWS * 16, 128);
+                    db = tc::make_desc(tc::smem_u32(sB) + k * 2 * (ST_ROWS * 16), ST_ROWS * 16, 128);
+                }
+                tc::mma_f16(tbase + (rep & 1) * 128, da, db, idesc, k > 0);
+            }
+        }
+        long long t1 = clock64();
+        tc::mma_commit(&bar);
+        out_cycles[0] = t1 - t0;
+        tc::mbar_wait(&bar, 0);
+        out_cycles[1] = clock64() - t0;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 256);
+}
+
 }  // namespace
 
+// Debug: cycles to ISSUE and to COMPLETE `reps` chains of eight 128x128x16 fp16 MMAs on one SM.
+extern "C" int vrec_debug_tc_mma_rate(vrec_ctx *ctx, int swizzled, int reps, int64_t *out2) {
+    if (!ctx || !out2 || reps <= 0) return VREC_EINVAL;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<long long> d;
+    VREC_TRY(d.alloc(2));
+    size_t smem = 2 * ST_ROWS * ST_D * 2 + 1024;
+    VREC_CUDA(cudaFuncSetAttribute(tc_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_rate_kernel<<<1, 128, smem, ctx->stream>>>(swizzled, reps, d.p);
+    VREC_LAUNCHED(ctx);
+    VREC_CUDA(cudaMemcpyAsync(out2, d.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VREC_OK;
+}
+
 // Debug: C[128x128] = A[128x128] * B[128x128]^T for caller-supplied fp16 bit patterns (row-major).
-extern "C" int vrec_debug_tc_matmul(vrec_ctx *ctx, const uint16_t *A, const uint16_t *B, float *C) {
+extern "C" int vrec_debug_tc_matmul(vrec_ctx *ctx, const uint16_t *A, const uint16_t *B, float *C, int swizzled) {
     if (!ctx || !A || !B || !C) return VREC_EINVAL;
     VREC_CUDA(cudaSetDevice(ctx->device));
     DevBuf<__half> dA, dB;
@@ -71,7 +139,7 @@ extern "C" int vrec_debug_tc_matmul(vrec_ctx *ctx, const uint16_t *A, const uint
     VREC_TRY(dC.alloc(ST_ROWS * 128));
     size_t smem = 2 * ST_ROWS * ST_D * 2 + 1024;
     VREC_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_selftest_kernel<<<1, 128, smem, ctx->stream>>>(dA.p, dB.p, dC.p);
+    tc_selftest_kernel<<<1, 128, smem, ctx->stream>>>(dA.p, dB.p, dC.p, swizzled);
     VREC_LAUNCHED(ctx);
     VREC_CUDA(cudaMemcpyAsync(C, dC.p, ST_ROWS * 128 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     VREC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -99,19 +167,22 @@ extern "C" int vrec_debug_tc_selftest(vrec_ctx *ctx, double *out_max_abs_err) {
     VREC_TRY(dC.alloc(ST_ROWS * 128));
     size_t smem = 2 * ST_ROWS * ST_D * 2 + 1024;
     VREC_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_selftest_kernel<<<1, 128, smem, ctx->stream>>>(dA.p, dB.p, dC.p);
-    VREC_LAUNCHED(ctx);
-    std::vector<float> hC(ST_ROWS * 128);
-    VREC_CUDA(cudaMemcpyAsync(hC.data(), dC.p, hC.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    VREC_CUDA(cudaStreamSynchronize(ctx->stream));
     double worst = 0.0;
-    for (int i = 0; i < ST_ROWS; ++i)
-        for (int j = 0; j < 128; ++j) {
-            double ref = 0.0;
-            for (int k = 0; k < ST_D; ++k) ref += (double)__half2float(hA[i * ST_D + k]) * (double)__half2float(hB[j * ST_D + k]);
-            double e = fabs(ref - (double)hC[i * 128 + j]);
-            if (e > worst) worst = e;
-        }
+    for (int swizzled = 0; swizzled < 2; ++swizzled) {      // both operand layouts
+        tc_selftest_kernel<<<1, 128, smem, ctx->stream>>>(dA.p, dB.p, dC.p, swizzled);
+        VREC_LAUNCHED(ctx);
+        std::vector<float> hC(ST_ROWS * 128);
+        VREC_CUDA(cudaMemcpyAsync(hC.data(), dC.p, hC.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        VREC_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < ST_ROWS; ++i)
+            for (int j = 0; j < 128; ++j) {
+                double ref = 0.0;
+                for (int k = 0; k < ST_D; ++k)
+                    ref += (double)__half2float(hA[i * ST_D + k]) * (double)__half2float(hB[j * ST_D + k]);
+                double e = fabs(ref - (double)hC[i * 128 + j]);
+                if (e > worst) worst = e;
+            }
+    }
     *out_max_abs_err = worst;
     return VREC_OK;
 }

@@ -43,7 +43,7 @@ d_rating = torch.empty((B, m), dtype=torch.float64, device="cuda")
 d_count = torch.empty(B, dtype=torch.int32, device="cuda")
 d_status = torch.empty(B, dtype=torch.int32, device="cuda")
 stats = (C.c_uint64 * 4)()
-cyc = (C.c_uint64 * 8)()
+cyc = (C.c_uint64 * 12)()
 for s in range(a.warmup + a.steps):
     t = torch.from_numpy(inp.person_id[(np.arange(B) + s * B) % P]).cuda()
     lib.vrec_knn_debug_stats(rs._h, stats)
@@ -67,6 +67,6 @@ for s in range(a.warmup + a.steps):
         print(f"   per-block Mcycles: dense mean {bcs[0].mean():.1f} max {bcs[0].max():.1f} | postings mean "
               f"{bcs[1].mean():.1f} max {bcs[1].max():.1f} | total max {(bcs[0] + bcs[1]).max():.1f}")
         print(f"   tc block0 cycles/tile: load-wait {cy[0] / cy[5]:.0f}, mma {cy[1] / cy[5]:.0f}, epilogue {cy[2] / cy[5]:.0f}, "
-              f"sync+drain {cy[3] / cy[5]:.0f}; postings pass total {cy[4] / 1e6:.2f} Mcycles; tiles {cy[5]}")
+              f"mma issue {cy[8] / cy[5]:.0f}, load issue {cy[3] / cy[5]:.0f} [cp.async wait {cy[6] / cy[5]:.0f}, barrier {cy[7] / cy[5]:.0f}]; postings pass total {cy[4] / 1e6:.2f} Mcycles; tiles {cy[5]}")
     print(f"kernel={a.kernel} step {s}: {ms:.1f} ms  {B / ms * 1e3:,.0f} persons/s   per target: postings evals {st[0] / B:.0f}, "
           f"filter survivors {st[1] / B:.0f}, heap inserts {st[2] / B:.0f}, queue overflow {st[3] / B:.0f}", flush=True)

@@ -5,11 +5,12 @@ sys.path.insert(0, os.path.join(ROOT, "locations-recommender_b200"))
 import vrec
 ctx = vrec.Context(0)
 lib = ctx.lib
-lib.vrec_debug_tc_matmul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.vrec_debug_tc_matmul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+SW = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 def mm(A, B):
     A = np.ascontiguousarray(A, dtype=np.float16); B = np.ascontiguousarray(B, dtype=np.float16)
     out = np.zeros((128, 128), dtype=np.float32)
-    rc = lib.vrec_debug_tc_matmul(ctx._h, A.ctypes.data, B.ctypes.data, out.ctypes.data)
+    rc = lib.vrec_debug_tc_matmul(ctx._h, A.ctypes.data, B.ctypes.data, out.ctypes.data, SW)
     assert rc == 0
     return out
 ones = np.ones((128, 128))
@@ -28,3 +29,8 @@ for k0 in (0, 1, 7, 8, 9, 15, 16, 17, 31, 64, 127):
 for k0 in (0, 9, 100):
     A = np.zeros((128, 128)); A[:, k0] = np.arange(128); B = np.zeros((128, 128)); B[:, k0] = 1
     c = mm(A, B); print(f"T4 k0={k0}: C[:,0] == arange ? {np.array_equal(c[:,0], np.arange(128))}", c[:10, 0])
+
+rng = np.random.default_rng(0)
+A = rng.random((128, 128)).astype(np.float16); B = (rng.random((128, 128)) * 0.5).astype(np.float16)
+c = mm(A, B); ref = A.astype(np.float64) @ B.astype(np.float64).T
+print("random max err", np.abs(c - ref).max())
