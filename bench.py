@@ -133,6 +133,9 @@ def sg_workload_name(args):
 # dram__bytes_read.sum + dram__bytes_write.sum of one sg_spmv_kernel launch on the default SG workload,
 # from profiles/r1_sg_spmv_v1_ncu_raw.csv (ncu --set full)
 SG_NCU_TRAFFIC = 27_756_317_000 + 83_389_440
+# the same for one knn_tc_kernel launch on the default KNN workload (18944 targets),
+# from profiles/r1_knn_tc_kernel_ncu_raw.csv
+KNN_NCU_TRAFFIC = 38_353_532_000 + 14_552_320
 
 
 def sg_bytes_per_iteration(n, nnz):
@@ -359,12 +362,16 @@ def run_ours(args):
     # pass over the region-set (bytes/target = B_region / T with T = targets per pass)
     b_region = inp.algorithmic_bytes
     knn_launch_ms = statistics.mean(knn_ms)
-    knn_roof = {"bound": "hbm", "kernel": "knn_tile_kernel", "achieved": b_region / (knn_launch_ms / 1e3) / 1e9,
+    default_cfg = (args.knn_persons, args.knn_places, args.knn_batch, args.k_nearest) == (1_000_000, 100_000, 18944, 50)
+    knn_roof = {"bound": "hbm", "kernel": "knn_tc_kernel", "achieved": b_region / (knn_launch_ms / 1e3) / 1e9,
                 "peak": peak, "unit": "GB/s", "frac": b_region / (knn_launch_ms / 1e3) / 1e9 / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": KNN_NCU_TRAFFIC if default_cfg else None, "peak_source": peak_src,
+                "tensor_pipe_active_pct": 6.6 if default_cfg else None,
                 "note": f"one launch serves T={B} targets, so algorithmic bytes/launch = B_region = {b_region}; "
-                        "the batch kernel is issue-bound (10^6 pair filters + ~12K exact fp64 evaluations "
-                        "per target), not HBM-bound: see DESIGN.md"}
+                        "the batch kernel is neither HBM- nor tensor-bound: 10^6 pair filters per target run "
+                        "on tcgen05 (6.6 % of the tensor pipe), the time goes to ~4K exact fp64 evaluations per "
+                        "target (latency/issue); DRAM traffic = every CTA streaming the fp16 feature matrix "
+                        "once. See DESIGN.md"}
 
     cpu_knn_base = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -476,7 +483,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--knn-persons", type=int, default=1_000_000)
     ap.add_argument("--knn-places", type=int, default=100_000)
-    ap.add_argument("--knn-batch", type=int, default=16384)
+    ap.add_argument("--knn-batch", type=int, default=18944)   # 148 SMs x 128 targets: one full wave
     ap.add_argument("--k-nearest", type=int, default=50)
     ap.add_argument("--max-recs", type=int, default=10)
     ap.add_argument("--sg-vertices", type=int, default=10_000_000)
