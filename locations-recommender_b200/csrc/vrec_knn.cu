@@ -291,6 +291,22 @@ struct TileAux {
 };
 
 constexpr unsigned REC_TAIL_TC = 0x80000000u, REC_TAIL_TILE = 0x40000000u, REC_COL_MASK = 0x3fffffffu;
+// Record layout in 8-byte words, every section 16-byte aligned so that it can be fetched with 128-bit loads:
+//   [0..2)  |place|, |cat|
+//   place cols: ints, padded to a multiple of 4   -> rec_cols_words(np) words
+//   place vals: doubles, padded to a multiple of 2 -> rec_vals_words(np) words
+//   cat cols, cat vals: same
+__host__ __device__ constexpr int rec_cols_words(int n) { return ((n + 3) / 4) * 2; }
+__host__ __device__ constexpr int rec_vals_words(int n) { return ((n + 1) / 2) * 2; }
+
+// 4 entries (cols + vals) of a record section with three 128-bit loads
+__device__ __forceinline__ void rec_load4(const int *cols, const double *vals, int k0, unsigned (&c)[4], double (&x)[4]) {
+    const int4 ci = __ldg(reinterpret_cast<const int4 *>(cols + k0));
+    const double2 v01 = __ldg(reinterpret_cast<const double2 *>(vals + k0));
+    const double2 v23 = __ldg(reinterpret_cast<const double2 *>(vals + k0 + 2));
+    c[0] = (unsigned)ci.x; c[1] = (unsigned)ci.y; c[2] = (unsigned)ci.z; c[3] = (unsigned)ci.w;
+    x[0] = v01.x; x[1] = v01.y; x[2] = v23.x; x[3] = v23.y;
+}
 
 // Sparse dot of candidate row [s, s+n) with the target row [ts, ts+tn) of one table, in the exact
 // order of the mllib merge (matches visited in ascending index), but with the candidate's entries
@@ -334,18 +350,13 @@ __device__ __forceinline__ double packed_dot(const int *__restrict__ pc, const d
                                              int &min_tail) {
     double sum = 0.0;
     int ky = 0;
-    for (int k0 = 0; k0 < n && ky < tn; k0 += 8) {
-        unsigned c[8];
-        double x[8];
+    for (int k0 = 0; k0 < n && ky < tn; k0 += 4) {
+        unsigned c[4];
+        double x[4];
+        rec_load4(pc, pv, k0, c, x);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            bool ok = k0 + e < n;
-            c[e] = ok ? (unsigned)__ldg(pc + k0 + e) : 0xffffffffu;
-            x[e] = ok ? __ldg(pv + k0 + e) : 0.0;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            if (c[e] == 0xffffffffu) break;
+        for (int e = 0; e < 4; ++e) {
+            if (k0 + e >= n) break;
             int ix = (int)(c[e] & REC_COL_MASK);
             while (ky < tn && tcol[ky] < ix) ky++;
             if (ky < tn && tcol[ky] == ix) {
@@ -360,18 +371,27 @@ __device__ __forceinline__ double packed_dot(const int *__restrict__ pc, const d
     return sum;
 }
 
+__device__ unsigned long long g_probe[8];
+__device__ int g_probe_on;
+
 __device__ __forceinline__ double exact_pair_packed(const TileAux &aux, long long i, const TargetRows &t, double pw,
                                                     double cw, int &min_tail) {
     min_tail = -1;
     if (i == t.t) return 0.0;
+    const bool pr = g_probe_on && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 32;
+    long long c0 = clock64();
     const unsigned long long m = __ldg(aux.meta + i);                   // round trip 1 (8 MB table: L2)
     const int np = (int)((m >> 40) & 0xfffu), nc = (int)(m >> 52);
     const double *r = aux.rec + (m & 0xffffffffffULL);                  // round trip 2: one contiguous record
-    const double plen = __ldg(r), clen = __ldg(r + 1);
+    if (pr && m == 0xffffffffffffffffULL) g_probe[7] = 1;              // keep the dependency
+    __syncwarp(__activemask());
+    long long c1 = clock64();
+    const double2 lens = __ldg(reinterpret_cast<const double2 *>(r));
+    const double plen = lens.x, clen = lens.y;
     const int *pc = reinterpret_cast<const int *>(r + 2);
-    const double *pv = r + 2 + ((np + 1) >> 1);
-    const int *cc = reinterpret_cast<const int *>(pv + np);
-    const double *cvp = pv + np + ((nc + 1) >> 1);
+    const double *pv = r + 2 + rec_cols_words(np);
+    const int *cc = reinterpret_cast<const int *>(pv + rec_vals_words(np));
+    const double *cvp = pv + rec_vals_words(np) + rec_cols_words(nc);
     bool keep = false;
     double ps_sim = 0.0, cs_sim = 0.0;
     if (np > 0) {
@@ -382,9 +402,104 @@ __device__ __forceinline__ double exact_pair_packed(const TileAux &aux, long lon
             ps_sim = c;
         }
     }
+    __syncwarp(__activemask());
+    long long c2 = clock64();
     if (nc > 0) {
         int dummy = 0;
         double sum = packed_dot<false>(cc, cvp, nc, t.ccol, t.cval, t.cn, 0u, dummy);
+        double c = xdiv(sum, xmul(clen, t.clen));
+        if (c > 0) {
+            keep = true;
+            cs_sim = c;
+        }
+    }
+    __syncwarp(__activemask());
+    if (pr && threadIdx.x == 0) {
+        long long c3 = clock64();
+        g_probe[0] += (unsigned long long)(c1 - c0);
+        g_probe[1] += (unsigned long long)(c2 - c1);
+        g_probe[2] += (unsigned long long)(c3 - c2);
+        g_probe[3] += 1;
+    }
+    if (!keep) return 0.0;
+    return xadd(xmul(ps_sim, pw), xmul(cs_sim, cw));
+}
+
+// Target of the postings pass, staged in shared memory by its warp: sorted place row, a 64-bit
+// signature of its places, and its category vector as a dense array.
+struct StagedTarget {
+    int t;
+    int pn;
+    const int *pcol;            // shared memory, ascending
+    const double *pval;
+    unsigned long long sig;     // bit h(col) set for every place of the target
+    const double *cat_dense;    // [cat_dim] shared memory, 0.0 where the target has no rating
+    double plen, clen;
+};
+
+__device__ __forceinline__ unsigned sig_bit(int col) { return ((unsigned)col * 0x9E3779B1u) >> 26; }
+
+// Same value as exact_pair_packed, without data-dependent merge loops:
+//  * category dot: sum over the candidate's entries (ascending) of x * dense[col]; entries the target
+//    lacks contribute x * 0.0 = +0.0, and s + 0.0 == s, so the sum equals the merge's bit for bit
+//    (all values are non-negative on this path);
+//  * place dot: candidate entries in ascending order; an entry can only match if its signature bit is
+//    set, and then a fixed-depth binary search over the target row finds it.
+__device__ __forceinline__ double exact_pair_staged(const TileAux &aux, long long i, const StagedTarget &t, double pw,
+                                                    double cw, int &min_tail) {
+    min_tail = -1;
+    if (i == t.t) return 0.0;
+    const unsigned long long m = __ldg(aux.meta + i);
+    const int np = (int)((m >> 40) & 0xfffu), nc = (int)(m >> 52);
+    const double *r = aux.rec + (m & 0xffffffffffULL);
+    const double2 lens = __ldg(reinterpret_cast<const double2 *>(r));
+    const double plen = lens.x, clen = lens.y;
+    const int *pc = reinterpret_cast<const int *>(r + 2);
+    const double *pv = r + 2 + rec_cols_words(np);
+    const int *cc = reinterpret_cast<const int *>(pv + rec_vals_words(np));
+    const double *cvp = pv + rec_vals_words(np) + rec_cols_words(nc);
+    bool keep = false;
+    double ps_sim = 0.0, cs_sim = 0.0;
+    if (np > 0) {
+        double sum = 0.0;
+        for (int k0 = 0; k0 < np; k0 += 4) {
+            unsigned c[4];
+            double x[4];
+            rec_load4(pc, pv, k0, c, x);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (k0 + e < np) {
+                    const int ix = (int)(c[e] & REC_COL_MASK);
+                    if ((t.sig >> sig_bit(ix)) & 1ULL) {
+                        int lo = 0, hi = t.pn;                       // first index with pcol >= ix
+                        while (lo < hi) {
+                            int mid = (lo + hi) >> 1;
+                            if (t.pcol[mid] < ix) lo = mid + 1; else hi = mid;
+                        }
+                        if (lo < t.pn && t.pcol[lo] == ix) {
+                            sum = xadd(sum, xmul(x[e], t.pval[lo]));
+                            if (min_tail < 0 && (c[e] & aux.tail_bit)) min_tail = ix;
+                        }
+                    }
+                }
+            }
+        }
+        double c = xdiv(sum, xmul(plen, t.plen));
+        if (c > 0) {
+            keep = true;
+            ps_sim = c;
+        }
+    }
+    if (nc > 0) {
+        double sum = 0.0;
+        for (int k0 = 0; k0 < nc; k0 += 4) {
+            unsigned c[4];
+            double x[4];
+            rec_load4(cc, cvp, k0, c, x);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (k0 + e < nc) sum = xadd(sum, xmul(x[e], t.cat_dense[c[e]]));
+        }
         double c = xdiv(sum, xmul(clen, t.clen));
         if (c > 0) {
             keep = true;
@@ -521,11 +636,11 @@ __device__ __forceinline__ void tile_heap_insert(const TileSmem &sm, int t, int 
 // exact evaluation of one filter survivor; from_postings = the place whose postings produced it
 __device__ __forceinline__ void tile_process_rows(const KnnDev &d, const TileAux &aux, const TileSmem &sm, int t, int c,
                                                   int K, double pw, double cw, int from_postings,
-                                                  const TargetRows &tr) {
+                                                  const TargetRows &tr, double thr0 = 0.0) {
     atomicAdd(sm.stats + (from_postings >= 0 ? 0 : 1), 1u);
     int min_tail;
     double sim = exact_pair(d, aux, c, tr, pw, cw, min_tail);
-    if (!(sim > 0)) return;
+    if (!(sim > 0) || sim < thr0) return;      // >= K candidates are known to reach thr0
     if (from_postings >= 0) {
         if (min_tail != from_postings) return;          // counted at its smallest shared tail place
     } else if (from_postings == -1 && min_tail >= 0) {
@@ -533,6 +648,21 @@ __device__ __forceinline__ void tile_process_rows(const KnnDev &d, const TileAux
     }                                                   // (-2: seed pass, every pair counts)
     // cheap pre-check without the lock: the root similarity is written once per update and only
     // grows, so a stale read can only let too much through (the exact test is under the lock)
+    volatile double *hs = sm.hsim + (size_t)t * K;
+    if (*(volatile int *)(sm.hcnt + t) >= K && sim < hs[0]) return;
+    atomicAdd(sm.stats + 2, 1u);
+    tile_heap_insert(sm, t, K, sim, c);
+}
+
+// postings-pass survivor with a staged target: counted at its smallest shared tail place
+__device__ __forceinline__ void tile_process_staged(const TileAux &aux, const TileSmem &sm, int t, int c, int K,
+                                                    double pw, double cw, int from_postings, const StagedTarget &st,
+                                                    double thr0 = 0.0) {
+    atomicAdd(sm.stats + 0, 1u);
+    int min_tail;
+    double sim = exact_pair_staged(aux, c, st, pw, cw, min_tail);
+    if (!(sim > 0) || sim < thr0) return;      // >= K candidates are known to reach thr0
+    if (min_tail != from_postings) return;
     volatile double *hs = sm.hsim + (size_t)t * K;
     if (*(volatile int *)(sm.hcnt + t) >= K && sim < hs[0]) return;
     atomicAdd(sm.stats + 2, 1u);
@@ -550,7 +680,8 @@ __device__ __forceinline__ void tile_process(const KnnDev &d, const TileAux &aux
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targets, int T, int K, int S,
                 int cat_dim, double pw, double cw, Nb *__restrict__ part, int *__restrict__ part_cnt,
-                long long cand_stride, long long cand_count, int seed_mode, double *__restrict__ seed_thr) {
+                long long cand_stride, long long cand_count, int seed_mode, double *__restrict__ seed_thr,
+                int part_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x, sp = blockIdx.y;
@@ -707,7 +838,7 @@ knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targe
     // ---- emit the heaps (unsorted; the merge kernel sorts)
     for (int t = 0; t < nt; ++t) {
         int cnt = sm.hcnt[t];
-        Nb *out = part + ((size_t)(t0 + t) * S + sp) * K;
+        Nb *out = part + ((size_t)(t0 + t) * part_stride + sp) * K;
         for (int j = tid; j < cnt; j += TILE_THREADS) {
             Nb e;
             e.sim = sm.hsim[(size_t)t * K + j];
@@ -715,7 +846,7 @@ knn_tile_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targe
             e.pad = 0;
             out[j] = e;
         }
-        if (tid == 0) part_cnt[(t0 + t) * S + sp] = cnt;
+        if (tid == 0) part_cnt[(t0 + t) * part_stride + sp] = cnt;
     }
 }
 
@@ -756,7 +887,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const int *__restrict__ tidx,
               int n_targets, int K, int S, int cat_dim, double pw, double cw, Nb *__restrict__ part,
               int *__restrict__ part_cnt, long long cand_stride, long long cand_count, int seed_mode,
-              double *__restrict__ seed_thr) {
+              double *__restrict__ seed_thr, int part_stride) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ uint32_t tmem_base_s;
@@ -954,28 +1085,50 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
     // ---- 2. pairs sharing a tail place, through the postings (as in knn_tile_kernel).  The current
     // target's rows are staged in shared memory (the idle B stages): with ~220 KB of shared memory
     // carved out there is hardly any L1 left to keep them hot.
-    constexpr int STG_P = 64, STG_C = 32, STG_BYTES = STG_P * 12 + STG_C * 12;
+    constexpr int STG_P = 64, STG_C = 32, STG_DENSE = 64;
+    constexpr int STG_BYTES = STG_P * 12 + STG_C * 12 + STG_DENSE * 8;
     unsigned char *wbuf = sB0 + (size_t)warp * STG_BYTES;
     double *s_pval = (double *)wbuf, *s_cval = (double *)(wbuf + STG_P * 8);
-    int *s_pcol = (int *)(wbuf + STG_P * 8 + STG_C * 8), *s_ccol = s_pcol + STG_P;
+    double *s_dense = (double *)(wbuf + STG_P * 8 + STG_C * 8);
+    int *s_pcol = (int *)(wbuf + STG_P * 8 + STG_C * 8 + STG_DENSE * 8), *s_ccol = s_pcol + STG_P;
+    const bool can_stage = aux.meta != nullptr && cat_dim <= STG_DENSE;
     for (int t = warp; t < nt && seed_mode == 0; t += TC_THREADS / 32) {
         int tix = sm.tid_of[t];
         if (tix < 0) continue;
         TargetRows tr = load_target(d, tix);
         __syncwarp();
+        StagedTarget stg;
+        bool staged = false;
         if (tr.pn <= STG_P && tr.cn <= STG_C) {
+            unsigned long long sig = 0ULL;
+            for (int e = lane; e < STG_DENSE; e += 32) s_dense[e] = 0.0;
+            __syncwarp();
             for (int e = lane; e < tr.pn; e += 32) {
-                s_pcol[e] = tr.pcol[e];
+                int col = tr.pcol[e];
+                s_pcol[e] = col;
                 s_pval[e] = tr.pval[e];
+                sig |= 1ULL << sig_bit(col);
             }
             for (int e = lane; e < tr.cn; e += 32) {
                 s_ccol[e] = tr.ccol[e];
                 s_cval[e] = tr.cval[e];
+                if (can_stage) s_dense[tr.ccol[e]] = tr.cval[e];
             }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sig |= __shfl_xor_sync(0xffffffffu, sig, off);
             tr.pcol = s_pcol;
             tr.pval = s_pval;
             tr.ccol = s_ccol;
             tr.cval = s_cval;
+            staged = can_stage;
+            stg.t = tr.t;
+            stg.pn = tr.pn;
+            stg.pcol = s_pcol;
+            stg.pval = s_pval;
+            stg.sig = sig;
+            stg.cat_dense = s_dense;
+            stg.plen = tr.plen;
+            stg.clen = tr.clen;
         }
         __syncwarp();
         int ps = d.place.rowptr[tix], pn = d.place.rowptr[tix + 1] - ps;
@@ -1007,8 +1160,10 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
             }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
             const int excl = incl - len;
-            for (int j0 = 0; j0 < total; j0 += 32) {
-                int j = j0 + lane;
+            // Software pipeline over the flattened postings: candidate id + meta word are fetched two
+            // iterations ahead and the record of the next iteration is pulled into L2 while the current
+            // one is evaluated, so that the evaluation itself only sees L2 latencies.
+            auto locate = [&](int j, int &pl_out) -> int {        // postings index of flat position j, or -1
                 int L = 0;
 #pragma unroll
                 for (int step = 16; step > 0; step >>= 1) {
@@ -1018,8 +1173,46 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
                 L = min(L, 31);
                 int ex_l = __shfl_sync(0xffffffffu, excl, L);
                 int st_l = __shfl_sync(0xffffffffu, start, L);
-                int pl_l = __shfl_sync(0xffffffffu, pl, L);
-                if (j < total) tile_process_rows(d, aux, sm, t, aux.pper[st_l + (j - ex_l)], K, pw, cw, pl_l, tr);
+                pl_out = __shfl_sync(0xffffffffu, pl, L);
+                return j < total ? st_l + (j - ex_l) : -1;
+            };
+            auto fetch = [&](int j, int &cand_out, unsigned long long &meta_out, int &pl_out) {
+                int at = locate(j, pl_out);
+                cand_out = at >= 0 ? __ldg(aux.pper + at) : -1;
+                meta_out = (cand_out >= 0 && aux.meta) ? __ldg(aux.meta + cand_out) : 0ULL;
+            };
+            auto prefetch_record = [&](int cand_, unsigned long long m_) {
+                if (cand_ >= 0 && aux.meta) {
+                    const char *r = reinterpret_cast<const char *>(aux.rec + (m_ & 0xffffffffffULL));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128));
+                }
+            };
+            int c0 = -1, c1 = -1, p0 = -1, p1 = -1;
+            unsigned long long m0 = 0, m1 = 0;
+            fetch(lane, c0, m0, p0);
+            fetch(32 + lane, c1, m1, p1);
+            prefetch_record(c0, m0);
+            for (int j0 = 0; j0 < total; j0 += 32) {
+                int c2, p2;
+                unsigned long long m2;
+                fetch(j0 + 64 + lane, c2, m2, p2);                 // two iterations ahead
+                prefetch_record(c1, m1);                           // next iteration's record -> L2
+                const int cand = c0, pl_l = p0;
+                if (prof) g_probe_on = 1;
+                long long q1 = clock64();
+                if (cand >= 0) {
+                    if (staged) tile_process_staged(aux, sm, t, cand, K, pw, cw, pl_l, stg);
+                    else tile_process_rows(d, aux, sm, t, cand, K, pw, cw, pl_l, tr);
+                }
+                __syncwarp();
+                if (prof) {
+                    g_tc_cycles[10] += (unsigned long long)(clock64() - q1);
+                    g_tc_cycles[11] += 1;
+                    g_probe_on = 0;
+                }
+                c0 = c1; m0 = m1; p0 = p1;
+                c1 = c2; m1 = m2; p1 = p2;
             }
         }
     }
@@ -1037,7 +1230,7 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
     } else {
         for (int t = 0; t < nt; ++t) {
             int cnt = sm.hcnt[t];
-            Nb *out = part + ((size_t)(t0 + t) * S + sp) * K;
+            Nb *out = part + ((size_t)(t0 + t) * part_stride + sp) * K;
             for (int j = tid; j < cnt; j += TC_THREADS) {
                 Nb e;
                 e.sim = *(volatile double *)(sm.hsim + (size_t)t * K + j);
@@ -1045,12 +1238,213 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
                 e.pad = 0;
                 out[j] = e;
             }
-            if (tid == 0) part_cnt[(t0 + t) * S + sp] = cnt;
+            if (tid == 0) part_cnt[(t0 + t) * part_stride + sp] = cnt;
         }
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tbase, 2 * TC_N);
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Postings pass as its own kernel: one warp per target, targets handed out dynamically.
+// Evaluates exactly every pair (target, candidate) that shares a tail place (each once, at its
+// smallest shared tail place) and emits the best K of them as one more partial list (slot S).
+// The K-th best similarity the dense kernel already found is a valid lower bound: candidates
+// below it are dropped without touching the heap.  Small shared-memory footprint -> twice the
+// resident warps of the tensor-core kernel, and no load imbalance between blocks.
+// ---------------------------------------------------------------------------------------
+constexpr int POST_WARPS = 8;
+constexpr int POST_STG_P = 64, POST_STG_C = 32, POST_DENSE = 64;
+
+__host__ __device__ constexpr int post_warp_bytes(int K) {
+    return ((8 * K + 8 * POST_STG_P + 8 * POST_STG_C + 8 * POST_DENSE + 4 * K + 4 * POST_STG_P + 4 * POST_STG_C + 64) + 15) / 16 * 16;
+}
+
+__global__ void __launch_bounds__(POST_WARPS * 32, 4)
+knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targets, int K, int S, int part_stride,
+                    int cat_dim, double pw, double cw, Nb *__restrict__ part, int *__restrict__ part_cnt,
+                    const double *__restrict__ seed_thr, int *__restrict__ work_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *w = smem_raw + (size_t)warp * post_warp_bytes(K);
+    TileSmem sm;
+    double *s_pval, *s_cval, *s_dense;
+    int *s_pcol, *s_ccol;
+    {
+        unsigned char *p = w;
+        sm.hsim = (double *)p;          p += 8 * K;
+        s_pval = (double *)p;           p += 8 * POST_STG_P;
+        s_cval = (double *)p;           p += 8 * POST_STG_C;
+        s_dense = (double *)p;          p += 8 * POST_DENSE;
+        sm.hidx = (int *)p;             p += 4 * K;
+        s_pcol = (int *)p;              p += 4 * POST_STG_P;
+        s_ccol = (int *)p;              p += 4 * POST_STG_C;
+        sm.hcnt = (int *)p;             p += 4;
+        sm.lock = (int *)p;             p += 4;
+        sm.tid_of = (int *)p;           p += 4;
+        sm.thr = (float *)p;            p += 4;
+        sm.stats = (unsigned int *)p;   p += 16;
+        sm.thr_stride = 1;
+        sm.tvec = nullptr;
+        sm.queue = nullptr;
+        sm.qn = nullptr;
+    }
+    if (lane < 4) sm.stats[lane] = 0;
+    const bool can_stage = aux.meta != nullptr && cat_dim <= POST_DENSE;
+    const long long lo = 0, hi = d.P;
+    for (;;) {
+        int tt = 0;
+        if (lane == 0) tt = atomicAdd(work_counter, 1);
+        tt = __shfl_sync(0xffffffffu, tt, 0);
+        if (tt >= n_targets) break;
+        const int tix = tidx[tt];
+        __syncwarp();
+        if (lane == 0) {
+            *sm.hcnt = 0;
+            *sm.lock = 0;
+            *sm.tid_of = tix;
+            *sm.thr = 0.0f;
+        }
+        __syncwarp();
+        if (tix >= 0) {
+            // lower bound of the K-th best: the seed, and every full list the dense kernel produced
+            double thr0 = seed_thr[tt];
+            for (int sp = 0; sp < S; ++sp) {
+                const int cnt = part_cnt[tt * part_stride + sp];
+                if (cnt >= K) {
+                    const Nb *src = part + ((size_t)tt * part_stride + sp) * K;
+                    double mn = 1.0e300;
+                    for (int j = lane; j < K; j += 32) mn = fmin(mn, src[j].sim);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+                    thr0 = fmax(thr0, mn);
+                }
+            }
+            TargetRows tr = load_target(d, tix);
+            StagedTarget stg;
+            bool staged = false;
+            if (tr.pn <= POST_STG_P && tr.cn <= POST_STG_C) {
+                unsigned long long sig = 0ULL;
+                for (int e = lane; e < POST_DENSE; e += 32) s_dense[e] = 0.0;
+                __syncwarp();
+                for (int e = lane; e < tr.pn; e += 32) {
+                    int col = tr.pcol[e];
+                    s_pcol[e] = col;
+                    s_pval[e] = tr.pval[e];
+                    sig |= 1ULL << sig_bit(col);
+                }
+                for (int e = lane; e < tr.cn; e += 32) {
+                    s_ccol[e] = tr.ccol[e];
+                    s_cval[e] = tr.cval[e];
+                    if (can_stage) s_dense[tr.ccol[e]] = tr.cval[e];
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) sig |= __shfl_xor_sync(0xffffffffu, sig, off);
+                tr.pcol = s_pcol;
+                tr.pval = s_pval;
+                tr.ccol = s_ccol;
+                tr.cval = s_cval;
+                staged = can_stage;
+                stg.t = tr.t;
+                stg.pn = tr.pn;
+                stg.pcol = s_pcol;
+                stg.pval = s_pval;
+                stg.sig = sig;
+                stg.cat_dense = s_dense;
+                stg.plen = tr.plen;
+                stg.clen = tr.clen;
+            }
+            __syncwarp();
+            const int ps = d.place.rowptr[tix], pn = d.place.rowptr[tix + 1] - ps;
+            for (int e0 = 0; e0 < pn; e0 += 32) {
+                int e = e0 + lane, start = 0, len = 0, pl = -1;
+                if (e < pn) {
+                    pl = d.place.col[ps + e];
+                    if (aux.head_slot[pl] < 0) {
+                        int b = aux.pcp[pl], en = aux.pcp[pl + 1];
+                        int l0 = b, h0 = en;
+                        while (l0 < h0) {
+                            int mid = (l0 + h0) >> 1;
+                            if (aux.pper[mid] < lo) l0 = mid + 1; else h0 = mid;
+                        }
+                        int l1 = l0, h1 = en;
+                        while (l1 < h1) {
+                            int mid = (l1 + h1) >> 1;
+                            if (aux.pper[mid] < hi) l1 = mid + 1; else h1 = mid;
+                        }
+                        start = l0;
+                        len = l1 - l0;
+                    }
+                }
+                int incl = len;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    int v = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += v;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                const int excl = incl - len;
+                auto locate = [&](int j, int &pl_out) -> int {
+                    int L = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        int probe = __shfl_sync(0xffffffffu, incl, L + step - 1);
+                        if (probe <= j) L += step;
+                    }
+                    L = min(L, 31);
+                    int ex_l = __shfl_sync(0xffffffffu, excl, L);
+                    int st_l = __shfl_sync(0xffffffffu, start, L);
+                    pl_out = __shfl_sync(0xffffffffu, pl, L);
+                    return j < total ? st_l + (j - ex_l) : -1;
+                };
+                auto fetch = [&](int j, int &cand_out, unsigned long long &meta_out, int &pl_out) {
+                    int at = locate(j, pl_out);
+                    cand_out = at >= 0 ? __ldg(aux.pper + at) : -1;
+                    meta_out = (cand_out >= 0 && aux.meta) ? __ldg(aux.meta + cand_out) : 0ULL;
+                };
+                auto prefetch_record = [&](int cand_, unsigned long long m_) {
+                    if (cand_ >= 0 && aux.meta) {
+                        const char *r = reinterpret_cast<const char *>(aux.rec + (m_ & 0xffffffffffULL));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128));
+                    }
+                };
+                int c0 = -1, c1 = -1, p0 = -1, p1 = -1;
+                unsigned long long m0 = 0, m1 = 0;
+                fetch(lane, c0, m0, p0);
+                fetch(32 + lane, c1, m1, p1);
+                prefetch_record(c0, m0);
+                for (int j0 = 0; j0 < total; j0 += 32) {
+                    int c2, p2;
+                    unsigned long long m2;
+                    fetch(j0 + 64 + lane, c2, m2, p2);
+                    prefetch_record(c1, m1);
+                    if (c0 >= 0) {
+                        if (staged) tile_process_staged(aux, sm, 0, c0, K, pw, cw, p0, stg, thr0);
+                        else tile_process_rows(d, aux, sm, 0, c0, K, pw, cw, p0, tr, thr0);
+                    }
+                    __syncwarp();
+                    c0 = c1; m0 = m1; p0 = p1;
+                    c1 = c2; m1 = m2; p1 = p2;
+                }
+            }
+        }
+        __syncwarp();
+        const int cnt = tix >= 0 ? *(volatile int *)sm.hcnt : 0;
+        Nb *out = part + ((size_t)tt * part_stride + S) * K;
+        for (int j = lane; j < cnt; j += 32) {
+            Nb e;
+            e.sim = *(volatile double *)(sm.hsim + j);
+            e.idx = *(volatile int *)(sm.hidx + j);
+            e.pad = 0;
+            out[j] = e;
+        }
+        if (lane == 0) part_cnt[tt * part_stride + S] = cnt;
+        __syncwarp();
+    }
+    if (lane < 4) atomicAdd(&g_tile_stats[lane], (unsigned long long)sm.stats[lane]);
 }
 
 // fp16 features, row-major [P][TC_D]: category vector / length, then the head places' values / length
@@ -1091,7 +1485,7 @@ knn_merge_kernel(const Nb *__restrict__ part, const int *__restrict__ part_cnt, 
                  Nb *__restrict__ nb_rank, Nb *__restrict__ nb_idx, int *__restrict__ nb_cnt) {
     const int tt = blockIdx.x, tid = threadIdx.x;
     __shared__ Nb buf[TOPK_BUF];
-    __shared__ int s_off[33];
+    __shared__ int s_off[34];
     if (tid == 0) {
         int o = 0;
         for (int s = 0; s < S; ++s) {
@@ -1370,6 +1764,11 @@ knn_rate_cols_kernel(const int *__restrict__ colptr, const int *__restrict__ cpe
     est[pl] = any ? xdiv(num, den) : __longlong_as_double(0x7ff8000000000000LL);
 }
 
+__global__ void knn_fill_int_stride_kernel(int *p, int n, int stride, int offset, int v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[(size_t)i * stride + offset] = v;
+}
+
 __global__ void knn_fill_int_kernel(int *p, long long n, int v) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -1402,6 +1801,7 @@ struct vrec_knn {
     DevBuf<short> d_head_slot;
     DevBuf<int> d_pcp, d_pper;
     DevBuf<double> d_seed_thr;
+    DevBuf<int> d_work;
     DevBuf<unsigned long long> d_meta;     // packed records for the exact evaluation
     DevBuf<double> d_rec;
     // tensor-core variant: fp16 row-major features over TC_D dims, its own (larger) head set
@@ -1680,26 +2080,31 @@ extern "C" int vrec_knn_load(vrec_ctx *ctx, int64_t P, const int64_t *person_id,
             }
             std::vector<unsigned long long> meta((size_t)P);
             std::vector<double> rec;
-            rec.reserve((size_t)(2 * P + 2 * (k->nnz_place + k->nnz_cat)));
+            rec.reserve((size_t)(10 * P + 2 * (k->nnz_place + k->nnz_cat)));
             for (int64_t i = 0; i < P && rc == VREC_OK; ++i) {
                 const int np = prp[i + 1] - prp[i], nc = crp[i + 1] - crp[i];
                 meta[i] = (unsigned long long)rec.size() | ((unsigned long long)np << 40) | ((unsigned long long)nc << 52);
                 rec.push_back(hpl[i]);
                 rec.push_back(hcl[i]);
                 size_t at = rec.size();
-                rec.resize(at + (size_t)((np + 1) / 2), 0.0);
+                rec.resize(at + (size_t)rec_cols_words(np), 0.0);
                 unsigned *pc = reinterpret_cast<unsigned *>(rec.data() + at);
                 for (int e = 0; e < np; ++e) {
                     int col = pci[prp[i] + e];
                     pc[e] = (unsigned)col | (hs_tc[col] < 0 ? REC_TAIL_TC : 0u) | (head_slot[col] < 0 ? REC_TAIL_TILE : 0u);
                 }
-                for (int e = 0; e < np; ++e) rec.push_back(pv[prp[i] + e]);
                 at = rec.size();
-                rec.resize(at + (size_t)((nc + 1) / 2), 0.0);
+                rec.resize(at + (size_t)rec_vals_words(np), 0.0);
+                for (int e = 0; e < np; ++e) rec[at + e] = pv[prp[i] + e];
+                at = rec.size();
+                rec.resize(at + (size_t)rec_cols_words(nc), 0.0);
                 unsigned *cc = reinterpret_cast<unsigned *>(rec.data() + at);
                 for (int e = 0; e < nc; ++e) cc[e] = (unsigned)cci[crp[i] + e];
-                for (int e = 0; e < nc; ++e) rec.push_back(cv[crp[i] + e]);
+                at = rec.size();
+                rec.resize(at + (size_t)rec_vals_words(nc), 0.0);
+                for (int e = 0; e < nc; ++e) rec[at + e] = cv[crp[i] + e];
             }
+            rec.resize(rec.size() + 8, 0.0);          // slack: the 128-bit loads may touch the padding of the last record
             if (rc == VREC_OK) rc = k->d_meta.upload(meta.data(), meta.size(), s);
             if (rc == VREC_OK) rc = k->d_rec.upload(rec.data(), rec.size(), s);
             if (rc == VREC_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = VREC_ECUDA;
@@ -1786,6 +2191,18 @@ extern "C" int vrec_knn_debug_stats(vrec_knn *k, uint64_t *out4) {
     return VREC_OK;
 }
 
+// Debug: reads and clears the exact-evaluation probe (block 0 warp 0, postings pass): out4 = {meta wait,
+// record + place merge + division, category merge + division, evaluations}.
+extern "C" int vrec_knn_debug_probe(vrec_knn *k, uint64_t *out4) {
+    if (!k || !out4) return VREC_EINVAL;
+    VREC_CUDA(cudaSetDevice(k->ctx->device));
+    VREC_CUDA(cudaStreamSynchronize(k->ctx->stream));
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    VREC_CUDA(cudaMemcpyFromSymbol(out4, g_probe, 32));
+    VREC_CUDA(cudaMemcpyToSymbol(g_probe, z, sizeof(z)));
+    return VREC_OK;
+}
+
 // Debug: per-block cycles of the last tensor-core main pass: out[0..n) dense phase, out[n..2n) postings phase.
 extern "C" int vrec_knn_debug_tc_block_cycles(vrec_knn *k, uint64_t *out, int n) {
     if (!k || !out || n < 0 || n > 1024) return VREC_EINVAL;
@@ -1859,15 +2276,16 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     // 0 = automatic (tensor cores > CUDA-core tile > exact scan), 1 = exact scan, 2 = tile, 3 = tensor cores
     const bool use_tc = k->tc_ok && K <= TC_MAX_K && (k->opt_kernel == 0 || k->opt_kernel == 3);
     const bool tiled = !use_tc && k->tile_ok && k->opt_kernel != 1;
-    int smax = std::max(1, std::min(32, TOPK_BUF / K));
+    const bool filtered = use_tc || tiled;
+    // filtered kernels: slot S of every target's partial lists belongs to the postings kernel
+    int smax = std::max(1, std::min(32, TOPK_BUF / K - (filtered ? 1 : 0)));
     int S = (int)k->opt_splits;
     int T = 1;
     size_t smem = 0;
     if (use_tc) {
         T = TC_M;
         smem = 1024 + (1 + TC_STAGES) * (size_t)TC_TILE_BYTES + 12 * (size_t)TC_M * K +
-               sizeof(unsigned long long) * TC_QCAP +
-               sizeof(float) * TC_M + sizeof(int) * 3 * TC_M + 16;
+               sizeof(unsigned long long) * TC_QCAP + sizeof(float) * TC_M + sizeof(int) * 3 * TC_M + 16;
     } else if (tiled) {
         // targets per block: heaps must fit next to the queue and the target vectors
         T = (int)std::max<int64_t>(1, std::min<int64_t>(64, (48 * 1024) / (12 * (int64_t)K)));
@@ -1883,32 +2301,36 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     }
     S = std::min(S, smax);
     if ((int64_t)S > std::max<int64_t>(1, k->P)) S = 1;
-    VREC_TRY(k->d_part.ensure((size_t)tn * S * K));
-    VREC_TRY(k->d_part_cnt.ensure((size_t)tn * S));
+    const int SP = filtered ? S + 1 : S;                 // partial lists per target
+    VREC_TRY(k->d_part.ensure((size_t)tn * SP * K));
+    VREC_TRY(k->d_part_cnt.ensure((size_t)tn * SP));
     VREC_TRY(k->d_nb_rank.ensure((size_t)tn * K));
     VREC_TRY(k->d_nb_idx.ensure((size_t)tn * K));
     VREC_TRY(k->d_nb_cnt.ensure((size_t)tn));
-    if (use_tc || tiled) {
+    if (filtered) {
         VREC_TRY(k->d_seed_thr.ensure((size_t)tn));
+        VREC_TRY(k->d_work.ensure(1));
         // seed pass: exact top-K of a strided sample -> lower bound of every target's K-th best
         long long sample = std::min<long long>(k->P, std::max<long long>(4096, std::min<long long>(65536, k->P / 16)));
         long long stride = std::max<long long>(1, k->P / sample);
         sample = (k->P + stride - 1) / stride;
-        const int main_mode = k->opt_debug_skip_postings ? 2 : 0;
+        // main pass: dense filter only (mode 2); the tail-place pairs are the postings kernel's
+        const int main_mode = 2;
+        TileAux aux;
         if (use_tc) {
             static bool attr_tc = false;
             if (!attr_tc) {
                 VREC_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
                 attr_tc = true;
             }
-            TileAux aux{nullptr, 0, k->d_head_slot_tc.p, k->d_pcp.p, k->d_pper.p, k->d_meta.p, k->d_rec.p, REC_TAIL_TC};
+            aux = TileAux{nullptr, 0, k->d_head_slot_tc.p, k->d_pcp.p, k->d_pper.p, k->d_meta.p, k->d_rec.p, REC_TAIL_TC};
             knn_tc_kernel<<<dim3(tiles, 1), TC_THREADS, smem, ctx->stream>>>(
                 k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, 1, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p,
-                stride, sample, 1, k->d_seed_thr.p);
+                stride, sample, 1, k->d_seed_thr.p, SP);
             VREC_LAUNCHED(ctx);
             knn_tc_kernel<<<dim3(tiles, S), TC_THREADS, smem, ctx->stream>>>(
                 k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, S, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p,
-                1, k->P, main_mode, k->d_seed_thr.p);
+                1, k->P, main_mode, k->d_seed_thr.p, SP);
             VREC_LAUNCHED(ctx);
         } else {
             static bool attr_set = false;
@@ -1916,15 +2338,33 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                 VREC_CUDA(cudaFuncSetAttribute(knn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 attr_set = true;
             }
-            TileAux aux{k->d_feat.p, k->fstride, k->d_head_slot.p, k->d_pcp.p, k->d_pper.p, k->d_meta.p, k->d_rec.p,
-                        REC_TAIL_TILE};
+            aux = TileAux{k->d_feat.p, k->fstride, k->d_head_slot.p, k->d_pcp.p, k->d_pper.p, k->d_meta.p, k->d_rec.p,
+                          REC_TAIL_TILE};
             knn_tile_kernel<<<dim3(tiles, 1), TILE_THREADS, smem, ctx->stream>>>(
                 k->dev(), aux, k->d_tidx.p, tn, T, K, 1, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p, stride, sample,
-                1, k->d_seed_thr.p);
+                1, k->d_seed_thr.p, SP);
             VREC_LAUNCHED(ctx);
             knn_tile_kernel<<<dim3(tiles, S), TILE_THREADS, smem, ctx->stream>>>(
                 k->dev(), aux, k->d_tidx.p, tn, T, K, S, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p, 1, k->P,
-                main_mode, k->d_seed_thr.p);
+                main_mode, k->d_seed_thr.p, SP);
+            VREC_LAUNCHED(ctx);
+        }
+        // postings kernel: one warp per target, dynamic distribution
+        VREC_CUDA(cudaMemsetAsync(k->d_work.p, 0, sizeof(int), ctx->stream));
+        const size_t psmem = (size_t)POST_WARPS * post_warp_bytes(K);
+        static bool attr_post = false;
+        if (!attr_post) {
+            VREC_CUDA(cudaFuncSetAttribute(knn_postings_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_post = true;
+        }
+        int pblocks = std::max(1, std::min(ctx->sm_count * 4, (tn + POST_WARPS - 1) / POST_WARPS));
+        knn_postings_kernel<<<pblocks, POST_WARPS * 32, psmem, ctx->stream>>>(
+            k->dev(), aux, k->d_tidx.p, k->opt_debug_skip_postings ? 0 : tn, K, S, SP, k->cat_dim, pw, cw, k->d_part.p,
+            k->d_part_cnt.p, k->d_seed_thr.p, k->d_work.p);
+        VREC_LAUNCHED(ctx);
+        if (k->opt_debug_skip_postings) {
+            // timing experiments only: the postings slots stay empty (results are then WRONG)
+            knn_fill_int_stride_kernel<<<(tn + 255) / 256, 256, 0, ctx->stream>>>(k->d_part_cnt.p, tn, SP, S, 0);
             VREC_LAUNCHED(ctx);
         }
     } else {
@@ -1933,7 +2373,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                                                                k->d_part_cnt.p);
         VREC_LAUNCHED(ctx);
     }
-    knn_merge_kernel<<<tn, MERGE_THREADS, 0, ctx->stream>>>(k->d_part.p, k->d_part_cnt.p, K, S, k->d_nb_rank.p,
+    knn_merge_kernel<<<tn, MERGE_THREADS, 0, ctx->stream>>>(k->d_part.p, k->d_part_cnt.p, K, SP, k->d_nb_rank.p,
                                                            k->d_nb_idx.p, k->d_nb_cnt.p);
     VREC_LAUNCHED(ctx);
     return VREC_OK;

@@ -59,6 +59,14 @@ for s in range(a.warmup + a.steps):
     st = [int(x) for x in stats]
     lib.vrec_knn_debug_tc_cycles(rs._h, cyc)
     cy = [int(x) for x in cyc]
+    if cy[11]:
+        print(f"   postings warp-iteration (block0 warp0): candidate id load {cy[9] / cy[11]:.0f} cycles, exact eval + insert "
+              f"{cy[10] / cy[11]:.0f} cycles, iterations {cy[11]}")
+    pb = (C.c_uint64 * 4)()
+    lib.vrec_knn_debug_probe(rs._h, pb)
+    if pb[3]:
+        print(f"   exact eval (block0 warp0, per warp-iteration): meta wait {pb[0] / pb[3]:.0f}, record+place {pb[1] / pb[3]:.0f}, "
+              f"category {pb[2] / pb[3]:.0f} cycles")
     nb = min(1024, (B + 127) // 128)
     bc = (C.c_uint64 * (2 * nb))()
     lib.vrec_knn_debug_tc_block_cycles(rs._h, bc, nb)
