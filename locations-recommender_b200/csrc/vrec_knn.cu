@@ -1811,6 +1811,7 @@ struct vrec_knn {
     // options
     int64_t opt_rating_path = 0, opt_tile = 0, opt_splits = 0, opt_kernel = 0;
     int64_t opt_debug_skip_postings = 0;     // timing experiments only: results are then WRONG
+    int64_t opt_tc_seed = 0;                 // run the sampled seed pass before the tensor-core main pass
     // scratch
     DevBuf<long long> d_targets;
     DevBuf<int> d_tidx, d_status;
@@ -2168,6 +2169,10 @@ extern "C" int vrec_knn_set_option(vrec_knn *k, const char *name, int64_t value)
         k->opt_kernel = value;
         return VREC_OK;
     }
+    if (!strcmp(name, "tc_seed")) {
+        k->opt_tc_seed = value;
+        return VREC_OK;
+    }
     if (!strcmp(name, "debug_skip_postings")) {
         k->opt_debug_skip_postings = value;
         return VREC_OK;
@@ -2324,10 +2329,19 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                 attr_tc = true;
             }
             aux = TileAux{nullptr, 0, k->d_head_slot_tc.p, k->d_pcp.p, k->d_pper.p, k->d_meta.p, k->d_rec.p, REC_TAIL_TC};
-            knn_tc_kernel<<<dim3(tiles, 1), TC_THREADS, smem, ctx->stream>>>(
-                k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, 1, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p,
-                stride, sample, 1, k->d_seed_thr.p, SP);
-            VREC_LAUNCHED(ctx);
+            // No seed pass here: it cost more (heap warm-up on a sample, ~9 ms per 19K targets) than the
+            // ~250 extra survivors per target it saves the main pass (~2 ms).  Optional via "tc_seed".
+            if (k->opt_tc_seed) {
+                long long smp = std::min<long long>(k->P, std::max<long long>(TC_N, k->opt_tc_seed));
+                long long str = std::max<long long>(1, k->P / smp);
+                smp = (k->P + str - 1) / str;
+                knn_tc_kernel<<<dim3(tiles, 1), TC_THREADS, smem, ctx->stream>>>(
+                    k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, 1, k->cat_dim, pw, cw, k->d_part.p,
+                    k->d_part_cnt.p, str, smp, 1, k->d_seed_thr.p, SP);
+                VREC_LAUNCHED(ctx);
+            } else {
+                VREC_CUDA(cudaMemsetAsync(k->d_seed_thr.p, 0, sizeof(double) * (size_t)tn, ctx->stream));
+            }
             knn_tc_kernel<<<dim3(tiles, S), TC_THREADS, smem, ctx->stream>>>(
                 k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, S, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p,
                 1, k->P, main_mode, k->d_seed_thr.p, SP);
