@@ -1447,6 +1447,236 @@ knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_t
     if (lane < 4) atomicAdd(&g_tile_stats[lane], (unsigned long long)sm.stats[lane]);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Warp-specialised tensor-core kernel (the default batch path).
+//   warp 16 (one elected thread) = producer: streams B tiles with TMA bulk copies -- the fp16
+//       features are stored in HBM as ready-made 32 KB shared-memory images (128 persons, K-major,
+//       SWIZZLE_128B), so one cp.async.bulk per tile lands them in place -- and issues the MMA
+//       chains into two alternating TMEM accumulators;
+//   warps 0..15 = consumers: pull a tile's accumulator out of TMEM, apply the threshold filter,
+//       queue the survivors and (every few tiles, by a named-barrier vote) evaluate them exactly.
+// Synchronisation is mbarrier-only on the data path: full[stage] (TMA transaction bytes),
+// tfull[acc] / sempty[stage] (tcgen05.commit), tempty[acc] (one arrival per consumer warp).
+// ---------------------------------------------------------------------------------------
+constexpr int WS_WORKERS = 512;
+constexpr int WS_THREADS = WS_WORKERS + 32;
+constexpr int WS_VOTE_EVERY = 4;
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const int *__restrict__ tidx,
+                 int n_targets, int K, int S, int cat_dim, double pw, double cw, Nb *__restrict__ part,
+                 int *__restrict__ part_cnt, const double *__restrict__ seed_thr, int part_stride, int total_tiles) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[TC_STAGES], sempty[TC_STAGES], tfull[2], tempty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ unsigned int s_stats[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool worker = tid < WS_WORKERS;
+    const int tile_m = blockIdx.x, sp = blockIdx.y;
+    const int t0 = tile_m * TC_M;
+    const int nt = min(TC_M, n_targets - t0);
+    unsigned char *base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *sA = base, *sB0 = base + TC_TILE_BYTES;
+    TileSmem sm;
+    {
+        unsigned char *p = base + (1 + TC_STAGES) * TC_TILE_BYTES;
+        sm.hsim = (double *)p;                      p += sizeof(double) * (size_t)TC_M * K;
+        sm.queue = (unsigned long long *)p;         p += sizeof(unsigned long long) * TC_QCAP;
+        sm.hidx = (int *)p;                         p += sizeof(int) * (size_t)TC_M * K;
+        sm.thr = (float *)p;                        p += sizeof(float) * TC_M;
+        sm.thr_stride = 1;
+        sm.tvec = nullptr;
+        sm.hcnt = (int *)p;                         p += sizeof(int) * TC_M;
+        sm.lock = (int *)p;                         p += sizeof(int) * TC_M;
+        sm.tid_of = (int *)p;                       p += sizeof(int) * TC_M;
+        sm.qn = (int *)p;
+        sm.stats = s_stats;
+    }
+    if (tid < 4) s_stats[tid] = 0;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 2 * TC_N);
+    if (tid == 0) {
+        for (int s_ = 0; s_ < TC_STAGES; ++s_) {
+            tc::mbar_init(&full[s_], 1);
+            tc::mbar_init(&sempty[s_], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(&tfull[a], 1);
+            tc::mbar_init(&tempty[a], WS_WORKERS / 32);
+        }
+        tc::mbar_init_fence();
+        *sm.qn = 0;
+    }
+    // this CTA's share of the candidate tiles, visited in a rotated order
+    const int tlo = (int)((long long)total_tiles * sp / S), thi = (int)((long long)total_tiles * (sp + 1) / S);
+    const int ntiles = thi - tlo;
+    const int rot = ntiles > 0 ? (int)(((long long)blockIdx.x * 67 + (long long)blockIdx.y * 29) % ntiles) : 0;
+    auto tile_index = [&](int i) {
+        int w_ = i + rot;
+        if (w_ >= ntiles) w_ -= ntiles;
+        return tlo + w_;
+    };
+    if (worker) {
+        for (int t = tid; t < TC_M; t += WS_WORKERS) {
+            int tix = t < nt ? tidx[t0 + t] : -1;
+            sm.tid_of[t] = tix;
+            sm.hcnt[t] = 0;
+            sm.lock[t] = 0;
+            sm.thr[t] = tix >= 0 ? __double2float_rd(seed_thr[t0 + t]) : 3.0e38f;
+        }
+    }
+    __syncthreads();
+    if (worker) {
+        // A tile: the targets' features (read from their tile images) with the weights folded in
+        for (int q = tid; q < TC_M * (TC_D / 8); q += WS_WORKERS) {
+            int r = q >> 4, c = q & 15;
+            int tix = sm.tid_of[r];
+            __align__(16) __half h[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) h[e] = __float2half(0.0f);
+            if (tix >= 0) {
+                const unsigned char *img = reinterpret_cast<const unsigned char *>(featsw) + (size_t)(tix >> 7) * TC_TILE_BYTES;
+                uint4 raw = *reinterpret_cast<const uint4 *>(img + tc::sw128_offset(TC_N, tix & 127, c));
+                const __half *src = reinterpret_cast<const __half *>(&raw);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    int dd = c * 8 + e;
+                    h[e] = __float2half(__half2float(src[e]) * (float)(dd < cat_dim ? cw : pw));
+                }
+            }
+            *reinterpret_cast<uint4 *>(sA + tc::sw128_offset(TC_M, r, c)) = *reinterpret_cast<const uint4 *>(h);
+        }
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_base_s;
+
+    if (!worker) {
+        // ================= producer: TMA loads + MMA issue (one thread) =================
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_f16(TC_M, TC_N);
+            const uint32_t a_addr = tc::smem_u32(sA), b_addr0 = tc::smem_u32(sB0);
+            auto issue_load = [&](int li) {
+                const int st = li % TC_STAGES;
+                if (li >= TC_STAGES) tc::mbar_wait(&sempty[st], (uint32_t)((li / TC_STAGES - 1) & 1));   // MMA(li-3) done
+                tc::mbar_expect_tx(&full[st], TC_TILE_BYTES);
+                tc::bulk_copy_g2s(sB0 + (size_t)st * TC_TILE_BYTES,
+                                  reinterpret_cast<const unsigned char *>(featsw) + (size_t)tile_index(li) * TC_TILE_BYTES,
+                                  TC_TILE_BYTES, &full[st]);
+            };
+            for (int li = 0; li < min(2, ntiles); ++li) issue_load(li);
+            for (int i = 0; i < ntiles; ++i) {
+                if (i + 2 < ntiles) issue_load(i + 2);
+                const int st = i % TC_STAGES, a = i & 1;
+                tc::mbar_wait(&full[st], (uint32_t)((i / TC_STAGES) & 1));                 // B(i) landed
+                if (i >= 2) tc::mbar_wait(&tempty[a], (uint32_t)((i / 2 - 1) & 1));        // accumulator drained
+                tc::fence_after_sync();
+                const uint32_t b_addr = b_addr0 + (uint32_t)st * TC_TILE_BYTES;
+                const uint32_t acc = tbase + (uint32_t)a * TC_N;
+#pragma unroll
+                for (int k = 0; k < TC_D / 16; ++k) {
+                    uint64_t da = tc::make_desc_sw128(tc::sw128_kstep_addr(a_addr, TC_M, k));
+                    uint64_t db = tc::make_desc_sw128(tc::sw128_kstep_addr(b_addr, TC_N, k));
+                    tc::mma_f16(acc, da, db, idesc, k > 0);
+                }
+                tc::mma_commit(&tfull[a]);        // accumulator ready for the consumers
+                tc::mma_commit(&sempty[st]);      // B stage reusable
+            }
+        }
+        __syncwarp();                             // the idle lanes of the producer warp wait for lane 0 here
+    } else {
+        // ================= consumers: TMEM epilogue + exact survivors =================
+        const int lq = warp & 3, cq = warp >> 2;
+        const int my_t = lq * 32 + lane;
+        for (int i = 0; i <= ntiles; ++i) {
+            const bool live = i < ntiles;
+            if (!live || (i % WS_VOTE_EVERY) == 0) {
+                // block-uniform decision (consumers only) whether the survivor queue is drained now
+                const int drain = tc::bar_red_or(1, WS_WORKERS, (*(volatile int *)sm.qn >= TC_QCAP / 2) || !live);
+                if (drain) {
+                    int m = min(*(volatile int *)sm.qn, TC_QCAP);
+                    for (int qi = tid; qi < m; qi += WS_WORKERS) {
+                        unsigned long long e = sm.queue[qi];
+                        tile_process(d, aux, sm, (int)(e >> 32), (int)(unsigned)(e & 0xffffffffu), K, pw, cw, -1);
+                    }
+                    tc::bar_sync(1, WS_WORKERS);
+                    if (tid == 0) *sm.qn = 0;
+                    tc::bar_sync(1, WS_WORKERS);
+                }
+            }
+            if (!live) break;
+            const int a = i & 1;
+            tc::mbar_wait(&tfull[a], (uint32_t)((i / 2) & 1));
+            tc::fence_after_sync();
+            const float thr = *(volatile float *)(sm.thr + my_t);
+            const long long tile = (long long)tile_index(i) * TC_N;
+            const int c0 = cq * 32;
+            float v[32];
+            tc::tmem_ld32(tbase + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * TC_N + c0), v);
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tempty[a]);            // this warp is done with the accumulator
+            unsigned pass = 0;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) pass |= (v[jj] * 1.002f + 2e-5f >= thr ? 1u : 0u) << jj;
+            while (pass) {
+                const int jj = __ffs(pass) - 1;
+                pass &= pass - 1;
+                const long long j = tile + c0 + jj;
+                if (j < d.P) {
+                    int pos = atomicAdd(sm.qn, 1);
+                    if (pos < TC_QCAP) {
+                        sm.queue[pos] = ((unsigned long long)my_t << 32) | (unsigned long long)(unsigned)j;
+                    } else {
+                        atomicAdd(sm.stats + 3, 1u);
+                        tile_process(d, aux, sm, my_t, (int)j, K, pw, cw, -1);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < 4) atomicAdd(&g_tile_stats[tid], (unsigned long long)s_stats[tid]);
+    if (worker) {
+        for (int t = 0; t < nt; ++t) {
+            int cnt = sm.hcnt[t];
+            Nb *out = part + ((size_t)(t0 + t) * part_stride + sp) * K;
+            for (int j = tid; j < cnt; j += WS_WORKERS) {
+                Nb e;
+                e.sim = sm.hsim[(size_t)t * K + j];
+                e.idx = sm.hidx[(size_t)t * K + j];
+                e.pad = 0;
+                out[j] = e;
+            }
+            if (tid == 0) part_cnt[(t0 + t) * part_stride + sp] = cnt;
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 2 * TC_N);
+}
+
+// fp16 features as ready-made shared-memory tile images: tile b = persons [128 b, 128 b + 128),
+// 32 KB each in the SWIZZLE_128B K-major layout of vrec_tc.cuh (rows past P stay zero)
+__global__ void knn_features16sw_kernel(KnnDev d, const short *__restrict__ head_slot, int cat_dim,
+                                        unsigned char *__restrict__ featsw) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.P) return;
+    __half row[TC_D];
+    for (int dd = 0; dd < TC_D; ++dd) row[dd] = __float2half(0.0f);
+    double cl = d.cat.len[i], pl = d.place.len[i];
+    for (int k = d.cat.rowptr[i]; k < d.cat.rowptr[i + 1]; ++k) row[d.cat.col[k]] = __double2half(d.cat.val[k] / cl);
+    for (int k = d.place.rowptr[i]; k < d.place.rowptr[i + 1]; ++k) {
+        int slot = head_slot[d.place.col[k]];
+        if (slot >= 0) row[cat_dim + slot] = __double2half(d.place.val[k] / pl);
+    }
+    unsigned char *img = featsw + (size_t)(i >> 7) * TC_TILE_BYTES;
+    for (int c = 0; c < TC_D / 8; ++c)
+        *reinterpret_cast<uint4 *>(img + tc::sw128_offset(TC_N, (int)(i & 127), c)) = *reinterpret_cast<const uint4 *>(row + c * 8);
+}
+
 // fp16 features, row-major [P][TC_D]: category vector / length, then the head places' values / length
 __global__ void knn_features16_kernel(KnnDev d, const short *__restrict__ head_slot, int cat_dim,
                                       __half *__restrict__ feat16) {
@@ -1807,6 +2037,8 @@ struct vrec_knn {
     // tensor-core variant: fp16 row-major features over TC_D dims, its own (larger) head set
     bool tc_ok = false;
     DevBuf<__half> d_feat16;
+    DevBuf<unsigned char> d_featsw;          // the same features as 32 KB swizzled tile images
+    int tc_tiles = 0;
     DevBuf<short> d_head_slot_tc;
     // options
     int64_t opt_rating_path = 0, opt_tile = 0, opt_splits = 0, opt_kernel = 0;
@@ -2065,6 +2297,18 @@ extern "C" int vrec_knn_load(vrec_ctx *ctx, int64_t P, const int64_t *person_id,
                 ctx->launches++;
                 if (cudaGetLastError() != cudaSuccess) rc = VREC_ECUDA;
             }
+            if (rc == VREC_OK) {
+                k->tc_tiles = (int)((P + TC_N - 1) / TC_N);
+                rc = k->d_featsw.alloc((size_t)k->tc_tiles * TC_TILE_BYTES);
+                if (rc == VREC_OK && cudaMemsetAsync(k->d_featsw.p, 0, (size_t)k->tc_tiles * TC_TILE_BYTES, s) != cudaSuccess)
+                    rc = VREC_ECUDA;
+                if (rc == VREC_OK) {
+                    knn_features16sw_kernel<<<(int)((P + 127) / 128), 128, 0, s>>>(k->dev(), k->d_head_slot_tc.p, cat_dim,
+                                                                                  k->d_featsw.p);
+                    ctx->launches++;
+                    if (cudaGetLastError() != cudaSuccess) rc = VREC_ECUDA;
+                }
+            }
             k->tc_ok = rc == VREC_OK;
         }
         // packed records (needs the device-computed lengths): one contiguous block per person
@@ -2157,8 +2401,8 @@ extern "C" int vrec_knn_set_option(vrec_knn *k, const char *name, int64_t value)
         k->opt_tile = value;
         return VREC_OK;
     }
-    if (!strcmp(name, "knn_kernel") && value >= 0 && value <= 3) {
-        if (value == 3 && !k->tc_ok) {
+    if (!strcmp(name, "knn_kernel") && value >= 0 && value <= 4) {
+        if (value >= 3 && !k->tc_ok) {
             vrec_set_error("knn_kernel=3 (tensor cores) needs cat_dim <= 64 and non-negative rating values");
             return VREC_EINVAL;
         }
@@ -2278,8 +2522,10 @@ bool use_gather_path(const vrec_knn *k, int K) {
 // neighbours of a tile of targets by the fused top-K kernels (K <= 1024)
 int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     vrec_ctx *ctx = k->ctx;
-    // 0 = automatic (tensor cores > CUDA-core tile > exact scan), 1 = exact scan, 2 = tile, 3 = tensor cores
-    const bool use_tc = k->tc_ok && K <= TC_MAX_K && (k->opt_kernel == 0 || k->opt_kernel == 3);
+    // 0 = automatic (tensor cores > CUDA-core tile > exact scan), 1 = exact scan, 2 = tile,
+    // 3 = tensor cores (all warps do everything), 4 = tensor cores, warp-specialised (the automatic choice)
+    const bool use_tc = k->tc_ok && K <= TC_MAX_K && (k->opt_kernel == 0 || k->opt_kernel >= 3);
+    const bool use_ws = use_tc && k->opt_kernel != 3;
     const bool tiled = !use_tc && k->tile_ok && k->opt_kernel != 1;
     const bool filtered = use_tc || tiled;
     // filtered kernels: slot S of every target's partial lists belongs to the postings kernel
@@ -2342,10 +2588,22 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
             } else {
                 VREC_CUDA(cudaMemsetAsync(k->d_seed_thr.p, 0, sizeof(double) * (size_t)tn, ctx->stream));
             }
-            knn_tc_kernel<<<dim3(tiles, S), TC_THREADS, smem, ctx->stream>>>(
-                k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, S, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p,
-                1, k->P, main_mode, k->d_seed_thr.p, SP);
-            VREC_LAUNCHED(ctx);
+            if (use_ws) {
+                static bool attr_ws = false;
+                if (!attr_ws) {
+                    VREC_CUDA(cudaFuncSetAttribute(knn_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+                    attr_ws = true;
+                }
+                knn_tc_ws_kernel<<<dim3(tiles, S), WS_THREADS, smem, ctx->stream>>>(
+                    k->dev(), aux, (const __half *)k->d_featsw.p, k->d_tidx.p, tn, K, S, k->cat_dim, pw, cw, k->d_part.p,
+                    k->d_part_cnt.p, k->d_seed_thr.p, SP, k->tc_tiles);
+                VREC_LAUNCHED(ctx);
+            } else {
+                knn_tc_kernel<<<dim3(tiles, S), TC_THREADS, smem, ctx->stream>>>(
+                    k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, S, k->cat_dim, pw, cw, k->d_part.p,
+                    k->d_part_cnt.p, 1, k->P, main_mode, k->d_seed_thr.p, SP);
+                VREC_LAUNCHED(ctx);
+            }
         } else {
             static bool attr_set = false;
             if (!attr_set) {

@@ -107,6 +107,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (no tensor map): `bytes` (multiple of 16) land at smem_dst and are
+// accounted as transaction bytes on `bar`
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// named barrier `id` over `nthreads` threads with an OR-reduction of a predicate
+__device__ __forceinline__ int bar_red_or(int id, int nthreads, int pred) {
+    int out;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %3, 0;\n\t"
+        "barrier.cta.red.or.pred.aligned p, %1, %2, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(out)
+        : "r"(id), "r"(nthreads), "r"(pred)
+        : "memory");
+    return out;
+}
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("barrier.cta.sync.aligned %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // 32 lanes x 32 columns of fp32 accumulators: thread i of the warp gets lane (taddr.lane + i)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];

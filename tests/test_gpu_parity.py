@@ -160,11 +160,11 @@ def _check_knn(vrec, oracle, rs, inp, pw, cw, k, targets, flt, max_recs):
 
 @pytest.mark.parametrize("seed", [1, 2])
 @pytest.mark.parametrize("k", [1, 7, 50, 5000])
-@pytest.mark.parametrize("path,kernel", [(0, 0), (1, 1), (1, 2), (1, 3), (2, 0)])
+@pytest.mark.parametrize("path,kernel", [(0, 0), (1, 1), (1, 2), (1, 3), (1, 4), (2, 0)])
 def test_knn_random_bit_exact(vrec, ctx, synth, oracle, seed, k, path, kernel):
     # path: rating reduction (0 auto, 1 neighbour-row gather, 2 column scan)
     # kernel: similarity + top-K (0 auto, 1 per-target exact scan, 2 tiled fp32 filter + exact survivors,
-    #         3 tcgen05 fp16 filter + exact survivors)
+    #         3 tcgen05 fp16 filter + exact survivors, 4 the same, warp-specialised with TMA bulk copies)
     if path == 1 and k > 1024:
         pytest.skip("gather path needs k <= 1024")
     inp = synth.random_knn_inputs(700, 60, 9, seed=seed, separate_ratings=(seed == 2))
@@ -253,7 +253,7 @@ def test_knn_g2_shape(vrec, ctx, synth, oracle):
     rs.set_option("splits", 1)
     _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 50, targets[:10], places.id, 10)
     rs.set_option("splits", 0)
-    for kern in (1, 2, 3):                  # exact scan, CUDA-core tile, tensor-core tile: same answers
+    for kern in (1, 2, 3, 4):               # exact scan, CUDA-core tile, tensor-core tiles: same answers
         rs.set_option("knn_kernel", kern)
         _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 50, targets[:10], places.id, 10)
     rs.set_option("knn_kernel", 0)
