@@ -1460,8 +1460,9 @@ knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_t
 // tfull[acc] / sempty[stage] (tcgen05.commit), tempty[acc] (one arrival per consumer warp).
 // ---------------------------------------------------------------------------------------
 constexpr int WS_WORKERS = 512;
-constexpr int WS_THREADS = WS_WORKERS + 32;
+constexpr int WS_THREADS = WS_WORKERS + 64;           // + MMA warp + loader warp
 constexpr int WS_VOTE_EVERY = 4;
+constexpr int WS_BOOT_TILES = 256;   // multiple of 16; 64 groups of 512 candidates per target
 
 __global__ void __launch_bounds__(WS_THREADS, 1)
 knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const int *__restrict__ tidx,
@@ -1511,8 +1512,12 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
     const int tlo = (int)((long long)total_tiles * sp / S), thi = (int)((long long)total_tiles * (sp + 1) / S);
     const int ntiles = thi - tlo;
     const int rot = ntiles > 0 ? (int)(((long long)blockIdx.x * 67 + (long long)blockIdx.y * 29) % ntiles) : 0;
+    // Bootstrap: the first `boot` tiles of the sequence are only scanned for group maxima (below) and
+    // are visited again, normally, at the end of the sequence.
+    const int boot = ntiles >= 2 * WS_BOOT_TILES ? WS_BOOT_TILES : 0;
+    const int nseq = ntiles + boot;
     auto tile_index = [&](int i) {
-        int w_ = i + rot;
+        int w_ = (i >= ntiles ? i - ntiles : i) + rot;
         if (w_ >= ntiles) w_ -= ntiles;
         return tlo + w_;
     };
@@ -1554,24 +1559,36 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
     const uint32_t tbase = tmem_base_s;
 
     if (!worker) {
-        // ================= producer: TMA loads + MMA issue (one thread) =================
-        if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_f16(TC_M, TC_N);
-            const uint32_t a_addr = tc::smem_u32(sA), b_addr0 = tc::smem_u32(sB0);
-            auto issue_load = [&](int li) {
-                const int st = li % TC_STAGES;
-                if (li >= TC_STAGES) tc::mbar_wait(&sempty[st], (uint32_t)((li / TC_STAGES - 1) & 1));   // MMA(li-3) done
-                tc::mbar_expect_tx(&full[st], TC_TILE_BYTES);
-                tc::bulk_copy_g2s(sB0 + (size_t)st * TC_TILE_BYTES,
-                                  reinterpret_cast<const unsigned char *>(featsw) + (size_t)tile_index(li) * TC_TILE_BYTES,
-                                  TC_TILE_BYTES, &full[st]);
-            };
-            for (int li = 0; li < min(2, ntiles); ++li) issue_load(li);
-            for (int i = 0; i < ntiles; ++i) {
-                if (i + 2 < ntiles) issue_load(i + 2);
+        const uint32_t idesc = tc::make_idesc_f16(TC_M, TC_N);
+        const uint32_t a_addr = tc::smem_u32(sA), b_addr0 = tc::smem_u32(sB0);
+        if (warp == WS_WORKERS / 32 + 1) {
+            // ================= loader warp: TMA bulk copies, up to TC_STAGES tiles ahead =================
+            if (lane == 0) {
+                for (int li = 0; li < nseq; ++li) {
+                    const int st = li % TC_STAGES;
+                    if (li >= TC_STAGES) tc::mbar_wait(&sempty[st], (uint32_t)((li / TC_STAGES - 1) & 1));   // MMA(li-3) done
+                    tc::mbar_expect_tx(&full[st], TC_TILE_BYTES);
+                    tc::bulk_copy_g2s(sB0 + (size_t)st * TC_TILE_BYTES,
+                                      reinterpret_cast<const unsigned char *>(featsw) + (size_t)tile_index(li) * TC_TILE_BYTES,
+                                      TC_TILE_BYTES, &full[st]);
+                }
+            }
+        } else if (lane == 0) {
+            // ================= MMA warp: one thread issues every tile's chain =================
+            const bool pprof = blockIdx.x == 0 && blockIdx.y == 0;
+            long long pk0 = clock64(), pk1;
+#define WS_PTICK(slot)                                                 \
+    if (pprof) {                                                       \
+        pk1 = clock64();                                               \
+        g_tc_cycles[slot] += (unsigned long long)(pk1 - pk0);          \
+        pk0 = pk1;                                                     \
+    }
+            for (int i = 0; i < nseq; ++i) {
                 const int st = i % TC_STAGES, a = i & 1;
                 tc::mbar_wait(&full[st], (uint32_t)((i / TC_STAGES) & 1));                 // B(i) landed
+                WS_PTICK(0)
                 if (i >= 2) tc::mbar_wait(&tempty[a], (uint32_t)((i / 2 - 1) & 1));        // accumulator drained
+                WS_PTICK(7)
                 tc::fence_after_sync();
                 const uint32_t b_addr = b_addr0 + (uint32_t)st * TC_TILE_BYTES;
                 const uint32_t acc = tbase + (uint32_t)a * TC_N;
@@ -1583,15 +1600,63 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                 }
                 tc::mma_commit(&tfull[a]);        // accumulator ready for the consumers
                 tc::mma_commit(&sempty[st]);      // B stage reusable
+                WS_PTICK(8)
+                if (pprof) g_tc_cycles[5] += 1;
             }
+#undef WS_PTICK
         }
-        __syncwarp();                             // the idle lanes of the producer warp wait for lane 0 here
+        __syncwarp();                             // the idle lanes of the producer warps wait for lane 0 here
     } else {
         // ================= consumers: TMEM epilogue + exact survivors =================
         const int lq = warp & 3, cq = warp >> 2;
         const int my_t = lq * 32 + lane;
-        for (int i = 0; i <= ntiles; ++i) {
-            const bool live = i < ntiles;
+        const bool cprof = tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+        long long ck0 = clock64(), ck1;
+#define WS_CTICK(slot)                                                 \
+    if (cprof) {                                                       \
+        ck1 = clock64();                                               \
+        g_tc_cycles[slot] += (unsigned long long)(ck1 - ck0);          \
+        ck0 = ck1;                                                     \
+    }
+        // ---- bootstrap: 16 running maxima of U per thread (group = tile % 16 within this thread's 32
+        // columns).  A target row has 4 threads -> 64 disjoint groups; each group maximum is attained by a
+        // distinct candidate, at most one of them the target itself, so >= 63 >= K real candidates have
+        // U >= theta = min of the 64 maxima, and their exact similarity is >= theta / 1.002 - 2e-5.
+        if (boot > 0) {
+            float gmax[16];
+#pragma unroll
+            for (int g = 0; g < 16; ++g) gmax[g] = 0.0f;
+            for (int i = 0; i < boot; ++i) {
+                const int a = i & 1;
+                tc::mbar_wait(&tfull[a], (uint32_t)((i / 2) & 1));
+                tc::fence_after_sync();
+                float v[32];
+                tc::tmem_ld32(tbase + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * TC_N + cq * 32), v);
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tempty[a]);
+                float m = v[0];
+#pragma unroll
+                for (int jj = 1; jj < 32; ++jj) m = fmaxf(m, v[jj]);
+#pragma unroll
+                for (int g = 0; g < 16; ++g)
+                    if (g == (i & 15)) gmax[g] = fmaxf(gmax[g], m);
+            }
+            float *scratch = reinterpret_cast<float *>(sm.hsim);          // heaps are still empty
+#pragma unroll
+            for (int g = 0; g < 16; ++g) scratch[(size_t)my_t * 64 + cq * 16 + g] = gmax[g];
+            tc::bar_sync(1, WS_WORKERS);
+            if (tid < TC_M && sm.tid_of[tid] >= 0) {
+                float theta = scratch[(size_t)tid * 64];
+                for (int g = 1; g < 64; ++g) theta = fminf(theta, scratch[(size_t)tid * 64 + g]);
+                float thr0 = theta / 1.002f - 2e-5f;
+                thr0 = nextafterf(thr0, 0.0f);                             // keep the bound on the safe side
+                if (thr0 > sm.thr[tid]) sm.thr[tid] = thr0;
+            }
+            tc::bar_sync(1, WS_WORKERS);
+        }
+        for (int i = boot; i <= nseq; ++i) {
+            const bool live = i < nseq;
             if (!live || (i % WS_VOTE_EVERY) == 0) {
                 // block-uniform decision (consumers only) whether the survivor queue is drained now
                 const int drain = tc::bar_red_or(1, WS_WORKERS, (*(volatile int *)sm.qn >= TC_QCAP / 2) || !live);
@@ -1607,9 +1672,11 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                 }
             }
             if (!live) break;
+            WS_CTICK(6)                                       // vote + drain
             const int a = i & 1;
             tc::mbar_wait(&tfull[a], (uint32_t)((i / 2) & 1));
             tc::fence_after_sync();
+            WS_CTICK(1)                                       // wait for the accumulator
             const float thr = *(volatile float *)(sm.thr + my_t);
             const long long tile = (long long)tile_index(i) * TC_N;
             const int c0 = cq * 32;
@@ -1635,7 +1702,9 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                     }
                 }
             }
+            WS_CTICK(2)                                       // epilogue
         }
+#undef WS_CTICK
     }
     __syncthreads();
     if (tid < 4) atomicAdd(&g_tile_stats[tid], (unsigned long long)s_stats[tid]);

@@ -73,9 +73,15 @@ for s in range(a.warmup + a.steps):
     bc = (C.c_uint64 * (2 * nb))()
     lib.vrec_knn_debug_tc_block_cycles(rs._h, bc, nb)
     bcs = np.array([int(x) for x in bc], dtype=np.float64).reshape(2, nb) / 1e6
-    if cy[5]:
+    if cy[5] and a.kernel in (0, 4):
+        n = cy[5]
+        print(f"   ws block0 cycles/tile: producer [load issue+stage wait {cy[3] / n:.0f}, B-tile wait {cy[0] / n:.0f}, "
+              f"accumulator wait {cy[7] / n:.0f}, mma issue {cy[8] / n:.0f}] consumer warp0 [vote+drain {cy[6] / n:.0f}, "
+              f"accumulator wait {cy[1] / n:.0f}, epilogue {cy[2] / n:.0f}] tiles {n}")
+    elif cy[5]:
         print(f"   per-block Mcycles: dense mean {bcs[0].mean():.1f} max {bcs[0].max():.1f} | postings mean "
               f"{bcs[1].mean():.1f} max {bcs[1].max():.1f} | total max {(bcs[0] + bcs[1]).max():.1f}")
+    if cy[5] and a.kernel == 3:
         print(f"   tc block0 cycles/tile: load-wait {cy[0] / cy[5]:.0f}, mma {cy[1] / cy[5]:.0f}, epilogue {cy[2] / cy[5]:.0f}, "
               f"mma issue {cy[8] / cy[5]:.0f}, load issue {cy[3] / cy[5]:.0f} [cp.async wait {cy[6] / cy[5]:.0f}, barrier {cy[7] / cy[5]:.0f}]; postings pass total {cy[4] / 1e6:.2f} Mcycles; tiles {cy[5]}")
     print(f"kernel={a.kernel} step {s}: {ms:.1f} ms  {B / ms * 1e3:,.0f} persons/s   per target: postings evals {st[0] / B:.0f}, "
