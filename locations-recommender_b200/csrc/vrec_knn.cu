@@ -510,6 +510,112 @@ __device__ __forceinline__ double exact_pair_staged(const TileAux &aux, long lon
     return xadd(xmul(ps_sim, pw), xmul(cs_sim, cw));
 }
 
+// One table of exact_pair_records: the target's section (<= 16 entries) is held in registers; the
+// candidate's entries are visited in ascending order, each matches at most one target entry, and the
+// products are added in that order -- the same sequence of operations as the mllib merge.
+template <bool TRACK_TAIL>
+__device__ __forceinline__ double records_dot(const int *__restrict__ cc, const double *__restrict__ cv, int nc,
+                                              const int *__restrict__ tc_, const double *__restrict__ tv_, int nt,
+                                              unsigned tail_bit, int &min_tail) {
+    unsigned tcol[16];
+    double tval[16];
+#pragma unroll
+    for (int f0 = 0; f0 < 16; f0 += 4) {
+        unsigned c4[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        double x4[4] = {0.0, 0.0, 0.0, 0.0};
+        if (f0 < nt) rec_load4(tc_, tv_, f0, c4, x4);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            tcol[f0 + f] = (f0 + f < nt) ? (c4[f] & REC_COL_MASK) : 0xffffffffu;
+            tval[f0 + f] = x4[f];
+        }
+    }
+    double sum = 0.0;
+    for (int k0 = 0; k0 < nc; k0 += 4) {
+        unsigned c[4];
+        double x[4];
+        rec_load4(cc, cv, k0, c, x);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (k0 + e < nc) {
+                const unsigned ix = c[e] & REC_COL_MASK;
+                double m = 0.0;
+                bool hit = false;
+#pragma unroll
+                for (int f = 0; f < 16; ++f) {
+                    const bool eq = tcol[f] == ix;
+                    m = eq ? tval[f] : m;
+                    hit = hit || eq;
+                }
+                if (hit) {
+                    sum = xadd(sum, xmul(x[e], m));
+                    if (TRACK_TAIL) {
+                        if (min_tail < 0 && (c[e] & tail_bit)) min_tail = (int)ix;
+                    }
+                }
+            }
+        }
+    }
+    return sum;
+}
+
+// exact_pair for two persons that both have a packed record and a target with <= 16 entries per table:
+// two independent meta loads, then both records with 128-bit loads, the match in registers.
+__device__ __forceinline__ bool exact_pair_records(const TileAux &aux, int cand, int tix, double pw, double cw,
+                                                   int &min_tail, double &out) {
+    min_tail = -1;
+    out = 0.0;
+    if (cand == tix) return true;
+    const bool pr = threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+    long long z0 = clock64();
+    const unsigned long long mc = __ldg(aux.meta + cand), mt = __ldg(aux.meta + tix);
+    const int npc = (int)((mc >> 40) & 0xfffu), ncc = (int)(mc >> 52);
+    const int npt = (int)((mt >> 40) & 0xfffu), nct = (int)(mt >> 52);
+    if (npt > 16 || nct > 16) return false;                         // caller falls back to the general path
+    const double *rc = aux.rec + (mc & 0xffffffffffULL), *rt = aux.rec + (mt & 0xffffffffffULL);
+    if (pr && (mc | mt) == 0xffffffffffffffffULL) g_probe[7] = 1;   // consume the meta words here
+    long long z1 = clock64();
+    const double2 lc = __ldg(reinterpret_cast<const double2 *>(rc)), lt = __ldg(reinterpret_cast<const double2 *>(rt));
+    if (pr && lc.x + lt.x == -1.0) g_probe[7] = 2;                  // consume the headers here
+    long long z2 = clock64();
+    const int *pcc = reinterpret_cast<const int *>(rc + 2);
+    const double *pvc = rc + 2 + rec_cols_words(npc);
+    const int *ccc = reinterpret_cast<const int *>(pvc + rec_vals_words(npc));
+    const double *cvc = pvc + rec_vals_words(npc) + rec_cols_words(ncc);
+    const int *pct = reinterpret_cast<const int *>(rt + 2);
+    const double *pvt = rt + 2 + rec_cols_words(npt);
+    const int *cct = reinterpret_cast<const int *>(pvt + rec_vals_words(npt));
+    const double *cvt = pvt + rec_vals_words(npt) + rec_cols_words(nct);
+    bool keep = false;
+    double ps_sim = 0.0, cs_sim = 0.0;
+    if (npc > 0) {
+        double sum = records_dot<true>(pcc, pvc, npc, pct, pvt, npt, aux.tail_bit, min_tail);
+        double c = xdiv(sum, xmul(lc.x, lt.x));
+        if (c > 0) {
+            keep = true;
+            ps_sim = c;
+        }
+    }
+    if (ncc > 0) {
+        int dummy = 0;
+        double sum = records_dot<false>(ccc, cvc, ncc, cct, cvt, nct, 0u, dummy);
+        double c = xdiv(sum, xmul(lc.y, lt.y));
+        if (c > 0) {
+            keep = true;
+            cs_sim = c;
+        }
+    }
+    if (keep) out = xadd(xmul(ps_sim, pw), xmul(cs_sim, cw));
+    if (pr) {
+        long long z3 = clock64();
+        g_probe[0] += (unsigned long long)(z1 - z0);
+        g_probe[1] += (unsigned long long)(z2 - z1);
+        g_probe[2] += (unsigned long long)(z3 - z2);
+        g_probe[3] += 1;
+    }
+    return true;
+}
+
 // exact combined similarity + the smallest shared tail place (-1 if none)
 __device__ __forceinline__ double exact_pair(const KnnDev &d, const TileAux &aux, long long i, const TargetRows &t,
                                              double pw, double cw, int &min_tail) {
@@ -673,6 +779,30 @@ __device__ __forceinline__ void tile_process(const KnnDev &d, const TileAux &aux
                                              int K, double pw, double cw, int from_postings) {
     int tix = sm.tid_of[t];
     if (tix < 0) return;
+    if (aux.meta) {
+        // both persons have packed records: no dependent loads, no data-dependent merge loops
+        int min_tail;
+        double sim;
+        if (exact_pair_records(aux, c, tix, pw, cw, min_tail, sim)) {
+            atomicAdd(sm.stats + (from_postings >= 0 ? 0 : 1), 1u);
+            if (!(sim > 0)) return;
+            if (from_postings >= 0) {
+                if (min_tail != from_postings) return;
+            } else if (from_postings == -1 && min_tail >= 0) {
+                return;
+            }
+            volatile double *hs = sm.hsim + (size_t)t * K;
+            if (*(volatile int *)(sm.hcnt + t) >= K && sim < hs[0]) return;
+            atomicAdd(sm.stats + 2, 1u);
+            long long h0 = clock64();
+            tile_heap_insert(sm, t, K, sim, c);
+            if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+                g_probe[4] += (unsigned long long)(clock64() - h0);
+                g_probe[5] += 1;
+            }
+            return;
+        }
+    }
     TargetRows tr = load_target(d, tix);
     tile_process_rows(d, aux, sm, t, c, K, pw, cw, from_postings, tr);
 }
@@ -1660,15 +1790,18 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
             if (!live || (i % WS_VOTE_EVERY) == 0) {
                 // block-uniform decision (consumers only) whether the survivor queue is drained now
                 const int drain = tc::bar_red_or(1, WS_WORKERS, (*(volatile int *)sm.qn >= TC_QCAP / 2) || !live);
+                WS_CTICK(9)                                   // the vote barrier itself
                 if (drain) {
                     int m = min(*(volatile int *)sm.qn, TC_QCAP);
                     for (int qi = tid; qi < m; qi += WS_WORKERS) {
                         unsigned long long e = sm.queue[qi];
                         tile_process(d, aux, sm, (int)(e >> 32), (int)(unsigned)(e & 0xffffffffu), K, pw, cw, -1);
                     }
+                    WS_CTICK(10)                              // this thread's share of the drain
                     tc::bar_sync(1, WS_WORKERS);
                     if (tid == 0) *sm.qn = 0;
                     tc::bar_sync(1, WS_WORKERS);
+                    if (cprof) g_tc_cycles[11] += 1;
                 }
             }
             if (!live) break;
@@ -2516,7 +2649,7 @@ extern "C" int vrec_knn_debug_probe(vrec_knn *k, uint64_t *out4) {
     VREC_CUDA(cudaSetDevice(k->ctx->device));
     VREC_CUDA(cudaStreamSynchronize(k->ctx->stream));
     unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    VREC_CUDA(cudaMemcpyFromSymbol(out4, g_probe, 32));
+    VREC_CUDA(cudaMemcpyFromSymbol(out4, g_probe, 48));        // out4 holds 6 values
     VREC_CUDA(cudaMemcpyToSymbol(g_probe, z, sizeof(z)));
     return VREC_OK;
 }

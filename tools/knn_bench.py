@@ -61,14 +61,14 @@ for s in range(a.warmup + a.steps):
     st = [int(x) for x in stats]
     lib.vrec_knn_debug_tc_cycles(rs._h, cyc)
     cy = [int(x) for x in cyc]
-    if cy[11]:
+    if cy[11] and a.kernel == 3:
         print(f"   postings warp-iteration (block0 warp0): candidate id load {cy[9] / cy[11]:.0f} cycles, exact eval + insert "
               f"{cy[10] / cy[11]:.0f} cycles, iterations {cy[11]}")
-    pb = (C.c_uint64 * 4)()
+    pb = (C.c_uint64 * 6)()
     lib.vrec_knn_debug_probe(rs._h, pb)
     if pb[3]:
-        print(f"   exact eval (block0 warp0, per warp-iteration): meta wait {pb[0] / pb[3]:.0f}, record+place {pb[1] / pb[3]:.0f}, "
-              f"category {pb[2] / pb[3]:.0f} cycles")
+        print(f"   survivor eval (block0 thread0): meta {pb[0] / pb[3]:.0f}, headers {pb[1] / pb[3]:.0f}, sections+math {pb[2] / pb[3]:.0f} "
+              f"cycles over {pb[3]} evals; heap insert {pb[4] / max(1, pb[5]):.0f} cycles over {pb[5]} inserts")
     nb = min(1024, (B + 127) // 128)
     bc = (C.c_uint64 * (2 * nb))()
     lib.vrec_knn_debug_tc_block_cycles(rs._h, bc, nb)
@@ -76,7 +76,7 @@ for s in range(a.warmup + a.steps):
     if cy[5] and a.kernel in (0, 4):
         n = cy[5]
         print(f"   ws block0 cycles/tile: producer [load issue+stage wait {cy[3] / n:.0f}, B-tile wait {cy[0] / n:.0f}, "
-              f"accumulator wait {cy[7] / n:.0f}, mma issue {cy[8] / n:.0f}] consumer warp0 [vote+drain {cy[6] / n:.0f}, "
+              f"accumulator wait {cy[7] / n:.0f}, mma issue {cy[8] / n:.0f}] consumer warp0 [vote+drain {cy[6] / n:.0f} (vote barrier {cy[9] / n:.0f}, own drain work {cy[10] / n:.0f}, drains {cy[11]}), "
               f"accumulator wait {cy[1] / n:.0f}, epilogue {cy[2] / n:.0f}] tiles {n}")
     elif cy[5]:
         print(f"   per-block Mcycles: dense mean {bcs[0].mean():.1f} max {bcs[0].max():.1f} | postings mean "
