@@ -2,6 +2,7 @@
 // fused residual / convergence check, then ranked top-N place extraction.
 // Reference: stochastic/StochasticRecommender.scala:38-141, stochastic/StochasticRecommenderMain.scala:64-76.
 #include <algorithm>
+#include <memory>
 #include <numeric>
 
 #include "vrec_internal.cuh"
@@ -11,6 +12,7 @@ namespace {
 constexpr double kAlpha = 0.15;                 // stochastic/StochasticRecommender.scala:38
 constexpr int SPMV_THREADS = 256;
 constexpr int SPMV_WARPS = SPMV_THREADS / 32;
+constexpr int64_t SRC_BLOCK = 6291456;          // canonical source block, 3 * 2^21 vertices = 48 MB of x (oracle: CANON_SRC_BLOCK)
 
 // Device-side loop control (one per query slot).
 struct SgState {
@@ -35,12 +37,21 @@ struct vrec_sg {
     DevBuf<int> d_rowptr;                     // [rows+1]
     DevBuf<int> d_src;                        // source vertex index per in-edge
     DevBuf<double> d_w;
-    // rows longer than VREC_CANON_SEG are summed segment-wise
-    int n_long = 0, n_seg = 0;
-    DevBuf<int> d_long_rows;                  // [n_long] ascending local row
-    DevBuf<int> d_long_segptr;                // [n_long+1] offsets into partials
-    DevBuf<int> d_seg_row;                    // [n_seg] index into long_rows
-    DevBuf<double> d_partials;                // [n_seg]
+    // Source blocks (canonical order, see oracle/vrec_oracle.c): graphs with more than 3 * 2^21 vertices are
+    // swept once per block of 3 * 2^21 sources, so that the gathered part of x (<= 48 MB) stays L2-resident.
+    // Block b of row r is the in-edge range [start[r], end[r]); (sub-)ranges longer than
+    // VREC_CANON_SEG are summed segment-wise through the per-block tables.
+    struct Block {
+        const int *row_start = nullptr, *row_end = nullptr;   // device, [rows]
+        int n_long = 0, n_seg = 0;
+        DevBuf<int> long_rows;                // [n_long] ascending local row
+        DevBuf<int> long_segptr;              // [n_long+1] offsets into partials
+        DevBuf<int> seg_row;                  // [n_seg] index into long_rows
+        DevBuf<double> partials;              // [n_seg]
+    };
+    int nblocks = 1;
+    std::vector<std::unique_ptr<Block>> blocks;
+    DevBuf<int> d_bptr;                       // [(nblocks+1) x rows] block boundaries per row (nblocks > 1)
     DevBuf<double> d_x[2];
     DevBuf<double> d_block_partials;
     DevBuf<SgState> d_state;
@@ -120,7 +131,8 @@ __device__ __forceinline__ double canon_row_sum(const int *__restrict__ src, con
 
 // One warp per 1024-term segment of a long row.
 __global__ void __launch_bounds__(SPMV_THREADS)
-sg_long_partials_kernel(const int *__restrict__ rowptr, const int *__restrict__ src,
+sg_long_partials_kernel(const int *__restrict__ row_start, const int *__restrict__ row_end,
+                        const int *__restrict__ src,
                         const double *__restrict__ w, const double *__restrict__ x,
                         const int *__restrict__ long_rows, const int *__restrict__ long_segptr,
                         const int *__restrict__ seg_row, int n_seg, double *__restrict__ partials,
@@ -132,8 +144,8 @@ sg_long_partials_kernel(const int *__restrict__ rowptr, const int *__restrict__ 
     int slot = seg_row[seg];
     int row = long_rows[slot];
     int j = seg - long_segptr[slot];
-    int s = rowptr[row] + j * VREC_CANON_SEG;
-    int n = min(VREC_CANON_SEG, rowptr[row + 1] - s);
+    int s = row_start[row] + j * VREC_CANON_SEG;
+    int n = min(VREC_CANON_SEG, row_end[row] - s);
     double v = canon_row_sum<32>(src, w, x, s, n, lane, policy_evict_first(), policy_evict_last(keep_frac));
     if (lane == 0) partials[seg] = v;
 }
@@ -142,12 +154,13 @@ sg_long_partials_kernel(const int *__restrict__ rowptr, const int *__restrict__ 
 // (calcNextX, :108-128), squared-difference residual (isConverged, :130-141) reduced in a
 // fixed order, and the step() control (:92-106) updated by the last block.
 __global__ void __launch_bounds__(SPMV_THREADS, 4)
-sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ rowptr, const int *__restrict__ src,
+sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ row_start, const int *__restrict__ row_end,
+               const int *__restrict__ src,
                const double *__restrict__ w, const double *__restrict__ x, double *__restrict__ nx,
                long long uidx, const int *__restrict__ long_rows, const int *__restrict__ long_segptr,
                int n_long, const double *__restrict__ partials, SgState *st,
                double *__restrict__ block_partials, int iteration, int max_it, double eps2,
-               int check_convergence, float keep_frac) {
+               int check_convergence, float keep_frac, int acc_in, int finalize) {
     if (st->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long total_warps = (long long)gridDim.x * SPMV_WARPS;
@@ -159,8 +172,8 @@ sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ rowptr, con
         long long r = base + lane;
         int s = 0, e = 0;
         if (r < n_rows) {
-            s = rowptr[r];
-            e = rowptr[r + 1];
+            s = row_start[r];
+            e = row_end[r];
         }
         int n = e - s;
         double sigma = 0.0;
@@ -197,8 +210,14 @@ sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ rowptr, con
             acc = canon_butterfly(acc);
             if (lane == l) sigma = acc;
         }
-        if (r < n_rows) {
+        if (r < n_rows && !finalize) {
+            // not the last source block: keep the running sum of the block sums in nx
             long long gi = row_lo + r;
+            nx[gi] = acc_in ? xadd(nx[gi], sigma) : sigma;
+        }
+        if (r < n_rows && finalize) {
+            long long gi = row_lo + r;
+            if (acc_in) sigma = xadd(nx[gi], sigma);     // block sums are added left to right
             double u = (gi == uidx) ? 1.0 : 0.0;
             double v = xadd(xmul(u, kAlpha), xmul(sigma, one_minus));
             st_stream_f64(nx + gi, v, pol_stream);         // the written buffer is the old x: demote it
@@ -206,7 +225,7 @@ sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ rowptr, con
             dsum = xadd(dsum, xmul(d, d));
         }
     }
-    if (!check_convergence) return;
+    if (!check_convergence || !finalize) return;
     // fixed-order reduction of the residual
     __shared__ double s_part[SPMV_WARPS];
     __shared__ int s_last;
@@ -296,13 +315,11 @@ __global__ void sg_candidates_kernel(const long long *__restrict__ ids, long lon
     cand_key[i] = id;
 }
 
-int sg_setup_device(vrec_sg *g, const std::vector<int> &rowptr) {
-    vrec_ctx *ctx = g->ctx;
-    const int64_t rows = g->row_hi - g->row_lo;
-    // long rows and their segments
+// builds the long-(sub-)range tables of one block from host copies of its boundaries
+int sg_fill_block(vrec_sg *g, vrec_sg::Block &blk, const int *h_start, const int *h_end, int64_t rows) {
     std::vector<int> long_rows, long_segptr(1, 0), seg_row;
     for (int64_t r = 0; r < rows; ++r) {
-        int n = rowptr[r + 1] - rowptr[r];
+        int n = h_end[r] - h_start[r];
         if (n > VREC_CANON_SEG) {
             int m = (n + VREC_CANON_SEG - 1) / VREC_CANON_SEG;
             for (int j = 0; j < m; ++j) seg_row.push_back((int)long_rows.size());
@@ -310,12 +327,19 @@ int sg_setup_device(vrec_sg *g, const std::vector<int> &rowptr) {
             long_segptr.push_back(long_segptr.back() + m);
         }
     }
-    g->n_long = (int)long_rows.size();
-    g->n_seg = (int)seg_row.size();
-    VREC_TRY(g->d_long_rows.upload(long_rows.data(), long_rows.size(), ctx->stream));
-    VREC_TRY(g->d_long_segptr.upload(long_segptr.data(), long_segptr.size(), ctx->stream));
-    VREC_TRY(g->d_seg_row.upload(seg_row.data(), seg_row.size(), ctx->stream));
-    VREC_TRY(g->d_partials.alloc(std::max(1, g->n_seg)));
+    blk.n_long = (int)long_rows.size();
+    blk.n_seg = (int)seg_row.size();
+    cudaStream_t st = g->ctx->stream;
+    VREC_TRY(blk.long_rows.upload(long_rows.data(), long_rows.size(), st));
+    VREC_TRY(blk.long_segptr.upload(long_segptr.data(), long_segptr.size(), st));
+    VREC_TRY(blk.seg_row.upload(seg_row.data(), seg_row.size(), st));
+    VREC_TRY(blk.partials.alloc(std::max(1, blk.n_seg)));
+    return VREC_OK;
+}
+
+int sg_alloc_state(vrec_sg *g) {
+    vrec_ctx *ctx = g->ctx;
+    const int64_t rows = g->row_hi - g->row_lo;
     const int64_t xlen = g->partitioned ? g->slice * g->ctx->world : g->N;
     VREC_TRY(g->d_x[0].alloc((size_t)xlen));
     VREC_TRY(g->d_x[1].alloc((size_t)xlen));
@@ -326,7 +350,94 @@ int sg_setup_device(vrec_sg *g, const std::vector<int> &rowptr) {
     g->grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, 148 * 8));
     VREC_TRY(g->d_block_partials.alloc(g->grid));
     VREC_TRY(g->d_state.alloc(1));
+    return VREC_OK;
+}
+
+// host-built graphs: rowptr / src are host copies of this process's rows
+int sg_setup_device(vrec_sg *g, const std::vector<int> &rowptr, const int *h_src) {
+    vrec_ctx *ctx = g->ctx;
+    const int64_t rows = g->row_hi - g->row_lo;
+    g->nblocks = g->N > SRC_BLOCK ? (int)((g->N + SRC_BLOCK - 1) / SRC_BLOCK) : 1;
+    g->blocks.clear();
+    if (g->nblocks == 1) {
+        g->blocks.emplace_back(new vrec_sg::Block());
+        vrec_sg::Block &b = *g->blocks[0];
+        b.row_start = g->d_rowptr.p;
+        b.row_end = g->d_rowptr.p + 1;
+        VREC_TRY(sg_fill_block(g, b, rowptr.data(), rowptr.data() + 1, rows));
+    } else {
+        // boundaries of every source block inside every (source-sorted) row
+        std::vector<int> bptr((size_t)(g->nblocks + 1) * (size_t)rows);
+        for (int64_t r = 0; r < rows; ++r) {
+            const int *lo = h_src + rowptr[r], *hi = h_src + rowptr[r + 1];
+            bptr[r] = rowptr[r];
+            for (int b = 1; b < g->nblocks; ++b)
+                bptr[(size_t)b * rows + r] = (int)(std::lower_bound(lo, hi, (int)((int64_t)b * SRC_BLOCK)) - h_src);
+            bptr[(size_t)g->nblocks * rows + r] = rowptr[r + 1];
+        }
+        VREC_TRY(g->d_bptr.upload(bptr.data(), bptr.size(), ctx->stream));
+        for (int b = 0; b < g->nblocks; ++b) {
+            g->blocks.emplace_back(new vrec_sg::Block());
+            vrec_sg::Block &blk = *g->blocks[b];
+            blk.row_start = g->d_bptr.p + (size_t)b * rows;
+            blk.row_end = g->d_bptr.p + (size_t)(b + 1) * rows;
+            VREC_TRY(sg_fill_block(g, blk, bptr.data() + (size_t)b * rows, bptr.data() + (size_t)(b + 1) * rows, rows));
+        }
+    }
+    VREC_TRY(sg_alloc_state(g));
     VREC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VREC_OK;
+}
+
+// block boundaries of device-generated rows (every row has at most VREC_CANON_SEG in-edges: no long tables)
+__global__ void sg_block_ptr_kernel(int n_rows, const int *__restrict__ rowptr, const int *__restrict__ src, int nblocks,
+                                    int *__restrict__ bptr) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_rows * (nblocks + 1)) return;
+    int b = (int)(i / n_rows), r = (int)(i % n_rows);
+    int lo = rowptr[r], hi = rowptr[r + 1];
+    if (b == 0) {
+        bptr[i] = lo;
+    } else if (b == nblocks) {
+        bptr[i] = hi;
+    } else {
+        const int key = (int)((long long)b * SRC_BLOCK);
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (src[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        bptr[i] = lo;
+    }
+}
+
+int sg_setup_generated(vrec_sg *g) {
+    vrec_ctx *ctx = g->ctx;
+    const int64_t rows = g->row_hi - g->row_lo;
+    g->nblocks = g->N > SRC_BLOCK ? (int)((g->N + SRC_BLOCK - 1) / SRC_BLOCK) : 1;
+    g->blocks.clear();
+    if (g->nblocks > 1) {
+        VREC_TRY(g->d_bptr.alloc((size_t)(g->nblocks + 1) * (size_t)rows));
+        long long n = (long long)rows * (g->nblocks + 1);
+        sg_block_ptr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((int)rows, g->d_rowptr.p, g->d_src.p,
+                                                                               g->nblocks, g->d_bptr.p);
+        VREC_LAUNCHED(ctx);
+    }
+    for (int b = 0; b < g->nblocks; ++b) {
+        g->blocks.emplace_back(new vrec_sg::Block());
+        vrec_sg::Block &blk = *g->blocks[b];
+        if (g->nblocks == 1) {
+            blk.row_start = g->d_rowptr.p;
+            blk.row_end = g->d_rowptr.p + 1;
+        } else {
+            blk.row_start = g->d_bptr.p + (size_t)b * rows;
+            blk.row_end = g->d_bptr.p + (size_t)(b + 1) * rows;
+        }
+        VREC_TRY(blk.long_rows.alloc(1));
+        VREC_TRY(blk.long_segptr.alloc(2));
+        VREC_TRY(blk.seg_row.alloc(1));
+        VREC_TRY(blk.partials.alloc(1));
+    }
+    VREC_TRY(sg_alloc_state(g));
     return VREC_OK;
 }
 
@@ -339,7 +450,8 @@ int sg_run_device(vrec_sg *g, long long uidx, double epsilon, int max_it, bool c
     // pin at most ~60 MiB of x in L2 (measured: 64 MB of evict_last data stays resident on B200
     // next to the streamed matrix, 80 MB does not)
     const double keep_bytes = 60.0 * 1024 * 1024;
-    const float keep_frac = (float)std::min(1.0, keep_bytes / (8.0 * (double)std::max<int64_t>(1, g->N)));
+    const double gathered = 8.0 * (double)std::min<int64_t>(std::max<int64_t>(1, g->N), SRC_BLOCK);
+    const float keep_frac = (float)std::min(1.0, keep_bytes / gathered);
     sg_reset_state_kernel<<<1, 1, 0, ctx->stream>>>(g->d_state.p, max_it);
     VREC_LAUNCHED(ctx);
     int fill_grid = (int)std::min<int64_t>((g->N + 255) / 256, 148 * 16);
@@ -348,18 +460,22 @@ int sg_run_device(vrec_sg *g, long long uidx, double epsilon, int max_it, bool c
     for (int it = 0; it < max_it; ++it) {
         const double *x = g->d_x[it & 1].p;
         double *nx = g->d_x[(it + 1) & 1].p;
-        if (g->n_seg > 0) {
-            int pg = (g->n_seg + SPMV_WARPS - 1) / SPMV_WARPS;
-            sg_long_partials_kernel<<<pg, SPMV_THREADS, 0, ctx->stream>>>(
-                g->d_rowptr.p, g->d_src.p, g->d_w.p, x, g->d_long_rows.p, g->d_long_segptr.p,
-                g->d_seg_row.p, g->n_seg, g->d_partials.p, g->d_state.p, keep_frac);
+        for (int b = 0; b < g->nblocks; ++b) {
+            vrec_sg::Block &blk = *g->blocks[b];
+            if (blk.n_seg > 0) {
+                int pg = (blk.n_seg + SPMV_WARPS - 1) / SPMV_WARPS;
+                sg_long_partials_kernel<<<pg, SPMV_THREADS, 0, ctx->stream>>>(
+                    blk.row_start, blk.row_end, g->d_src.p, g->d_w.p, x, blk.long_rows.p, blk.long_segptr.p,
+                    blk.seg_row.p, blk.n_seg, blk.partials.p, g->d_state.p, keep_frac);
+                VREC_LAUNCHED(ctx);
+            }
+            sg_spmv_kernel<<<g->grid, SPMV_THREADS, 0, ctx->stream>>>(
+                rows, g->row_lo, blk.row_start, blk.row_end, g->d_src.p, g->d_w.p, x, nx, uidx, blk.long_rows.p,
+                blk.long_segptr.p, blk.n_long, blk.partials.p, g->d_state.p, g->d_block_partials.p, it, max_it, eps2,
+                check_convergence ? (g->partitioned ? 2 : 1) : 0, keep_frac, b > 0 ? 1 : 0,
+                b == g->nblocks - 1 ? 1 : 0);
             VREC_LAUNCHED(ctx);
         }
-        sg_spmv_kernel<<<g->grid, SPMV_THREADS, 0, ctx->stream>>>(
-            rows, g->row_lo, g->d_rowptr.p, g->d_src.p, g->d_w.p, x, nx, uidx, g->d_long_rows.p,
-            g->d_long_segptr.p, g->n_long, g->d_partials.p, g->d_state.p, g->d_block_partials.p, it,
-            max_it, eps2, check_convergence ? (g->partitioned ? 2 : 1) : 0, keep_frac);
-        VREC_LAUNCHED(ctx);
         if (g->partitioned) {
             // the one exchange step of the path: every rank needs the whole x' for its gathers
             VREC_TRY(vrec_comm_allgather_f64(ctx, nx, (size_t)g->slice));
@@ -482,7 +598,7 @@ extern "C" int vrec_sg_load(vrec_ctx *ctx, int64_t nnz, const int64_t *source_id
     if (rc == VREC_OK) rc = g->d_rowptr.upload(rowptr.data(), rowptr.size(), ctx->stream);
     if (rc == VREC_OK) rc = g->d_src.upload(src.data(), src.size(), ctx->stream);
     if (rc == VREC_OK) rc = g->d_w.upload(w.data(), w.size(), ctx->stream);
-    if (rc == VREC_OK) rc = sg_setup_device(g, rowptr);
+    if (rc == VREC_OK) rc = sg_setup_device(g, rowptr, src.data());
     if (rc != VREC_OK) {
         delete g;
         return rc;
@@ -521,8 +637,8 @@ extern "C" int vrec_sg_load_partitioned(vrec_ctx *ctx, int64_t nnz, const int64_
         if (rc == VREC_OK) rc = g->d_rowptr.upload(rowptr.data(), rowptr.size(), ctx->stream);
         if (rc == VREC_OK) rc = g->d_src.upload(src.data() + e0, (size_t)g->nnz, ctx->stream);
         if (rc == VREC_OK) rc = g->d_w.upload(w.data() + e0, (size_t)g->nnz, ctx->stream);
+        if (rc == VREC_OK) rc = sg_setup_device(g, rowptr, src.data() + e0);
     }
-    if (rc == VREC_OK) rc = sg_setup_device(g, rowptr);
     if (rc != VREC_OK) {
         delete g;
         return rc;
@@ -785,24 +901,8 @@ extern "C" int vrec_sg_generate(vrec_ctx *ctx, int64_t n_vertices, int32_t out_d
         }
     }
     if (rc == VREC_OK) {
-        // every row has out_degree <= 1024 terms: no long rows
-        std::vector<int> fake_rowptr(2, 0);
-        g->n_long = g->n_seg = 0;
-        rc = g->d_long_rows.alloc(1);
-        if (rc == VREC_OK) rc = g->d_long_segptr.alloc(2);
-        if (rc == VREC_OK) rc = g->d_seg_row.alloc(1);
-        if (rc == VREC_OK) rc = g->d_partials.alloc(1);
-        const size_t xlen = (size_t)(g->partitioned ? slice * world : g->N);
-        if (rc == VREC_OK) rc = g->d_x[0].alloc(xlen);
-        if (rc == VREC_OK) rc = g->d_x[1].alloc(xlen);
-        if (rc == VREC_OK) {
-            cudaMemsetAsync(g->d_x[0].p, 0, sizeof(double) * xlen, ctx->stream);
-            cudaMemsetAsync(g->d_x[1].p, 0, sizeof(double) * xlen, ctx->stream);
-        }
-        int64_t want = (rows + 32 * SPMV_WARPS - 1) / (32 * SPMV_WARPS);
-        g->grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, 148 * 8));
-        if (rc == VREC_OK) rc = g->d_block_partials.alloc(g->grid);
-        if (rc == VREC_OK) rc = g->d_state.alloc(1);
+        // every row has out_degree <= 1024 terms: no long (sub-)ranges; block boundaries on the device
+        rc = sg_setup_generated(g);
     }
     if (rc == VREC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         vrec_set_error("vrec_sg_generate: %s", cudaGetErrorString(cudaGetLastError()));

@@ -32,7 +32,10 @@
  *     duplicates), summed in the CANONICAL ORDER `canon_sum` below -- a fixed
  *     32-lane strided + xor-butterfly order (what a warp does), segmented
  *     every 1024 terms.  For <= 3 terms it is identical to left-to-right
- *     summation, which is what the reference KATs pin.
+ *     summation, which is what the reference KATs pin.  In graphs with more
+ *     than 3 * 2^21 vertices the in-edges of a vertex are first grouped by source
+ *     block (source index / (3 * 2^21)); every group is summed in the canonical
+ *     order and the group sums are added left to right.
  *   - SG residual: sum of squared differences left to right over ascending
  *     vertex id.
  */
@@ -51,6 +54,7 @@
 
 #define CANON_LANES 32
 #define CANON_SEG 1024
+#define CANON_SRC_BLOCK 6291456      /* graphs with more vertices than this: sources grouped in blocks of 3 * 2^21 */
 
 /* ------------------------------------------------------------------ */
 /* knn/Distance.scala                                                  */
@@ -562,10 +566,9 @@ int vro_sg_from_csr(int64_t N, const int64_t *rowptr, const int32_t *src, const 
 int64_t vro_sg_vertex_count(const vro_sg *g) { return g->N; }
 void vro_sg_vertex_ids(const vro_sg *g, int64_t *out) { memcpy(out, g->ids, sizeof(int64_t) * (size_t)g->N); }
 
-/* sigma of one vertex in the canonical order */
-static double sg_sigma(const vro_sg *g, const double *x, int64_t i, double *terms)
+/* canonical sum of the terms x[src] * w of the in-edges [s, s + n) */
+static double sg_canon_range(const vro_sg *g, const double *x, int64_t s, int64_t n, double *terms)
 {
-    int64_t s = g->rowptr[i], n = g->rowptr[i + 1] - s;
     if (n <= CANON_SEG) {
         for (int64_t k = 0; k < n; ++k) terms[k] = x[g->src[s + k]] * g->w[s + k];   /* :112 */
         return warp_sum(terms, n);
@@ -581,6 +584,24 @@ static double sg_sigma(const vro_sg *g, const double *x, int64_t i, double *term
     double r = warp_sum(part, m);
     free(part);
     return r;
+}
+
+/* sigma of one vertex in the canonical order */
+static double sg_sigma(const vro_sg *g, const double *x, int64_t i, double *terms)
+{
+    int64_t s = g->rowptr[i], e = g->rowptr[i + 1];
+    if (g->N <= (int64_t)CANON_SRC_BLOCK) return sg_canon_range(g, x, s, e - s, terms);
+    /* large graph: one canonical sum per source block, added left to right */
+    double total = 0.0;
+    while (s < e) {
+        int32_t blk = g->src[s] / CANON_SRC_BLOCK;
+        int64_t t = s;
+        while (t < e && g->src[t] / CANON_SRC_BLOCK == blk) t++;
+        double sb = sg_canon_range(g, x, s, t - s, terms);
+        total = total + sb;
+        s = t;
+    }
+    return total;
 }
 
 /* calcNextX, stochastic/StochasticRecommender.scala:108-128.  Rows are

@@ -143,6 +143,31 @@ def test_sg_generated_graph_matches_oracle(vrec, ctx, oracle):
         assert np.array_equal(x, ox)
 
 
+def test_sg_source_blocked_order(vrec, ctx, synth, oracle):
+    # more than 3 * 2^21 vertices: the engine sweeps the graph once per block of 3 * 2^21 sources and the
+    # canonical order adds the block sums left to right (oracle: CANON_SRC_BLOCK)
+    g = vrec.StochasticGraph.generate(7_000_000, 6, seed=7, ctx=ctx)
+    rowptr, src, w = g.export_csr()
+    og = oracle.SgGraph.from_csr(rowptr.astype(np.int64), src, w)
+    rec = vrec.StochasticRecommender(g, 0.0, 3)
+    x = rec.stationary(0)
+    rc, ox, oit, oconv, ores = og.run(0, 0.0, 3)
+    assert rc == 0 and np.array_equal(x, ox)
+    assert abs(rec.last_residual - ores) <= 1e-9 * ores     # two different fixed summation orders
+    g.close()
+    # host-loaded graph whose hub rows are long in BOTH source blocks (per-block segment tables)
+    s, t, w = synth.random_stochastic_graph(6_400_000, 2, seed=8, hub_fraction=0.3)
+    g = vrec.StochasticGraph(s, t, w, ctx=ctx)
+    og = oracle.SgGraph(s, t, w)
+    v = int(og.ids[12345])
+    rec = vrec.StochasticRecommender(g, 1e-4, 6)
+    x = rec.stationary(v)
+    rc, ox, oit, oconv, _ = og.run(v, 1e-4, 6)
+    assert (rec.last_iterations, rec.last_converged) == (oit, oconv)
+    assert np.array_equal(x, ox)
+    g.close()
+
+
 # ------------------------------------------------------------------ KNN
 def _check_knn(vrec, oracle, rs, inp, pw, cw, k, targets, flt, max_recs):
     rec = vrec.KnnRecommender(rs, pw, cw, k)
