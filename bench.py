@@ -132,10 +132,12 @@ def sg_workload_name(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one sg_spmv_kernel launch on the default SG workload,
 # from profiles/r1_sg_spmv_v1_ncu_raw.csv (ncu --set full)
-SG_NCU_TRAFFIC = 27_756_317_000 + 83_389_440
-# the same for one knn_tc_kernel launch on the default KNN workload (18944 targets),
-# from profiles/r1_knn_tc_kernel_ncu_raw.csv
-KNN_NCU_TRAFFIC = 38_353_532_000 + 14_552_320
+# (two launches per iteration: one per source block) -- profiles/r1_sg_spmv_r1b_ncu_raw.csv
+SG_NCU_TRAFFIC = 10_383_476_000 + 80_896_000 + 6_942_931_000 + 68_708_864
+# the same for one knn_tc_ws_kernel launch on the default KNN workload (18944 targets),
+# from profiles/r1_knn_final_r1_ncu_raw.csv
+KNN_NCU_TRAFFIC = 29_429_142_000 + 251_530_240
+KNN_NCU_TENSOR_PIPE_PCT = 16.1
 
 
 def sg_bytes_per_iteration(n, nnz):
@@ -358,20 +360,25 @@ def run_ours(args):
     d2h = B * m * 16 + B * 8
     log(f"[bench] knn e2e: {e2e_value:,.0f} persons/s")
 
-    # roofline of the dominant KNN kernel (knn_topk_kernel): algorithmic bytes of one launch = one
-    # pass over the region-set (bytes/target = B_region / T with T = targets per pass)
+    # Roofline of the dominant KNN kernel (knn_tc_ws_kernel, ~55 % of the step, profiles/r1_knn_step_launches.csv).
+    # Its algorithmic HBM traffic: every CTA (128 targets) streams the fp16 feature matrix (256 B / person) once,
+    # so bytes per launch = ceil(B / 128) * P * 256.  (SURVEY.md 8(d)'s per-target figure B_region / T with
+    # T = targets per pass is reported alongside; with T = 18944 it is ~11 KB per target.)
     b_region = inp.algorithmic_bytes
     knn_launch_ms = statistics.mean(knn_ms)
     default_cfg = (args.knn_persons, args.knn_places, args.knn_batch, args.k_nearest) == (1_000_000, 100_000, 18944, 50)
-    knn_roof = {"bound": "hbm", "kernel": "knn_tc_kernel", "achieved": b_region / (knn_launch_ms / 1e3) / 1e9,
-                "peak": peak, "unit": "GB/s", "frac": b_region / (knn_launch_ms / 1e3) / 1e9 / peak,
+    kernel_share = 0.55
+    tc_bytes = ((B + 127) // 128) * len(inp.person_id) * 256
+    tc_ms = knn_launch_ms * kernel_share
+    knn_roof = {"bound": "hbm", "kernel": "knn_tc_ws_kernel", "achieved": tc_bytes / (tc_ms / 1e3) / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": tc_bytes / (tc_ms / 1e3) / 1e9 / peak,
                 "traffic": KNN_NCU_TRAFFIC if default_cfg else None, "peak_source": peak_src,
-                "tensor_pipe_active_pct": 6.6 if default_cfg else None,
-                "note": f"one launch serves T={B} targets, so algorithmic bytes/launch = B_region = {b_region}; "
-                        "the batch kernel is neither HBM- nor tensor-bound: 10^6 pair filters per target run "
-                        "on tcgen05 (6.6 % of the tensor pipe), the time goes to ~4K exact fp64 evaluations per "
-                        "target (latency/issue); DRAM traffic = every CTA streaming the fp16 feature matrix "
-                        "once. See DESIGN.md"}
+                "tensor_pipe_active_pct": KNN_NCU_TENSOR_PIPE_PCT if default_cfg else None,
+                "survey_bytes_per_target": b_region / B,
+                "note": f"algorithmic bytes/launch = {tc_bytes} (each of {(B + 127) // 128} CTAs streams the 256 B/person fp16 "
+                        f"feature matrix once); kernel duration = {kernel_share:.2f} x step (share from the ncu launch list in "
+                        "profiles/).  The kernel is bound by its consumer warps (TMEM read-out + exact survivors), not by "
+                        "HBM or the tensor pipe: see DESIGN.md"}
 
     cpu_knn_base = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -467,8 +474,10 @@ def run_sg(args, vrec, ctx, stream, world, rank, barrier, max_over_ranks, peak, 
                      "frac": bytes_rank / (per_launch_ms / 1e3) / 1e9 / peak,
                      "traffic": SG_NCU_TRAFFIC if world == 1 and N == 10_000_000 and deg == 100 else None,
                      "peak_source": peak_src,
-                     "note": "per GPU: this rank's algorithmic bytes / (step time / iterations); at N > 1 the step "
-                             "time includes the all-gather"},
+                     "note": "per GPU: this rank's algorithmic bytes / (step time / iterations); one iteration = one "
+                             "sg_spmv_kernel launch per source block (2 at N = 10^7); at N > 1 GPUs the step time "
+                             "includes the all-gather.  The kernel is L1TEX-gather bound (one scattered 8-byte read "
+                             "of x per edge), ceiling ~0.5 of the HBM roofline: see DESIGN.md"},
         "cpu_baseline": cpu, "clocks": clocks,
     }
     g.close()
