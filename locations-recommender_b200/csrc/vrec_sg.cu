@@ -12,7 +12,7 @@ namespace {
 constexpr double kAlpha = 0.15;                 // stochastic/StochasticRecommender.scala:38
 constexpr int SPMV_THREADS = 256;
 constexpr int SPMV_WARPS = SPMV_THREADS / 32;
-constexpr int64_t SRC_BLOCK = 6291456;          // canonical source block, 3 * 2^21 vertices = 48 MB of x (oracle: CANON_SRC_BLOCK)
+constexpr int64_t SRC_BLOCK = 6291456;          // canonical source block, 3 * 2^21 vertices = 48 MB of x
 
 // Device-side loop control (one per query slot).
 struct SgState {
@@ -37,7 +37,7 @@ struct vrec_sg {
     DevBuf<int> d_rowptr;                     // [rows+1]
     DevBuf<int> d_src;                        // source vertex index per in-edge
     DevBuf<double> d_w;
-    // Source blocks (canonical order, see oracle/vrec_oracle.c): graphs with more than 3 * 2^21 vertices are
+    // Source blocks (canonical order): graphs with more than 3 * 2^21 vertices are
     // swept once per block of 3 * 2^21 sources, so that the gathered part of x (<= 48 MB) stays L2-resident.
     // Block b of row r is the in-edge range [start[r], end[r]); (sub-)ranges longer than
     // VREC_CANON_SEG are summed segment-wise through the per-block tables.
