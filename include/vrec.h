@@ -208,6 +208,17 @@ int vrec_sg_query(vrec_sg *sg, const int64_t *vertices, int32_t n,
                   int64_t *out_id, double *out_prob, int32_t *out_count,
                   int32_t *out_iterations, int32_t *out_converged, int32_t *out_status);
 
+/* Tuning / inspection of the batch kernel that serves start vertices without in-edges (every
+ * person vertex of the reference's graphs; csrc/vrec_sg_batch.cu).  Results are identical either way.
+ *  vrec_sg_set_option  "batch": 0 = per-query kernels only, 1 = batch kernel when a call has >= 4
+ *                      eligible start vertices (default), 2 = for every eligible start vertex;
+ *                      "batch_targets_per_cta": 0 = auto, 1, 2 or 4
+ *  vrec_sg_batch_info  what = 0: start vertices the last vrec_sg_query served with the batch kernel;
+ *                      1: batch path available for this graph; 2: vertices with in-edges; 3: edges
+ *                      between them                                                              */
+int vrec_sg_set_option(vrec_sg *sg, const char *name, int32_t value);
+int64_t vrec_sg_batch_info(vrec_sg *sg, int32_t what);
+
 /* The full stationary vector of one vertex (the DataFrame step() returns, before the
  * `id != vertex and probability > 0` filter): out_x[vertex_count], in vertex_ids order.   */
 int vrec_sg_stationary(vrec_sg *sg, int64_t vertex, double epsilon, int32_t max_iterations,

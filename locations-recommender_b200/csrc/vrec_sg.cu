@@ -5,65 +5,7 @@
 #include <memory>
 #include <numeric>
 
-#include "vrec_internal.cuh"
-
-namespace {
-
-constexpr double kAlpha = 0.15;                 // stochastic/StochasticRecommender.scala:38
-constexpr int SPMV_THREADS = 256;
-constexpr int SPMV_WARPS = SPMV_THREADS / 32;
-constexpr int64_t SRC_BLOCK = 6291456;          // canonical source block, 3 * 2^21 vertices = 48 MB of x
-
-// Device-side loop control (one per query slot).
-struct SgState {
-    int done;          // 1 once the iteration stopped
-    int iterations;    // the `iteration` of step()'s message (:94,:100)
-    int converged;     // 1 = "Converged in ...", 0 = "... reached the maximum ..."
-    unsigned int ticket;
-    double residual;   // last sum of squared differences (:131-139)
-    double residual_partial;   // this rank's share before the all-reduce (partitioned graphs)
-};
-
-}  // namespace
-
-struct vrec_sg {
-    vrec_ctx *ctx = nullptr;
-    int64_t N = 0, nnz = 0;
-    int64_t row_lo = 0, row_hi = 0;           // rows of P^T owned by this process
-    int64_t slice = 0;                        // rows per rank (equal, padded): x buffers hold slice * world values
-    bool partitioned = false;
-    std::vector<int64_t> h_ids;               // ascending vertex ids (host copy for lookups)
-    DevBuf<long long> d_ids;
-    DevBuf<int> d_rowptr;                     // [rows+1]
-    DevBuf<int> d_src;                        // source vertex index per in-edge
-    DevBuf<double> d_w;
-    // Source blocks (canonical order): graphs with more than 3 * 2^21 vertices are
-    // swept once per block of 3 * 2^21 sources, so that the gathered part of x (<= 48 MB) stays L2-resident.
-    // Block b of row r is the in-edge range [start[r], end[r]); (sub-)ranges longer than
-    // VREC_CANON_SEG are summed segment-wise through the per-block tables.
-    struct Block {
-        const int *row_start = nullptr, *row_end = nullptr;   // device, [rows]
-        int n_long = 0, n_seg = 0;
-        DevBuf<int> long_rows;                // [n_long] ascending local row
-        DevBuf<int> long_segptr;              // [n_long+1] offsets into partials
-        DevBuf<int> seg_row;                  // [n_seg] index into long_rows
-        DevBuf<double> partials;              // [n_seg]
-    };
-    int nblocks = 1;
-    std::vector<std::unique_ptr<Block>> blocks;
-    DevBuf<int> d_bptr;                       // [(nblocks+1) x rows] block boundaries per row (nblocks > 1)
-    DevBuf<double> d_x[2];
-    DevBuf<double> d_block_partials;
-    DevBuf<SgState> d_state;
-    int grid = 0;
-    // top-N scratch
-    DevBuf<long long> d_filter_ids;
-    DevBuf<double> d_cand_val;
-    DevBuf<long long> d_cand_key;
-    DevBuf<long long> d_out_key;
-    DevBuf<double> d_out_val;
-    DevBuf<int> d_out_count;
-};
+#include "vrec_sg.cuh"
 
 namespace {
 
@@ -441,6 +383,8 @@ int sg_setup_generated(vrec_sg *g) {
     return VREC_OK;
 }
 
+}  // namespace
+
 // launches the whole step() loop for one vertex index; results stay on the device
 int sg_run_device(vrec_sg *g, long long uidx, double epsilon, int max_it, bool check_convergence) {
     vrec_ctx *ctx = g->ctx;
@@ -509,8 +453,6 @@ int64_t sg_lookup(const vrec_sg *g, int64_t id) {
     if (it == g->h_ids.end() || *it != id) return -1;
     return it - g->h_ids.begin();
 }
-
-}  // namespace
 
 // ---------------------------------------------------------------------------------------
 // Host-side construction of the vertex table and the CSR of P^T (exposed for CPU tests).
@@ -599,6 +541,7 @@ extern "C" int vrec_sg_load(vrec_ctx *ctx, int64_t nnz, const int64_t *source_id
     if (rc == VREC_OK) rc = g->d_src.upload(src.data(), src.size(), ctx->stream);
     if (rc == VREC_OK) rc = g->d_w.upload(w.data(), w.size(), ctx->stream);
     if (rc == VREC_OK) rc = sg_setup_device(g, rowptr, src.data());
+    if (rc == VREC_OK) rc = sg_batch_analyse(g, rowptr, src.data(), w.data());
     if (rc != VREC_OK) {
         delete g;
         return rc;
@@ -736,7 +679,37 @@ extern "C" int vrec_sg_query(vrec_sg *sg, const int64_t *vertices, int32_t n, do
     VREC_TRY(sg->d_out_count.ensure(1));
     std::vector<long long> h_key(m);
     std::vector<double> h_val(m);
+    // Start vertices without in-edges (every person) go to the batch kernel when there are enough of
+    // them and the shared first iteration is not already the answer.
+    std::vector<char> batched((size_t)n, 0);
+    SgBatch &bt = sg->batch;
+    bt.last_batched = 0;
+    if (bt.ok && bt.mode > 0 && max_iterations >= 1 && n > 0) {
+        std::vector<int> qidx, qvertex;
+        for (int q = 0; q < n; ++q) {
+            int64_t v = sg_lookup(sg, vertices[q]);
+            if (v >= 0 && bt.h_act_of[v] < 0) {
+                qidx.push_back(q);
+                qvertex.push_back((int)v);
+            }
+        }
+        if (!qidx.empty() && (bt.mode == 2 || qidx.size() >= 4)) {
+            VREC_TRY(sg_batch_prepare(sg));
+            // residual of iteration 0 with the start vertex's own term (0.15 - x0)^2 in place of (0 - x0)^2
+            const double x0 = 1.0 / (double)sg->N;
+            const double r1 = bt.r1_base - x0 * x0 + (kAlpha - x0) * (kAlpha - x0);
+            if (!(r1 <= epsilon * epsilon)) {
+                VREC_TRY(sg_batch_query(sg, qidx, qvertex, epsilon, max_iterations, place_filter, n_filter, max_recs,
+                                        out_id, out_prob, out_count, out_iterations, out_converged));
+                for (int q : qidx) {
+                    batched[q] = 1;
+                    out_status[q] = VREC_OK;
+                }
+            }
+        }
+    }
     for (int q = 0; q < n; ++q) {
+        if (batched[q]) continue;
         out_count[q] = 0;
         if (out_iterations) out_iterations[q] = 0;
         if (out_converged) out_converged[q] = 0;
@@ -777,6 +750,35 @@ extern "C" int vrec_sg_query(vrec_sg *sg, const int64_t *vertices, int32_t n, do
         }
     }
     return VREC_OK;
+}
+
+// "batch": 0 = per-query kernels only, 1 = batch kernel for >= 4 eligible start vertices (default),
+// 2 = batch kernel for every eligible start vertex; "batch_targets_per_cta": 0 = auto, 1 / 2 / 4.
+extern "C" int vrec_sg_set_option(vrec_sg *sg, const char *name, int32_t value) {
+    if (!sg || !name) return VREC_EINVAL;
+    std::string k(name);
+    if (k == "batch" && value >= 0 && value <= 2) {
+        sg->batch.mode = value;
+    } else if (k == "batch_targets_per_cta" && (value == 0 || value == 1 || value == 2 || value == 4)) {
+        sg->batch.force_t = value;
+    } else {
+        vrec_set_error("vrec_sg_set_option: unknown option or bad value: %s = %d", name, (int)value);
+        return VREC_EINVAL;
+    }
+    return VREC_OK;
+}
+
+// what: 0 = start vertices the last vrec_sg_query served with the batch kernel, 1 = batch path
+// available for this graph (0/1), 2 = active vertices, 3 = edges between active vertices.
+extern "C" int64_t vrec_sg_batch_info(vrec_sg *sg, int32_t what) {
+    if (!sg) return -1;
+    switch (what) {
+        case 0: return sg->batch.last_batched;
+        case 1: return sg->batch.ok ? 1 : 0;
+        case 2: return sg->batch.n_a;
+        case 3: return sg->batch.r_nnz;
+        default: return -1;
+    }
 }
 
 // Copies the device CSR of P^T (rows owned by this process) back to the host, for tests.

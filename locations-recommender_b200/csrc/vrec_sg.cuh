@@ -1,0 +1,94 @@
+// Types shared by the SG translation units (vrec_sg.cu, vrec_sg_batch.cu); not part of the ABI.
+#pragma once
+#include <memory>
+
+#include "vrec_internal.cuh"
+
+constexpr double kAlpha = 0.15;                 // stochastic/StochasticRecommender.scala:38
+constexpr int SPMV_THREADS = 256;
+constexpr int SPMV_WARPS = SPMV_THREADS / 32;
+constexpr int64_t SRC_BLOCK = 6291456;          // canonical source block, 3 * 2^21 vertices = 48 MB of x
+
+// Device-side loop control (one per query slot).
+struct SgState {
+    int done;          // 1 once the iteration stopped
+    int iterations;    // the `iteration` of step()'s message (:94,:100)
+    int converged;     // 1 = "Converged in ...", 0 = "... reached the maximum ..."
+    unsigned int ticket;
+    double residual;   // last sum of squared differences (:131-139)
+    double residual_partial;   // this rank's share before the all-reduce (partitioned graphs)
+};
+
+// Batch path (vrec_sg_batch.cu): many personalised queries whose start vertex has no in-edge
+// (every person vertex of the reference's graphs).  See the comment at the top of that file.
+struct SgBatch {
+    bool analysed = false, ok = false;
+    int n_a = 0;                              // active vertices (in-degree > 0)
+    int64_t r_nnz = 0;                        // edges between active vertices
+    std::vector<int> h_act_of;                // [N] active index or -1
+    DevBuf<int> r_rowptr, r_src, full_len;    // reduced CSR of P^T over the active vertices
+    DevBuf<double> r_w;
+    DevBuf<int> z_rowptr, z_row, z_pos;       // out-edges of the in-degree-0 vertices: (active row, position in its full row)
+    DevBuf<double> z_w;
+    DevBuf<double> x1a;                       // x after the first (start-vertex independent) iteration, active part
+    bool x1_ready = false;
+    double r1_base = 0.0;                     // residual of that iteration without the start vertex's own term
+    DevBuf<double> scratch;
+    DevBuf<int> counter, q_vertex, cand_act, out_count, out_it, out_conv;
+    DevBuf<long long> cand_id, out_id;
+    DevBuf<double> out_prob;
+    int mode = 1;                             // 0 never, 1 auto (>= 4 eligible queries), 2 whenever eligible
+    int force_t = 0;                          // debug: targets per CTA (0 = largest that fits)
+    int64_t last_batched = 0;                 // queries the last vrec_sg_query served by the batch kernel
+};
+
+struct vrec_sg {
+    vrec_ctx *ctx = nullptr;
+    int64_t N = 0, nnz = 0;
+    int64_t row_lo = 0, row_hi = 0;           // rows of P^T owned by this process
+    int64_t slice = 0;                        // rows per rank (equal, padded): x buffers hold slice * world values
+    bool partitioned = false;
+    std::vector<int64_t> h_ids;               // ascending vertex ids (host copy for lookups)
+    DevBuf<long long> d_ids;
+    DevBuf<int> d_rowptr;                     // [rows+1]
+    DevBuf<int> d_src;                        // source vertex index per in-edge
+    DevBuf<double> d_w;
+    // Source blocks (canonical order): graphs with more than 3 * 2^21 vertices are
+    // swept once per block of 3 * 2^21 sources, so that the gathered part of x (<= 48 MB) stays L2-resident.
+    // Block b of row r is the in-edge range [start[r], end[r]); (sub-)ranges longer than
+    // VREC_CANON_SEG are summed segment-wise through the per-block tables.
+    struct Block {
+        const int *row_start = nullptr, *row_end = nullptr;   // device, [rows]
+        int n_long = 0, n_seg = 0;
+        DevBuf<int> long_rows;                // [n_long] ascending local row
+        DevBuf<int> long_segptr;              // [n_long+1] offsets into partials
+        DevBuf<int> seg_row;                  // [n_seg] index into long_rows
+        DevBuf<double> partials;              // [n_seg]
+    };
+    int nblocks = 1;
+    std::vector<std::unique_ptr<Block>> blocks;
+    DevBuf<int> d_bptr;                       // [(nblocks+1) x rows] block boundaries per row (nblocks > 1)
+    DevBuf<double> d_x[2];
+    DevBuf<double> d_block_partials;
+    DevBuf<SgState> d_state;
+    int grid = 0;
+    // top-N scratch
+    DevBuf<long long> d_filter_ids;
+    DevBuf<double> d_cand_val;
+    DevBuf<long long> d_cand_key;
+    DevBuf<long long> d_out_key;
+    DevBuf<double> d_out_val;
+    DevBuf<int> d_out_count;
+    SgBatch batch;
+};
+
+int sg_run_device(vrec_sg *g, long long uidx, double epsilon, int max_it, bool check_convergence);
+int sg_fetch_state(vrec_sg *g, int max_it, SgState *h, int *result_buf);
+int64_t sg_lookup(const vrec_sg *g, int64_t id);
+// vrec_sg_batch.cu
+int sg_batch_analyse(vrec_sg *g, const std::vector<int> &rowptr, const int *h_src, const double *h_w);
+int sg_batch_prepare(vrec_sg *g);
+int sg_batch_query(vrec_sg *g, const std::vector<int> &qidx, const std::vector<int> &qvertex,
+                   double epsilon, int max_it, const int64_t *place_filter, int64_t n_filter, int max_recs,
+                   int64_t *out_id, double *out_prob, int32_t *out_count, int32_t *out_iterations,
+                   int32_t *out_converged);

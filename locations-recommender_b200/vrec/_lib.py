@@ -58,6 +58,8 @@ SIGNATURES = {
                                 i64p, f64p, i32p, i32p, i32p, i32p]),
     "vrec_sg_stationary": (C.c_int, [vp, C.c_int64, C.c_double, C.c_int32, f64p, i32p, i32p, f64p]),
     "vrec_sg_iterate_device": (C.c_int, [vp, C.c_int32]),
+    "vrec_sg_set_option": (C.c_int, [vp, C.c_char_p, C.c_int32]),
+    "vrec_sg_batch_info": (C.c_int64, [vp, C.c_int32]),
     "vrec_sg_resident_bytes": (C.c_int64, [vp]),
     "vrec_sg_generate": (C.c_int, [vp, C.c_int64, C.c_int32, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(vp)]),
     "vrec_host_sg_csr": (C.c_int, [C.c_int64, i64p, i64p, f64p, i64p, i64p, i32p, i32p, f64p]),

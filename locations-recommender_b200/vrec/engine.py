@@ -279,6 +279,13 @@ class StochasticGraph:
     def iterate_device(self, iterations: int) -> None:
         _check(self.ctx.lib.vrec_sg_iterate_device(self._h, int(iterations)))
 
+    def set_option(self, name: str, value: int) -> None:
+        """"batch": 0 / 1 (default) / 2; "batch_targets_per_cta": 0 (auto) / 1 / 2 / 4 -- see include/vrec.h."""
+        _check(self.ctx.lib.vrec_sg_set_option(self._h, name.encode(), int(value)))
+
+    def batch_info(self, what: int) -> int:
+        return int(self.ctx.lib.vrec_sg_batch_info(self._h, int(what)))
+
     @property
     def resident_bytes(self) -> int:
         return int(self.ctx.lib.vrec_sg_resident_bytes(self._h))

@@ -323,3 +323,46 @@ def random_stochastic_graph(n_vertices: int, out_degree: int, seed: int, id_stri
     tot = np.bincount(src, weights=w, minlength=n_vertices)
     w = w / tot[src]
     return ids[src], ids[dst], w
+
+
+def random_layered_graph(n_categories: int, n_places: int, n_persons: int, seed: int,
+                         places_per_person: int = 6, cats_per_person: int = 3, similar_per_place: int = 8,
+                         hub_places: int = 2, hub_fraction: float = 0.3, duplicate_fraction: float = 0.02,
+                         beta_place: float = 0.5, beta_category: float = 0.5):
+    """Random graph with the edge families of stochastic/StochasticGraphBuilder.scala:8-28 and the
+    id layout of the sample data (categories < places < persons, SampleGeneratorMain.scala:36-37,54):
+    person->place (beta_place), person->category (beta_category), place->place, category->place, every
+    family row-normalised.  A hub_fraction of the person->place and place->place edges point at the
+    first hub_places places (rows of P^T far longer than the canonical segment); a
+    duplicate_fraction of the person->place edges is repeated (duplicate (s, t) rows are separate
+    terms, stochastic/StochasticRecommender.scala:108-114)."""
+    rng = np.random.default_rng(seed)
+    cat_ids = np.arange(n_categories, dtype=np.int64)
+    place_ids = 2 * n_categories + np.arange(n_places, dtype=np.int64) * 2        # sparse ids
+    person_ids = place_ids[-1] + 5 + np.arange(n_persons, dtype=np.int64) * 3
+
+    def family(src_ids, n_dst, per_src, hub, beta, dst_ids):
+        s = np.repeat(np.arange(len(src_ids)), per_src)
+        d = rng.integers(0, n_dst, len(s))
+        if hub and hub_places > 0:
+            h = rng.random(len(s)) < hub_fraction
+            d = np.where(h, rng.integers(0, min(hub_places, n_dst), len(s)), d)
+        w = rng.random(len(s)) + 0.05
+        tot = np.bincount(s, weights=w, minlength=len(src_ids))
+        return src_ids[s], dst_ids[d], beta * w / tot[s]
+
+    pp = family(person_ids, n_places, places_per_person, True, beta_place, place_ids)
+    pc = family(person_ids, n_categories, cats_per_person, False, beta_category, cat_ids)
+    ll = family(place_ids, n_places, similar_per_place, True, 1.0, place_ids)
+    cl = family(cat_ids, n_places, min(100, n_places), False, 1.0, place_ids)
+    src = np.concatenate([pp[0], pc[0], ll[0], cl[0]])
+    dst = np.concatenate([pp[1], pc[1], ll[1], cl[1]])
+    w = np.concatenate([pp[2], pc[2], ll[2], cl[2]])
+    if duplicate_fraction > 0:
+        n_dup = int(len(pp[0]) * duplicate_fraction)
+        pick = rng.integers(0, len(pp[0]), n_dup)
+        src = np.concatenate([src, pp[0][pick]])
+        dst = np.concatenate([dst, pp[1][pick]])
+        w = np.concatenate([w, pp[2][pick]])
+    perm = rng.permutation(len(src))
+    return src[perm], dst[perm], w[perm], person_ids, place_ids, cat_ids

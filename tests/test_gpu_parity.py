@@ -168,6 +168,92 @@ def test_sg_source_blocked_order(vrec, ctx, synth, oracle):
     g.close()
 
 
+def _check_sg_batch(rec, og, vertices, flt, max_recs, eps, max_it):
+    oi, op, cnt, its, conv, st = rec.recommend(vertices, flt, max_recs)
+    for q, v in enumerate(vertices):
+        rc, wi, wp, oit, oconv = og.query(int(v), eps, max_it, flt, max_recs)
+        assert st[q] == rc
+        if rc:
+            assert cnt[q] == 0
+            continue
+        assert (int(its[q]), int(conv[q])) == (oit, oconv), (q, v)
+        assert oi[q, :cnt[q]].tolist() == wi.tolist(), (q, v)
+        assert op[q, :cnt[q]].tolist() == wp.tolist(), (q, v)             # bit-exact
+
+
+@pytest.mark.parametrize("tpc", [0, 1, 2, 4])
+def test_sg_batch_kernel_bit_exact(vrec, ctx, synth, oracle, tpc):
+    # config 4 shape: many person start vertices on one graph; hub rows longer than the canonical
+    # segment in both the place->place prefix and the person part, duplicate edges
+    s, t, w, persons, places, cats = synth.random_layered_graph(5, 1500, 4000, seed=11)
+    g = vrec.StochasticGraph(s, t, w, ctx=ctx)
+    og = oracle.SgGraph(s, t, w)
+    assert g.batch_info(1) == 1 and g.batch_info(2) == 1505
+    g.set_option("batch", 2)
+    g.set_option("batch_targets_per_cta", tpc)
+    rng = np.random.default_rng(tpc)
+    some = rng.choice(persons, 37, replace=False)
+    flt = np.concatenate([places[::2], [places[3], 10 ** 9]])          # a duplicate and an unknown id
+    for eps, max_it, f, m in [(0.01, 20, flt, 10), (0.0, 4, None, 7), (1e-6, 20, flt, 3), (0.01, 1, flt, 10),
+                              (0.01, 2, places, 2000), (1e-3, 20, flt, 0)]:
+        rec = vrec.StochasticRecommender(g, eps, max_it)
+        _check_sg_batch(rec, og, some, f, m, eps, max_it)
+        assert g.batch_info(0) == len(some)
+    # a call that mixes persons, a place, a category and an unknown id
+    mixed = np.array([persons[0], places[0], 10 ** 9 + 1, persons[5], cats[1], persons[0]])
+    rec = vrec.StochasticRecommender(g, 0.01, 20)
+    _check_sg_batch(rec, og, mixed, flt, 10, 0.01, 20)
+    assert g.batch_info(0) == 3
+    # parameters for which the shared first iteration is already the answer use the per-query path
+    rec = vrec.StochasticRecommender(g, 10.0, 20)
+    _check_sg_batch(rec, og, some[:5], flt, 10, 10.0, 20)
+    assert g.batch_info(0) == 0
+    rec = vrec.StochasticRecommender(g, 0.01, 0)
+    _check_sg_batch(rec, og, some[:5], flt, 10, 0.01, 0)
+    assert g.batch_info(0) == 0
+    g.set_option("batch", 0)
+    rec = vrec.StochasticRecommender(g, 0.01, 20)
+    _check_sg_batch(rec, og, some[:5], flt, 10, 0.01, 20)
+    assert g.batch_info(0) == 0
+    with pytest.raises(ValueError):
+        g.set_option("batch", 7)
+
+
+def test_sg_batch_default_sample_graph(vrec, ctx, synth, oracle):
+    # per-region graph of sample-generator data through the four edge calculators
+    pl = synth.sample_places(30000, seed=0)
+    v = synth.sample_place_visits(pl, 0, persons_per_region=30000, person_count_total=3_000_000, seed=0)
+    s, t, w = synth.build_stochastic_graph(v)
+    g = vrec.StochasticGraph(s, t, w, ctx=ctx)
+    og = oracle.SgGraph(s, t, w)
+    assert g.batch_info(1) == 1
+    persons = np.unique(v.person_id)[:300]
+    rec = vrec.StochasticRecommender(g, 0.01, 20)                     # bin/stochastic_recommender.sh:32-35
+    _check_sg_batch(rec, og, persons, pl.of_region(0), 10, 0.01, 20)
+    assert g.batch_info(0) == len(persons)
+
+
+def test_sg_batch_not_applicable(vrec, ctx, synth, oracle):
+    # every vertex has in-edges: no batch path, same results through the per-query kernels
+    s, t, w = synth.random_stochastic_graph(3000, 6, seed=2)
+    g = vrec.StochasticGraph(s, t, w, ctx=ctx)
+    og = oracle.SgGraph(s, t, w)
+    g.set_option("batch", 2)
+    rec = vrec.StochasticRecommender(g, 1e-3, 20)
+    _check_sg_batch(rec, og, og.ids[:6], og.ids[::3], 10, 1e-3, 20)
+    assert g.batch_info(0) == 0
+    # active sources that follow in-degree-0 sources in a row (person ids below place ids)
+    s, t, w, persons, places, cats = synth.random_layered_graph(4, 300, 500, seed=3)
+    remap = {int(p): -int(p) for p in persons}
+    s2 = np.array([remap.get(int(x), int(x)) for x in s], dtype=np.int64)
+    g = vrec.StochasticGraph(s2, t, w, ctx=ctx)
+    og = oracle.SgGraph(s2, t, w)
+    assert g.batch_info(1) == 0
+    rec = vrec.StochasticRecommender(g, 0.01, 20)
+    _check_sg_batch(rec, og, [-int(persons[0]), -int(persons[7]), -int(persons[9]), -int(persons[11])], places, 10,
+                    0.01, 20)
+
+
 # ------------------------------------------------------------------ KNN
 def _check_knn(vrec, oracle, rs, inp, pw, cw, k, targets, flt, max_recs):
     rec = vrec.KnnRecommender(rs, pw, cw, k)
