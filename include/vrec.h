@@ -212,10 +212,12 @@ int vrec_sg_query(vrec_sg *sg, const int64_t *vertices, int32_t n,
  * person vertex of the reference's graphs; csrc/vrec_sg_batch.cu).  Results are identical either way.
  *  vrec_sg_set_option  "batch": 0 = per-query kernels only, 1 = batch kernel when a call has >= 4
  *                      eligible start vertices (default), 2 = for every eligible start vertex;
- *                      "batch_targets_per_cta": 0 = auto, 1, 2 or 4
+ *                      "batch_targets_per_cta": 0 = auto, 1 or 2
  *  vrec_sg_batch_info  what = 0: start vertices the last vrec_sg_query served with the batch kernel;
  *                      1: batch path available for this graph; 2: vertices with in-edges; 3: edges
- *                      between them                                                              */
+ *                      between them; 4: the same with the slice padding;
+ *                      5 / 6 / 7: host-clock microseconds of the last batch call (uploads / kernel /
+ *                      copy-back)                                                            */
 int vrec_sg_set_option(vrec_sg *sg, const char *name, int32_t value);
 int64_t vrec_sg_batch_info(vrec_sg *sg, int32_t what);
 

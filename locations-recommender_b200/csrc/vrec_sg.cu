@@ -753,13 +753,13 @@ extern "C" int vrec_sg_query(vrec_sg *sg, const int64_t *vertices, int32_t n, do
 }
 
 // "batch": 0 = per-query kernels only, 1 = batch kernel for >= 4 eligible start vertices (default),
-// 2 = batch kernel for every eligible start vertex; "batch_targets_per_cta": 0 = auto, 1 / 2 / 4.
+// 2 = batch kernel for every eligible start vertex; "batch_targets_per_cta": 0 = auto, 1 or 2.
 extern "C" int vrec_sg_set_option(vrec_sg *sg, const char *name, int32_t value) {
     if (!sg || !name) return VREC_EINVAL;
     std::string k(name);
     if (k == "batch" && value >= 0 && value <= 2) {
         sg->batch.mode = value;
-    } else if (k == "batch_targets_per_cta" && (value == 0 || value == 1 || value == 2 || value == 4)) {
+    } else if (k == "batch_targets_per_cta" && (value >= 0 && value <= 2)) {
         sg->batch.force_t = value;
     } else {
         vrec_set_error("vrec_sg_set_option: unknown option or bad value: %s = %d", name, (int)value);
@@ -777,6 +777,10 @@ extern "C" int64_t vrec_sg_batch_info(vrec_sg *sg, int32_t what) {
         case 1: return sg->batch.ok ? 1 : 0;
         case 2: return sg->batch.n_a;
         case 3: return sg->batch.r_nnz;
+        case 4: return sg->batch.sell_nnz;
+        case 5: return sg->batch.us_prepare;
+        case 6: return sg->batch.us_kernel;
+        case 7: return sg->batch.us_results;
         default: return -1;
     }
 }

@@ -24,21 +24,29 @@ struct SgState {
 struct SgBatch {
     bool analysed = false, ok = false;
     int n_a = 0;                              // active vertices (in-degree > 0)
+    int n_fast_chunks = 0, n_slow = 0;        // slices of 32 rows summed one row per thread / rows behind them
     int64_t r_nnz = 0;                        // edges between active vertices
     std::vector<int> h_act_of;                // [N] active index or -1
     DevBuf<int> r_rowptr, r_src, full_len;    // reduced CSR of P^T over the active vertices
     DevBuf<double> r_w;
+    DevBuf<int> chunk_r;                      // the same graph in slices of 32 rows (see vrec_sg_batch.cu)
+    DevBuf<long long> chunk_ptr, act_id;
+    DevBuf<unsigned short> sell_src;
+    DevBuf<double> sell_w;
+    DevBuf<unsigned> cand_mask;
+    long long sell_nnz = 0;
     DevBuf<int> z_rowptr, z_row, z_pos;       // out-edges of the in-degree-0 vertices: (active row, position in its full row)
     DevBuf<double> z_w;
     DevBuf<double> x1a;                       // x after the first (start-vertex independent) iteration, active part
     bool x1_ready = false;
     double r1_base = 0.0;                     // residual of that iteration without the start vertex's own term
     DevBuf<double> scratch;
-    DevBuf<int> counter, q_vertex, cand_act, out_count, out_it, out_conv;
-    DevBuf<long long> cand_id, out_id;
+    DevBuf<int> counter, q_vertex, out_count, out_it, out_conv;
+    DevBuf<long long> out_id;
     DevBuf<double> out_prob;
     int mode = 1;                             // 0 never, 1 auto (>= 4 eligible queries), 2 whenever eligible
     int force_t = 0;                          // debug: targets per CTA (0 = largest that fits)
+    long long us_prepare = 0, us_kernel = 0, us_results = 0;   // host-clock split of the last batch call
     int64_t last_batched = 0;                 // queries the last vrec_sg_query served by the batch kernel
 };
 

@@ -18,33 +18,50 @@
 // otherwise, or for start vertices with in-edges, vrec_sg_query falls back to the per-query kernels.
 //
 // One CTA owns T start vertices at a time: their x vectors over A live in shared memory, the
-// reduced graph (12 B per edge, L2-resident) is streamed once per iteration for all T, rows are
-// summed two per warp in the canonical order, and the step() loop (:92-106), the convergence test
-// (:130-141) and the ranked top-N all run inside the kernel -- no launch per iteration or per query.
+// reduced graph (10 B per edge, L2-resident) is streamed once per iteration for all T, and the
+// step() loop (:92-106), the convergence test (:130-141) and the ranked top-N all run inside the
+// kernel -- no launch per iteration or per query.
+//
+// Layout of the reduced graph: the active vertices are renumbered by ceil(in-edges / 32) and stored
+// in slices of 32 rows (sliced ELLPACK, one row per lane, coalesced).  Inside a slice a row's terms
+// are stored canonical lane by canonical lane (term k -> step (k % 32) * R + k / 32, R = terms per
+// lane), so ONE THREAD sums a whole row in exactly the canonical order: the 32 lane sums one after
+// the other, combined by a binary-counter stack that reproduces the xor-butterfly tree
+// ((L0+L1)+(L2+L3))+... -- no shuffles, no dependent cross-lane latency.  Padding terms are
+// x[0] * 0.0 = +0.0.  Rows with more than 1024 active in-edges keep the CSR form and a whole warp.
 #include <algorithm>
+#include <chrono>
 #include <climits>
 
 #include "vrec_sg.cuh"
 
 namespace {
 
-constexpr int BT = 1024;            // threads per CTA
+constexpr int BT = 512;             // threads per CTA
 constexpr int BW = BT / 32;
-constexpr size_t SMEM_LIMIT = 227 * 1024 - 3 * 1024;   // dynamic part; statics + reserve stay below 3 KB
+constexpr int TOPN_FAST = 16;       // max_recs up to this use the warp-local selection
+constexpr size_t SMEM_LIMIT = 227 * 1024 - 12 * 1024;   // dynamic part; ~9 KB of statics + reserve
 
 struct SgBatchArgs {
     int n_a, n_chunks;
+    int n_fast_chunks, n_slow;        // slices summed one row per thread; rows behind them, one per warp
+    // sliced layout: slice c holds rows [32c, 32c+32); chunk_r[c] = terms of its longest row (> 1024: CSR path)
+    const int *chunk_r;
+    const long long *chunk_ptr;
+    const unsigned short *sell_src;
+    const double *sell_w;
+    // CSR of the same reduced graph (rows that receive the start vertex's term, rows > 1024 terms)
     const int *r_rowptr, *r_src, *full_len;
     const double *r_w;
     const int *z_rowptr, *z_row, *z_pos;
     const double *z_w;
     const double *x1a;
+    const long long *act_id;
     const int *q_vertex;
     int n_q, max_it;
     double eps2;
-    const int *cand_act;
-    const long long *cand_id;
-    int n_cand, max_recs;
+    const unsigned *cand_mask;        // bit per active vertex: member of the place filter
+    int max_recs;
     long long *out_id;
     double *out_prob;
     int *out_count, *out_it, *out_conv;
@@ -52,9 +69,9 @@ struct SgBatchArgs {
     int *counter;
 };
 
-__device__ __forceinline__ int ld_nc_i32(const int *p) {
-    int v;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+__device__ __forceinline__ unsigned ld_nc_u16(const unsigned short *p) {
+    unsigned short v;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ double ld_nc_f64(const double *p) {
@@ -63,95 +80,279 @@ __device__ __forceinline__ double ld_nc_f64(const double *p) {
     return v;
 }
 
-// Canonical sums of one reduced row (n <= VREC_CANON_SEG terms starting at edge s) for T x vectors
-// in shared memory, by a group of G lanes; same lane rules as canon_row_sum in vrec_sg.cu.
-template <int G, int T>
-__device__ __forceinline__ void canon_row_sum_s(const int *__restrict__ src, const double *__restrict__ w,
-                                                const double *xs, int n_a, int s, int n, int sublane,
-                                                double (&out)[T]) {
-    constexpr int V = 32 / G;
-    constexpr int U = 4 / V > 0 ? 4 / V : 1;
-    double acc[T][V];
+// x of the T start vertices of a CTA is interleaved in shared memory (xs[i * T + t]): one 128-bit
+// load fetches both values of a source when T = 2 (fewer bank-conflict wavefronts than two 64-bit loads).
+template <int T>
+__device__ __forceinline__ void load_x(const double *xs, unsigned c, double (&xv)[T]) {
+    if constexpr (T == 2) {
+        const double2 v = *reinterpret_cast<const double2 *>(xs + 2 * c);
+        xv[0] = v.x;
+        xv[1] = v.y;
+    } else {
 #pragma unroll
-    for (int t = 0; t < T; ++t)
-#pragma unroll
-        for (int j = 0; j < V; ++j) acc[t][j] = 0.0;
-    for (int kb = 0; kb < n; kb += 32 * U) {
-        int c[U * V];
-        double ww[U * V];
-        bool ok[U * V];
-#pragma unroll
-        for (int q = 0; q < U * V; ++q) {
-            int k = kb + sublane + G * q;
-            ok[q] = k < n;
-            c[q] = ok[q] ? ld_nc_i32(src + s + k) : 0;
-            ww[q] = ok[q] ? ld_nc_f64(w + s + k) : 0.0;
-        }
-#pragma unroll
-        for (int q = 0; q < U * V; ++q)
-#pragma unroll
-            for (int t = 0; t < T; ++t)
-                if (ok[q]) acc[t][q % V] = xadd(acc[t][q % V], xmul(xs[t * n_a + c[q]], ww[q]));
-    }
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-#pragma unroll
-        for (int off = 1; off < G; off <<= 1) {
-#pragma unroll
-            for (int j = 0; j < V; ++j) acc[t][j] = xadd(acc[t][j], __shfl_xor_sync(0xffffffffu, acc[t][j], off));
-        }
-#pragma unroll
-        for (int off = 1; off < V; off <<= 1) {
-            double tmp[V];
-#pragma unroll
-            for (int j = 0; j < V; ++j) tmp[j] = xadd(acc[t][j], acc[t][j ^ off]);
-#pragma unroll
-            for (int j = 0; j < V; ++j) acc[t][j] = tmp[j];
-        }
-        out[t] = acc[t][0];
+        for (int t = 0; t < T; ++t) xv[t] = xs[c * T + t];
     }
 }
 
-// General row sum by a whole warp: the reduced prefix of `row` (m terms at positions 0..m-1 of the
-// full row) plus the start vertex's own terms z[e..ee) (positions z_pos >= m, ascending, value
-// 0.15 * w).  Rows whose FULL length exceeds VREC_CANON_SEG are summed per 1024-term segment and the
-// segment sums by the same lane rule; all-zero segments are skipped.
+// One thread, one row of a slice whose longest row has n_max = 32 * (R - 1) + rem terms (1 <= rem <= 32):
+// canonical lane l has R terms if l < rem, else R - 1.  Storage: first the (R - 1) leading terms of every
+// lane, lane by lane (step l * (R - 1) + c2), then the rem last terms (step 32 * (R - 1) + l).  The
+// lanes are summed 0..31 in turn and merged by a binary-counter stack = the xor-butterfly tree.
+__host__ __device__ constexpr int trailing_ones(int l) { return (l & 1) ? 1 + trailing_ones(l >> 1) : 0; }
+
+template <int T, int L>
+__device__ __forceinline__ void tree_push(double (&st)[T][6], const double (&acc)[T]) {
+    constexpr int TZ = trailing_ones(L);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        double v = acc[t];
+#pragma unroll
+        for (int bit = 0; bit < TZ; ++bit) v = xadd(st[t][bit], v);
+        st[t][TZ] = v;
+    }
+}
+
+// lanes [L0, L0 + GL) of the row: all their loads first (GL * R <= 8 in flight), then the sums
+template <int T, int R, int GL, int L0>
+struct SellGroup {
+    static __device__ __forceinline__ void run(const unsigned short *__restrict__ src, const double *__restrict__ w,
+                                               const double *xs, int n_a, int rem, double (&st)[T][6]) {
+        unsigned c[GL][R];
+        double ww[GL][R];
+#pragma unroll
+        for (int g = 0; g < GL; ++g) {
+            const int l = L0 + g;
+#pragma unroll
+            for (int c2 = 0; c2 < R - 1; ++c2) {
+                c[g][c2] = ld_nc_u16(src + (l * (R - 1) + c2) * 32);
+                ww[g][c2] = ld_nc_f64(w + (l * (R - 1) + c2) * 32);
+            }
+            const bool last = l < rem;
+            c[g][R - 1] = last ? ld_nc_u16(src + (32 * (R - 1) + l) * 32) : 0u;
+            ww[g][R - 1] = last ? ld_nc_f64(w + (32 * (R - 1) + l) * 32) : 0.0;
+        }
+        tail<0>(c, ww, xs, n_a, rem, st);
+        SellGroup<T, R, GL, L0 + GL>::run(src, w, xs, n_a, rem, st);
+    }
+    template <int G>
+    static __device__ __forceinline__ void tail(const unsigned (&c)[GL][R], const double (&ww)[GL][R], const double *xs,
+                                                int n_a, int rem, double (&st)[T][6]) {
+        if constexpr (G < GL) {
+            double acc[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) acc[t] = 0.0;
+#pragma unroll
+            for (int c2 = 0; c2 < R - 1; ++c2) {
+                double xv[T];
+                load_x<T>(xs, c[G][c2], xv);
+#pragma unroll
+                for (int t = 0; t < T; ++t) acc[t] = xadd(acc[t], xmul(xv[t], ww[G][c2]));
+            }
+            if (L0 + G < rem) {
+                double xv[T];
+                load_x<T>(xs, c[G][R - 1], xv);
+#pragma unroll
+                for (int t = 0; t < T; ++t) acc[t] = xadd(acc[t], xmul(xv[t], ww[G][R - 1]));
+            }
+            tree_push<T, L0 + G>(st, acc);
+            tail<G + 1>(c, ww, xs, n_a, rem, st);
+        }
+    }
+};
+template <int T, int R, int GL>
+struct SellGroup<T, R, GL, 32> {
+    static __device__ __forceinline__ void run(const unsigned short *, const double *, const double *, int, int,
+                                               double (&)[T][6]) {}
+};
+
+template <int T, int R>
+__device__ __forceinline__ void sell_row_sum(const unsigned short *__restrict__ src, const double *__restrict__ w,
+                                             const double *xs, int n_a, int rem, double (&out)[T]) {
+    constexpr int GL = R == 1 ? 8 : (R == 2 ? 4 : 2);
+    double st[T][6];
+    SellGroup<T, R, GL, 0>::run(src, w, xs, n_a, rem, st);
+#pragma unroll
+    for (int t = 0; t < T; ++t) out[t] = st[t][5];
+}
+
+// The same for any R <= 32 (rows with more than 128 active in-edges): runtime inner loop, the
+// canonical lane L as a template parameter so that the tree stack stays in registers.
+template <int T, int L>
+struct SellLane {
+    static __device__ __forceinline__ void run(const unsigned short *__restrict__ src, const double *__restrict__ w,
+                                               const double *xs, int n_a, int R, int rem, double (&st)[T][6]) {
+        double acc[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) acc[t] = 0.0;
+        const unsigned short *ps = src + (size_t)L * (R - 1) * 32;
+        const double *pw = w + (size_t)L * (R - 1) * 32;
+#pragma unroll 4
+        for (int c2 = 0; c2 < R - 1; ++c2) {
+            unsigned c = ld_nc_u16(ps + c2 * 32);
+            double ww = ld_nc_f64(pw + c2 * 32);
+            double xv[T];
+            load_x<T>(xs, c, xv);
+#pragma unroll
+            for (int t = 0; t < T; ++t) acc[t] = xadd(acc[t], xmul(xv[t], ww));
+        }
+        if (L < rem) {
+            unsigned c = ld_nc_u16(src + (size_t)(32 * (R - 1) + L) * 32);
+            double ww = ld_nc_f64(w + (size_t)(32 * (R - 1) + L) * 32);
+            double xv[T];
+            load_x<T>(xs, c, xv);
+#pragma unroll
+            for (int t = 0; t < T; ++t) acc[t] = xadd(acc[t], xmul(xv[t], ww));
+        }
+        tree_push<T, L>(st, acc);
+        SellLane<T, L + 1>::run(src, w, xs, n_a, R, rem, st);
+    }
+};
+template <int T>
+struct SellLane<T, 32> {
+    static __device__ __forceinline__ void run(const unsigned short *, const double *, const double *, int, int, int,
+                                               double (&)[T][6]) {}
+};
+
+template <int T>
+__device__ __forceinline__ void sell_row_sum_any(const unsigned short *__restrict__ src, const double *__restrict__ w,
+                                                 const double *xs, int n_a, int R, int rem, double (&out)[T]) {
+    double st[T][6];
+    SellLane<T, 0>::run(src, w, xs, n_a, R, rem, st);
+#pragma unroll
+    for (int t = 0; t < T; ++t) out[t] = st[t][5];
+}
+
+// Lane-strided partial sums of the CSR terms [s, s+len): this lane's canonical lane sum (terms
+// k = lane, lane+32, ... in ascending order), four loads in flight.  NT x vectors with values at
+// xs[c * S + t], t < NT (S = vectors interleaved in shared memory).
+template <int NT, int S>
+__device__ __forceinline__ void csr_lane_sum(const SgBatchArgs &a, const double *xs, int s, int len, int lane,
+                                             double (&acc)[NT]) {
+    const int *__restrict__ src = a.r_src + s;
+    const double *__restrict__ w = a.r_w + s;
+    int k = lane;
+    for (; k + 96 < len; k += 128) {
+        int c[4];
+        double ww[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            c[q] = __ldg(src + k + 32 * q);
+            ww[q] = __ldg(w + k + 32 * q);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double xv[NT];
+            if constexpr (NT == S) {
+                load_x<NT>(xs, (unsigned)c[q], xv);
+            } else {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) xv[t] = xs[c[q] * S + t];
+            }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc[t] = xadd(acc[t], xmul(xv[t], ww[q]));
+        }
+    }
+    for (; k < len; k += 32) {
+        const int c = __ldg(src + k);
+        const double ww = __ldg(w + k);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc[t] = xadd(acc[t], xmul(xs[c * S + t], ww));
+    }
+}
+
+// Row sum by a whole warp, for T x vectors: the reduced prefix of `row` (m terms at positions
+// 0..m-1 of the full row).  Rows whose FULL length exceeds VREC_CANON_SEG are summed per 1024-term
+// segment and the segment sums by the same lane rule; all-zero segments are
+// skipped.
+template <int T>
+__device__ void warp_prefix_sigma(const SgBatchArgs &a, const double *xs, int row, int lane, double (&out)[T]) {
+    const int s = a.r_rowptr[row], m = a.r_rowptr[row + 1] - s;
+    const int fl = a.full_len[row];
+    double acc[T];
+    if (fl <= VREC_CANON_SEG) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) acc[t] = 0.0;
+        csr_lane_sum<T, T>(a, xs, s, m, lane, acc);
+#pragma unroll
+        for (int t = 0; t < T; ++t) out[t] = canon_butterfly(acc[t]);
+        return;
+    }
+    const int nsp = (m + VREC_CANON_SEG - 1) / VREC_CANON_SEG;
+    double acc2[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc2[t] = 0.0;
+    for (int j = 0; j < nsp; ++j) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) acc[t] = 0.0;
+        csr_lane_sum<T, T>(a, xs, s + j * VREC_CANON_SEG, min(VREC_CANON_SEG, m - j * VREC_CANON_SEG), lane, acc);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            double part = canon_butterfly(acc[t]);
+            if ((j & 31) == lane) acc2[t] = xadd(acc2[t], part);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) out[t] = canon_butterfly(acc2[t]);
+}
+
+// The same for one x vector (values at xs[c * S]) plus the start vertex's own terms z[e..ee) (positions z_pos >= m,
+// ascending, value 0.15 * w): they follow the prefix terms of their canonical lane and segment.
+template <int S>
 __device__ double warp_row_sigma(const SgBatchArgs &a, const double *xs, int row, int e, int ee, int lane) {
     const int s = a.r_rowptr[row], m = a.r_rowptr[row + 1] - s;
     const int fl = a.full_len[row];
+    double acc[1];
     if (fl <= VREC_CANON_SEG) {
-        double acc = 0.0;
-        for (int k = lane; k < m; k += 32) acc = xadd(acc, xmul(xs[a.r_src[s + k]], a.r_w[s + k]));
+        acc[0] = 0.0;
+        csr_lane_sum<1, S>(a, xs, s, m, lane, acc);
         for (int q = e; q < ee; ++q)
-            if ((a.z_pos[q] & 31) == lane) acc = xadd(acc, xmul(kAlpha, a.z_w[q]));
-        return canon_butterfly(acc);
+            if ((a.z_pos[q] & 31) == lane) acc[0] = xadd(acc[0], xmul(kAlpha, a.z_w[q]));
+        return canon_butterfly(acc[0]);
     }
     const int nsp = (m + VREC_CANON_SEG - 1) / VREC_CANON_SEG;
     double acc2 = 0.0;
     int q = e;
     for (int j = 0; j < nsp; ++j) {
-        const int len = min(VREC_CANON_SEG, m - j * VREC_CANON_SEG);
-        const int s2 = s + j * VREC_CANON_SEG;
-        double acc = 0.0;
-        for (int k = lane; k < len; k += 32) acc = xadd(acc, xmul(xs[a.r_src[s2 + k]], a.r_w[s2 + k]));
+        acc[0] = 0.0;
+        csr_lane_sum<1, S>(a, xs, s + j * VREC_CANON_SEG, min(VREC_CANON_SEG, m - j * VREC_CANON_SEG), lane, acc);
         while (q < ee && a.z_pos[q] / VREC_CANON_SEG == j) {
-            if ((a.z_pos[q] & 31) == lane) acc = xadd(acc, xmul(kAlpha, a.z_w[q]));
+            if ((a.z_pos[q] & 31) == lane) acc[0] = xadd(acc[0], xmul(kAlpha, a.z_w[q]));
             ++q;
         }
-        double part = canon_butterfly(acc);
+        double part = canon_butterfly(acc[0]);
         if ((j & 31) == lane) acc2 = xadd(acc2, part);
     }
     while (q < ee) {
         const int j = a.z_pos[q] / VREC_CANON_SEG;
-        double acc = 0.0;
+        double accz = 0.0;
         while (q < ee && a.z_pos[q] / VREC_CANON_SEG == j) {
-            if ((a.z_pos[q] & 31) == lane) acc = xadd(acc, xmul(kAlpha, a.z_w[q]));
+            if ((a.z_pos[q] & 31) == lane) accz = xadd(accz, xmul(kAlpha, a.z_w[q]));
             ++q;
         }
-        double part = canon_butterfly(acc);
+        double part = canon_butterfly(accz);
         if ((j & 31) == lane) acc2 = xadd(acc2, part);
     }
     return canon_butterfly(acc2);
+}
+
+// (value desc, id asc) with the id looked up only when the values tie
+__device__ __forceinline__ bool act_before(const SgBatchArgs &a, double va, int ia, double vb, int ib) {
+    if (va != vb) return va > vb;
+    if (ia < 0 || ib < 0) return ib < 0 && ia >= 0;
+    return a.act_id[ia] < a.act_id[ib];
+}
+
+// warp-wide best of (v, i) pairs; i < 0 = none
+__device__ __forceinline__ void warp_best(const SgBatchArgs &a, double &bv, int &bi) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (oi >= 0 && (bi < 0 || act_before(a, ov, oi, bv, bi))) {
+            bv = ov;
+            bi = oi;
+        }
+    }
 }
 
 template <int T>
@@ -161,17 +362,20 @@ __global__ void __launch_bounds__(BT, 1) sg_batch_kernel(const SgBatchArgs a) {
     double *xs = reinterpret_cast<double *>(smem_raw);                      // [T][n_a]
     double *chunk_res = xs + (size_t)T * n_a;                               // [T][n_chunks]
     unsigned *flag = reinterpret_cast<unsigned *>(chunk_res + (size_t)T * n_chunks);   // [T][n_chunks] row bitmaps
+    unsigned *cmask = flag + (size_t)T * n_chunks;                          // [n_chunks] place-filter bitmap
+    double *slow_res = reinterpret_cast<double *>(cmask + n_chunks + (((T + 1) * n_chunks) & 1));   // [T][n_slow], 8-byte aligned
+    const int n_fast = a.n_fast_chunks, n_slow = a.n_slow;
     __shared__ int s_grp, s_next_chunk;
     __shared__ int s_done[T], s_iter[T], s_conv[T], s_copy[T];
-    __shared__ double s_bv[BW];
-    __shared__ long long s_bk[BW];
+    __shared__ double s_lv[BW * TOPN_FAST];
+    __shared__ int s_li[BW * TOPN_FAST];
     __shared__ double s_sel_v;
-    __shared__ long long s_sel_k;
+    __shared__ int s_sel_i, s_list_n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int half = lane >> 4, sub = lane & 15;
     const double one_minus = 1 - kAlpha;                                    // :121
     double *nx = a.scratch + (size_t)blockIdx.x * T * n_a;                  // x' of this CTA's start vertices
     const int n_groups = (a.n_q + T - 1) / T;
+    for (int i = tid; i < n_chunks; i += BT) cmask[i] = a.cand_mask[i];
 
     for (;;) {
         __syncthreads();
@@ -183,7 +387,7 @@ __global__ void __launch_bounds__(BT, 1) sg_batch_kernel(const SgBatchArgs a) {
         for (int i = tid; i < n_a; i += BT) {
             double v = a.x1a[i];
 #pragma unroll
-            for (int t = 0; t < T; ++t) xs[t * n_a + i] = v;
+            for (int t = 0; t < T; ++t) xs[i * T + t] = v;
         }
         if (tid < T) {
             s_done[tid] = tid >= nt;
@@ -216,7 +420,7 @@ __global__ void __launch_bounds__(BT, 1) sg_batch_kernel(const SgBatchArgs a) {
                     if (e > e0 && a.z_row[e - 1] == row) continue;          // duplicate edge: summed with its first
                     int ee = e + 1;
                     while (ee < e1 && a.z_row[ee] == row) ++ee;
-                    double sigma = warp_row_sigma(a, xs + t * n_a, row, e, ee, lane);
+                    double sigma = warp_row_sigma<T>(a, xs + t, row, e, ee, lane);
                     if (lane == 0) {
                         nx[t * n_a + row] = xadd(xmul(0.0, kAlpha), xmul(sigma, one_minus));   // :120-122
                         atomicOr(&flag[t * n_chunks + (row >> 5)], 1u << (row & 31));
@@ -224,47 +428,51 @@ __global__ void __launch_bounds__(BT, 1) sg_batch_kernel(const SgBatchArgs a) {
                 }
             }
             __syncthreads();
-            // every other row: calcNextX (:108-128) over the reduced graph, 32 rows per warp-chunk
+            // every other row: calcNextX (:108-128) over the reduced graph.  Work items, longest first:
+            // the rows behind the fast slices (one warp per row), then one slice of 32 rows per warp turn.
             for (;;) {
-                int c = 0;
-                if (lane == 0) c = atomicAdd(&s_next_chunk, 1);
-                c = __shfl_sync(0xffffffffu, c, 0);
-                if (c >= n_chunks) break;
-                const int r = c * 32 + lane;
-                int s = 0, n = 0;
-                if (r < n_a) {
-                    s = a.r_rowptr[r];
-                    n = a.r_rowptr[r + 1] - s;
+                int item = 0;
+                if (lane == 0) item = atomicAdd(&s_next_chunk, 1);
+                item = __shfl_sync(0xffffffffu, item, 0);
+                if (item >= n_slow + n_fast) break;
+                if (item < n_slow) {
+                    const int r = n_fast * 32 + item;
+                    double sg[T];
+                    warp_prefix_sigma<T>(a, xs, r, lane, sg);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int t = 0; t < T; ++t) {
+                            const bool own = (flag[t * n_chunks + (r >> 5)] >> (r & 31)) & 1u;
+                            double v;
+                            if (own) {
+                                v = nx[t * n_a + r];
+                            } else {
+                                v = xadd(xmul(0.0, kAlpha), xmul(sg[t], one_minus));
+                                nx[t * n_a + r] = v;
+                            }
+                            double d = xsub(v, xs[r * T + t]);
+                            slow_res[t * n_slow + item] = xmul(d, d);
+                        }
+                    }
+                    continue;
                 }
+                const int c = item - n_slow;
+                const int r = c * 32 + lane;
+                const int n_max = a.chunk_r[c];                  // terms of the longest row of the slice
+                const int R = (n_max + 31) >> 5, rem = n_max - 32 * (R - 1);
                 double sigma[T];
 #pragma unroll
                 for (int t = 0; t < T; ++t) sigma[t] = 0.0;
-                const unsigned shortm = __ballot_sync(0xffffffffu, n > 0 && n <= VREC_CANON_SEG);
-                unsigned longm = __ballot_sync(0xffffffffu, n > VREC_CANON_SEG);
-                unsigned pairs = (shortm | (shortm >> 1)) & 0x55555555u;
-                while (pairs) {
-                    const int l0 = __ffs(pairs) - 1;
-                    pairs &= pairs - 1;
-                    const int l = l0 + half;
-                    const int rs = __shfl_sync(0xffffffffu, s, l);
-                    int rn = __shfl_sync(0xffffffffu, n, l);
-                    if (rn > VREC_CANON_SEG) rn = 0;
-                    double acc[T];
-                    canon_row_sum_s<16, T>(a.r_src, a.r_w, xs, n_a, rs, rn, sub, acc);
-#pragma unroll
-                    for (int t = 0; t < T; ++t) {
-                        double other = __shfl_xor_sync(0xffffffffu, acc[t], 16);
-                        if (lane == l0) sigma[t] = half == 0 ? acc[t] : other;
-                        if (lane == l0 + 1) sigma[t] = half == 1 ? acc[t] : other;
-                    }
-                }
-                while (longm) {
-                    const int l = __ffs(longm) - 1;
-                    longm &= longm - 1;
-#pragma unroll
-                    for (int t = 0; t < T; ++t) {
-                        double v = warp_row_sigma(a, xs + t * n_a, c * 32 + l, 0, 0, lane);
-                        if (lane == l) sigma[t] = v;
+                if (R > 0) {
+                    const long long base = a.chunk_ptr[c] + lane;
+                    const unsigned short *ps = a.sell_src + base;
+                    const double *pw = a.sell_w + base;
+                    switch (R) {
+                        case 1: sell_row_sum<T, 1>(ps, pw, xs, n_a, rem, sigma); break;
+                        case 2: sell_row_sum<T, 2>(ps, pw, xs, n_a, rem, sigma); break;
+                        case 3: sell_row_sum<T, 3>(ps, pw, xs, n_a, rem, sigma); break;
+                        case 4: sell_row_sum<T, 4>(ps, pw, xs, n_a, rem, sigma); break;
+                        default: sell_row_sum_any<T>(ps, pw, xs, n_a, R, rem, sigma); break;
                     }
                 }
 #pragma unroll
@@ -279,7 +487,7 @@ __global__ void __launch_bounds__(BT, 1) sg_batch_kernel(const SgBatchArgs a) {
                             v = xadd(xmul(0.0, kAlpha), xmul(sigma[t], one_minus));
                             nx[t * n_a + r] = v;
                         }
-                        double d = xsub(v, xs[t * n_a + r]);                // isConverged, :131-139
+                        double d = xsub(v, xs[r * T + t]);                    // isConverged, :131-139
                         sq = xmul(d, d);
                     }
                     sq = canon_butterfly(sq);
@@ -290,7 +498,8 @@ __global__ void __launch_bounds__(BT, 1) sg_batch_kernel(const SgBatchArgs a) {
             if (warp < T) {
                 const int t = warp;
                 double acc = 0.0;
-                for (int k = lane; k < n_chunks; k += 32) acc = xadd(acc, chunk_res[t * n_chunks + k]);
+                for (int k = lane; k < n_fast; k += 32) acc = xadd(acc, chunk_res[t * n_chunks + k]);
+                for (int k = lane; k < n_slow; k += 32) acc = xadd(acc, slow_res[t * n_slow + k]);
                 acc = canon_butterfly(acc);
                 if (lane == 0) {
                     s_copy[t] = !s_done[t];
@@ -305,7 +514,7 @@ __global__ void __launch_bounds__(BT, 1) sg_batch_kernel(const SgBatchArgs a) {
 #pragma unroll
             for (int t = 0; t < T; ++t) {
                 if (!s_copy[t]) continue;
-                for (int i = tid; i < n_a; i += BT) xs[t * n_a + i] = nx[t * n_a + i];
+                for (int i = tid; i < n_a; i += BT) xs[i * T + t] = nx[t * n_a + i];
             }
             __syncthreads();
             bool all = true;
@@ -313,63 +522,166 @@ __global__ void __launch_bounds__(BT, 1) sg_batch_kernel(const SgBatchArgs a) {
             for (int t = 0; t < T; ++t) all = all && s_done[t];
             if (all) break;
         }
-        // makeRecommendations0's filter (:85-88) + printRecommendations' ranked top-N (Main :69-73)
+        // makeRecommendations0's filter (:85-88) + printRecommendations' ranked top-N (Main :69-73).
+        // Candidates = active vertices in the place filter with probability > 0.
         for (int t = 0; t < nt; ++t) {
             const int q = grp * T + t;
-            double pv = __longlong_as_double(0x7ff0000000000000LL);
-            long long pk = LLONG_MIN;
+            const double *xt = xs + t;                           // values at xt[i * T]
             int count = 0;
-            for (int r = 0; r < a.max_recs; ++r) {
-                double bv = -1.0;
-                long long bk = LLONG_MAX;
-                for (int i = tid; i < a.n_cand; i += BT) {
-                    double v = xs[t * n_a + a.cand_act[i]];
-                    long long k = a.cand_id[i];
-                    if (v > 0 && ranks_before(pv, pk, v, k) && ranks_before(v, k, bv, bk)) {
-                        bv = v;
-                        bk = k;
-                    }
+            bool ranked = false;
+            if (a.max_recs > 0 && a.max_recs <= TOPN_FAST) {
+                // (1) every thread's largest candidate; (2) the max_recs-th largest of those 512 maxima
+                // is a lower bound of the max_recs-th best (each maximum is a distinct candidate);
+                // (3) the few candidates at or above it are listed; (4) warp 0 ranks the list exactly.
+                const int K = a.max_recs;
+                double mx = 0.0;
+                for (int base = warp * 32; base < n_a; base += BT) {
+                    const int i = base + lane;
+                    const double v = (i < n_a && ((cmask[base >> 5] >> lane) & 1u)) ? xt[i * T] : 0.0;
+                    mx = v > mx ? v : mx;
                 }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                    long long ok = __shfl_xor_sync(0xffffffffu, bk, off);
-                    if (ranks_before(ov, ok, bv, bk)) {
-                        bv = ov;
-                        bk = ok;
-                    }
-                }
-                if (lane == 0) {
-                    s_bv[warp] = bv;
-                    s_bk[warp] = bk;
-                }
-                __syncthreads();
-                if (warp == 0) {
-                    bv = s_bv[lane];
-                    bk = s_bk[lane];
+                for (int r = 0; r < K; ++r) {                     // warp-local top K (values, with multiplicity)
+                    double wm = mx;
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1) {
-                        double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                        long long ok = __shfl_xor_sync(0xffffffffu, bk, off);
-                        if (ranks_before(ov, ok, bv, bk)) {
-                            bv = ov;
-                            bk = ok;
+                        double o = __shfl_xor_sync(0xffffffffu, wm, off);
+                        wm = o > wm ? o : wm;
+                    }
+                    const unsigned holders = __ballot_sync(0xffffffffu, mx == wm);
+                    if (lane == __ffs(holders) - 1) mx = -1.0;     // remove one instance
+                    if (lane == 0) s_lv[warp * TOPN_FAST + r] = wm;
+                }
+                if (tid == 0) s_list_n = 0;
+                __syncthreads();
+                if (warp == 0) {
+                    double e[BW * TOPN_FAST / 32];
+#pragma unroll
+                    for (int j = 0; j < BW * TOPN_FAST / 32; ++j) {
+                        const int idx = lane + 32 * j;
+                        e[j] = (idx % TOPN_FAST) < K ? s_lv[idx] : -1.0;
+                    }
+                    double theta = 0.0;
+                    for (int r = 0; r < K; ++r) {
+                        double lm = e[0];
+#pragma unroll
+                        for (int j = 1; j < BW * TOPN_FAST / 32; ++j) lm = e[j] > lm ? e[j] : lm;
+                        double wm = lm;
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) {
+                            double o = __shfl_xor_sync(0xffffffffu, wm, off);
+                            wm = o > wm ? o : wm;
+                        }
+                        theta = wm;
+                        const unsigned holders = __ballot_sync(0xffffffffu, lm == wm);
+                        if (lane == __ffs(holders) - 1) {
+                            bool gone = false;
+#pragma unroll
+                            for (int j = 0; j < BW * TOPN_FAST / 32; ++j)
+                                if (!gone && e[j] == wm) {
+                                    e[j] = -1.0;
+                                    gone = true;
+                                }
                         }
                     }
-                    if (lane == 0) {
-                        s_sel_v = bv;
-                        s_sel_k = bk;
+                    if (lane == 0) s_sel_v = theta;                // <= 0: fewer than K positive candidates
+                }
+                __syncthreads();
+                const double theta = s_sel_v;
+                __syncthreads();                                   // s_lv is reused as the list below
+                for (int base = warp * 32; base < n_a; base += BT) {
+                    const int i = base + lane;
+                    if (i < n_a && ((cmask[base >> 5] >> lane) & 1u)) {
+                        const double v = xt[i * T];
+                        if (v > 0 && v >= theta) {
+                            const int pos = atomicAdd(&s_list_n, 1);
+                            if (pos < BW * TOPN_FAST) {
+                                s_lv[pos] = v;
+                                s_li[pos] = i;
+                            }
+                        }
                     }
                 }
                 __syncthreads();
-                pv = s_sel_v;
-                pk = s_sel_k;
-                if (!(pv > 0)) break;
-                if (tid == 0) {
-                    a.out_id[(size_t)q * a.max_recs + r] = pk;
-                    a.out_prob[(size_t)q * a.max_recs + r] = pv;
+                const int n_list = s_list_n;
+                if (n_list <= BW * TOPN_FAST) {
+                    ranked = true;
+                    if (warp == 0) {
+                        double ev[BW * TOPN_FAST / 32];
+                        int ei[BW * TOPN_FAST / 32];
+#pragma unroll
+                        for (int j = 0; j < BW * TOPN_FAST / 32; ++j) {
+                            const int idx = lane + 32 * j;
+                            ei[j] = idx < n_list ? s_li[idx] : -1;
+                            ev[j] = idx < n_list ? s_lv[idx] : 0.0;
+                        }
+                        for (int r = 0; r < K; ++r) {
+                            double bv = 0.0;
+                            int bi = -1;
+#pragma unroll
+                            for (int j = 0; j < BW * TOPN_FAST / 32; ++j)
+                                if (ei[j] >= 0 && (bi < 0 || act_before(a, ev[j], ei[j], bv, bi))) {
+                                    bv = ev[j];
+                                    bi = ei[j];
+                                }
+                            warp_best(a, bv, bi);
+                            if (bi < 0) break;
+#pragma unroll
+                            for (int j = 0; j < BW * TOPN_FAST / 32; ++j)
+                                if (ei[j] == bi) ei[j] = -1;
+                            if (lane == 0) {
+                                a.out_id[(size_t)q * a.max_recs + r] = a.act_id[bi];
+                                a.out_prob[(size_t)q * a.max_recs + r] = bv;
+                            }
+                            ++count;
+                        }
+                        if (lane == 0) s_sel_i = count;
+                    }
+                    __syncthreads();
+                    count = s_sel_i;
                 }
-                ++count;
+            }
+            if (!ranked) {
+                // any max_recs: one block-wide pick per rank
+                double pv = 0.0;
+                int pi = -1;
+                for (int r = 0; r < a.max_recs; ++r) {
+                    double bv = 0.0;
+                    int bi = -1;
+                    for (int base = warp * 32; base < n_a; base += BT) {
+                        const int i = base + lane;
+                        if (i < n_a && ((cmask[base >> 5] >> lane) & 1u)) {
+                            double v = xt[i * T];
+                            if (v > 0 && (pi < 0 || act_before(a, pv, pi, v, i)) && (bi < 0 || act_before(a, v, i, bv, bi))) {
+                                bv = v;
+                                bi = i;
+                            }
+                        }
+                    }
+                    warp_best(a, bv, bi);
+                    if (lane == 0) {
+                        s_lv[warp] = bv;
+                        s_li[warp] = bi;
+                    }
+                    __syncthreads();
+                    if (warp == 0) {
+                        bv = lane < BW ? s_lv[lane] : 0.0;
+                        bi = lane < BW ? s_li[lane] : -1;
+                        warp_best(a, bv, bi);
+                        if (lane == 0) {
+                            s_sel_v = bv;
+                            s_sel_i = bi;
+                        }
+                    }
+                    __syncthreads();
+                    pv = s_sel_v;
+                    pi = s_sel_i;
+                    if (pi < 0) break;
+                    if (tid == 0) {
+                        a.out_id[(size_t)q * a.max_recs + r] = a.act_id[pi];
+                        a.out_prob[(size_t)q * a.max_recs + r] = pv;
+                    }
+                    ++count;
+                }
             }
             if (tid == 0) {
                 a.out_count[q] = count;
@@ -387,9 +699,10 @@ __global__ void sg_gather_active_kernel(const double *__restrict__ x, const int 
     if (i < n_a) out[i] = x[act_vertex[i]];
 }
 
-size_t batch_smem(int T, int n_a) {
+size_t batch_smem(int T, int n_a, int n_slow) {
     size_t n_chunks = (size_t)(n_a + 31) / 32;
-    return (size_t)T * n_a * 8 + (size_t)T * n_chunks * 8 + (size_t)T * n_chunks * 4 + 16;
+    return (size_t)T * n_a * 8 + (size_t)T * n_chunks * 8 + (size_t)T * n_chunks * 4 + (n_chunks + 1) * 4 +
+           (size_t)T * n_slow * 8 + 16;
 }
 
 template <int T>
@@ -402,50 +715,83 @@ int launch_batch(vrec_ctx *ctx, const SgBatchArgs &a, int grid, size_t smem) {
 
 }  // namespace
 
-// Load-time analysis of a host-built graph: active set, reduced CSR, out-edges of the in-degree-0
-// vertices with their positions in the full rows.  Leaves batch.ok = false when the graph does not
-// have the required shape.
+// Load-time analysis of a host-built graph: active set (renumbered by row length), reduced graph in
+// sliced and CSR form, out-edges of the in-degree-0 vertices with their positions in the full rows.
+// Leaves batch.ok = false when the graph does not have the required shape.
 int sg_batch_analyse(vrec_sg *g, const std::vector<int> &rowptr, const int *h_src, const double *h_w) {
     SgBatch &b = g->batch;
     b.analysed = true;
     b.ok = false;
     const int64_t N = g->N;
     if (N <= 0 || g->partitioned || g->nblocks != 1 || g->row_lo != 0 || g->row_hi != N) return VREC_OK;
-    b.h_act_of.assign((size_t)N, -1);
-    std::vector<int> act_vertex;
+    std::vector<char> active((size_t)N, 0);
+    int n_a = 0;
     for (int64_t v = 0; v < N; ++v)
         if (rowptr[v + 1] > rowptr[v]) {
-            b.h_act_of[v] = (int)act_vertex.size();
-            act_vertex.push_back((int)v);
+            active[v] = 1;
+            ++n_a;
         }
-    const int n_a = (int)act_vertex.size();
-    if (n_a == 0 || n_a == N || batch_smem(1, n_a) > SMEM_LIMIT) return VREC_OK;
-    std::vector<int> r_rowptr((size_t)n_a + 1, 0), full_len((size_t)n_a), zcnt((size_t)N + 1, 0);
+    if (n_a == 0 || n_a == N || batch_smem(1, n_a, 0) > SMEM_LIMIT) return VREC_OK;
+    // active prefix of every row; rows ordered by terms per canonical lane
+    std::vector<int> act_vertex, m_of((size_t)N, 0);
+    act_vertex.reserve((size_t)n_a);
+    for (int64_t v = 0; v < N; ++v) {
+        if (!active[v]) continue;
+        const int s = rowptr[v], e = rowptr[v + 1];
+        int m = 0;
+        while (s + m < e && active[h_src[s + m]]) ++m;
+        for (int k = s + m; k < e; ++k)
+            if (active[h_src[k]]) return VREC_OK;              // an active source after a Z source: not this shape
+        m_of[v] = m;
+        act_vertex.push_back((int)v);
+    }
+    // rows by length, so that the rows of a slice are (almost) equally long
+    std::stable_sort(act_vertex.begin(), act_vertex.end(), [&](int x, int y) { return m_of[x] < m_of[y]; });
+    b.h_act_of.assign((size_t)N, -1);
+    for (int a = 0; a < n_a; ++a) b.h_act_of[act_vertex[a]] = a;
+    const int n_chunks = (n_a + 31) / 32;
+    std::vector<int> r_rowptr((size_t)n_a + 1, 0), full_len((size_t)n_a), zcnt((size_t)N + 1, 0), chunk_r((size_t)n_chunks, 0);
+    std::vector<long long> chunk_ptr((size_t)n_chunks + 1, 0), act_id((size_t)n_a);
     for (int a = 0; a < n_a; ++a) {
         const int v = act_vertex[a], s = rowptr[v], e = rowptr[v + 1];
-        int m = 0;
-        while (s + m < e && b.h_act_of[h_src[s + m]] >= 0) ++m;
-        for (int k = s + m; k < e; ++k) {
-            if (b.h_act_of[h_src[k]] >= 0) return VREC_OK;     // an active source after a Z source: not this shape
-            zcnt[h_src[k] + 1]++;
-        }
-        r_rowptr[a + 1] = r_rowptr[a] + m;
+        r_rowptr[a + 1] = r_rowptr[a] + m_of[v];
         full_len[a] = e - s;
+        act_id[a] = (long long)g->h_ids[v];
+        chunk_r[a >> 5] = std::max(chunk_r[a >> 5], m_of[v]);
+        for (int k = s + m_of[v]; k < e; ++k) zcnt[h_src[k] + 1]++;
     }
+    int n_fast_chunks = n_chunks;                            // slices in front of the first row with > 1024 terms
+    for (int c = n_chunks - 1; c >= 0 && chunk_r[c] > VREC_CANON_SEG; --c) n_fast_chunks = c;
+    const int n_slow = n_a - std::min(n_a, n_fast_chunks * 32);
+    if (batch_smem(1, n_a, n_slow) > SMEM_LIMIT) return VREC_OK;
+    for (int c = 0; c < n_chunks; ++c)
+        chunk_ptr[c + 1] = chunk_ptr[c] + (chunk_r[c] <= VREC_CANON_SEG ? (long long)chunk_r[c] * 32 : 0);
+    const long long sell_n = std::max<long long>(1, chunk_ptr[n_chunks]);
     const int r_nnz = r_rowptr[n_a];
+    if (sell_n > 4LL * (r_nnz + 1024LL * n_chunks)) return VREC_OK;   // pathological padding: keep the per-query path
     std::vector<int> r_src((size_t)std::max(1, r_nnz));
     std::vector<double> r_w((size_t)std::max(1, r_nnz));
+    std::vector<unsigned short> sell_src((size_t)sell_n, 0);
+    std::vector<double> sell_w((size_t)sell_n, 0.0);
     for (int64_t i = 0; i < N; ++i) zcnt[i + 1] += zcnt[i];
     const int z_nnz = zcnt[N];
     std::vector<int> z_rowptr(zcnt), z_row((size_t)std::max(1, z_nnz)), z_pos((size_t)std::max(1, z_nnz));
     std::vector<double> z_w((size_t)std::max(1, z_nnz));
     std::vector<int> fill(zcnt.begin(), zcnt.end() - 1);
     for (int a = 0; a < n_a; ++a) {                            // ascending rows, ascending positions: lists end up sorted
-        const int v = act_vertex[a], s = rowptr[v], e = rowptr[v + 1];
-        const int m = r_rowptr[a + 1] - r_rowptr[a];
+        const int v = act_vertex[a], s = rowptr[v], e = rowptr[v + 1], m = m_of[v];
+        const int n_max = chunk_r[a >> 5], R = (n_max + 31) / 32;
         for (int k = 0; k < m; ++k) {
-            r_src[r_rowptr[a] + k] = b.h_act_of[h_src[s + k]];
+            const int sa = b.h_act_of[h_src[s + k]];
+            r_src[r_rowptr[a] + k] = sa;
             r_w[r_rowptr[a] + k] = h_w[s + k];
+            if (n_max <= VREC_CANON_SEG) {
+                const int l = k & 31, c2 = k >> 5;
+                const long long step = c2 < R - 1 ? (long long)l * (R - 1) + c2 : 32LL * (R - 1) + l;
+                const long long p = chunk_ptr[a >> 5] + step * 32 + (a & 31);
+                sell_src[p] = (unsigned short)sa;
+                sell_w[p] = h_w[s + k];
+            }
         }
         for (int k = s + m; k < e; ++k) {
             const int p = fill[h_src[k]]++;
@@ -459,6 +805,11 @@ int sg_batch_analyse(vrec_sg *g, const std::vector<int> &rowptr, const int *h_sr
     VREC_TRY(b.r_src.upload(r_src.data(), r_src.size(), st));
     VREC_TRY(b.r_w.upload(r_w.data(), r_w.size(), st));
     VREC_TRY(b.full_len.upload(full_len.data(), full_len.size(), st));
+    VREC_TRY(b.chunk_r.upload(chunk_r.data(), chunk_r.size(), st));
+    VREC_TRY(b.chunk_ptr.upload(chunk_ptr.data(), chunk_ptr.size(), st));
+    VREC_TRY(b.sell_src.upload(sell_src.data(), sell_src.size(), st));
+    VREC_TRY(b.sell_w.upload(sell_w.data(), sell_w.size(), st));
+    VREC_TRY(b.act_id.upload(act_id.data(), act_id.size(), st));
     VREC_TRY(b.z_rowptr.upload(z_rowptr.data(), z_rowptr.size(), st));
     VREC_TRY(b.z_row.upload(z_row.data(), z_row.size(), st));
     VREC_TRY(b.z_pos.upload(z_pos.data(), z_pos.size(), st));
@@ -466,7 +817,10 @@ int sg_batch_analyse(vrec_sg *g, const std::vector<int> &rowptr, const int *h_sr
     VREC_TRY(b.x1a.alloc((size_t)n_a));
     VREC_CUDA(cudaStreamSynchronize(st));
     b.n_a = n_a;
+    b.n_fast_chunks = n_fast_chunks;
+    b.n_slow = n_slow;
     b.r_nnz = r_nnz;
+    b.sell_nnz = chunk_ptr[n_chunks];
     b.x1_ready = false;
     b.ok = true;
     return VREC_OK;
@@ -507,30 +861,24 @@ int sg_batch_query(vrec_sg *g, const std::vector<int> &qidx, const std::vector<i
     cudaStream_t st = ctx->stream;
     const int n_q = (int)qidx.size();
     const int n_a = b.n_a;
+    const int n_chunks = (n_a + 31) / 32;
     VREC_TRY(sg_batch_prepare(g));
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) {
+        return (long long)std::chrono::duration_cast<std::chrono::microseconds>(y - x).count();
+    };
+    const auto t_begin = now();
     // candidates of the ranked top-N: the filter's places that are active vertices (the others have
     // probability 0 after the first iteration and fail `probability > 0`, :85-88)
-    std::vector<int> cand_act;
-    std::vector<long long> cand_id;
+    std::vector<unsigned> mask((size_t)n_chunks, place_filter ? 0u : 0xffffffffu);
     if (place_filter) {
         for (int64_t k = 0; k < n_filter; ++k) {
             int64_t v = sg_lookup(g, place_filter[k]);
-            if (v >= 0 && b.h_act_of[v] >= 0) {
-                cand_act.push_back(b.h_act_of[v]);
-                cand_id.push_back((long long)place_filter[k]);
-            }
+            if (v >= 0 && b.h_act_of[v] >= 0) mask[b.h_act_of[v] >> 5] |= 1u << (b.h_act_of[v] & 31);
         }
-    } else {
-        for (int64_t v = 0; v < g->N; ++v)
-            if (b.h_act_of[v] >= 0) {
-                cand_act.push_back(b.h_act_of[v]);
-                cand_id.push_back((long long)g->h_ids[v]);
-            }
     }
-    const int n_cand = (int)cand_act.size();
     const int m = std::max(1, max_recs);
-    VREC_TRY(b.cand_act.upload(cand_act.data(), cand_act.size(), st));
-    VREC_TRY(b.cand_id.upload(cand_id.data(), cand_id.size(), st));
+    VREC_TRY(b.cand_mask.upload(mask.data(), mask.size(), st));
     VREC_TRY(b.q_vertex.upload(qvertex.data(), qvertex.size(), st));
     VREC_TRY(b.out_id.ensure((size_t)n_q * m));
     VREC_TRY(b.out_prob.ensure((size_t)n_q * m));
@@ -541,17 +889,20 @@ int sg_batch_query(vrec_sg *g, const std::vector<int> &qidx, const std::vector<i
     VREC_CUDA(cudaMemsetAsync(b.counter.p, 0, sizeof(int), st));
     // targets per CTA: as many as fit in shared memory, but keep every SM busy
     int T = 1;
-    for (int cand : {2, 4})
-        if (batch_smem(cand, n_a) <= SMEM_LIMIT && (n_q + cand - 1) / cand >= ctx->sm_count) T = cand;
-    if (b.force_t == 1 || b.force_t == 2 || b.force_t == 4) {
-        if (batch_smem(b.force_t, n_a) <= SMEM_LIMIT) T = b.force_t;
-    }
+    if (batch_smem(2, n_a, b.n_slow) <= SMEM_LIMIT && (n_q + 1) / 2 >= ctx->sm_count) T = 2;
+    if ((b.force_t == 1 || b.force_t == 2) && batch_smem(b.force_t, n_a, b.n_slow) <= SMEM_LIMIT) T = b.force_t;
     const int n_groups = (n_q + T - 1) / T;
     const int grid = std::max(1, std::min(n_groups, ctx->sm_count));
     VREC_TRY(b.scratch.ensure((size_t)grid * T * n_a));
     SgBatchArgs a;
     a.n_a = n_a;
-    a.n_chunks = (n_a + 31) / 32;
+    a.n_chunks = n_chunks;
+    a.n_fast_chunks = b.n_fast_chunks;
+    a.n_slow = b.n_slow;
+    a.chunk_r = b.chunk_r.p;
+    a.chunk_ptr = b.chunk_ptr.p;
+    a.sell_src = b.sell_src.p;
+    a.sell_w = b.sell_w.p;
     a.r_rowptr = b.r_rowptr.p;
     a.r_src = b.r_src.p;
     a.full_len = b.full_len.p;
@@ -561,13 +912,12 @@ int sg_batch_query(vrec_sg *g, const std::vector<int> &qidx, const std::vector<i
     a.z_pos = b.z_pos.p;
     a.z_w = b.z_w.p;
     a.x1a = b.x1a.p;
+    a.act_id = b.act_id.p;
     a.q_vertex = b.q_vertex.p;
     a.n_q = n_q;
     a.max_it = max_it;
     a.eps2 = epsilon * epsilon;                                    // :40
-    a.cand_act = b.cand_act.p;
-    a.cand_id = b.cand_id.p;
-    a.n_cand = n_cand;
+    a.cand_mask = b.cand_mask.p;
     a.max_recs = max_recs;
     a.out_id = b.out_id.p;
     a.out_prob = b.out_prob.p;
@@ -576,10 +926,13 @@ int sg_batch_query(vrec_sg *g, const std::vector<int> &qidx, const std::vector<i
     a.out_conv = b.out_conv.p;
     a.scratch = b.scratch.p;
     a.counter = b.counter.p;
-    const size_t smem = batch_smem(T, n_a);
-    if (T == 4) VREC_TRY(launch_batch<4>(ctx, a, grid, smem));
-    else if (T == 2) VREC_TRY(launch_batch<2>(ctx, a, grid, smem));
+    const size_t smem = batch_smem(T, n_a, b.n_slow);
+    VREC_CUDA(cudaStreamSynchronize(st));
+    const auto t_launch = now();
+    if (T == 2) VREC_TRY(launch_batch<2>(ctx, a, grid, smem));
     else VREC_TRY(launch_batch<1>(ctx, a, grid, smem));
+    VREC_CUDA(cudaStreamSynchronize(st));
+    const auto t_kernel = now();
     std::vector<long long> h_id((size_t)n_q * m);
     std::vector<double> h_prob((size_t)n_q * m);
     std::vector<int> h_count((size_t)n_q), h_it((size_t)n_q), h_conv((size_t)n_q);
@@ -602,5 +955,8 @@ int sg_batch_query(vrec_sg *g, const std::vector<int> &qidx, const std::vector<i
         }
     }
     b.last_batched = n_q;
+    b.us_prepare = us(t_begin, t_launch);
+    b.us_kernel = us(t_launch, t_kernel);
+    b.us_results = us(t_kernel, now());
     return VREC_OK;
 }

@@ -280,7 +280,7 @@ class StochasticGraph:
         _check(self.ctx.lib.vrec_sg_iterate_device(self._h, int(iterations)))
 
     def set_option(self, name: str, value: int) -> None:
-        """"batch": 0 / 1 (default) / 2; "batch_targets_per_cta": 0 (auto) / 1 / 2 / 4 -- see include/vrec.h."""
+        """"batch": 0 / 1 (default) / 2; "batch_targets_per_cta": 0 (auto) / 1 / 2 -- see include/vrec.h."""
         _check(self.ctx.lib.vrec_sg_set_option(self._h, name.encode(), int(value)))
 
     def batch_info(self, what: int) -> int:
@@ -347,9 +347,10 @@ class StochasticRecommender:
                                        _ptr(f, L.i64p), 0 if f is None else len(f), int(max_recommendations),
                                        _ptr(out_id, L.i64p), _ptr(out_prob, L.f64p), _ptr(cnt, L.i32p),
                                        _ptr(its, L.i32p), _ptr(conv, L.i32p), _ptr(status, L.i32p)))
-        for q in range(n):
-            if status[q] == L.OK:
-                self._message(int(its[q]), int(conv[q]))
+        if self.verbose:
+            for q in range(n):
+                if status[q] == L.OK:
+                    self._message(int(its[q]), int(conv[q]))
         return out_id, out_prob, cnt[:n], its[:n], conv[:n], status[:n]
 
 

@@ -181,7 +181,7 @@ def _check_sg_batch(rec, og, vertices, flt, max_recs, eps, max_it):
         assert op[q, :cnt[q]].tolist() == wp.tolist(), (q, v)             # bit-exact
 
 
-@pytest.mark.parametrize("tpc", [0, 1, 2, 4])
+@pytest.mark.parametrize("tpc", [0, 1, 2])
 def test_sg_batch_kernel_bit_exact(vrec, ctx, synth, oracle, tpc):
     # config 4 shape: many person start vertices on one graph; hub rows longer than the canonical
     # segment in both the place->place prefix and the person part, duplicate edges

@@ -28,11 +28,11 @@ ctx = vrec.Context(0)
 t0 = time.time()
 g = vrec.StochasticGraph(s, t, w, ctx=ctx)
 print(f"load {time.time() - t0:.2f}s  N={g.N} nnz={g.nnz} batch_ok={g.batch_info(1)} n_active={g.batch_info(2)} "
-      f"r_nnz={g.batch_info(3)}", flush=True)
+      f"r_nnz={g.batch_info(3)} sell_nnz={g.batch_info(4)}", flush=True)
 g.set_option("batch_targets_per_cta", tpc)
 rng = np.random.default_rng(0)
 q = rng.choice(persons, n_q, replace=False)
-for eps, max_it in [(0.01, 20), (0.0, 20), (1e-4, 20)]:
+for eps, max_it in [(0.01, 1), (0.01, 20), (0.0, 20), (1e-4, 20)]:
     rec = vrec.StochasticRecommender(g, eps, max_it)
     rec.recommend(q[:2000], places, 10)      # warm-up (x1, allocations)
     t0 = time.time()
@@ -41,8 +41,14 @@ for eps, max_it in [(0.01, 20), (0.0, 20), (1e-4, 20)]:
     assert g.batch_info(0) == n_q
     tot_it = int((its - 1 + conv).sum())      # SpMV passes after the shared first one
     print(f"eps={eps} max_it={max_it}: {n_q / dt:.0f} persons/s  ({dt * 1e3:.1f} ms, mean iterations {its.mean():.2f}, "
-          f"{tot_it * g.batch_info(3) / dt / 1e9:.1f} G edge-terms/s, {tot_it * g.batch_info(3) * 12 / dt / 1e12:.2f} TB/s L2 stream)",
-          flush=True)
+          f"{tot_it * g.batch_info(3) / dt / 1e9:.1f} G edge-terms/s; us prepare/kernel/results "
+          f"{g.batch_info(5)}/{g.batch_info(6)}/{g.batch_info(7)})", flush=True)
+rec = vrec.StochasticRecommender(g, 0.01, 1)
+for nq in (100, 2000, 20000):
+    t0 = time.time()
+    rec.recommend(q[:nq], places, 10)
+    print(f"max_it=1 n_q={nq}: {(time.time() - t0) * 1e3:.2f} ms  (us prepare/kernel/results: "
+          f"{g.batch_info(5)}/{g.batch_info(6)}/{g.batch_info(7)})", flush=True)
 # per-query path for comparison
 g.set_option("batch", 0)
 rec = vrec.StochasticRecommender(g, 0.01, 20)
