@@ -391,6 +391,7 @@ def run_ours(args):
     sg = None
     if not args.no_sg:
         sg = run_sg(args, vrec, ctx, stream, world, rank, barrier, max_over_ranks, peak, peak_src)
+        sg["batch"] = run_sg_batch(args, vrec, ctx, world, rank, barrier, max_over_ranks)
 
     if rank == 0:
         line = {
@@ -484,6 +485,70 @@ def run_sg(args, vrec, ctx, stream, world, rank, barrier, max_over_ranks, peak, 
     return out
 
 
+def run_sg_batch(args, vrec, ctx, world, rank, barrier, max_over_ranks):
+    """BASELINE config 4 shape: one per-region graph of the default-data size, a recommendation for many
+    persons.  Persons are sharded over the ranks (graph replicated, no collective); every step is one
+    vrec_sg_query call with host buffers (ids in, ranked top-10 places out)."""
+    from vrec import synth
+    t0 = time.time()
+    s, t, w, persons, places, cats = synth.random_layered_graph(
+        20, args.sgb_places, args.sgb_persons, seed=4, places_per_person=2, cats_per_person=2,
+        similar_per_place=50, hub_places=20, hub_fraction=0.1, duplicate_fraction=0.0)
+    g = vrec.StochasticGraph(s, t, w, ctx=ctx)
+    log(f"[bench] sg batch graph: N={g.N} nnz={g.nnz} active={g.batch_info(2)} active edges={g.batch_info(3)} "
+        f"({time.time() - t0:.1f}s)")
+    n_q = args.sgb_batch
+    rng = np.random.default_rng(100 + rank)
+    rec = vrec.StochasticRecommender(g, 0.01, 20)                 # bin/stochastic_recommender.sh:32-35
+    for _ in range(args.warmup):
+        rec.recommend(rng.choice(persons, n_q, replace=False), places, 10)
+    kernel_us, its_sum, n_done = 0, 0, 0
+    l0 = ctx.launch_count
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        q = rng.choice(persons, n_q, replace=False)
+        oi, op, cnt, its, conv, st = rec.recommend(q, places, 10)
+        kernel_us += g.batch_info(6)
+        its_sum += int(its.sum())
+        n_done += g.batch_info(0)
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    launches = ctx.launch_count - l0
+    assert n_done == n_q * args.steps, "batch kernel did not serve the queries"
+    value = world * n_q * args.steps / dt
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        oracle.set_threads(os.cpu_count() or 1)
+        og = oracle.SgGraph(s, t, w)
+        sample = persons[:24]
+        t1 = time.perf_counter()
+        for v in sample:
+            og.query(int(v), 0.01, 20, places, 10)
+        cdt = time.perf_counter() - t1
+        cpu = {"value": len(sample) / cdt, "unit": "persons/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"{len(sample)} persons of the same graph, one query at a time, {cdt:.2f}s, "
+                         f"oracle/vrec_oracle.c with OpenMP over rows"}
+        log(f"[bench] sg batch cpu baseline: {cpu['value']:.1f} persons/s")
+    out = {
+        "metric": "SG recommendations, persons/s (power iteration to eps=0.01 + ranked top-10 per person)",
+        "value": value, "unit": "persons/s", "ms_per_step": 1e3 * dt / args.steps, "n_gpus": world, "scaling": "weak",
+        "config": {"workload": f"sg_batch persons={args.sgb_persons} places={args.sgb_places} categories=20 "
+                               f"nnz={g.nnz} eps=0.01 maxIt=20 top10, {n_q} persons/step/GPU (BASELINE config 4 shape)",
+                   "parallelism": f"persons sharded over {world} GPU(s), graph replicated, no collective"},
+        "e2e": {"value": value, "unit": "persons/s", "h2d_bytes_per_step": 8 * n_q + 8 * len(places),
+                "d2h_bytes_per_step": n_q * (10 * 16 + 12)},
+        "kernel_ms_per_step": kernel_us / 1e3 / args.steps, "mean_iterations": its_sum / max(1, n_q * args.steps),
+        "gpu_launches": int(launches), "cpu_baseline": cpu,
+        "note": "value == e2e: every step goes through vrec_sg_query with host buffers; kernel_ms_per_step is "
+                "sg_batch_kernel alone (host clock around the launch)",
+    }
+    g.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -502,6 +567,9 @@ def main():
     ap.add_argument("--cpu-sg-vertices", type=int, default=1_000_000)
     ap.add_argument("--ref-knn-targets", type=int, default=512)
     ap.add_argument("--ref-sg-vertices", type=int, default=1_000_000)
+    ap.add_argument("--sgb-persons", type=int, default=770_000)
+    ap.add_argument("--sgb-places", type=int, default=10_000)
+    ap.add_argument("--sgb-batch", type=int, default=20_000)
     ap.add_argument("--no-sg", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
