@@ -164,9 +164,10 @@ int vrec_knn_debug_stats(vrec_knn *knn, uint64_t *out4);
 int vrec_knn_debug_tc_cycles(vrec_knn *knn, uint64_t *out8);
 /* Debug: cycles per block of the last tensor-core main pass: out[0..n) dense phase, out[n..2n) postings. */
 int vrec_knn_debug_tc_block_cycles(vrec_knn *knn, uint64_t *out, int n);
-/* Debug: exact-evaluation probe of block 0 / warp 0 in the postings pass: out4 = {cycles waiting for the
- * meta word, record + place merge, category merge, evaluations}.                                       */
-int vrec_knn_debug_probe(vrec_knn *knn, uint64_t *out4);
+/* Debug: exact-evaluation probe of block 0 / thread 0 of the dense kernel, cycles summed over its
+ * evaluations: out8 = {meta words, record headers, place matching, evaluations, heap inserts (cycles),
+ * heap inserts (count), place section load, category section + dense row}.                            */
+int vrec_knn_debug_probe(vrec_knn *knn, uint64_t *out8);
 
 /* ---------------------------------------------------------------- SG path */
 

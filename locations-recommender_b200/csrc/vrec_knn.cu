@@ -288,6 +288,9 @@ struct TileAux {
     const unsigned long long *meta;
     const double *rec;
     unsigned tail_bit;          // which flag applies to this kernel's head set
+    // knn_tc_ws_kernel: the targets' category vectors as dense rows [n_targets][cat_dim] (global scratch)
+    double *tdense = nullptr;
+    int cat_dim = 0;
 };
 
 constexpr unsigned REC_TAIL_TC = 0x80000000u, REC_TAIL_TILE = 0x40000000u, REC_COL_MASK = 0x3fffffffu;
@@ -573,6 +576,14 @@ __device__ __forceinline__ bool exact_pair_records(const TileAux &aux, int cand,
     const int npt = (int)((mt >> 40) & 0xfffu), nct = (int)(mt >> 52);
     if (npt > 16 || nct > 16) return false;                         // caller falls back to the general path
     const double *rc = aux.rec + (mc & 0xffffffffffULL), *rt = aux.rec + (mt & 0xffffffffffULL);
+    {
+        // the sections are read by dependent loads below: start all of the candidate's 128-byte lines
+        // now, so that only the first of those loads pays the HBM latency
+        const int words = 2 + rec_cols_words(npc) + rec_vals_words(npc) + rec_cols_words(ncc) + rec_vals_words(ncc);
+        const char *pb = reinterpret_cast<const char *>(rc);
+        const int lines = min(8, (int)(((reinterpret_cast<unsigned long long>(pb) & 127ULL) + 8ULL * words + 127ULL) >> 7));
+        for (int l = 1; l < lines; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + 128 * l));
+    }
     if (pr && (mc | mt) == 0xffffffffffffffffULL) g_probe[7] = 1;   // consume the meta words here
     long long z1 = clock64();
     const double2 lc = __ldg(reinterpret_cast<const double2 *>(rc)), lt = __ldg(reinterpret_cast<const double2 *>(rt));
@@ -614,6 +625,117 @@ __device__ __forceinline__ bool exact_pair_records(const TileAux &aux, int cand,
         g_probe[3] += 1;
     }
     return true;
+}
+
+// exact_pair for two persons with packed records, the target described by a 64-bit signature of its
+// places and its category vector as a dense row (both prepared once per CTA): the same operations in the
+// same order as exact_pair_staged, i.e. as the mllib merge, with ~10x fewer instructions than matching
+// every candidate entry against every target entry.
+//  * category dot: sum over the candidate's entries (ascending) of x * dense[col]; entries the target
+//    lacks contribute x * 0.0 = +0.0 and leave the sum unchanged (values are non-negative on this path);
+//  * place dot: an entry can only match if its signature bit is set; then a binary search over the
+//    target's own record finds it.
+__device__ __forceinline__ double exact_pair_sig(const TileAux &aux, int cand, int tix, unsigned long long tsig,
+                                                 const double *__restrict__ tdense, const int *tcols_s, double pw,
+                                                 double cw, int &min_tail) {
+    min_tail = -1;
+    if (cand == tix) return 0.0;
+    const bool pr = threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+    long long z0 = clock64();
+    const unsigned long long mc = __ldg(aux.meta + cand), mt = __ldg(aux.meta + tix);
+    const int np = (int)((mc >> 40) & 0xfffu), nc = (int)(mc >> 52);
+    const int npt = (int)((mt >> 40) & 0xfffu);
+    const double *r = aux.rec + (mc & 0xffffffffffULL), *rt = aux.rec + (mt & 0xffffffffffULL);
+    {
+        // the sections are read by dependent loads below: start all of the candidate's 128-byte lines now
+        const int words = 2 + rec_cols_words(np) + rec_vals_words(np) + rec_cols_words(nc) + rec_vals_words(nc);
+        const char *pb = reinterpret_cast<const char *>(r);
+        const int lines = min(8, (int)(((reinterpret_cast<unsigned long long>(pb) & 127ULL) + 8ULL * words + 127ULL) >> 7));
+        for (int l = 1; l < lines; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + 128 * l));
+    }
+    long long z1 = clock64();
+    const double2 lens = __ldg(reinterpret_cast<const double2 *>(r)), lt = __ldg(reinterpret_cast<const double2 *>(rt));
+    if (pr && lens.x + lt.x == -1.0) g_probe[5] = 2;                // consume the headers here
+    long long z2 = clock64();
+    const long long zh = z2;
+    const int *pc = reinterpret_cast<const int *>(r + 2);
+    const double *pv = r + 2 + rec_cols_words(np);
+    const int *cc = reinterpret_cast<const int *>(pv + rec_vals_words(np));
+    const double *cvp = pv + rec_vals_words(np) + rec_cols_words(nc);
+    const int *tpc = reinterpret_cast<const int *>(rt + 2);
+    const double *tpv = rt + 2 + rec_cols_words(npt);
+    bool keep = false;
+    double ps_sim = 0.0, cs_sim = 0.0;
+    if (np > 0) {
+        double sum = 0.0;
+        for (int k0 = 0; k0 < np; k0 += 4) {
+            unsigned c[4];
+            double x[4];
+            rec_load4(pc, pv, k0, c, x);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (k0 + e < np) {
+                    const int ix = (int)(c[e] & REC_COL_MASK);
+                    if ((tsig >> sig_bit(ix)) & 1ULL) {
+                        int lo = 0, hi = npt;                        // first index with target col >= ix
+                        bool match;
+                        if (tcols_s) {                               // the target's columns are in shared memory
+                            while (lo < hi) {
+                                int mid = (lo + hi) >> 1;
+                                if (tcols_s[mid] < ix) lo = mid + 1; else hi = mid;
+                            }
+                            match = lo < npt && tcols_s[lo] == ix;
+                        } else {
+                            while (lo < hi) {
+                                int mid = (lo + hi) >> 1;
+                                if ((int)((unsigned)__ldg(tpc + mid) & REC_COL_MASK) < ix) lo = mid + 1; else hi = mid;
+                            }
+                            match = lo < npt && (int)((unsigned)__ldg(tpc + lo) & REC_COL_MASK) == ix;
+                        }
+                        if (match) {
+                            sum = xadd(sum, xmul(x[e], __ldg(tpv + lo)));
+                            if (min_tail < 0 && (c[e] & aux.tail_bit)) min_tail = ix;
+                        }
+                    }
+                }
+            }
+        }
+        double c = xdiv(sum, xmul(lens.x, lt.x));
+        if (c > 0) {
+            keep = true;
+            ps_sim = c;
+        }
+    }
+    if (pr) {
+        long long zz = clock64();
+        g_probe[2] += (unsigned long long)(zz - z2);                  // place section + matching
+        z2 = zz;
+    }
+    if (nc > 0) {
+        double sum = 0.0;
+        for (int k0 = 0; k0 < nc; k0 += 4) {
+            unsigned c[4];
+            double x[4];
+            rec_load4(cc, cvp, k0, c, x);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (k0 + e < nc) sum = xadd(sum, xmul(x[e], __ldg(tdense + c[e])));
+        }
+        double c = xdiv(sum, xmul(lens.y, lt.y));
+        if (c > 0) {
+            keep = true;
+            cs_sim = c;
+        }
+    }
+    if (pr) {
+        long long z3 = clock64();
+        g_probe[0] += (unsigned long long)(z1 - z0);
+        g_probe[1] += (unsigned long long)(zh - z1);
+        g_probe[7] += (unsigned long long)(z3 - z2);                  // category section + dense row + divisions
+        g_probe[3] += 1;
+    }
+    if (!keep) return 0.0;
+    return xadd(xmul(ps_sim, pw), xmul(cs_sim, cw));
 }
 
 // exact combined similarity + the smallest shared tail place (-1 if none)
@@ -672,6 +794,10 @@ struct TileSmem {
     unsigned long long *queue;  // [TILE_QCAP]  (t << 32 | candidate)
     int *qn;
     unsigned int *stats;        // [4] per-block event counters, flushed to g_tile_stats at the end
+    unsigned long long *tsig = nullptr;   // [T] 64-bit signature of the target's places (knn_tc_ws_kernel)
+    int t_base = 0;                       // batch position of target slot 0 (row of aux.tdense)
+    const int *tpool = nullptr;           // place columns of the targets (ascending, flags stripped), packed
+    const unsigned short *toff = nullptr; // [T] offset of target t's columns in tpool, 0xffff = not staged
 };
 
 __device__ __forceinline__ bool nb_worse(double sa, int ia, double sb, int ib) {
@@ -773,6 +899,51 @@ __device__ __forceinline__ void tile_process_staged(const TileAux &aux, const Ti
     if (*(volatile int *)(sm.hcnt + t) >= K && sim < hs[0]) return;
     atomicAdd(sm.stats + 2, 1u);
     tile_heap_insert(sm, t, K, sim, c);
+}
+
+// Survivors of knn_tc_ws_kernel's dense filter, one per lane of a converged warp (t < 0: none):
+// signature / dense-row evaluation, then the heap inserts in rounds -- in every round the lanes that
+// still hold a result elect one lane per distinct target (__match_any_sync), so the lanes of a warp
+// never spin on the same heap lock (a warp's survivors all belong to the 32 targets of its lane quarter).
+// One copy of the code (not inlined): the kernel stays small enough for the instruction cache.
+__device__ __noinline__ void tile_process_sig(const TileAux &aux, const TileSmem &sm, int t, int c, int K, double pw,
+                                              double cw) {
+    double sim = 0.0;
+    bool pending = false;
+    if (t >= 0) {
+        const int tix = sm.tid_of[t];
+        if (tix >= 0) {
+            int min_tail;
+            const unsigned short off = sm.toff[t];
+            sim = exact_pair_sig(aux, c, tix, sm.tsig[t], aux.tdense + (size_t)(sm.t_base + t) * aux.cat_dim,
+                                 off == 0xffffu ? nullptr : sm.tpool + off, pw, cw, min_tail);
+            atomicAdd(sm.stats + 1, 1u);
+            pending = sim > 0 && min_tail < 0;      // pairs sharing a tail place belong to the postings kernel
+        }
+    }
+    __syncwarp();
+    for (;;) {
+        if (pending) {
+            volatile double *hs = sm.hsim + (size_t)t * K;
+            if (*(volatile int *)(sm.hcnt + t) >= K && sim < hs[0]) pending = false;   // cannot enter any more
+        }
+        const unsigned todo = __ballot_sync(0xffffffffu, pending);
+        if (!todo) break;
+        if (pending) {
+            const unsigned same = __match_any_sync(todo, t);
+            if ((int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) {
+                atomicAdd(sm.stats + 2, 1u);
+                long long h0 = clock64();
+                tile_heap_insert(sm, t, K, sim, c);
+                if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+                    g_probe[4] += (unsigned long long)(clock64() - h0);
+                    g_probe[5] += 1;
+                }
+                pending = false;
+            }
+        }
+        __syncwarp();
+    }
 }
 
 __device__ __forceinline__ void tile_process(const KnnDev &d, const TileAux &aux, const TileSmem &sm, int t, int c,
@@ -1583,7 +1754,7 @@ knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_t
 //   warp 16 (one elected thread) = producer: streams B tiles with TMA bulk copies -- the fp16
 //       features are stored in HBM as ready-made 32 KB shared-memory images (128 persons, K-major,
 //       SWIZZLE_128B), so one cp.async.bulk per tile lands them in place -- and issues the MMA
-//       chains into two alternating TMEM accumulators;
+//       chains into WS_NACC rotating TMEM accumulators;
 //   warps 0..15 = consumers: pull a tile's accumulator out of TMEM, apply the threshold filter,
 //       queue the survivors and (every few tiles, by a named-barrier vote) evaluate them exactly.
 // Synchronisation is mbarrier-only on the data path: full[stage] (TMA transaction bytes),
@@ -1592,16 +1763,22 @@ knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_t
 constexpr int WS_WORKERS = 512;
 constexpr int WS_THREADS = WS_WORKERS + 64;           // + MMA warp + loader warp
 constexpr int WS_VOTE_EVERY = 4;
+constexpr int WS_WQ = TC_QCAP / (WS_WORKERS / 32);   // survivor queue entries per consumer warp
+constexpr int WS_NACC = 4;           // TMEM accumulators (4 x 128 columns = the whole TMEM): the MMA warp runs up to 3 tiles ahead
 constexpr int WS_BOOT_TILES = 256;   // multiple of 16; 64 groups of 512 candidates per target
 
 __global__ void __launch_bounds__(WS_THREADS, 1)
 knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const int *__restrict__ tidx,
                  int n_targets, int K, int S, int cat_dim, double pw, double cw, Nb *__restrict__ part,
-                 int *__restrict__ part_cnt, const double *__restrict__ seed_thr, int part_stride, int total_tiles) {
+                 int *__restrict__ part_cnt, const double *__restrict__ seed_thr, int part_stride, int total_tiles,
+                 int pool_ints) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full[TC_STAGES], sempty[TC_STAGES], tfull[2], tempty[2];
+    __shared__ __align__(8) uint64_t full[TC_STAGES], sempty[TC_STAGES], tfull[WS_NACC], tempty[WS_NACC];
+    __shared__ unsigned short s_toff[TC_M];
+    __shared__ unsigned short s_tnp[TC_M];
     __shared__ uint32_t tmem_base_s;
     __shared__ unsigned int s_stats[4];
+    __shared__ int s_next_unit[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool worker = tid < WS_WORKERS;
     const int tile_m = blockIdx.x, sp = blockIdx.y;
@@ -1621,17 +1798,21 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
         sm.hcnt = (int *)p;                         p += sizeof(int) * TC_M;
         sm.lock = (int *)p;                         p += sizeof(int) * TC_M;
         sm.tid_of = (int *)p;                       p += sizeof(int) * TC_M;
-        sm.qn = (int *)p;
+        sm.qn = (int *)p;                           p += 16;
+        sm.tsig = (unsigned long long *)p;          p += sizeof(unsigned long long) * TC_M;
+        sm.tpool = (const int *)p;
+        sm.toff = s_toff;
+        sm.t_base = t0;
         sm.stats = s_stats;
     }
     if (tid < 4) s_stats[tid] = 0;
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 2 * TC_N);
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, WS_NACC * TC_N);
     if (tid == 0) {
         for (int s_ = 0; s_ < TC_STAGES; ++s_) {
             tc::mbar_init(&full[s_], 1);
             tc::mbar_init(&sempty[s_], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < WS_NACC; ++a) {
             tc::mbar_init(&tfull[a], 1);
             tc::mbar_init(&tempty[a], WS_WORKERS / 32);
         }
@@ -1646,6 +1827,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
     // are visited again, normally, at the end of the sequence.
     const int boot = ntiles >= 2 * WS_BOOT_TILES ? WS_BOOT_TILES : 0;
     const int nseq = ntiles + boot;
+    if (tid < 4) s_next_unit[tid] = boot * 4;
     auto tile_index = [&](int i) {
         int w_ = (i >= ntiles ? i - ntiles : i) + rot;
         if (w_ >= ntiles) w_ -= ntiles;
@@ -1682,6 +1864,55 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
             *reinterpret_cast<uint4 *>(sA + tc::sw128_offset(TC_M, r, c)) = *reinterpret_cast<const uint4 *>(h);
         }
     }
+    if (worker) {
+        // the targets' place columns, packed into what is left of shared memory (first come, first served)
+        int *pool = const_cast<int *>(sm.tpool);
+        if (tid < TC_M) {
+            const int tix = sm.tid_of[tid];
+            s_tnp[tid] = tix >= 0 ? (unsigned short)((__ldg(aux.meta + tix) >> 40) & 0xfffu) : 0;
+        }
+        tc::bar_sync(1, WS_WORKERS);
+        if (tid == 0) {
+            int at = 0;
+            for (int t = 0; t < TC_M; ++t) {
+                const int n = s_tnp[t];
+                if (at + n <= pool_ints && at + n < 0xffff) {
+                    s_toff[t] = (unsigned short)at;
+                    at += n;
+                } else {
+                    s_toff[t] = 0xffffu;
+                }
+            }
+        }
+        tc::bar_sync(1, WS_WORKERS);
+        // per target: signature of its places (shared memory) and its category vector as a dense row
+        for (int t = warp; t < TC_M; t += WS_WORKERS / 32) {
+            const int tix = sm.tid_of[t];
+            unsigned long long sig = 0ULL;
+            if (tix >= 0) {
+                const unsigned long long mt = __ldg(aux.meta + tix);
+                const int npt = (int)((mt >> 40) & 0xfffu), nct = (int)(mt >> 52);
+                const double *rt = aux.rec + (mt & 0xffffffffffULL);
+                const int *tpc = reinterpret_cast<const int *>(rt + 2);
+                const double *tpv = rt + 2 + rec_cols_words(npt);
+                const int *tcc = reinterpret_cast<const int *>(tpv + rec_vals_words(npt));
+                const double *tcv = tpv + rec_vals_words(npt) + rec_cols_words(nct);
+                for (int k = lane; k < npt; k += 32) {
+                    const int col = (int)((unsigned)tpc[k] & REC_COL_MASK);
+                    sig |= 1ULL << sig_bit(col);
+                    if (s_toff[t] != 0xffffu) pool[s_toff[t] + k] = col;
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) sig |= __shfl_xor_sync(0xffffffffu, sig, off);
+                double *row = aux.tdense + (size_t)(t0 + t) * aux.cat_dim;
+                for (int c = lane; c < aux.cat_dim; c += 32) row[c] = 0.0;
+                __syncwarp();
+                for (int k = lane; k < nct; k += 32) row[tcc[k]] = tcv[k];
+            }
+            if (lane == 0) sm.tsig[t] = sig;
+        }
+        __threadfence_block();
+    }
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
@@ -1714,10 +1945,10 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
         pk0 = pk1;                                                     \
     }
             for (int i = 0; i < nseq; ++i) {
-                const int st = i % TC_STAGES, a = i & 1;
+                const int st = i % TC_STAGES, a = i % WS_NACC;
                 tc::mbar_wait(&full[st], (uint32_t)((i / TC_STAGES) & 1));                 // B(i) landed
                 WS_PTICK(0)
-                if (i >= 2) tc::mbar_wait(&tempty[a], (uint32_t)((i / 2 - 1) & 1));        // accumulator drained
+                if (i >= WS_NACC) tc::mbar_wait(&tempty[a], (uint32_t)((i / WS_NACC - 1) & 1));   // accumulator drained
                 WS_PTICK(7)
                 tc::fence_after_sync();
                 const uint32_t b_addr = b_addr0 + (uint32_t)st * TC_TILE_BYTES;
@@ -1757,8 +1988,8 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
 #pragma unroll
             for (int g = 0; g < 16; ++g) gmax[g] = 0.0f;
             for (int i = 0; i < boot; ++i) {
-                const int a = i & 1;
-                tc::mbar_wait(&tfull[a], (uint32_t)((i / 2) & 1));
+                const int a = i % WS_NACC;
+                tc::mbar_wait(&tfull[a], (uint32_t)((i / WS_NACC) & 1));
                 tc::fence_after_sync();
                 float v[32];
                 tc::tmem_ld32(tbase + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * TC_N + cq * 32), v);
@@ -1785,58 +2016,95 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
             }
             tc::bar_sync(1, WS_WORKERS);
         }
-        for (int i = boot; i <= nseq; ++i) {
-            const bool live = i < nseq;
-            if (!live || (i % WS_VOTE_EVERY) == 0) {
-                // block-uniform decision (consumers only) whether the survivor queue is drained now
-                const int drain = tc::bar_red_or(1, WS_WORKERS, (*(volatile int *)sm.qn >= TC_QCAP / 2) || !live);
-                WS_CTICK(9)                                   // the vote barrier itself
-                if (drain) {
-                    int m = min(*(volatile int *)sm.qn, TC_QCAP);
-                    for (int qi = tid; qi < m; qi += WS_WORKERS) {
-                        unsigned long long e = sm.queue[qi];
-                        tile_process(d, aux, sm, (int)(e >> 32), (int)(unsigned)(e & 0xffffffffu), K, pw, cw, -1);
-                    }
-                    WS_CTICK(10)                              // this thread's share of the drain
-                    tc::bar_sync(1, WS_WORKERS);
-                    if (tid == 0) *sm.qn = 0;
-                    tc::bar_sync(1, WS_WORKERS);
-                    if (cprof) g_tc_cycles[11] += 1;
-                }
+        // ---- main sequence.  The unit of consumer work is (tile, lane quarter, column quarter) = 32 target
+        // rows x 32 candidates; the warps claim units in order from shared counters, so a warp that is busy
+        // with exact evaluations (a chain of dependent HBM reads, tens of thousands of cycles) never holds up
+        // an accumulator: the others take over its units and the tensor pipe keeps running.  Survivors go
+        // to a per-warp queue that the warp drains by itself once it holds one candidate per lane.
+        unsigned long long *wq = sm.queue + (size_t)warp * WS_WQ;
+        int wn = 0;                                              // warp-uniform
+        auto drain_own = [&]() {
+            for (int q0 = 0; q0 < wn; q0 += 32) {
+                const int qi = q0 + lane;
+                const unsigned long long e = qi < wn ? wq[qi] : 0xffffffff00000000ULL;      // target -1: idle lane
+                tile_process_sig(aux, sm, (int)(e >> 32), (int)(unsigned)(e & 0xffffffffu), K, pw, cw);
             }
-            if (!live) break;
-            WS_CTICK(6)                                       // vote + drain
-            const int a = i & 1;
-            tc::mbar_wait(&tfull[a], (uint32_t)((i / 2) & 1));
+            __syncwarp();
+            wn = 0;
+        };
+        // (a warp can only read the TMEM lanes 32 * (warp % 4) ..: the four warps of a lane quarter share
+        // that quarter's units)
+        const int n_units = nseq * 4;
+        const int ulq = lq;
+        for (;;) {
+            int u = 0;
+            if (lane == 0) u = atomicAdd(&s_next_unit[ulq], 1);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= n_units) break;
+            const int i = u >> 2, ucq = u & 3;
+            const int a = i % WS_NACC;
+            tc::mbar_wait(&tfull[a], (uint32_t)((i / WS_NACC) & 1));
             tc::fence_after_sync();
-            WS_CTICK(1)                                       // wait for the accumulator
-            const float thr = *(volatile float *)(sm.thr + my_t);
+            WS_CTICK(1)                                       // claim + wait for the accumulator
+            const int ut = ulq * 32 + lane;
+            const float thr = *(volatile float *)(sm.thr + ut);
             const long long tile = (long long)tile_index(i) * TC_N;
-            const int c0 = cq * 32;
+            const int c0 = ucq * 32;
             float v[32];
-            tc::tmem_ld32(tbase + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * TC_N + c0), v);
+            tc::tmem_ld32(tbase + ((uint32_t)(ulq * 32) << 16) + (uint32_t)(a * TC_N + c0), v);
             tc::fence_before_sync();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&tempty[a]);            // this warp is done with the accumulator
-            unsigned pass = 0;
+            if (lane == 0) tc::mbar_arrive(&tempty[a]);            // this unit is out of the accumulator
+            // most rows have no survivor among their 32 values: one running maximum first, the per-value
+            // test only for the rows whose maximum passes a (slightly lower, hence safe) bound
+            float vmax = v[0];
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) pass |= (v[jj] * 1.002f + 2e-5f >= thr ? 1u : 0u) << jj;
-            while (pass) {
-                const int jj = __ffs(pass) - 1;
-                pass &= pass - 1;
-                const long long j = tile + c0 + jj;
-                if (j < d.P) {
-                    int pos = atomicAdd(sm.qn, 1);
-                    if (pos < TC_QCAP) {
-                        sm.queue[pos] = ((unsigned long long)my_t << 32) | (unsigned long long)(unsigned)j;
-                    } else {
-                        atomicAdd(sm.stats + 3, 1u);
-                        tile_process(d, aux, sm, my_t, (int)j, K, pw, cw, -1);
-                    }
-                }
+            for (int jj = 1; jj < 32; ++jj) vmax = fmaxf(vmax, v[jj]);
+            unsigned pass = 0;
+            if (vmax * 1.002f + 2e-5f >= thr) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) pass |= (v[jj] * 1.002f + 2e-5f >= thr ? 1u : 0u) << jj;
             }
+            if (tile + c0 + 32 > d.P) {                            // last tile: columns past the last person
+                const long long over = tile + c0 + 32 - d.P;
+                pass = over >= 32 ? 0u : (pass & (0xffffffffu >> over));
+            }
+            const unsigned any = __ballot_sync(0xffffffffu, pass != 0u);
             WS_CTICK(2)                                       // epilogue
+            if (any) {
+                int cnt = __popc(pass), incl = cnt;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    int o = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += o;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (wn + total > WS_WQ) drain_own();
+                if (total > WS_WQ) {
+                    // more survivors in one unit than the queue holds (thresholds still loose): inline
+                    while (__any_sync(0xffffffffu, pass != 0u)) {
+                        const int jj = pass ? __ffs(pass) - 1 : 0;
+                        const int tt = pass ? ut : -1;
+                        pass &= pass - 1;
+                        tile_process_sig(aux, sm, tt, (int)(tile + c0 + jj), K, pw, cw);
+                    }
+                    __syncwarp();
+                } else {
+                    int pos = wn + incl - cnt;
+                    while (pass) {
+                        const int jj = __ffs(pass) - 1;
+                        pass &= pass - 1;
+                        wq[pos++] = ((unsigned long long)ut << 32) | (unsigned long long)(unsigned)(tile + c0 + jj);
+                        if (aux.meta) asm volatile("prefetch.global.L2 [%0];" ::"l"(aux.meta + tile + c0 + jj));
+                    }
+                    __syncwarp();
+                    wn += total;
+                    if (wn >= 32) drain_own();
+                }
+                WS_CTICK(10)                                  // queueing + own drains
+            }
         }
+        drain_own();
 #undef WS_CTICK
     }
     __syncthreads();
@@ -1857,7 +2125,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tbase, 2 * TC_N);
+    if (warp == 0) tc::tmem_dealloc(tbase, WS_NACC * TC_N);
 }
 
 // fp16 features as ready-made shared-memory tile images: tile b = persons [128 b, 128 b + 128),
@@ -2233,6 +2501,7 @@ struct vrec_knn {
     DevBuf<short> d_head_slot;
     DevBuf<int> d_pcp, d_pper;
     DevBuf<double> d_seed_thr;
+    DevBuf<double> d_tdense;                 // [targets of the batch][cat_dim] dense category rows (knn_tc_ws_kernel)
     DevBuf<int> d_work;
     DevBuf<unsigned long long> d_meta;     // packed records for the exact evaluation
     DevBuf<double> d_rec;
@@ -2551,7 +2820,7 @@ extern "C" int vrec_knn_load(vrec_ctx *ctx, int64_t P, const int64_t *person_id,
                 rec.resize(at + (size_t)rec_vals_words(nc), 0.0);
                 for (int e = 0; e < nc; ++e) rec[at + e] = cv[crp[i] + e];
             }
-            rec.resize(rec.size() + 8, 0.0);          // slack: the 128-bit loads may touch the padding of the last record
+            rec.resize(rec.size() + 64, 0.0);         // slack: the 128-bit loads may touch the padding of the last record
             if (rc == VREC_OK) rc = k->d_meta.upload(meta.data(), meta.size(), s);
             if (rc == VREC_OK) rc = k->d_rec.upload(rec.data(), rec.size(), s);
             if (rc == VREC_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = VREC_ECUDA;
@@ -2644,12 +2913,13 @@ extern "C" int vrec_knn_debug_stats(vrec_knn *k, uint64_t *out4) {
 
 // Debug: reads and clears the exact-evaluation probe (block 0 warp 0, postings pass): out4 = {meta wait,
 // record + place merge + division, category merge + division, evaluations}.
-extern "C" int vrec_knn_debug_probe(vrec_knn *k, uint64_t *out4) {
+extern "C" int vrec_knn_debug_probe(vrec_knn *k, uint64_t *out8) {
+    uint64_t *out4 = out8;
     if (!k || !out4) return VREC_EINVAL;
     VREC_CUDA(cudaSetDevice(k->ctx->device));
     VREC_CUDA(cudaStreamSynchronize(k->ctx->stream));
     unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    VREC_CUDA(cudaMemcpyFromSymbol(out4, g_probe, 48));        // out4 holds 6 values
+    VREC_CUDA(cudaMemcpyFromSymbol(out4, g_probe, 64));        // 8 values
     VREC_CUDA(cudaMemcpyToSymbol(g_probe, z, sizeof(z)));
     return VREC_OK;
 }
@@ -2735,10 +3005,18 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     int S = (int)k->opt_splits;
     int T = 1;
     size_t smem = 0;
+    int ws_pool_ints = 0;
     if (use_tc) {
         T = TC_M;
         smem = 1024 + (1 + TC_STAGES) * (size_t)TC_TILE_BYTES + 12 * (size_t)TC_M * K +
-               sizeof(unsigned long long) * TC_QCAP + sizeof(float) * TC_M + sizeof(int) * 3 * TC_M + 16;
+               sizeof(unsigned long long) * TC_QCAP + sizeof(float) * TC_M + sizeof(int) * 3 * TC_M + 16 +
+               sizeof(unsigned long long) * TC_M;
+        if (use_ws) {
+            // what is left of the 227 KB holds the targets' place columns (knn_tc_ws_kernel)
+            const size_t limit = 227 * 1024 - 2048;
+            ws_pool_ints = smem < limit ? (int)((limit - smem) / sizeof(int)) : 0;
+            smem += sizeof(int) * (size_t)ws_pool_ints;
+        }
     } else if (tiled) {
         // targets per block: heaps must fit next to the queue and the target vectors
         T = (int)std::max<int64_t>(1, std::min<int64_t>(64, (48 * 1024) / (12 * (int64_t)K)));
@@ -2791,6 +3069,9 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                 VREC_CUDA(cudaMemsetAsync(k->d_seed_thr.p, 0, sizeof(double) * (size_t)tn, ctx->stream));
             }
             if (use_ws) {
+                VREC_TRY(k->d_tdense.ensure((size_t)tn * (size_t)std::max(1, (int)k->cat_dim)));
+                aux.tdense = k->d_tdense.p;
+                aux.cat_dim = (int)k->cat_dim;
                 static bool attr_ws = false;
                 if (!attr_ws) {
                     VREC_CUDA(cudaFuncSetAttribute(knn_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -2798,7 +3079,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                 }
                 knn_tc_ws_kernel<<<dim3(tiles, S), WS_THREADS, smem, ctx->stream>>>(
                     k->dev(), aux, (const __half *)k->d_featsw.p, k->d_tidx.p, tn, K, S, k->cat_dim, pw, cw, k->d_part.p,
-                    k->d_part_cnt.p, k->d_seed_thr.p, SP, k->tc_tiles);
+                    k->d_part_cnt.p, k->d_seed_thr.p, SP, k->tc_tiles, ws_pool_ints);
                 VREC_LAUNCHED(ctx);
             } else {
                 knn_tc_kernel<<<dim3(tiles, S), TC_THREADS, smem, ctx->stream>>>(

@@ -64,11 +64,13 @@ for s in range(a.warmup + a.steps):
     if cy[11] and a.kernel == 3:
         print(f"   postings warp-iteration (block0 warp0): candidate id load {cy[9] / cy[11]:.0f} cycles, exact eval + insert "
               f"{cy[10] / cy[11]:.0f} cycles, iterations {cy[11]}")
-    pb = (C.c_uint64 * 6)()
+    pb = (C.c_uint64 * 8)()
     lib.vrec_knn_debug_probe(rs._h, pb)
     if pb[3]:
-        print(f"   survivor eval (block0 thread0): meta {pb[0] / pb[3]:.0f}, headers {pb[1] / pb[3]:.0f}, sections+math {pb[2] / pb[3]:.0f} "
-              f"cycles over {pb[3]} evals; heap insert {pb[4] / max(1, pb[5]):.0f} cycles over {pb[5]} inserts")
+        n = pb[3]
+        print(f"   survivor eval (block0 thread0), cycles per eval over {n}: meta {pb[0] / n:.0f}, headers {pb[1] / n:.0f}, "
+              f"place section {pb[6] / n:.0f}, place matching {pb[2] / n:.0f}, category {pb[7] / n:.0f}; heap insert "
+              f"{pb[4] / max(1, pb[5]):.0f} over {pb[5]} inserts")
     nb = min(1024, (B + 127) // 128)
     bc = (C.c_uint64 * (2 * nb))()
     lib.vrec_knn_debug_tc_block_cycles(rs._h, bc, nb)
