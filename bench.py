@@ -44,6 +44,14 @@ def emit(line: dict) -> None:
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
+def measured_peaks_all() -> dict:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -136,8 +144,8 @@ def sg_workload_name(args):
 SG_NCU_TRAFFIC = 10_383_476_000 + 80_896_000 + 6_942_931_000 + 68_708_864
 # the same for one knn_tc_ws_kernel launch on the default KNN workload (18944 targets),
 # from profiles/r1_knn_final_r1_ncu_raw.csv
-KNN_NCU_TRAFFIC = 29_429_142_000 + 251_530_240
-KNN_NCU_TENSOR_PIPE_PCT = 16.1
+KNN_NCU_TRAFFIC = 572_646_912 + 643_610_368      # profiles/r1_knn_final_r1d_ncu_raw.csv (+ the stagger-1 launch)
+KNN_NCU_TENSOR_PIPE_PCT = 23.4
 
 
 def sg_bytes_per_iteration(n, nnz):
@@ -360,25 +368,35 @@ def run_ours(args):
     d2h = B * m * 16 + B * 8
     log(f"[bench] knn e2e: {e2e_value:,.0f} persons/s")
 
-    # Roofline of the dominant KNN kernel (knn_tc_ws_kernel, ~55 % of the step, profiles/r1_knn_step_launches.csv).
-    # Its algorithmic HBM traffic: every CTA (128 targets) streams the fp16 feature matrix (256 B / person) once,
-    # so bytes per launch = ceil(B / 128) * P * 256.  (SURVEY.md 8(d)'s per-target figure B_region / T with
-    # T = targets per pass is reported alongside; with T = 18944 it is ~11 KB per target.)
+    # Roofline of the dominant KNN kernel, knn_tc_ws_kernel: a [B x 128] x [128 x P] fp16 product on tcgen05 with
+    # the threshold filter fused into its TMEM epilogue.  (SURVEY.md 8(d)'s per-target byte figure B_region / T,
+    # T = targets per pass, is reported alongside; with T = 18944 it is ~11 KB per target.)
     b_region = inp.algorithmic_bytes
     knn_launch_ms = statistics.mean(knn_ms)
     default_cfg = (args.knn_persons, args.knn_places, args.knn_batch, args.k_nearest) == (1_000_000, 100_000, 18944, 50)
-    kernel_share = 0.55
-    tc_bytes = ((B + 127) // 128) * len(inp.person_id) * 256
-    tc_ms = knn_launch_ms * kernel_share
-    knn_roof = {"bound": "hbm", "kernel": "knn_tc_ws_kernel", "achieved": tc_bytes / (tc_ms / 1e3) / 1e9,
-                "peak": peak, "unit": "GB/s", "frac": tc_bytes / (tc_ms / 1e3) / 1e9 / peak,
-                "traffic": KNN_NCU_TRAFFIC if default_cfg else None, "peak_source": peak_src,
+    # dominant kernel: the dense filter on tcgen05 (knn_tc_ws_kernel); its duration comes from CUDA events the
+    # library records around the launch on its own stream (last timed step)
+    dense_ms = C.c_double(0.0)
+    lib.vrec_knn_last_dense_ms(rs._h, C.byref(dense_ms))
+    tc_ms = dense_ms.value if dense_ms.value > 0 else knn_launch_ms * 0.47
+    P_ = len(inp.person_id)
+    tc_flops = 2.0 * B * P_ * 128                      # [B x 128] x [128 x P] fp16, fp32 accumulate
+    tc_bytes = ((B + 127) // 128) * P_ * 256           # every CTA streams the feature matrix once (from L2)
+    peaks = measured_peaks_all()
+    tf_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1652.7
+    knn_roof = {"bound": "tensor", "kernel": "knn_tc_ws_kernel", "achieved": tc_flops / (tc_ms / 1e3) / 1e12,
+                "peak": tf_peak, "unit": "TFLOP/s", "frac": tc_flops / (tc_ms / 1e3) / 1e12 / tf_peak,
+                "traffic": KNN_NCU_TRAFFIC if default_cfg else None,
+                "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)",
+                "kernel_ms": tc_ms, "kernel_share_of_step": tc_ms / knn_launch_ms,
                 "tensor_pipe_active_pct": KNN_NCU_TENSOR_PIPE_PCT if default_cfg else None,
+                "l2_to_sm_gbs": tc_bytes / (tc_ms / 1e3) / 1e9,
                 "survey_bytes_per_target": b_region / B,
-                "note": f"algorithmic bytes/launch = {tc_bytes} (each of {(B + 127) // 128} CTAs streams the 256 B/person fp16 "
-                        f"feature matrix once); kernel duration = {kernel_share:.2f} x step (share from the ncu launch list in "
-                        "profiles/).  The kernel is bound by its consumer warps (TMEM read-out + exact survivors), not by "
-                        "HBM or the tensor pipe: see DESIGN.md"}
+                "note": f"flops/launch = 2 x {B} targets x {P_} candidates x 128 dims; the operand stream is "
+                        f"{tc_bytes} B per launch from L2 (neighbouring CTAs walk the tiles one apart, so HBM "
+                        "delivers each 32 KB tile image once: `traffic` = ncu dram bytes read + written).  The kernel "
+                        "is paced by its MMA-issue / accumulator hand-over chain and the consumer warps' exact "
+                        "evaluations, not by HBM: see DESIGN.md"}
 
     cpu_knn_base = None
     if rank == 0 and not args.no_cpu_baseline:

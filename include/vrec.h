@@ -164,6 +164,9 @@ int vrec_knn_debug_stats(vrec_knn *knn, uint64_t *out4);
 int vrec_knn_debug_tc_cycles(vrec_knn *knn, uint64_t *out8);
 /* Debug: cycles per block of the last tensor-core main pass: out[0..n) dense phase, out[n..2n) postings. */
 int vrec_knn_debug_tc_block_cycles(vrec_knn *knn, uint64_t *out, int n);
+/* Duration in milliseconds of the last dense-filter kernel launch (knn_tc_ws_kernel), from CUDA events on
+ * vrec_stream(); 0 if that kernel has not run.  bench.py's roofline uses it.                          */
+int vrec_knn_last_dense_ms(vrec_knn *knn, double *out_ms);
 /* Debug: exact-evaluation probe of block 0 / thread 0 of the dense kernel, cycles summed over its
  * evaluations: out8 = {meta words, record headers, place matching, evaluations, heap inserts (cycles),
  * heap inserts (count), place section load, category section + dense row}.                            */

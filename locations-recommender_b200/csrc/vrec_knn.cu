@@ -1765,6 +1765,7 @@ constexpr int WS_THREADS = WS_WORKERS + 64;           // + MMA warp + loader war
 constexpr int WS_VOTE_EVERY = 4;
 constexpr int WS_WQ = TC_QCAP / (WS_WORKERS / 32);   // survivor queue entries per consumer warp
 constexpr int WS_NACC = 4;           // TMEM accumulators (4 x 128 columns = the whole TMEM): the MMA warp runs up to 3 tiles ahead
+constexpr int WS_STAGGER = 1;        // tiles between the starting points of neighbouring CTAs (small: the CTAs share each tile through L2)
 constexpr int WS_BOOT_TILES = 256;   // multiple of 16; 64 groups of 512 candidates per target
 
 __global__ void __launch_bounds__(WS_THREADS, 1)
@@ -1822,7 +1823,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
     // this CTA's share of the candidate tiles, visited in a rotated order
     const int tlo = (int)((long long)total_tiles * sp / S), thi = (int)((long long)total_tiles * (sp + 1) / S);
     const int ntiles = thi - tlo;
-    const int rot = ntiles > 0 ? (int)(((long long)blockIdx.x * 67 + (long long)blockIdx.y * 29) % ntiles) : 0;
+    const int rot = ntiles > 0 ? (int)(((long long)blockIdx.x * WS_STAGGER + (long long)blockIdx.y * 29) % ntiles) : 0;
     // Bootstrap: the first `boot` tiles of the sequence are only scanned for group maxima (below) and
     // are visited again, normally, at the end of the sequence.
     const int boot = ntiles >= 2 * WS_BOOT_TILES ? WS_BOOT_TILES : 0;
@@ -2479,6 +2480,7 @@ __global__ void knn_fill_int_kernel(int *p, long long n, int v) {
 // ------------------------------------------------------------------ host object
 struct vrec_knn {
     vrec_ctx *ctx = nullptr;
+    cudaEvent_t ev_dense[2] = {nullptr, nullptr};   // around the last dense-filter kernel launch (bench roofline)
     int64_t P = 0;
     int place_dim = 0, cat_dim = 0, rdim = 0;
     int max_rating_row = 0;
@@ -2846,6 +2848,8 @@ extern "C" void vrec_knn_free(vrec_knn *knn) {
     if (!knn) return;
     cudaSetDevice(knn->ctx->device);
     cudaStreamSynchronize(knn->ctx->stream);
+    for (cudaEvent_t e : knn->ev_dense)
+        if (e) cudaEventDestroy(e);
     delete knn;
 }
 
@@ -2901,6 +2905,20 @@ extern "C" int vrec_knn_set_option(vrec_knn *k, const char *name, int64_t value)
 }
 
 // Debug: reads and clears the event counters of the tiled kernel (see g_tile_stats).
+// Duration of the last knn_tc_ws_kernel launch (CUDA events on the library's stream), in milliseconds;
+// 0 if that kernel has not run.  Synchronises the stream.
+extern "C" int vrec_knn_last_dense_ms(vrec_knn *k, double *out_ms) {
+    if (!k || !out_ms) return VREC_EINVAL;
+    *out_ms = 0.0;
+    if (!k->ev_dense[0]) return VREC_OK;
+    VREC_CUDA(cudaSetDevice(k->ctx->device));
+    VREC_CUDA(cudaStreamSynchronize(k->ctx->stream));
+    float ms = 0.0f;
+    VREC_CUDA(cudaEventElapsedTime(&ms, k->ev_dense[0], k->ev_dense[1]));
+    *out_ms = ms;
+    return VREC_OK;
+}
+
 extern "C" int vrec_knn_debug_stats(vrec_knn *k, uint64_t *out4) {
     if (!k || !out4) return VREC_EINVAL;
     VREC_CUDA(cudaSetDevice(k->ctx->device));
@@ -3077,10 +3095,16 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                     VREC_CUDA(cudaFuncSetAttribute(knn_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
                     attr_ws = true;
                 }
+                if (!k->ev_dense[0]) {
+                    VREC_CUDA(cudaEventCreate(&k->ev_dense[0]));
+                    VREC_CUDA(cudaEventCreate(&k->ev_dense[1]));
+                }
+                VREC_CUDA(cudaEventRecord(k->ev_dense[0], ctx->stream));
                 knn_tc_ws_kernel<<<dim3(tiles, S), WS_THREADS, smem, ctx->stream>>>(
                     k->dev(), aux, (const __half *)k->d_featsw.p, k->d_tidx.p, tn, K, S, k->cat_dim, pw, cw, k->d_part.p,
                     k->d_part_cnt.p, k->d_seed_thr.p, SP, k->tc_tiles, ws_pool_ints);
                 VREC_LAUNCHED(ctx);
+                VREC_CUDA(cudaEventRecord(k->ev_dense[1], ctx->stream));
             } else {
                 knn_tc_kernel<<<dim3(tiles, S), TC_THREADS, smem, ctx->stream>>>(
                     k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, S, k->cat_dim, pw, cw, k->d_part.p,
