@@ -1764,7 +1764,9 @@ constexpr int WS_WORKERS = 512;
 constexpr int WS_THREADS = WS_WORKERS + 64;           // + MMA warp + loader warp
 constexpr int WS_VOTE_EVERY = 4;
 constexpr int WS_WQ = TC_QCAP / (WS_WORKERS / 32);   // survivor queue entries per consumer warp
-constexpr int WS_NACC = 4;           // TMEM accumulators (4 x 128 columns = the whole TMEM): the MMA warp runs up to 3 tiles ahead
+constexpr int WS_NACC = 3;           // TMEM accumulators (3 x 128 columns); the A operand (128 targets x 128 halves) takes 64 more
+constexpr int WS_STAGES = 4;         // B tiles in flight (the A operand lives in tensor memory, not in shared memory)
+constexpr int WS_TMEM_A = WS_NACC * TC_N;   // first TMEM column of the A operand
 constexpr int WS_STAGGER = 1;        // tiles between the starting points of neighbouring CTAs (small: the CTAs share each tile through L2)
 constexpr int WS_BOOT_TILES = 256;   // multiple of 16; 64 groups of 512 candidates per target
 
@@ -1774,7 +1776,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                  int *__restrict__ part_cnt, const double *__restrict__ seed_thr, int part_stride, int total_tiles,
                  int pool_ints) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full[TC_STAGES], sempty[TC_STAGES], tfull[WS_NACC], tempty[WS_NACC];
+    __shared__ __align__(8) uint64_t full[WS_STAGES], sempty[WS_STAGES], tfull[WS_NACC], tempty[WS_NACC];
     __shared__ unsigned short s_toff[TC_M];
     __shared__ unsigned short s_tnp[TC_M];
     __shared__ uint32_t tmem_base_s;
@@ -1786,10 +1788,10 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
     const int t0 = tile_m * TC_M;
     const int nt = min(TC_M, n_targets - t0);
     unsigned char *base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char *sA = base, *sB0 = base + TC_TILE_BYTES;
+    unsigned char *sB0 = base;
     TileSmem sm;
     {
-        unsigned char *p = base + (1 + TC_STAGES) * TC_TILE_BYTES;
+        unsigned char *p = base + WS_STAGES * TC_TILE_BYTES;
         sm.hsim = (double *)p;                      p += sizeof(double) * (size_t)TC_M * K;
         sm.queue = (unsigned long long *)p;         p += sizeof(unsigned long long) * TC_QCAP;
         sm.hidx = (int *)p;                         p += sizeof(int) * (size_t)TC_M * K;
@@ -1807,9 +1809,9 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
         sm.stats = s_stats;
     }
     if (tid < 4) s_stats[tid] = 0;
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, WS_NACC * TC_N);
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
-        for (int s_ = 0; s_ < TC_STAGES; ++s_) {
+        for (int s_ = 0; s_ < WS_STAGES; ++s_) {
             tc::mbar_init(&full[s_], 1);
             tc::mbar_init(&sempty[s_], 1);
         }
@@ -1844,26 +1846,37 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
         }
     }
     __syncthreads();
-    if (worker) {
-        // A tile: the targets' features (read from their tile images) with the weights folded in
-        for (int q = tid; q < TC_M * (TC_D / 8); q += WS_WORKERS) {
-            int r = q >> 4, c = q & 15;
-            int tix = sm.tid_of[r];
-            __align__(16) __half h[8];
+    __syncthreads();                              // tmem_base_s
+    if (tid < TC_M) {
+        // A operand in tensor memory: thread = target row = TMEM lane; 32-bit column j holds the halves
+        // (2j, 2j+1) of the row -- the target's features (read from their tile image) with the weights folded in
+        const int tix = sm.tid_of[tid];
+        const uint32_t ta = tmem_base_s + ((uint32_t)(warp * 32) << 16) + WS_TMEM_A;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) h[e] = __float2half(0.0f);
-            if (tix >= 0) {
-                const unsigned char *img = reinterpret_cast<const unsigned char *>(featsw) + (size_t)(tix >> 7) * TC_TILE_BYTES;
-                uint4 raw = *reinterpret_cast<const uint4 *>(img + tc::sw128_offset(TC_N, tix & 127, c));
+        for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {                       // 16-byte chunk c = h * 8 + c4: 8 halves
+                const int c = h * 8 + c4;
+                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+                if (tix >= 0) {
+                    const unsigned char *img = reinterpret_cast<const unsigned char *>(featsw) + (size_t)(tix >> 7) * TC_TILE_BYTES;
+                    raw = *reinterpret_cast<const uint4 *>(img + tc::sw128_offset(TC_N, tix & 127, c));
+                }
                 const __half *src = reinterpret_cast<const __half *>(&raw);
+                __align__(16) __half hh[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    int dd = c * 8 + e;
-                    h[e] = __float2half(__half2float(src[e]) * (float)(dd < cat_dim ? cw : pw));
+                    const int dd = c * 8 + e;
+                    hh[e] = __float2half(__half2float(src[e]) * (float)(dd < cat_dim ? cw : pw));
                 }
+                const uint32_t *pk = reinterpret_cast<const uint32_t *>(hh);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) r[c4 * 4 + e] = pk[e];
             }
-            *reinterpret_cast<uint4 *>(sA + tc::sw128_offset(TC_M, r, c)) = *reinterpret_cast<const uint4 *>(h);
+            tc::tmem_st32(ta + h * 32, r);
         }
+        tc::tmem_wait_st();
     }
     if (worker) {
         // the targets' place columns, packed into what is left of shared memory (first come, first served)
@@ -1922,13 +1935,13 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
 
     if (!worker) {
         const uint32_t idesc = tc::make_idesc_f16(TC_M, TC_N);
-        const uint32_t a_addr = tc::smem_u32(sA), b_addr0 = tc::smem_u32(sB0);
+        const uint32_t b_addr0 = tc::smem_u32(sB0);
         if (warp == WS_WORKERS / 32 + 1) {
             // ================= loader warp: TMA bulk copies, up to TC_STAGES tiles ahead =================
             if (lane == 0) {
                 for (int li = 0; li < nseq; ++li) {
-                    const int st = li % TC_STAGES;
-                    if (li >= TC_STAGES) tc::mbar_wait(&sempty[st], (uint32_t)((li / TC_STAGES - 1) & 1));   // MMA(li-3) done
+                    const int st = li % WS_STAGES;
+                    if (li >= WS_STAGES) tc::mbar_wait(&sempty[st], (uint32_t)((li / WS_STAGES - 1) & 1));   // MMA(li-4) done
                     tc::mbar_expect_tx(&full[st], TC_TILE_BYTES);
                     tc::bulk_copy_g2s(sB0 + (size_t)st * TC_TILE_BYTES,
                                       reinterpret_cast<const unsigned char *>(featsw) + (size_t)tile_index(li) * TC_TILE_BYTES,
@@ -1939,15 +1952,16 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
             // ================= MMA warp: one thread issues every tile's chain =================
             const bool pprof = blockIdx.x == 0 && blockIdx.y == 0;
             long long pk0 = clock64(), pk1;
+            unsigned long long pacc0 = 0, pacc7 = 0, pacc8 = 0;      // phase cycles, in registers until the end
 #define WS_PTICK(slot)                                                 \
     if (pprof) {                                                       \
         pk1 = clock64();                                               \
-        g_tc_cycles[slot] += (unsigned long long)(pk1 - pk0);          \
+        pacc##slot += (unsigned long long)(pk1 - pk0);                 \
         pk0 = pk1;                                                     \
     }
             for (int i = 0; i < nseq; ++i) {
-                const int st = i % TC_STAGES, a = i % WS_NACC;
-                tc::mbar_wait(&full[st], (uint32_t)((i / TC_STAGES) & 1));                 // B(i) landed
+                const int st = i % WS_STAGES, a = i % WS_NACC;
+                tc::mbar_wait(&full[st], (uint32_t)((i / WS_STAGES) & 1));                 // B(i) landed
                 WS_PTICK(0)
                 if (i >= WS_NACC) tc::mbar_wait(&tempty[a], (uint32_t)((i / WS_NACC - 1) & 1));   // accumulator drained
                 WS_PTICK(7)
@@ -1956,14 +1970,18 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                 const uint32_t acc = tbase + (uint32_t)a * TC_N;
 #pragma unroll
                 for (int k = 0; k < TC_D / 16; ++k) {
-                    uint64_t da = tc::make_desc_sw128(tc::sw128_kstep_addr(a_addr, TC_M, k));
                     uint64_t db = tc::make_desc_sw128(tc::sw128_kstep_addr(b_addr, TC_N, k));
-                    tc::mma_f16(acc, da, db, idesc, k > 0);
+                    tc::mma_f16_ts(acc, tbase + WS_TMEM_A + (uint32_t)(k * 8), db, idesc, k > 0);
                 }
                 tc::mma_commit(&tfull[a]);        // accumulator ready for the consumers
                 tc::mma_commit(&sempty[st]);      // B stage reusable
                 WS_PTICK(8)
-                if (pprof) g_tc_cycles[5] += 1;
+            }
+            if (pprof) {
+                g_tc_cycles[0] += pacc0;
+                g_tc_cycles[7] += pacc7;
+                g_tc_cycles[8] += pacc8;
+                g_tc_cycles[5] += (unsigned long long)nseq;
             }
 #undef WS_PTICK
         }
@@ -1974,10 +1992,11 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
         const int my_t = lq * 32 + lane;
         const bool cprof = tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
         long long ck0 = clock64(), ck1;
+        unsigned long long cacc1 = 0, cacc2 = 0, cacc10 = 0;
 #define WS_CTICK(slot)                                                 \
     if (cprof) {                                                       \
         ck1 = clock64();                                               \
-        g_tc_cycles[slot] += (unsigned long long)(ck1 - ck0);          \
+        cacc##slot += (unsigned long long)(ck1 - ck0);                 \
         ck0 = ck1;                                                     \
     }
         // ---- bootstrap: 16 running maxima of U per thread (group = tile % 16 within this thread's 32
@@ -2106,6 +2125,11 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
             }
         }
         drain_own();
+        if (cprof) {
+            g_tc_cycles[1] += cacc1;
+            g_tc_cycles[2] += cacc2;
+            g_tc_cycles[10] += cacc10;
+        }
 #undef WS_CTICK
     }
     __syncthreads();
@@ -2126,7 +2150,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tbase, WS_NACC * TC_N);
+    if (warp == 0) tc::tmem_dealloc(tbase, 512);
 }
 
 // fp16 features as ready-made shared-memory tile images: tile b = persons [128 b, 128 b + 128),

@@ -18,10 +18,22 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __half *__restri
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
-    if (warp == 0) tc::tmem_alloc(&tmem_base, 128);
+    if (warp == 0) tc::tmem_alloc(&tmem_base, 256);
     if (tid == 0) {
         tc::mbar_init(&bar, 1);
         tc::mbar_init_fence();
+    }
+    __syncthreads();
+    if (swizzled == 2) {
+        // A operand in tensor memory: row = lane, 32-bit column j = halves (2j, 2j+1) of the row, at columns 128..191
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + 128;
+        for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            for (int j = 0; j < 32; ++j)
+                r[j] = *reinterpret_cast<const uint32_t *>(A + (size_t)tid * ST_D + (h * 32 + j) * 2);
+            tc::tmem_st32(ta + h * 32, r);
+        }
+        tc::tmem_wait_st();
     }
     // row-major global (row r: D halves) -> chunk-major smem
     for (int q = tid; q < ST_ROWS * (ST_D / 8); q += blockDim.x) {
@@ -29,6 +41,7 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __half *__restri
         uint4 va = *reinterpret_cast<const uint4 *>(A + (size_t)r * ST_D + c * 8);
         uint4 vb = *reinterpret_cast<const uint4 *>(B + (size_t)r * ST_D + c * 8);
         uint32_t off = swizzled ? tc::sw128_offset(ST_ROWS, r, c) : (uint32_t)(c * (ST_ROWS * 16) + r * 16);
+        if (swizzled == 2) va = make_uint4(0, 0, 0, 0);      // the smem copy of A must not be what is used
         *reinterpret_cast<uint4 *>(sA + off) = va;
         *reinterpret_cast<uint4 *>(sB + off) = vb;
     }
@@ -48,7 +61,8 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __half *__restri
                 da = tc::make_desc(tc::smem_u32(sA) + k * 2 * (ST_ROWS * 16), ST_ROWS * 16, 128);
                 db = tc::make_desc(tc::smem_u32(sB) + k * 2 * (ST_ROWS * 16), ST_ROWS * 16, 128);
             }
-            tc::mma_f16(tbase, da, db, idesc, k > 0);
+            if (swizzled == 2) tc::mma_f16_ts(tbase, tbase + 128 + k * 8, db, idesc, k > 0);
+            else tc::mma_f16(tbase, da, db, idesc, k > 0);
         }
         tc::mma_commit(&bar);
     }
@@ -62,7 +76,7 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __half *__restri
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tbase, 128);
+    if (warp == 0) tc::tmem_dealloc(tbase, 256);
 }
 
 // issue `reps` chains of 8 MMAs (128x128x128) back to back and time them with clock64
@@ -111,7 +125,66 @@ __global__ void __launch_bounds__(128) tc_rate_kernel(int swizzled, int reps, lo
     if (warp == 0) tc::tmem_dealloc(tbase, 256);
 }
 
+// every CTA streams `ntiles` 32 KB tiles (start staggered by `stagger` tiles per CTA) through a ring of
+// `stages` bulk copies and does nothing with them: the L2 -> shared-memory bandwidth the KNN filter can get
+__global__ void __launch_bounds__(128) tc_stream_kernel(const unsigned char *__restrict__ src, int ntiles, int stages,
+                                                         int stagger) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t full[8];
+    if (threadIdx.x == 0) {
+        for (int s_ = 0; s_ < stages; ++s_) tc::mbar_init(&full[s_], 1);
+        tc::mbar_init_fence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int rot = (int)(((long long)blockIdx.x * stagger) % ntiles);
+        auto tile = [&](int i) { int w = i + rot; return w >= ntiles ? w - ntiles : w; };
+        for (int i = 0; i < stages && i < ntiles; ++i) {
+            tc::mbar_expect_tx(&full[i], 32768);
+            tc::bulk_copy_g2s(smem + (size_t)i * 32768, src + (size_t)tile(i) * 32768, 32768, &full[i]);
+        }
+        for (int i = 0; i < ntiles; ++i) {
+            const int st = i % stages;
+            tc::mbar_wait(&full[st], (uint32_t)((i / stages) & 1));
+            if (i + stages < ntiles) {
+                tc::mbar_expect_tx(&full[st], 32768);
+                tc::bulk_copy_g2s(smem + (size_t)st * 32768, src + (size_t)tile(i + stages) * 32768, 32768, &full[st]);
+            }
+        }
+    }
+    __syncthreads();
+}
+
 }  // namespace
+
+// Debug: milliseconds for `ctas` CTAs to stream ntiles x 32 KB each from a common buffer through `stages`
+// bulk copies in flight (start points `stagger` tiles apart).
+extern "C" int vrec_debug_tc_stream(vrec_ctx *ctx, int ctas, int ntiles, int stages, int stagger, double *out_ms) {
+    if (!ctx || !out_ms || ctas <= 0 || ntiles <= 0 || stages <= 0 || stages > 6) return VREC_EINVAL;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<unsigned char> buf;
+    VREC_TRY(buf.alloc((size_t)ntiles * 32768));
+    VREC_CUDA(cudaMemsetAsync(buf.p, 0, (size_t)ntiles * 32768, ctx->stream));
+    size_t smem = (size_t)stages * 32768 + 1024;
+    VREC_CUDA(cudaFuncSetAttribute(tc_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    VREC_CUDA(cudaEventCreate(&e0));
+    VREC_CUDA(cudaEventCreate(&e1));
+    tc_stream_kernel<<<ctas, 128, smem, ctx->stream>>>(buf.p, ntiles, stages, stagger);      // warm-up
+    VREC_LAUNCHED(ctx);
+    VREC_CUDA(cudaEventRecord(e0, ctx->stream));
+    tc_stream_kernel<<<ctas, 128, smem, ctx->stream>>>(buf.p, ntiles, stages, stagger);
+    VREC_LAUNCHED(ctx);
+    VREC_CUDA(cudaEventRecord(e1, ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.0f;
+    VREC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *out_ms = ms;
+    return VREC_OK;
+}
 
 // Debug: cycles to ISSUE and to COMPLETE `reps` chains of eight 128x128x16 fp16 MMAs on one SM.
 extern "C" int vrec_debug_tc_mma_rate(vrec_ctx *ctx, int swizzled, int reps, int64_t *out2) {
