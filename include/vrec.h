@@ -172,6 +172,27 @@ int vrec_knn_last_dense_ms(vrec_knn *knn, double *out_ms);
  * heap inserts (count), place section load, category section + dense row}.                            */
 int vrec_knn_debug_probe(vrec_knn *knn, uint64_t *out8);
 
+/* ---------------------------------------------------------------- rating vectors builder */
+
+/*
+ * The step in front of the KNN path, on the device: RatingsBuilder.calcRatings
+ * (knn/RatingsBuilder.scala:32-48: count(*) per (person_id, entity), keep rank() <= top_n per person
+ * ordered by count desc -- rank keeps ties) followed by RatingVectorsBuilder.calcRatingVectors
+ * (knn/RatingVectorsBuilder.scala:12-83: vector size = max(entity id) + 1, indices ascending, values =
+ * counts as doubles), for ONE entity column; call it with place_id and with category_id of the same
+ * rows (RatingVectorsBuilderMain.scala:41-63) to get the two tables vrec_knn_load takes.
+ *
+ *  person_id / entity_id [n_rows]  one row per visit (any order)
+ *  weight [n_rows] or NULL         visits the row stands for (NULL = 1: count(*))
+ *  out_person_id [<= n_rows]       ascending;  out_rowptr [<= n_rows + 1];  out_col / out_val [<= n_rows]
+ *  out_dim                         max kept entity id + 1
+ * An entity id outside [0, 2^31) gives VREC_EINVAL ("Index out of Int range", :36-41).
+ */
+int vrec_build_rating_vectors(vrec_ctx *ctx, int64_t n_rows, const int64_t *person_id, const int64_t *entity_id,
+                              const int64_t *weight, int32_t top_n, int64_t *out_n_persons, int64_t *out_nnz,
+                              int64_t *out_person_id, int64_t *out_rowptr, int32_t *out_col, double *out_val,
+                              int32_t *out_dim);
+
 /* ---------------------------------------------------------------- SG path */
 
 /*

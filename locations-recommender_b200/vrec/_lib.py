@@ -50,6 +50,8 @@ SIGNATURES = {
     "vrec_knn_debug_tc_block_cycles": (C.c_int, [vp, C.POINTER(C.c_uint64), C.c_int]),
     "vrec_knn_debug_probe": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
     "vrec_knn_last_dense_ms": (C.c_int, [vp, C.POINTER(C.c_double)]),
+    "vrec_build_rating_vectors": (C.c_int, [vp, C.c_int64, i64p, i64p, i64p, C.c_int32, C.POINTER(C.c_int64),
+                                            C.POINTER(C.c_int64), i64p, i64p, i32p, f64p, C.POINTER(C.c_int32)]),
     "vrec_sg_load": (C.c_int, [vp, C.c_int64, i64p, i64p, f64p, C.POINTER(vp)]),
     "vrec_sg_free": (None, [vp]),
     "vrec_sg_vertex_count": (C.c_int64, [vp]),

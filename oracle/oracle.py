@@ -226,3 +226,21 @@ def set_threads(n: int) -> None:
 
 def num_threads() -> int:
     return int(lib().vro_num_threads())
+
+
+# ---------------------------------------------------------------- rating vectors builder
+def build_rating_vectors(person_id, entity_id, weight, top_n):
+    """-> rc, persons, rowptr, col, val, dim  (RatingsBuilder.calcRatings + RatingVectorsBuilder.calcRatingVectors)"""
+    person_id, entity_id = _i64(person_id), _i64(entity_id)
+    n = len(person_id)
+    w = _i64(weight) if weight is not None else None
+    persons = np.zeros(max(1, n), dtype=np.int64)
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    col = np.zeros(max(1, n), dtype=np.int32)
+    val = np.zeros(max(1, n), dtype=np.float64)
+    P, nnz, dim = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+    rc = lib().vro_build_rating_vectors(C.c_int64(n), _p(person_id, C.c_int64), _p(entity_id, C.c_int64),
+                                        _p(w, C.c_int64) if w is not None else None, C.c_int32(int(top_n)),
+                                        C.byref(P), C.byref(nnz), _p(persons, C.c_int64), _p(rowptr, C.c_int64),
+                                        _p(col, C.c_int32), _p(val, C.c_double), C.byref(dim))
+    return rc, persons[:P.value], rowptr[:P.value + 1], col[:nnz.value], val[:nnz.value], dim.value

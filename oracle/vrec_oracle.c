@@ -722,3 +722,74 @@ int vro_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------ */
+/* knn/RatingsBuilder.scala + knn/RatingVectorsBuilder.scala           */
+/* (the step in front of the KNN path)          */
+/* ------------------------------------------------------------------ */
+
+typedef struct { int64_t person, entity, weight; } visit_t;
+
+static int visit_cmp(const void *a, const void *b)
+{
+    const visit_t *x = (const visit_t *)a, *y = (const visit_t *)b;
+    if (x->person != y->person) return x->person < y->person ? -1 : 1;
+    if (x->entity != y->entity) return x->entity < y->entity ? -1 : 1;
+    return 0;
+}
+
+/* RatingsBuilder.calcRatings (knn/RatingsBuilder.scala:32-48): count(*) per (person_id, entity) (:38-40; a
+ * row may stand for `weight` visits), rank() over (partition by person_id order by count desc) (:42-45),
+ * keep rank <= top_n (:46) -- rank() = 1 + number of rows of the person with a larger count, so ties
+ * all stay.  Then RatingVectorsBuilder.calcRatingVectors (knn/RatingVectorsBuilder.scala:12-83): size =
+ * max(entity id) + 1 (:26-34), ids must fit an Int (:36-41, VRO_EINVAL), indices ascending (:45-50), values
+ * = counts as doubles (:69).  Outputs in CSR form, persons ascending.                                      */
+int vro_build_rating_vectors(int64_t n_rows, const int64_t *person_id, const int64_t *entity_id,
+                             const int64_t *weight, int32_t top_n, int64_t *out_n_persons, int64_t *out_nnz,
+                             int64_t *out_person_id, int64_t *out_rowptr, int32_t *out_col, double *out_val,
+                             int32_t *out_dim)
+{
+    if (n_rows < 0 || top_n <= 0) return VRO_EINVAL;
+    *out_n_persons = 0; *out_nnz = 0; *out_dim = 1; out_rowptr[0] = 0;
+    if (n_rows == 0) return VRO_OK;
+    visit_t *v = (visit_t *)malloc(sizeof(visit_t) * (size_t)n_rows);
+    int64_t *cnt = (int64_t *)malloc(sizeof(int64_t) * (size_t)n_rows);
+    if (!v || !cnt) { free(v); free(cnt); return VRO_ENOMEM; }
+    for (int64_t i = 0; i < n_rows; ++i) {
+        v[i].person = person_id[i]; v[i].entity = entity_id[i]; v[i].weight = weight ? weight[i] : 1;
+    }
+    qsort(v, (size_t)n_rows, sizeof(visit_t), visit_cmp);
+    /* runs of equal (person, entity): v[0..m) keeps one row per run, cnt[] its count */
+    int64_t m = 0;
+    for (int64_t i = 0; i < n_rows; ++i) {
+        if (m > 0 && v[m - 1].person == v[i].person && v[m - 1].entity == v[i].entity) {
+            cnt[m - 1] += v[i].weight;
+        } else {
+            v[m] = v[i]; cnt[m] = v[i].weight; m++;
+        }
+    }
+    int64_t P = 0, nnz = 0, maxid = -1;
+    int rc = VRO_OK;
+    for (int64_t s = 0; s < m && rc == VRO_OK; ) {
+        int64_t e = s;
+        while (e < m && v[e].person == v[s].person) e++;
+        out_person_id[P] = v[s].person;
+        for (int64_t r = s; r < e; ++r) {
+            int64_t larger = 0;
+            for (int64_t q = s; q < e; ++q) larger += cnt[q] > cnt[r];
+            if (larger + 1 <= top_n) {
+                if (v[r].entity < 0 || v[r].entity > 0x7fffffffLL) { rc = VRO_EINVAL; break; }
+                out_col[nnz] = (int32_t)v[r].entity;
+                out_val[nnz] = (double)cnt[r];
+                if (v[r].entity > maxid) maxid = v[r].entity;
+                nnz++;
+            }
+        }
+        out_rowptr[++P] = nnz;
+        s = e;
+    }
+    free(v); free(cnt);
+    if (rc != VRO_OK) return rc;
+    *out_n_persons = P; *out_nnz = nnz; *out_dim = (int32_t)(maxid + 1);
+    return VRO_OK;
+}

@@ -385,3 +385,39 @@ def test_knn_default_sample_data(vrec, ctx, synth, oracle):
     _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 50, targets, pl.of_region(0), 10)
     _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 3000, targets[:2], pl.of_region(0), 10)   # radix-select path
     rs.close()
+
+
+# ------------------------------------------------------------------ rating vectors builder
+def test_rating_vectors_builder_bit_exact(vrec, ctx, synth, oracle):
+    from vrec import builders
+    v, places = synth.g2_place_visits(20000, 3000, seed=11, mean_places=9.0)
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(int(v.count.sum()))
+    pe = np.repeat(v.person_id, v.count)[perm]          # one row per visit, shuffled
+    pl = np.repeat(v.place_id, v.count)[perm]
+    ca = np.repeat(v.category_id, v.count)[perm]
+    for ent, top_n in ((pl, 5), (ca, 3), (pl, 100)):
+        rc, persons, rowptr, col, val, dim = oracle.build_rating_vectors(pe, ent, None, top_n)
+        g = builders.build_rating_vectors(pe, ent, top_n, ctx=ctx)
+        assert rc == 0 and g[4] == dim
+        for a, b in zip(g[:4], (persons, rowptr, col, val)):
+            assert np.array_equal(a, b)
+    # pre-aggregated rows with weights give the same tables
+    rc, persons, rowptr, col, val, dim = oracle.build_rating_vectors(v.person_id, v.place_id, v.count, 5)
+    g = builders.build_rating_vectors(v.person_id, v.place_id, 5, weight=v.count, ctx=ctx)
+    for a, b in zip(g[:4], (persons, rowptr, col, val)):
+        assert np.array_equal(a, b)
+    # the whole step, then the recommender on its output == the recommender on the numpy restatement's tables
+    inp = builders.rating_vectors_builder(pe, pl, ca, max_rated_places=5, max_rated_categories=3, ctx=ctx)
+    want = synth.build_rating_vectors(v, max_rated_places=5, max_rated_categories=3)
+    for a, b in zip(inp.load_args(), want.load_args()):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
+    _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 7, inp.person_id[:40], places.id, 10)
+    # corner cases: ties at the cut stay, out-of-range ids, empty input
+    g = builders.build_rating_vectors([5, 5, 5, 5, 9], [1, 2, 3, 4, 7], 2, weight=[3, 2, 2, 1, 1], ctx=ctx)
+    assert g[0].tolist() == [5, 9] and g[1].tolist() == [0, 3, 4] and g[2].tolist() == [1, 2, 3, 7] and g[4] == 8
+    with pytest.raises(ValueError, match="Index out of Int range"):
+        builders.build_rating_vectors([1], [2 ** 31], 10, ctx=ctx)
+    g = builders.build_rating_vectors([], [], 10, ctx=ctx)
+    assert len(g[0]) == 0 and g[1].tolist() == [0]

@@ -69,3 +69,32 @@ def test_sg_long_rows_segmenting(oracle):
     rc, x, it, conv, res = g.run(int(g.ids[10]), 1e-9, 50)
     assert rc == 0
     assert abs(x.sum() - 1.0) < 1e-9          # every vertex has out-edges: no mass is lost
+
+
+def test_rating_vectors_builder_oracle_vs_numpy_restatement(oracle):
+    """oracle/vro_build_rating_vectors against the numpy restatement of RatingsBuilder /
+    RatingVectorsBuilder in vrec/synth.py (rank() keeps ties; indices ascending; size = max id + 1)."""
+    v, places = synth.g2_place_visits(3000, 400, seed=7, mean_places=9.0)
+    want = synth.build_rating_vectors(v, max_rated_places=5, max_rated_categories=3)
+    for ent, top_n, rp, ci, cv_, dim in ((v.place_id, 5, want.place_rowptr, want.place_col, want.place_val, want.place_dim),
+                                         (v.category_id, 3, want.cat_rowptr, want.cat_col, want.cat_val, want.cat_dim)):
+        # pre-aggregated rows with weights, and the same visits expanded to one row per visit, shuffled
+        rc, persons, rowptr, col, val, d = oracle.build_rating_vectors(v.person_id, ent, v.count, top_n)
+        assert rc == 0 and d == dim
+        assert np.array_equal(persons, want.person_id) and np.array_equal(rowptr, rp)
+        assert np.array_equal(col, ci) and np.array_equal(val, cv_)
+        rng = np.random.default_rng(1)
+        perm = rng.permutation(int(v.count.sum()))
+        pe = np.repeat(v.person_id, v.count)[perm]
+        ee = np.repeat(ent, v.count)[perm]
+        rc, persons2, rowptr2, col2, val2, d2 = oracle.build_rating_vectors(pe, ee, None, top_n)
+        assert rc == 0 and d2 == dim and np.array_equal(persons2, persons) and np.array_equal(rowptr2, rowptr)
+        assert np.array_equal(col2, col) and np.array_equal(val2, val)
+    # ties at the cut all stay (rank(), knn/RatingsBuilder.scala:44-46); ids outside Int are an error (:36-41)
+    rc, persons, rowptr, col, val, d = oracle.build_rating_vectors([5, 5, 5, 5, 9], [1, 2, 3, 4, 7], [3, 2, 2, 1, 1], 2)
+    assert rc == 0 and persons.tolist() == [5, 9] and rowptr.tolist() == [0, 3, 4] and col.tolist() == [1, 2, 3, 7]
+    assert val.tolist() == [3.0, 2.0, 2.0, 1.0] and d == 8
+    rc, *_ = oracle.build_rating_vectors([1], [2 ** 31], None, 10)
+    assert rc == oracle.EINVAL
+    rc, persons, rowptr, *_ = oracle.build_rating_vectors([], [], None, 10)
+    assert rc == 0 and len(persons) == 0 and rowptr.tolist() == [0]
