@@ -410,6 +410,7 @@ def run_ours(args):
     if not args.no_sg:
         sg = run_sg(args, vrec, ctx, stream, world, rank, barrier, max_over_ranks, peak, peak_src)
         sg["batch"] = run_sg_batch(args, vrec, ctx, world, rank, barrier, max_over_ranks)
+    builder = run_builder(args, vrec, ctx, rank) if rank == 0 and not args.no_sg else None
 
     if rank == 0:
         line = {
@@ -427,6 +428,7 @@ def run_ours(args):
             "cpu_baseline": cpu_knn_base,
             "clocks": clocks_knn,
             "sg": sg,
+            "builder": builder,
         }
         emit(line)
     if world > 1:
@@ -565,6 +567,41 @@ def run_sg_batch(args, vrec, ctx, world, rank, barrier, max_over_ranks):
     }
     g.close()
     return out
+
+
+def run_builder(args, vrec, ctx, rank):
+    """SURVEY 8(f) rank 2, the step in front of the KNN path: RatingsBuilder + RatingVectorsBuilder for the place
+    column of the KNN workload's visits (one row per visit), through vrec_build_rating_vectors with host buffers."""
+    from vrec import builders, synth
+    v, _ = synth.g2_place_visits(args.knn_persons, args.knn_places)
+    rng = np.random.default_rng(9)
+    perm = rng.permutation(int(v.count.sum()))
+    pe = np.repeat(v.person_id, v.count)[perm]
+    pl = np.repeat(v.place_id, v.count)[perm]
+    builders.build_rating_vectors(pe[:100000], pl[:100000], 100, ctx=ctx)          # warm-up (module load)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        out = builders.build_rating_vectors(pe, pl, 100, ctx=ctx)
+    dt = (time.perf_counter() - t0) / reps
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        ns = min(len(pe), 4_000_000)
+        t1 = time.perf_counter()
+        rc, *_ = oracle.build_rating_vectors(pe[:ns], pl[:ns], None, 100)
+        cdt = time.perf_counter() - t1
+        cpu = {"value": ns / cdt, "unit": "visits/s", "cores": 1, "kind": "port",
+               "sample": f"first {ns} visit rows, {cdt:.2f}s, oracle/vrec_oracle.c (qsort, one thread)"}
+    return {"metric": "rating vectors builder, visit rows/s (count per (person, place), rank <= 100, CSR)",
+            "value": len(pe) / dt, "unit": "visits/s", "ms_per_step": dt * 1e3,
+            "config": {"workload": f"{len(pe)} visit rows of {args.knn_persons} persons x {args.knn_places} places "
+                                   f"(generator G2, shuffled), {len(out[2])} ratings kept"},
+            "e2e": {"value": len(pe) / dt, "unit": "visits/s", "h2d_bytes_per_step": 16 * len(pe),
+                    "d2h_bytes_per_step": 8 * len(out[0]) + 12 * len(out[2])},
+            "cpu_baseline": cpu,
+            "note": "value == e2e (host arrays in, host CSR out); the two radix sorts are cub::DeviceRadixSort"}
 
 
 def main():

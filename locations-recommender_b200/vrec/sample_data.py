@@ -21,6 +21,8 @@ def main(argv=None) -> None:
     ap.add_argument("--place-count", type=int, default=30_000)
     ap.add_argument("--uncorrelated", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--gpu-builder", action="store_true",
+                    help="build the rating vectors with vrec_build_rating_vectors (needs a B200) instead of numpy")
     a = ap.parse_args(argv)
     os.makedirs(a.data_dir, exist_ok=True)
     places = synth.sample_places(a.place_count, a.seed)
@@ -39,7 +41,12 @@ def main(argv=None) -> None:
     sets = [(r,) for r in range(n_reg)] + list(itertools.combinations(range(n_reg), 2))   # PlaceVisits.scala:63-67
     for regs in sets:
         v = synth.merge_visits([visits[r] for r in regs])
-        du.write_knn_inputs(synth.build_rating_vectors(v), regs, a.data_dir)
+        if a.gpu_builder:
+            from . import builders
+            inp = builders.rating_vectors_builder(v.person_id, v.place_id, v.category_id, weight=v.count)
+        else:
+            inp = synth.build_rating_vectors(v)
+        du.write_knn_inputs(inp, regs, a.data_dir)
         du.write_graph(*synth.build_stochastic_graph(v), regs, a.data_dir)
         print(f"wrote region set {regs}: {len(np.unique(v.person_id))} persons")
 
