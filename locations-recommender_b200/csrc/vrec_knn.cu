@@ -1563,10 +1563,57 @@ __host__ __device__ constexpr int post_warp_bytes(int K) {
     return ((8 * K + 8 * POST_STG_P + 8 * POST_STG_C + 8 * POST_DENSE + 4 * K + 4 * POST_STG_P + 4 * POST_STG_C + 64) + 15) / 16 * 16;
 }
 
+// Longest-processing-time-first order for the postings kernel: a target's work = the visitors of its tail
+// places.  Targets are binned by floor(log2(work)) and handed out from the heaviest bin down, so the long
+// ones start first and the kernel does not end on a straggler.
+__global__ void knn_post_work_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targets,
+                                     int *__restrict__ bin_of, int *__restrict__ bin_cnt) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_targets) return;
+    const int tix = tidx[t];
+    long long work = 0;
+    if (tix >= 0) {
+        for (int e = d.place.rowptr[tix]; e < d.place.rowptr[tix + 1]; ++e) {
+            const int pl = d.place.col[e];
+            if (aux.head_slot[pl] < 0) work += aux.pcp[pl + 1] - aux.pcp[pl];
+        }
+    }
+    int b = 0;
+    while (b < 31 && (work >> (b + 1)) > 0) ++b;
+    bin_of[t] = b;
+    atomicAdd(bin_cnt + b, 1);
+}
+__global__ void knn_post_order_kernel(int n_targets, const int *__restrict__ bin_of, int *__restrict__ bin_cnt,
+                                      int *__restrict__ bin_fill, int *__restrict__ order) {
+    // bin_cnt -> start offsets with the heaviest bin first (one thread; 32 bins), then a scatter
+    __shared__ int start[32];
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int at = 0;
+        for (int b = 31; b >= 0; --b) {
+            int c = bin_cnt[b];
+            bin_cnt[b] = at;
+            at += c;
+        }
+    }
+    (void)start;
+    (void)bin_fill;
+    (void)order;
+    (void)n_targets;
+    (void)bin_of;
+}
+__global__ void knn_post_scatter_kernel(int n_targets, const int *__restrict__ bin_of, const int *__restrict__ bin_start,
+                                        int *__restrict__ bin_fill, int *__restrict__ order) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_targets) return;
+    const int b = bin_of[t];
+    order[bin_start[b] + atomicAdd(bin_fill + b, 1)] = t;
+}
+
 __global__ void __launch_bounds__(POST_WARPS * 32, 4)
 knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targets, int K, int S, int part_stride,
                     int cat_dim, double pw, double cw, Nb *__restrict__ part, int *__restrict__ part_cnt,
-                    const double *__restrict__ seed_thr, int *__restrict__ work_counter) {
+                    const double *__restrict__ seed_thr, int *__restrict__ work_counter,
+                    const int *__restrict__ order) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *w = smem_raw + (size_t)warp * post_warp_bytes(K);
@@ -1600,6 +1647,7 @@ knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_t
         if (lane == 0) tt = atomicAdd(work_counter, 1);
         tt = __shfl_sync(0xffffffffu, tt, 0);
         if (tt >= n_targets) break;
+        if (order) tt = order[tt];                      // heaviest targets first
         const int tix = tidx[tt];
         __syncwarp();
         if (lane == 0) {
@@ -2527,6 +2575,7 @@ struct vrec_knn {
     DevBuf<short> d_head_slot;
     DevBuf<int> d_pcp, d_pper;
     DevBuf<double> d_seed_thr;
+    DevBuf<int> d_post_bin, d_post_order, d_post_bins;   // longest-first order of the postings kernel's targets
     DevBuf<double> d_tdense;                 // [targets of the batch][cat_dim] dense category rows (knn_tc_ws_kernel)
     DevBuf<int> d_work;
     DevBuf<unsigned long long> d_meta;     // packed records for the exact evaluation
@@ -3152,7 +3201,20 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                 main_mode, k->d_seed_thr.p, SP);
             VREC_LAUNCHED(ctx);
         }
-        // postings kernel: one warp per target, dynamic distribution
+        // postings kernel: one warp per target, dynamic distribution, heaviest targets first
+        VREC_TRY(k->d_post_bin.ensure((size_t)tn));
+        VREC_TRY(k->d_post_order.ensure((size_t)tn));
+        VREC_TRY(k->d_post_bins.ensure(64));
+        VREC_CUDA(cudaMemsetAsync(k->d_post_bins.p, 0, sizeof(int) * 64, ctx->stream));
+        knn_post_work_kernel<<<(tn + 255) / 256, 256, 0, ctx->stream>>>(k->dev(), aux, k->d_tidx.p, tn, k->d_post_bin.p,
+                                                                        k->d_post_bins.p);
+        VREC_LAUNCHED(ctx);
+        knn_post_order_kernel<<<1, 32, 0, ctx->stream>>>(tn, k->d_post_bin.p, k->d_post_bins.p, k->d_post_bins.p + 32,
+                                                        k->d_post_order.p);
+        VREC_LAUNCHED(ctx);
+        knn_post_scatter_kernel<<<(tn + 255) / 256, 256, 0, ctx->stream>>>(tn, k->d_post_bin.p, k->d_post_bins.p,
+                                                                           k->d_post_bins.p + 32, k->d_post_order.p);
+        VREC_LAUNCHED(ctx);
         VREC_CUDA(cudaMemsetAsync(k->d_work.p, 0, sizeof(int), ctx->stream));
         const size_t psmem = (size_t)POST_WARPS * post_warp_bytes(K);
         static bool attr_post = false;
@@ -3163,7 +3225,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
         int pblocks = std::max(1, std::min(ctx->sm_count * 4, (tn + POST_WARPS - 1) / POST_WARPS));
         knn_postings_kernel<<<pblocks, POST_WARPS * 32, psmem, ctx->stream>>>(
             k->dev(), aux, k->d_tidx.p, k->opt_debug_skip_postings ? 0 : tn, K, S, SP, k->cat_dim, pw, cw, k->d_part.p,
-            k->d_part_cnt.p, k->d_seed_thr.p, k->d_work.p);
+            k->d_part_cnt.p, k->d_seed_thr.p, k->d_work.p, k->d_post_order.p);
         VREC_LAUNCHED(ctx);
         if (k->opt_debug_skip_postings) {
             // timing experiments only: the postings slots stay empty (results are then WRONG)

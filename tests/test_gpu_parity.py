@@ -303,6 +303,17 @@ def test_knn_random_bit_exact(vrec, ctx, synth, oracle, seed, k, path, kernel):
     rs.close()
 
 
+@pytest.mark.parametrize("k", [5, 50])
+def test_knn_tail_places_postings_pass(vrec, ctx, synth, oracle, k):
+    # far more places than filter dimensions: most pairs that matter share a TAIL place and come from the
+    # postings pass; a target listed twice and an unknown person in the batch
+    inp = synth.random_knn_inputs(4000, 900, 9, seed=21)
+    rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
+    targets = np.concatenate([inp.person_id[:300], inp.person_id[:3], [999999]])
+    _check_knn(vrec, oracle, rs, inp, 0.7, 0.3, k, targets, np.arange(0, 900, 3), 10)
+    rs.close()
+
+
 def test_knn_errors(vrec, ctx, synth):
     inp = synth.random_knn_inputs(50, 10, 4, seed=3)
     rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
