@@ -1563,11 +1563,16 @@ __host__ __device__ constexpr int post_warp_bytes(int K) {
     return ((8 * K + 8 * POST_STG_P + 8 * POST_STG_C + 8 * POST_DENSE + 4 * K + 4 * POST_STG_P + 4 * POST_STG_C + 64) + 15) / 16 * 16;
 }
 
-// Longest-processing-time-first order for the postings kernel: a target's work = the visitors of its tail
-// places.  Targets are binned by floor(log2(work)) and handed out from the heaviest bin down, so the long
-// ones start first and the kernel does not end on a straggler.
-__global__ void knn_post_work_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targets,
-                                     int *__restrict__ bin_of, int *__restrict__ bin_cnt) {
+// Work items of the postings kernel, longest first.  A target's work = the visitors of its tail places;
+// a heavy target is split into up to `max_parts` parts (every part takes every max_parts-th block of 32
+// candidates and keeps its own heap -> its own partial list), so the kernel does not end on one long
+// target.  Item = target * 8 + part * 2... encoded as (target << 4) | (part << 2) | (parts - 1); items are
+// binned by floor(log2(work per part)) and handed out from the heaviest bin down.
+constexpr int POST_MAX_PARTS = 4;
+constexpr int POST_PART_WORK = 6144;     // candidates per part before a target is split further
+
+__global__ void knn_post_work_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targets, int max_parts,
+                                     int *__restrict__ bin_of, int *__restrict__ parts_of, int *__restrict__ bin_cnt) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_targets) return;
     const int tix = tidx[t];
@@ -1578,15 +1583,16 @@ __global__ void knn_post_work_kernel(KnnDev d, TileAux aux, const int *__restric
             if (aux.head_slot[pl] < 0) work += aux.pcp[pl + 1] - aux.pcp[pl];
         }
     }
+    int parts = (int)min((long long)max_parts, 1 + work / POST_PART_WORK);
+    work /= parts;
     int b = 0;
     while (b < 31 && (work >> (b + 1)) > 0) ++b;
     bin_of[t] = b;
-    atomicAdd(bin_cnt + b, 1);
+    parts_of[t] = parts;
+    atomicAdd(bin_cnt + b, parts);
 }
-__global__ void knn_post_order_kernel(int n_targets, const int *__restrict__ bin_of, int *__restrict__ bin_cnt,
-                                      int *__restrict__ bin_fill, int *__restrict__ order) {
-    // bin_cnt -> start offsets with the heaviest bin first (one thread; 32 bins), then a scatter
-    __shared__ int start[32];
+// bin counts -> start offsets, heaviest bin first (32 bins: one thread)
+__global__ void knn_post_order_kernel(int *__restrict__ bin_cnt, int *__restrict__ n_items) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int at = 0;
         for (int b = 31; b >= 0; --b) {
@@ -1594,26 +1600,24 @@ __global__ void knn_post_order_kernel(int n_targets, const int *__restrict__ bin
             bin_cnt[b] = at;
             at += c;
         }
+        *n_items = at;
     }
-    (void)start;
-    (void)bin_fill;
-    (void)order;
-    (void)n_targets;
-    (void)bin_of;
 }
-__global__ void knn_post_scatter_kernel(int n_targets, const int *__restrict__ bin_of, const int *__restrict__ bin_start,
-                                        int *__restrict__ bin_fill, int *__restrict__ order) {
+__global__ void knn_post_scatter_kernel(int n_targets, const int *__restrict__ bin_of, const int *__restrict__ parts_of,
+                                        const int *__restrict__ bin_start, int *__restrict__ bin_fill,
+                                        int *__restrict__ items) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_targets) return;
-    const int b = bin_of[t];
-    order[bin_start[b] + atomicAdd(bin_fill + b, 1)] = t;
+    const int b = bin_of[t], parts = parts_of[t];
+    const int at = bin_start[b] + atomicAdd(bin_fill + b, parts);
+    for (int p_ = 0; p_ < parts; ++p_) items[at + p_] = (t << 4) | (p_ << 2) | (parts - 1);
 }
 
 __global__ void __launch_bounds__(POST_WARPS * 32, 4)
 knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targets, int K, int S, int part_stride,
                     int cat_dim, double pw, double cw, Nb *__restrict__ part, int *__restrict__ part_cnt,
                     const double *__restrict__ seed_thr, int *__restrict__ work_counter,
-                    const int *__restrict__ order) {
+                    const int *__restrict__ items, const int *__restrict__ n_items) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *w = smem_raw + (size_t)warp * post_warp_bytes(K);
@@ -1646,8 +1650,14 @@ knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_t
         int tt = 0;
         if (lane == 0) tt = atomicAdd(work_counter, 1);
         tt = __shfl_sync(0xffffffffu, tt, 0);
-        if (tt >= n_targets) break;
-        if (order) tt = order[tt];                      // heaviest targets first
+        if (tt >= (items ? *n_items : n_targets)) break;
+        int part_i = 0, n_parts = 1;
+        if (items) {                                    // heaviest work items first
+            const int it_ = items[tt];
+            tt = it_ >> 4;
+            part_i = (it_ >> 2) & 3;
+            n_parts = (it_ & 3) + 1;
+        }
         const int tix = tidx[tt];
         __syncwarp();
         if (lane == 0) {
@@ -1760,15 +1770,17 @@ knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_t
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128));
                     }
                 };
+                // this part's blocks of 32 candidates: part_i, part_i + n_parts, ...
+                const int jstep = 32 * n_parts;
                 int c0 = -1, c1 = -1, p0 = -1, p1 = -1;
                 unsigned long long m0 = 0, m1 = 0;
-                fetch(lane, c0, m0, p0);
-                fetch(32 + lane, c1, m1, p1);
+                fetch(32 * part_i + lane, c0, m0, p0);
+                fetch(32 * part_i + jstep + lane, c1, m1, p1);
                 prefetch_record(c0, m0);
-                for (int j0 = 0; j0 < total; j0 += 32) {
+                for (int j0 = 32 * part_i; j0 < total; j0 += jstep) {
                     int c2, p2;
                     unsigned long long m2;
-                    fetch(j0 + 64 + lane, c2, m2, p2);
+                    fetch(j0 + 2 * jstep + lane, c2, m2, p2);
                     prefetch_record(c1, m1);
                     if (c0 >= 0) {
                         if (staged) tile_process_staged(aux, sm, 0, c0, K, pw, cw, p0, stg, thr0);
@@ -1782,7 +1794,7 @@ knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_t
         }
         __syncwarp();
         const int cnt = tix >= 0 ? *(volatile int *)sm.hcnt : 0;
-        Nb *out = part + ((size_t)tt * part_stride + S) * K;
+        Nb *out = part + ((size_t)tt * part_stride + S + part_i) * K;
         for (int j = lane; j < cnt; j += 32) {
             Nb e;
             e.sim = *(volatile double *)(sm.hsim + j);
@@ -1790,7 +1802,7 @@ knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_t
             e.pad = 0;
             out[j] = e;
         }
-        if (lane == 0) part_cnt[tt * part_stride + S] = cnt;
+        if (lane == 0) part_cnt[tt * part_stride + S + part_i] = cnt;
         __syncwarp();
     }
     if (lane < 4) atomicAdd(&g_tile_stats[lane], (unsigned long long)sm.stats[lane]);
@@ -3092,7 +3104,9 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     const bool tiled = !use_tc && k->tile_ok && k->opt_kernel != 1;
     const bool filtered = use_tc || tiled;
     // filtered kernels: slot S of every target's partial lists belongs to the postings kernel
-    int smax = std::max(1, std::min(32, TOPK_BUF / K - (filtered ? 1 : 0)));
+    // partial lists of the postings kernel per target: heavy targets are split when the merge buffer has room
+    const int post_parts = filtered ? (TOPK_BUF / K >= 2 * POST_MAX_PARTS ? POST_MAX_PARTS : 1) : 0;
+    int smax = std::max(1, std::min(32, TOPK_BUF / K - post_parts));
     int S = (int)k->opt_splits;
     int T = 1;
     size_t smem = 0;
@@ -3123,7 +3137,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     }
     S = std::min(S, smax);
     if ((int64_t)S > std::max<int64_t>(1, k->P)) S = 1;
-    const int SP = filtered ? S + 1 : S;                 // partial lists per target
+    const int SP = S + post_parts;                       // partial lists per target
     VREC_TRY(k->d_part.ensure((size_t)tn * SP * K));
     VREC_TRY(k->d_part_cnt.ensure((size_t)tn * SP));
     VREC_TRY(k->d_nb_rank.ensure((size_t)tn * K));
@@ -3201,20 +3215,23 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                 main_mode, k->d_seed_thr.p, SP);
             VREC_LAUNCHED(ctx);
         }
-        // postings kernel: one warp per target, dynamic distribution, heaviest targets first
-        VREC_TRY(k->d_post_bin.ensure((size_t)tn));
-        VREC_TRY(k->d_post_order.ensure((size_t)tn));
-        VREC_TRY(k->d_post_bins.ensure(64));
-        VREC_CUDA(cudaMemsetAsync(k->d_post_bins.p, 0, sizeof(int) * 64, ctx->stream));
-        knn_post_work_kernel<<<(tn + 255) / 256, 256, 0, ctx->stream>>>(k->dev(), aux, k->d_tidx.p, tn, k->d_post_bin.p,
-                                                                        k->d_post_bins.p);
+        // postings kernel: one warp per work item (a target or a part of a heavy one), heaviest first
+        VREC_TRY(k->d_post_bin.ensure((size_t)tn * 2));
+        VREC_TRY(k->d_post_order.ensure((size_t)tn * POST_MAX_PARTS));
+        VREC_TRY(k->d_post_bins.ensure(80));
+        VREC_CUDA(cudaMemsetAsync(k->d_post_bins.p, 0, sizeof(int) * 80, ctx->stream));
+        knn_post_work_kernel<<<(tn + 255) / 256, 256, 0, ctx->stream>>>(k->dev(), aux, k->d_tidx.p, tn, post_parts,
+                                                                        k->d_post_bin.p, k->d_post_bin.p + tn, k->d_post_bins.p);
         VREC_LAUNCHED(ctx);
-        knn_post_order_kernel<<<1, 32, 0, ctx->stream>>>(tn, k->d_post_bin.p, k->d_post_bins.p, k->d_post_bins.p + 32,
-                                                        k->d_post_order.p);
+        knn_post_order_kernel<<<1, 32, 0, ctx->stream>>>(k->d_post_bins.p, k->d_post_bins.p + 64);
         VREC_LAUNCHED(ctx);
-        knn_post_scatter_kernel<<<(tn + 255) / 256, 256, 0, ctx->stream>>>(tn, k->d_post_bin.p, k->d_post_bins.p,
-                                                                           k->d_post_bins.p + 32, k->d_post_order.p);
+        knn_post_scatter_kernel<<<(tn + 255) / 256, 256, 0, ctx->stream>>>(tn, k->d_post_bin.p, k->d_post_bin.p + tn,
+                                                                           k->d_post_bins.p, k->d_post_bins.p + 32, k->d_post_order.p);
         VREC_LAUNCHED(ctx);
+        for (int p_ = 0; p_ < post_parts; ++p_) {          // slots of parts that do not exist stay empty
+            knn_fill_int_stride_kernel<<<(tn + 255) / 256, 256, 0, ctx->stream>>>(k->d_part_cnt.p, tn, SP, S + p_, 0);
+            VREC_LAUNCHED(ctx);
+        }
         VREC_CUDA(cudaMemsetAsync(k->d_work.p, 0, sizeof(int), ctx->stream));
         const size_t psmem = (size_t)POST_WARPS * post_warp_bytes(K);
         static bool attr_post = false;
@@ -3225,13 +3242,9 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
         int pblocks = std::max(1, std::min(ctx->sm_count * 4, (tn + POST_WARPS - 1) / POST_WARPS));
         knn_postings_kernel<<<pblocks, POST_WARPS * 32, psmem, ctx->stream>>>(
             k->dev(), aux, k->d_tidx.p, k->opt_debug_skip_postings ? 0 : tn, K, S, SP, k->cat_dim, pw, cw, k->d_part.p,
-            k->d_part_cnt.p, k->d_seed_thr.p, k->d_work.p, k->d_post_order.p);
+            k->d_part_cnt.p, k->d_seed_thr.p, k->d_work.p, k->opt_debug_skip_postings ? nullptr : k->d_post_order.p,
+            k->d_post_bins.p + 64);
         VREC_LAUNCHED(ctx);
-        if (k->opt_debug_skip_postings) {
-            // timing experiments only: the postings slots stay empty (results are then WRONG)
-            knn_fill_int_stride_kernel<<<(tn + 255) / 256, 256, 0, ctx->stream>>>(k->d_part_cnt.p, tn, SP, S, 0);
-            VREC_LAUNCHED(ctx);
-        }
     } else {
         dim3 grid(tn, S);
         knn_topk_kernel<<<grid, TOPK_THREADS, 0, ctx->stream>>>(k->dev(), k->d_tidx.p, K, S, pw, cw, k->d_part.p,
