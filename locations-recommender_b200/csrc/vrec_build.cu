@@ -18,6 +18,57 @@
 
 namespace {
 
+// Scratch of one builder call, from the stream-ordered allocator: the driver's memory pool keeps the
+// blocks between calls (release threshold raised once), so a call does not pay ~25 cudaMalloc / cudaFree
+// round trips with their device-wide synchronisations.
+thread_local cudaStream_t g_pool_stream = nullptr;
+
+template <typename T>
+struct PoolBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    PoolBuf() = default;
+    PoolBuf(const PoolBuf &) = delete;
+    PoolBuf &operator=(const PoolBuf &) = delete;
+    ~PoolBuf() { release(); }
+    void release() {
+        if (p) cudaFreeAsync(p, g_pool_stream);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), g_pool_stream);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            vrec_set_error("cudaMallocAsync(%zu bytes) -> %s", count * sizeof(T), cudaGetErrorString(e));
+            return VREC_ENOMEM;
+        }
+        n = count;
+        return VREC_OK;
+    }
+    int ensure(size_t count) { return count <= n ? VREC_OK : alloc(count); }
+    int upload(const T *host, size_t count, cudaStream_t s) {
+        VREC_TRY(alloc(count));
+        if (count) VREC_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+        return VREC_OK;
+    }
+};
+
+int pool_setup(vrec_ctx *ctx) {
+    static thread_local int done_for = -1;
+    g_pool_stream = ctx->stream;
+    if (done_for != ctx->device) {
+        cudaMemPool_t pool;
+        VREC_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+        unsigned long long keep = ~0ULL;
+        VREC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        done_for = ctx->device;
+    }
+    return VREC_OK;
+}
+
 __global__ void bld_iota_kernel(long long n, long long *p) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i;
@@ -96,7 +147,7 @@ __global__ void bld_scatter_kernel(int n_runs, const int *__restrict__ keep, con
 }
 
 template <typename T>
-int scan_inclusive(vrec_ctx *ctx, const int *in, T *out, long long n, DevBuf<unsigned char> &tmp) {
+int scan_inclusive(vrec_ctx *ctx, const int *in, T *out, long long n, PoolBuf<unsigned char> &tmp) {
     size_t bytes = 0;
     VREC_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, (int)n, ctx->stream));
     VREC_TRY(tmp.ensure(bytes));
@@ -126,11 +177,12 @@ extern "C" int vrec_build_rating_vectors(vrec_ctx *ctx, int64_t n_rows, const in
     out_rowptr[0] = 0;
     if (n_rows == 0) return VREC_OK;
     VREC_CUDA(cudaSetDevice(ctx->device));
+    VREC_TRY(pool_setup(ctx));
     cudaStream_t st = ctx->stream;
     const long long n = n_rows;
     const int grid = (int)((n + 255) / 256);
-    DevBuf<long long> d_person, d_entity, d_idx, k_a, k_b, v_a, v_b, d_weight, d_wsorted;
-    DevBuf<unsigned char> tmp;
+    PoolBuf<long long> d_person, d_entity, d_idx, k_a, k_b, v_a, v_b, d_weight, d_wsorted;
+    PoolBuf<unsigned char> tmp;
     VREC_TRY(d_person.upload((const long long *)person_id, (size_t)n, st));
     VREC_TRY(d_entity.upload((const long long *)entity_id, (size_t)n, st));
     VREC_TRY(k_a.alloc((size_t)n));
@@ -152,7 +204,7 @@ extern "C" int vrec_build_rating_vectors(vrec_ctx *ctx, int64_t n_rows, const in
         // pass 1: by entity, values = row index
         VREC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_entity.p, k_a.p, d_idx.p, v_a.p, (int)n, 0, 64, st));
         // gather person by the permutation, then pass 2: by person, values = row index
-        DevBuf<long long> pg;
+        PoolBuf<long long> pg;
         VREC_TRY(pg.alloc((size_t)n));
         bld_gather_kernel<<<grid, 256, 0, st>>>(n, v_a.p, d_person.p, pg.p);
         VREC_LAUNCHED(ctx);
@@ -174,7 +226,7 @@ extern "C" int vrec_build_rating_vectors(vrec_ctx *ctx, int64_t n_rows, const in
     }
     const long long *s_person = k_b.p, *s_entity = k_a.p;
     // run heads, run / person numbering
-    DevBuf<int> head, phead, run_of, prow_of;
+    PoolBuf<int> head, phead, run_of, prow_of;
     VREC_TRY(head.alloc((size_t)n));
     VREC_TRY(phead.alloc((size_t)n));
     VREC_TRY(run_of.alloc((size_t)n));
@@ -187,10 +239,10 @@ extern "C" int vrec_build_rating_vectors(vrec_ctx *ctx, int64_t n_rows, const in
     VREC_CUDA(cudaMemcpyAsync(&n_runs, run_of.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
     VREC_CUDA(cudaMemcpyAsync(&n_persons, prow_of.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
     VREC_CUDA(cudaStreamSynchronize(st));
-    DevBuf<long long> run_person_row, run_entity, d_pid, d_max;
-    DevBuf<unsigned long long> run_count, row_cnt;
-    DevBuf<int> first_run, keep, kept_incl, d_col, d_bad;
-    DevBuf<double> d_val;
+    PoolBuf<long long> run_person_row, run_entity, d_pid, d_max;
+    PoolBuf<unsigned long long> run_count, row_cnt;
+    PoolBuf<int> first_run, keep, kept_incl, d_col, d_bad;
+    PoolBuf<double> d_val;
     VREC_TRY(run_person_row.alloc((size_t)n_runs));
     VREC_TRY(run_entity.alloc((size_t)n_runs));
     VREC_TRY(run_count.alloc((size_t)n_runs));
