@@ -449,7 +449,7 @@ __device__ __forceinline__ unsigned sig_bit(int col) { return ((unsigned)col * 0
 //  * place dot: candidate entries in ascending order; an entry can only match if its signature bit is
 //    set, and then a fixed-depth binary search over the target row finds it.
 __device__ __forceinline__ double exact_pair_staged(const TileAux &aux, long long i, const StagedTarget &t, double pw,
-                                                    double cw, int &min_tail) {
+                                                    double cw, int &min_tail, double thr = 0.0) {
     min_tail = -1;
     if (i == t.t) return 0.0;
     const unsigned long long m = __ldg(aux.meta + i);
@@ -493,6 +493,10 @@ __device__ __forceinline__ double exact_pair_staged(const TileAux &aux, long lon
             ps_sim = c;
         }
     }
+    // A cosine exceeds 1 by a few ulps at most: if even a category similarity of 1.0000001 leaves the pair
+    // below `thr` (a lower bound of what the caller still accepts), the category section -- three more
+    // dependent memory round trips -- is not read at all.
+    if (xadd(xmul(ps_sim, pw), xmul(1.0000001, cw)) < thr) return 0.0;
     if (nc > 0) {
         double sum = 0.0;
         for (int k0 = 0; k0 < nc; k0 += 4) {
@@ -892,7 +896,10 @@ __device__ __forceinline__ void tile_process_staged(const TileAux &aux, const Ti
                                                     double thr0 = 0.0) {
     atomicAdd(sm.stats + 0, 1u);
     int min_tail;
-    double sim = exact_pair_staged(aux, c, st, pw, cw, min_tail);
+    // what can still enter: thr0 (>= K candidates are known to reach it) and, once the heap is full, its root
+    double thr_eff = thr0;
+    if (*(volatile int *)(sm.hcnt + t) >= K) thr_eff = fmax(thr_eff, *(volatile double *)(sm.hsim + (size_t)t * K));
+    double sim = exact_pair_staged(aux, c, st, pw, cw, min_tail, thr_eff);
     if (!(sim > 0) || sim < thr0) return;      // >= K candidates are known to reach thr0
     if (min_tail != from_postings) return;
     volatile double *hs = sm.hsim + (size_t)t * K;
