@@ -144,8 +144,8 @@ def sg_workload_name(args):
 SG_NCU_TRAFFIC = 10_383_476_000 + 80_896_000 + 6_942_931_000 + 68_708_864
 # the same for one knn_tc_ws_kernel launch on the default KNN workload (18944 targets),
 # from profiles/r1_knn_final_r1_ncu_raw.csv
-KNN_NCU_TRAFFIC = 572_646_912 + 643_610_368      # profiles/r1_knn_final_r1d_ncu_raw.csv (+ the stagger-1 launch)
-KNN_NCU_TENSOR_PIPE_PCT = 23.4
+KNN_NCU_TRAFFIC = 485_070_000 + 64_673_792        # profiles/r1_knn_final_r1g_ncu_raw.csv: dram bytes read + written
+KNN_NCU_TENSOR_PIPE_PCT = 25.3
 
 
 def sg_bytes_per_iteration(n, nnz):
