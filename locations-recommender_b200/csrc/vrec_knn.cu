@@ -2360,9 +2360,28 @@ knn_rate_gather_kernel(const int *__restrict__ rrp, const int *__restrict__ rpl,
     for (int tt = slot; tt < T; tt += nslots) {
         const int n = nb_cnt[tt];
         int ntouched = 0;
+        double l_sim = 0.0;
+        int l_rs = 0, l_rn = 0;
         for (int k = 0; k < n; ++k) {
-            Nb nb = nb_idx[(size_t)tt * K + k];
-            const int rs = rrp[nb.idx], rn = rrp[nb.idx + 1] - rs;
+            // the neighbours' (similarity, rating row extent) are fetched 32 at a time, one per lane, and their
+            // rating rows prefetched: the serial loop below then only waits for the rows themselves
+            if ((k & 31) == 0) {
+                const int kk = k + lane;
+                l_sim = 0.0;
+                l_rs = 0;
+                l_rn = 0;
+                if (kk < n) {
+                    const Nb nbl = nb_idx[(size_t)tt * K + kk];
+                    l_sim = nbl.sim;
+                    l_rs = rrp[nbl.idx];
+                    l_rn = rrp[nbl.idx + 1] - l_rs;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rpl + l_rs));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rv + l_rs));
+                }
+            }
+            Nb nb;
+            nb.sim = __shfl_sync(0xffffffffu, l_sim, k & 31);
+            const int rs = __shfl_sync(0xffffffffu, l_rs, k & 31), rn = __shfl_sync(0xffffffffu, l_rn, k & 31);
             for (int e0 = 0; e0 < rn; e0 += 32) {
                 int e = e0 + lane;
                 bool valid = e < rn;
