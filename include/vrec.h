@@ -193,6 +193,28 @@ int vrec_build_rating_vectors(vrec_ctx *ctx, int64_t n_rows, const int64_t *pers
                               int64_t *out_person_id, int64_t *out_rowptr, int32_t *out_col, double *out_val,
                               int32_t *out_dim);
 
+/*
+ * The step in front of the SG path, on the device.
+ *  vrec_build_edge_family        one edge family of the stochastic graph, e.g. PersonLikesPlace
+ *      (stochastic/PersonLikesPlace.scala:12-41): count(*) per (source, target) (a row may stand for `weight`
+ *      rows), rank() <= top_n per source by count desc (ties stay), weight = count / (sum of the source's kept
+ *      counts), times beta (stochastic/StochasticGraphBuilder.scala:8-28).  Edges sorted by (source, target).
+ *  vrec_build_stochastic_graph   StochasticGraphBuilderMain.generateStochasticGraph
+ *      (stochastic/StochasticGraphBuilderMain.scala:47-66) from place visits (person, place, category,
+ *      timestamp in ms): PlaceSimilarPlace (visits of one person at different places at most 7 days apart,
+ *      top 50), CategorySelectedPlace (top 100), PersonLikesPlace (top 100, beta_person_place),
+ *      PersonLikesCategory (top 100, beta_person_category), in this order -- the input of vrec_sg_load.
+ * *out_n = number of edges; with capacity too small (or NULL outputs) the call returns VREC_ENOMEM after
+ * setting *out_n, so a first call can size the arrays.
+ */
+int vrec_build_edge_family(vrec_ctx *ctx, int64_t n_rows, const int64_t *source_id, const int64_t *target_id,
+                           const int64_t *weight, int32_t top_n, double beta, int64_t capacity, int64_t *out_n,
+                           int64_t *out_source, int64_t *out_target, double *out_weight);
+int vrec_build_stochastic_graph(vrec_ctx *ctx, int64_t n_visits, const int64_t *person_id, const int64_t *place_id,
+                                const int64_t *category_id, const int64_t *timestamp_ms, double beta_person_place,
+                                double beta_person_category, int64_t capacity, int64_t *out_n, int64_t *out_source,
+                                int64_t *out_target, double *out_weight);
+
 /* ---------------------------------------------------------------- SG path */
 
 /*

@@ -156,6 +156,207 @@ int scan_inclusive(vrec_ctx *ctx, const int *in, T *out, long long n, PoolBuf<un
     return VREC_OK;
 }
 
+
+// Everything the two entry points share: (src, dst[, weight]) rows on the device -> runs of equal (src, dst)
+// with their counts, the distinct sources, and the rank() <= top_n filter.
+struct FamilyCore {
+    int n_runs = 0, n_src = 0, nnz = 0;
+    PoolBuf<long long> run_src_row, run_dst, src_id;
+    PoolBuf<unsigned long long> run_count;
+    PoolBuf<int> first_run, keep, kept_incl;
+};
+
+int family_core(vrec_ctx *ctx, long long n, PoolBuf<long long> &d_src, PoolBuf<long long> &d_dst,
+                PoolBuf<long long> *d_weight, int top_n, FamilyCore &c) {
+    cudaStream_t st = ctx->stream;
+    const int grid = (int)((n + 255) / 256);
+    PoolBuf<long long> d_idx, k_a, k_b, v_a, v_b, d_wsorted;
+    PoolBuf<unsigned char> tmp;
+    VREC_TRY(k_a.alloc((size_t)n));
+    VREC_TRY(k_b.alloc((size_t)n));
+    VREC_TRY(v_a.alloc((size_t)n));
+    VREC_TRY(v_b.alloc((size_t)n));
+    // stable LSD: by dst, then by src; with weights the row index travels along and gathers them afterwards
+    size_t bytes = 0;
+    VREC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_dst.p, k_a.p, d_src.p, v_a.p, (int)n, 0, 64, st));
+    VREC_TRY(tmp.ensure(bytes));
+    if (d_weight) {
+        VREC_TRY(d_idx.alloc((size_t)n));
+        VREC_TRY(d_wsorted.alloc((size_t)n));
+        bld_iota_kernel<<<grid, 256, 0, st>>>(n, d_idx.p);
+        VREC_LAUNCHED(ctx);
+        VREC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_dst.p, k_a.p, d_idx.p, v_a.p, (int)n, 0, 64, st));
+        PoolBuf<long long> pg;
+        VREC_TRY(pg.alloc((size_t)n));
+        bld_gather_kernel<<<grid, 256, 0, st>>>(n, v_a.p, d_src.p, pg.p);
+        VREC_LAUNCHED(ctx);
+        VREC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, pg.p, k_b.p, v_a.p, v_b.p, (int)n, 0, 64, st));
+        bld_gather_kernel<<<grid, 256, 0, st>>>(n, v_b.p, d_dst.p, k_a.p);
+        VREC_LAUNCHED(ctx);
+        bld_gather_kernel<<<grid, 256, 0, st>>>(n, v_b.p, d_weight->p, d_wsorted.p);
+        VREC_LAUNCHED(ctx);
+        ctx->launches += 2;
+    } else {
+        VREC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_dst.p, k_a.p, d_src.p, v_a.p, (int)n, 0, 64, st));
+        VREC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, v_a.p, k_b.p, k_a.p, v_b.p, (int)n, 0, 64, st));
+        VREC_CUDA(cudaMemcpyAsync(k_a.p, v_b.p, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        ctx->launches += 2;
+    }
+    const long long *s_src = k_b.p, *s_dst = k_a.p;            // rows in (src, dst) order
+    PoolBuf<int> head, phead, run_of, prow_of;
+    VREC_TRY(head.alloc((size_t)n));
+    VREC_TRY(phead.alloc((size_t)n));
+    VREC_TRY(run_of.alloc((size_t)n));
+    VREC_TRY(prow_of.alloc((size_t)n));
+    bld_heads_kernel<<<grid, 256, 0, st>>>(n, s_src, s_dst, head.p, phead.p);
+    VREC_LAUNCHED(ctx);
+    VREC_TRY(scan_inclusive<int>(ctx, head.p, run_of.p, n, tmp));
+    VREC_TRY(scan_inclusive<int>(ctx, phead.p, prow_of.p, n, tmp));
+    VREC_CUDA(cudaMemcpyAsync(&c.n_runs, run_of.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    VREC_CUDA(cudaMemcpyAsync(&c.n_src, prow_of.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    VREC_CUDA(cudaStreamSynchronize(st));
+    VREC_TRY(c.run_src_row.alloc((size_t)c.n_runs));
+    VREC_TRY(c.run_dst.alloc((size_t)c.n_runs));
+    VREC_TRY(c.run_count.alloc((size_t)c.n_runs));
+    VREC_TRY(c.src_id.alloc((size_t)c.n_src));
+    VREC_TRY(c.first_run.alloc((size_t)c.n_src));
+    VREC_TRY(c.keep.alloc((size_t)c.n_runs));
+    VREC_TRY(c.kept_incl.alloc((size_t)c.n_runs));
+    VREC_CUDA(cudaMemsetAsync(c.run_count.p, 0, sizeof(unsigned long long) * (size_t)c.n_runs, st));
+    bld_runs_kernel<<<grid, 256, 0, st>>>(n, s_src, s_dst, d_weight ? d_wsorted.p : nullptr, head.p, run_of.p, prow_of.p,
+                                          c.run_src_row.p, c.run_dst.p, c.run_count.p, c.src_id.p, c.first_run.p);
+    VREC_LAUNCHED(ctx);
+    bld_rank_kernel<<<(int)(((long long)c.n_src * 32 + 255) / 256), 256, 0, st>>>(c.n_src, c.n_runs, c.first_run.p,
+                                                                                 c.run_count.p, top_n, c.keep.p);
+    VREC_LAUNCHED(ctx);
+    VREC_TRY(scan_inclusive<int>(ctx, c.keep.p, c.kept_incl.p, c.n_runs, tmp));
+    VREC_CUDA(cudaMemcpyAsync(&c.nnz, c.kept_incl.p + (c.n_runs - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    VREC_CUDA(cudaStreamSynchronize(st));
+    return VREC_OK;
+}
+
+// edge family: per source the sum of the kept counts (one warp per source), then weight = count / total * beta
+// for every kept run (PersonLikesPlace.scala:26-36 and the other three families; StochasticGraphBuilder.scala:8-28)
+__global__ void bld_totals_kernel(int n_src, int n_runs, const int *__restrict__ first_run,
+                                  const unsigned long long *__restrict__ run_count, const int *__restrict__ keep,
+                                  unsigned long long *__restrict__ total) {
+    const int lane = threadIdx.x & 31;
+    const int p = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (p >= n_src) return;
+    const int s = first_run[p], e = p + 1 < n_src ? first_run[p + 1] : n_runs;
+    unsigned long long t = 0;
+    for (int r = s + lane; r < e; r += 32) t += keep[r] ? run_count[r] : 0ULL;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    if (lane == 0) total[p] = t;
+}
+__global__ void bld_edges_kernel(int n_runs, const int *__restrict__ keep, const int *__restrict__ kept_incl,
+                                 const long long *__restrict__ run_src_row, const long long *__restrict__ run_dst,
+                                 const unsigned long long *__restrict__ run_count, const long long *__restrict__ src_id,
+                                 const unsigned long long *__restrict__ total, double beta, long long *__restrict__ out_src,
+                                 long long *__restrict__ out_dst, double *__restrict__ out_w) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs || !keep[r]) return;
+    const int at = kept_incl[r] - 1;
+    const long long p = run_src_row[r];
+    out_src[at] = src_id[p];
+    out_dst[at] = run_dst[r];
+    const double w = xdiv((double)run_count[r], (double)total[p]);   // visit_count / total_visit_count
+    out_w[at] = xmul(w, beta);                                        // weight * beta
+}
+
+// device rows -> one balanced edge family on the device (COO sorted by (source, target)); *out_n edges
+int family_edges(vrec_ctx *ctx, long long n, PoolBuf<long long> &d_src, PoolBuf<long long> &d_dst,
+                 PoolBuf<long long> *d_weight, int top_n, double beta, PoolBuf<long long> &e_src,
+                 PoolBuf<long long> &e_dst, PoolBuf<double> &e_w, int *out_n) {
+    *out_n = 0;
+    if (n == 0) return VREC_OK;
+    cudaStream_t st = ctx->stream;
+    FamilyCore c;
+    VREC_TRY(family_core(ctx, n, d_src, d_dst, d_weight, top_n, c));
+    PoolBuf<unsigned long long> total;
+    VREC_TRY(total.alloc((size_t)c.n_src));
+    VREC_TRY(e_src.alloc((size_t)std::max(1, c.nnz)));
+    VREC_TRY(e_dst.alloc((size_t)std::max(1, c.nnz)));
+    VREC_TRY(e_w.alloc((size_t)std::max(1, c.nnz)));
+    bld_totals_kernel<<<(int)(((long long)c.n_src * 32 + 255) / 256), 256, 0, st>>>(c.n_src, c.n_runs, c.first_run.p,
+                                                                                   c.run_count.p, c.keep.p, total.p);
+    VREC_LAUNCHED(ctx);
+    bld_edges_kernel<<<(c.n_runs + 255) / 256, 256, 0, st>>>(c.n_runs, c.keep.p, c.kept_incl.p, c.run_src_row.p,
+                                                             c.run_dst.p, c.run_count.p, c.src_id.p, total.p, beta,
+                                                             e_src.p, e_dst.p, e_w.p);
+    VREC_LAUNCHED(ctx);
+    VREC_CUDA(cudaStreamSynchronize(st));       // c's buffers are released on return
+    *out_n = c.nnz;
+    return VREC_OK;
+}
+
+// PlaceSimilarPlace.scala:18-42: the self-join of the visits on person_id, kept where the places differ and
+// the timestamps are at most `interval_ms` apart; one output row (place, that_place) per pair of visits.
+// Visits sorted by person; pair_cnt[i] = matching partners of visit i.
+__global__ void bld_pair_count_kernel(long long n, const long long *__restrict__ person, const long long *__restrict__ place,
+                                      const long long *__restrict__ ts, const int *__restrict__ seg_start_of,
+                                      const int *__restrict__ seg_end_of, long long interval_ms, int *__restrict__ pair_cnt) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = 0;
+    for (int j = seg_start_of[i]; j < seg_end_of[i]; ++j) {
+        long long dt = ts[i] - ts[j];
+        if (dt < 0) dt = -dt;
+        c += (place[j] != place[i] && dt <= interval_ms) ? 1 : 0;
+    }
+    (void)person;
+    pair_cnt[i] = c;
+}
+__global__ void bld_pair_emit_kernel(long long n, const long long *__restrict__ place, const long long *__restrict__ ts,
+                                     const int *__restrict__ seg_start_of, const int *__restrict__ seg_end_of,
+                                     long long interval_ms, const long long *__restrict__ pair_incl,
+                                     const int *__restrict__ pair_cnt, long long *__restrict__ out_a,
+                                     long long *__restrict__ out_b) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long at = pair_incl[i] - pair_cnt[i];
+    for (int j = seg_start_of[i]; j < seg_end_of[i]; ++j) {
+        long long dt = ts[i] - ts[j];
+        if (dt < 0) dt = -dt;
+        if (place[j] != place[i] && dt <= interval_ms) {
+            out_a[at] = place[i];
+            out_b[at] = place[j];
+            ++at;
+        }
+    }
+}
+// seg_start_of / seg_end_of for every row of a person-sorted visit list
+__global__ void bld_segments_kernel(long long n, const long long *__restrict__ person, int *__restrict__ seg_start_of,
+                                    int *__restrict__ seg_end_of) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // binary searches for the first / one-past-last row of person[i] (rows are sorted by person)
+    const long long key = person[i];
+    long long lo = 0, hi = i;
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (person[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    seg_start_of[i] = (int)lo;
+    lo = i;
+    hi = n;
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (person[mid] <= key) lo = mid + 1; else hi = mid;
+    }
+    seg_end_of[i] = (int)lo;
+}
+
+int scan_inclusive_ll(vrec_ctx *ctx, const int *in, long long *out, long long n, PoolBuf<unsigned char> &tmp) {
+    size_t bytes = 0;
+    VREC_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, (int)n, ctx->stream));
+    VREC_TRY(tmp.ensure(bytes));
+    VREC_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, bytes, in, out, (int)n, ctx->stream));
+    ctx->launches++;
+    return VREC_OK;
+}
+
 }  // namespace
 
 extern "C" int vrec_build_rating_vectors(vrec_ctx *ctx, int64_t n_rows, const int64_t *person_id,
@@ -180,98 +381,28 @@ extern "C" int vrec_build_rating_vectors(vrec_ctx *ctx, int64_t n_rows, const in
     VREC_TRY(pool_setup(ctx));
     cudaStream_t st = ctx->stream;
     const long long n = n_rows;
-    const int grid = (int)((n + 255) / 256);
-    PoolBuf<long long> d_person, d_entity, d_idx, k_a, k_b, v_a, v_b, d_weight, d_wsorted;
-    PoolBuf<unsigned char> tmp;
+    PoolBuf<long long> d_person, d_entity, d_weight;
     VREC_TRY(d_person.upload((const long long *)person_id, (size_t)n, st));
     VREC_TRY(d_entity.upload((const long long *)entity_id, (size_t)n, st));
-    VREC_TRY(k_a.alloc((size_t)n));
-    VREC_TRY(k_b.alloc((size_t)n));
-    VREC_TRY(v_a.alloc((size_t)n));
-    VREC_TRY(v_b.alloc((size_t)n));
-    // stable LSD: by entity (values = person), then by person (values = entity); a third pass carries the
-    // weights through the same permutation when there are any
-    size_t bytes = 0;
-    VREC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_entity.p, k_a.p, d_person.p, v_a.p, (int)n, 0, 64, st));
-    VREC_TRY(tmp.ensure(bytes));
-    if (weight) {
-        // sort (entity, row index) first so that the weights can follow: values = original row
-        VREC_TRY(d_idx.alloc((size_t)n));
-        VREC_TRY(d_weight.upload((const long long *)weight, (size_t)n, st));
-        VREC_TRY(d_wsorted.alloc((size_t)n));
-        bld_iota_kernel<<<grid, 256, 0, st>>>(n, d_idx.p);
-        VREC_LAUNCHED(ctx);
-        // pass 1: by entity, values = row index
-        VREC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_entity.p, k_a.p, d_idx.p, v_a.p, (int)n, 0, 64, st));
-        // gather person by the permutation, then pass 2: by person, values = row index
-        PoolBuf<long long> pg;
-        VREC_TRY(pg.alloc((size_t)n));
-        bld_gather_kernel<<<grid, 256, 0, st>>>(n, v_a.p, d_person.p, pg.p);
-        VREC_LAUNCHED(ctx);
-        VREC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, pg.p, k_b.p, v_a.p, v_b.p, (int)n, 0, 64, st));
-        // k_b = persons sorted; v_b = original rows in (person, entity) order
-        bld_gather_kernel<<<grid, 256, 0, st>>>(n, v_b.p, d_entity.p, k_a.p);
-        VREC_LAUNCHED(ctx);
-        bld_gather_kernel<<<grid, 256, 0, st>>>(n, v_b.p, d_weight.p, d_wsorted.p);
-        VREC_LAUNCHED(ctx);
-        VREC_CUDA(cudaStreamSynchronize(st));      // pg goes out of scope
-        ctx->launches += 2;
-    } else {
-        VREC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_entity.p, k_a.p, d_person.p, v_a.p, (int)n, 0, 64, st));
-        // k_a = entity sorted, v_a = person in that order; pass 2: by person, values = entity
-        VREC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, v_a.p, k_b.p, k_a.p, v_b.p, (int)n, 0, 64, st));
-        // k_b = persons sorted, v_b = entities in (person, entity) order
-        VREC_CUDA(cudaMemcpyAsync(k_a.p, v_b.p, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToDevice, st));
-        ctx->launches += 2;
-    }
-    const long long *s_person = k_b.p, *s_entity = k_a.p;
-    // run heads, run / person numbering
-    PoolBuf<int> head, phead, run_of, prow_of;
-    VREC_TRY(head.alloc((size_t)n));
-    VREC_TRY(phead.alloc((size_t)n));
-    VREC_TRY(run_of.alloc((size_t)n));
-    VREC_TRY(prow_of.alloc((size_t)n));
-    bld_heads_kernel<<<grid, 256, 0, st>>>(n, s_person, s_entity, head.p, phead.p);
-    VREC_LAUNCHED(ctx);
-    VREC_TRY(scan_inclusive<int>(ctx, head.p, run_of.p, n, tmp));
-    VREC_TRY(scan_inclusive<int>(ctx, phead.p, prow_of.p, n, tmp));
-    int n_runs = 0, n_persons = 0;
-    VREC_CUDA(cudaMemcpyAsync(&n_runs, run_of.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-    VREC_CUDA(cudaMemcpyAsync(&n_persons, prow_of.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-    VREC_CUDA(cudaStreamSynchronize(st));
-    PoolBuf<long long> run_person_row, run_entity, d_pid, d_max;
-    PoolBuf<unsigned long long> run_count, row_cnt;
-    PoolBuf<int> first_run, keep, kept_incl, d_col, d_bad;
+    if (weight) VREC_TRY(d_weight.upload((const long long *)weight, (size_t)n, st));
+    FamilyCore c;
+    VREC_TRY(family_core(ctx, n, d_person, d_entity, weight ? &d_weight : nullptr, top_n, c));
+    const int n_persons = c.n_src, n_runs = c.n_runs, nnz = c.nnz;
+    PoolBuf<unsigned long long> row_cnt;
+    PoolBuf<long long> d_max;
+    PoolBuf<int> d_col, d_bad;
     PoolBuf<double> d_val;
-    VREC_TRY(run_person_row.alloc((size_t)n_runs));
-    VREC_TRY(run_entity.alloc((size_t)n_runs));
-    VREC_TRY(run_count.alloc((size_t)n_runs));
-    VREC_TRY(d_pid.alloc((size_t)n_persons));
-    VREC_TRY(first_run.alloc((size_t)n_persons));
-    VREC_TRY(keep.alloc((size_t)n_runs));
-    VREC_TRY(kept_incl.alloc((size_t)n_runs));
     VREC_TRY(row_cnt.alloc((size_t)n_persons));
     VREC_TRY(d_max.alloc(1));
     VREC_TRY(d_bad.alloc(1));
-    VREC_CUDA(cudaMemsetAsync(run_count.p, 0, sizeof(unsigned long long) * (size_t)n_runs, st));
+    VREC_TRY(d_col.alloc((size_t)std::max(1, nnz)));
+    VREC_TRY(d_val.alloc((size_t)std::max(1, nnz)));
     VREC_CUDA(cudaMemsetAsync(row_cnt.p, 0, sizeof(unsigned long long) * (size_t)n_persons, st));
     VREC_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
     const long long minus1 = -1;
     VREC_CUDA(cudaMemcpyAsync(d_max.p, &minus1, sizeof(long long), cudaMemcpyHostToDevice, st));
-    bld_runs_kernel<<<grid, 256, 0, st>>>(n, s_person, s_entity, weight ? d_wsorted.p : nullptr, head.p, run_of.p,
-                                          prow_of.p, run_person_row.p, run_entity.p, run_count.p, d_pid.p, first_run.p);
-    VREC_LAUNCHED(ctx);
-    bld_rank_kernel<<<(int)(((long long)n_persons * 32 + 255) / 256), 256, 0, st>>>(n_persons, n_runs, first_run.p,
-                                                                                    run_count.p, top_n, keep.p);
-    VREC_LAUNCHED(ctx);
-    VREC_TRY(scan_inclusive<int>(ctx, keep.p, kept_incl.p, n_runs, tmp));
-    int nnz = 0;
-    VREC_CUDA(cudaMemcpyAsync(&nnz, kept_incl.p + (n_runs - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-    VREC_CUDA(cudaStreamSynchronize(st));
-    VREC_TRY(d_col.alloc((size_t)std::max(1, nnz)));
-    VREC_TRY(d_val.alloc((size_t)std::max(1, nnz)));
-    bld_scatter_kernel<<<(n_runs + 255) / 256, 256, 0, st>>>(n_runs, keep.p, kept_incl.p, run_person_row.p, run_entity.p,
-                                                             run_count.p, d_col.p, d_val.p, row_cnt.p, d_max.p, d_bad.p);
+    bld_scatter_kernel<<<(n_runs + 255) / 256, 256, 0, st>>>(n_runs, c.keep.p, c.kept_incl.p, c.run_src_row.p, c.run_dst.p,
+                                                             c.run_count.p, d_col.p, d_val.p, row_cnt.p, d_max.p, d_bad.p);
     VREC_LAUNCHED(ctx);
     std::vector<unsigned long long> h_cnt((size_t)n_persons);
     long long h_max = -1;
@@ -279,7 +410,7 @@ extern "C" int vrec_build_rating_vectors(vrec_ctx *ctx, int64_t n_rows, const in
     VREC_CUDA(cudaMemcpyAsync(h_cnt.data(), row_cnt.p, sizeof(unsigned long long) * (size_t)n_persons, cudaMemcpyDeviceToHost, st));
     VREC_CUDA(cudaMemcpyAsync(&h_max, d_max.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
     VREC_CUDA(cudaMemcpyAsync(&h_bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    VREC_CUDA(cudaMemcpyAsync(out_person_id, d_pid.p, sizeof(long long) * (size_t)n_persons, cudaMemcpyDeviceToHost, st));
+    VREC_CUDA(cudaMemcpyAsync(out_person_id, c.src_id.p, sizeof(long long) * (size_t)n_persons, cudaMemcpyDeviceToHost, st));
     VREC_CUDA(cudaMemcpyAsync(out_col, d_col.p, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, st));
     VREC_CUDA(cudaMemcpyAsync(out_val, d_val.p, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost, st));
     VREC_CUDA(cudaStreamSynchronize(st));
@@ -292,5 +423,135 @@ extern "C" int vrec_build_rating_vectors(vrec_ctx *ctx, int64_t n_rows, const in
     *out_n_persons = n_persons;
     *out_nnz = nnz;
     *out_dim = (int32_t)(h_max + 1);               // :26-34 max(entity id) + 1
+    return VREC_OK;
+}
+
+// One balanced edge family of the stochastic graph.
+extern "C" int vrec_build_edge_family(vrec_ctx *ctx, int64_t n_rows, const int64_t *source_id, const int64_t *target_id,
+                                      const int64_t *weight, int32_t top_n, double beta, int64_t capacity,
+                                      int64_t *out_n, int64_t *out_source, int64_t *out_target, double *out_weight) {
+    if (!ctx || n_rows < 0 || (n_rows > 0 && (!source_id || !target_id)) || !out_n || top_n <= 0 ||
+        n_rows >= (int64_t)0x7fffffff) {
+        vrec_set_error("vrec_build_edge_family: bad argument");
+        return VREC_EINVAL;
+    }
+    *out_n = 0;
+    if (n_rows == 0) return VREC_OK;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    VREC_TRY(pool_setup(ctx));
+    cudaStream_t st = ctx->stream;
+    PoolBuf<long long> d_src, d_dst, d_weight, e_src, e_dst;
+    PoolBuf<double> e_w;
+    VREC_TRY(d_src.upload((const long long *)source_id, (size_t)n_rows, st));
+    VREC_TRY(d_dst.upload((const long long *)target_id, (size_t)n_rows, st));
+    if (weight) VREC_TRY(d_weight.upload((const long long *)weight, (size_t)n_rows, st));
+    int ne = 0;
+    VREC_TRY(family_edges(ctx, n_rows, d_src, d_dst, weight ? &d_weight : nullptr, top_n, beta, e_src, e_dst, e_w, &ne));
+    *out_n = ne;
+    if (ne > capacity || !out_source || !out_target || !out_weight) {
+        vrec_set_error("vrec_build_edge_family: %d edges, capacity %lld", ne, (long long)capacity);
+        return VREC_ENOMEM;
+    }
+    VREC_CUDA(cudaMemcpyAsync(out_source, e_src.p, sizeof(long long) * (size_t)ne, cudaMemcpyDeviceToHost, st));
+    VREC_CUDA(cudaMemcpyAsync(out_target, e_dst.p, sizeof(long long) * (size_t)ne, cudaMemcpyDeviceToHost, st));
+    VREC_CUDA(cudaMemcpyAsync(out_weight, e_w.p, sizeof(double) * (size_t)ne, cudaMemcpyDeviceToHost, st));
+    VREC_CUDA(cudaStreamSynchronize(st));
+    return VREC_OK;
+}
+
+// StochasticGraphBuilderMain.generateStochasticGraph (stochastic/StochasticGraphBuilderMain.scala:47-66): the four
+// edge families in the reference's union order, each sorted by (source, target).
+extern "C" int vrec_build_stochastic_graph(vrec_ctx *ctx, int64_t n_visits, const int64_t *person_id,
+                                           const int64_t *place_id, const int64_t *category_id,
+                                           const int64_t *timestamp_ms, double beta_person_place,
+                                           double beta_person_category, int64_t capacity, int64_t *out_n,
+                                           int64_t *out_source, int64_t *out_target, double *out_weight) {
+    if (!ctx || n_visits < 0 || (n_visits > 0 && (!person_id || !place_id || !category_id || !timestamp_ms)) || !out_n ||
+        n_visits >= (int64_t)0x7fffffff) {
+        vrec_set_error("vrec_build_stochastic_graph: bad argument");
+        return VREC_EINVAL;
+    }
+    *out_n = 0;
+    if (n_visits == 0) return VREC_OK;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    VREC_TRY(pool_setup(ctx));
+    cudaStream_t st = ctx->stream;
+    const long long n = n_visits;
+    const int grid = (int)((n + 255) / 256);
+    PoolBuf<long long> d_person, d_place, d_cat, d_ts;
+    VREC_TRY(d_person.upload((const long long *)person_id, (size_t)n, st));
+    VREC_TRY(d_place.upload((const long long *)place_id, (size_t)n, st));
+    VREC_TRY(d_cat.upload((const long long *)category_id, (size_t)n, st));
+    VREC_TRY(d_ts.upload((const long long *)timestamp_ms, (size_t)n, st));
+    PoolBuf<long long> fam_src[4], fam_dst[4];
+    PoolBuf<double> fam_w[4];
+    int fam_n[4] = {0, 0, 0, 0};
+    {
+        // PlaceSimilarPlace (top 50, beta 1): sort the visits by person, expand the pairs, then the common pipeline
+        PoolBuf<long long> idx, s_person, s_idx, s_place, s_ts, pair_incl, pa, pb;
+        PoolBuf<int> seg_s, seg_e, pair_cnt;
+        PoolBuf<unsigned char> tmp;
+        VREC_TRY(idx.alloc((size_t)n));
+        VREC_TRY(s_person.alloc((size_t)n));
+        VREC_TRY(s_idx.alloc((size_t)n));
+        VREC_TRY(s_place.alloc((size_t)n));
+        VREC_TRY(s_ts.alloc((size_t)n));
+        VREC_TRY(seg_s.alloc((size_t)n));
+        VREC_TRY(seg_e.alloc((size_t)n));
+        VREC_TRY(pair_cnt.alloc((size_t)n));
+        VREC_TRY(pair_incl.alloc((size_t)n));
+        bld_iota_kernel<<<grid, 256, 0, st>>>(n, idx.p);
+        VREC_LAUNCHED(ctx);
+        size_t bytes = 0;
+        VREC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_person.p, s_person.p, idx.p, s_idx.p, (int)n, 0, 64, st));
+        VREC_TRY(tmp.ensure(bytes));
+        VREC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_person.p, s_person.p, idx.p, s_idx.p, (int)n, 0, 64, st));
+        ctx->launches++;
+        bld_gather_kernel<<<grid, 256, 0, st>>>(n, s_idx.p, d_place.p, s_place.p);
+        VREC_LAUNCHED(ctx);
+        bld_gather_kernel<<<grid, 256, 0, st>>>(n, s_idx.p, d_ts.p, s_ts.p);
+        VREC_LAUNCHED(ctx);
+        bld_segments_kernel<<<grid, 256, 0, st>>>(n, s_person.p, seg_s.p, seg_e.p);
+        VREC_LAUNCHED(ctx);
+        const long long interval_ms = 7LL * 24 * 3600 * 1000;          // PlaceSimilarPlace.scala:13-14
+        bld_pair_count_kernel<<<grid, 256, 0, st>>>(n, s_person.p, s_place.p, s_ts.p, seg_s.p, seg_e.p, interval_ms, pair_cnt.p);
+        VREC_LAUNCHED(ctx);
+        VREC_TRY(scan_inclusive_ll(ctx, pair_cnt.p, pair_incl.p, n, tmp));
+        long long n_pairs = 0;
+        VREC_CUDA(cudaMemcpyAsync(&n_pairs, pair_incl.p + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, st));
+        VREC_CUDA(cudaStreamSynchronize(st));
+        if (n_pairs >= (long long)0x7fffffff) {
+            vrec_set_error("vrec_build_stochastic_graph: %lld co-visit pairs exceed 2^31-1", n_pairs);
+            return VREC_EINVAL;
+        }
+        if (n_pairs > 0) {
+            VREC_TRY(pa.alloc((size_t)n_pairs));
+            VREC_TRY(pb.alloc((size_t)n_pairs));
+            bld_pair_emit_kernel<<<grid, 256, 0, st>>>(n, s_place.p, s_ts.p, seg_s.p, seg_e.p, interval_ms, pair_incl.p,
+                                                       pair_cnt.p, pa.p, pb.p);
+            VREC_LAUNCHED(ctx);
+            VREC_TRY(family_edges(ctx, n_pairs, pa, pb, nullptr, 50, 1.0, fam_src[0], fam_dst[0], fam_w[0], &fam_n[0]));
+        }
+        VREC_CUDA(cudaStreamSynchronize(st));
+    }
+    // CategorySelectedPlace (top 100, beta 1), PersonLikesPlace (top 100), PersonLikesCategory (top 100)
+    VREC_TRY(family_edges(ctx, n, d_cat, d_place, nullptr, 100, 1.0, fam_src[1], fam_dst[1], fam_w[1], &fam_n[1]));
+    VREC_TRY(family_edges(ctx, n, d_person, d_place, nullptr, 100, beta_person_place, fam_src[2], fam_dst[2], fam_w[2], &fam_n[2]));
+    VREC_TRY(family_edges(ctx, n, d_person, d_cat, nullptr, 100, beta_person_category, fam_src[3], fam_dst[3], fam_w[3], &fam_n[3]));
+    const int64_t total = (int64_t)fam_n[0] + fam_n[1] + fam_n[2] + fam_n[3];
+    *out_n = total;
+    if (total > capacity || !out_source || !out_target || !out_weight) {
+        vrec_set_error("vrec_build_stochastic_graph: %lld edges, capacity %lld", (long long)total, (long long)capacity);
+        return VREC_ENOMEM;
+    }
+    int64_t at = 0;
+    for (int f = 0; f < 4; ++f) {
+        if (fam_n[f] == 0) continue;
+        VREC_CUDA(cudaMemcpyAsync(out_source + at, fam_src[f].p, sizeof(long long) * (size_t)fam_n[f], cudaMemcpyDeviceToHost, st));
+        VREC_CUDA(cudaMemcpyAsync(out_target + at, fam_dst[f].p, sizeof(long long) * (size_t)fam_n[f], cudaMemcpyDeviceToHost, st));
+        VREC_CUDA(cudaMemcpyAsync(out_weight + at, fam_w[f].p, sizeof(double) * (size_t)fam_n[f], cudaMemcpyDeviceToHost, st));
+        at += fam_n[f];
+    }
+    VREC_CUDA(cudaStreamSynchronize(st));
     return VREC_OK;
 }

@@ -45,3 +45,40 @@ def rating_vectors_builder(person_id, place_id, category_id, weight=None, max_ra
     rat_person = np.repeat(persons, np.diff(prp))      # place_ratings = the non-zeros of the place vectors (:44-49,:71)
     return KnnInputs(persons, prp, pci, pv, place_dim, crp, cci, cv, cat_dim,
                      rat_person.astype(np.int64), pci.astype(np.int64), pv.astype(np.int64))
+
+
+def build_edge_family(source_id, target_id, top_n: int, beta: float, weight=None, ctx: Optional[Context] = None):
+    """One balanced edge family (source_id, target_id, balanced_weight), sorted by (source, target)."""
+    ctx = ctx or default_context()
+    s_, t_ = _i64(source_id), _i64(target_id)
+    w = _i64(weight) if weight is not None else None
+    n = len(s_)
+    cap = max(1, n)
+    os_, ot, ow = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.float64)
+    ne = C.c_int64(0)
+    _check(ctx.lib.vrec_build_edge_family(ctx._h, n, _ptr(s_, L.i64p), _ptr(t_, L.i64p), _ptr(w, L.i64p), int(top_n),
+                                          float(beta), cap, C.byref(ne), _ptr(os_, L.i64p), _ptr(ot, L.i64p),
+                                          _ptr(ow, L.f64p)))
+    return os_[:ne.value], ot[:ne.value], ow[:ne.value]
+
+
+def stochastic_graph_builder(person_id, place_id, category_id, timestamp_ms, beta_person_place: float = 0.5,
+                             beta_person_category: float = 0.5, ctx: Optional[Context] = None):
+    """Place visits of one region-set -> the stochastic graph's edges (source_id, target_id, balanced_weight)
+    (bin/stochastic_graph_builder.sh:32-34 defaults; stochastic/StochasticGraphBuilderMain.scala:47-66)."""
+    ctx = ctx or default_context()
+    pe, pl, ca, ts = _i64(person_id), _i64(place_id), _i64(category_id), _i64(timestamp_ms)
+    n = len(pe)
+    if not (len(pl) == len(ca) == len(ts) == n):
+        raise ValueError("visit columns differ in length")
+    ne = C.c_int64(0)
+    args = (ctx._h, n, _ptr(pe, L.i64p), _ptr(pl, L.i64p), _ptr(ca, L.i64p), _ptr(ts, L.i64p),
+            float(beta_person_place), float(beta_person_category))
+    rc = ctx.lib.vrec_build_stochastic_graph(*args, 0, C.byref(ne), None, None, None)      # sizes the outputs
+    if rc not in (L.OK, L.ENOMEM):
+        _check(rc)
+    cap = max(1, ne.value)
+    os_, ot, ow = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.float64)
+    _check(ctx.lib.vrec_build_stochastic_graph(*args, cap, C.byref(ne), _ptr(os_, L.i64p), _ptr(ot, L.i64p),
+                                               _ptr(ow, L.f64p)))
+    return os_[:ne.value], ot[:ne.value], ow[:ne.value]

@@ -244,3 +244,32 @@ def build_rating_vectors(person_id, entity_id, weight, top_n):
                                         C.byref(P), C.byref(nnz), _p(persons, C.c_int64), _p(rowptr, C.c_int64),
                                         _p(col, C.c_int32), _p(val, C.c_double), C.byref(dim))
     return rc, persons[:P.value], rowptr[:P.value + 1], col[:nnz.value], val[:nnz.value], dim.value
+
+
+def build_edge_family(source_id, target_id, weight, top_n, beta):
+    s, t = _i64(source_id), _i64(target_id)
+    n = len(s)
+    w = _i64(weight) if weight is not None else None
+    cap = max(1, n)
+    os_, ot, ow = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.float64)
+    ne = C.c_int64(0)
+    rc = lib().vro_build_edge_family(C.c_int64(n), _p(s, C.c_int64), _p(t, C.c_int64),
+                                     _p(w, C.c_int64) if w is not None else None, C.c_int32(int(top_n)),
+                                     C.c_double(beta), C.c_int64(cap), C.byref(ne), _p(os_, C.c_int64),
+                                     _p(ot, C.c_int64), _p(ow, C.c_double))
+    return rc, os_[:ne.value], ot[:ne.value], ow[:ne.value]
+
+
+def build_stochastic_graph(person_id, place_id, category_id, timestamp_ms, beta_person_place=0.5,
+                           beta_person_category=0.5):
+    pe, pl, ca, ts = _i64(person_id), _i64(place_id), _i64(category_id), _i64(timestamp_ms)
+    n = len(pe)
+    ne = C.c_int64(0)
+    args = (C.c_int64(n), _p(pe, C.c_int64), _p(pl, C.c_int64), _p(ca, C.c_int64), _p(ts, C.c_int64),
+            C.c_double(beta_person_place), C.c_double(beta_person_category))
+    rc = lib().vro_build_stochastic_graph(*args, C.c_int64(0), C.byref(ne), None, None, None)
+    cap = max(1, ne.value)
+    os_, ot, ow = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.float64)
+    rc = lib().vro_build_stochastic_graph(*args, C.c_int64(cap), C.byref(ne), _p(os_, C.c_int64), _p(ot, C.c_int64),
+                                          _p(ow, C.c_double))
+    return rc, os_[:ne.value], ot[:ne.value], ow[:ne.value]

@@ -793,3 +793,132 @@ int vro_build_rating_vectors(int64_t n_rows, const int64_t *person_id, const int
     *out_n_persons = P; *out_nnz = nnz; *out_dim = (int32_t)(maxid + 1);
     return VRO_OK;
 }
+
+/* ------------------------------------------------------------------ */
+/* the four edge families + StochasticGraphBuilder */
+/* ------------------------------------------------------------------ */
+
+/* One edge family, e.g. PersonLikesPlace.calcPersonLikesPlaceEdges (stochastic/PersonLikesPlace.scala:12-41):
+ * count(*) per (source, target) (:13-15), rank() <= top_n per source by count desc (:17-23, ties stay),
+ * weight = count / (sum of the kept counts of the source) as doubles (:25-32), then
+ * StochasticGraphBuilder.buildWithBalancedWeights' `weight * beta` (stochastic/StochasticGraphBuilder.scala:8-28).
+ * Output sorted by (source, target).  Returns the number of edges in *out_n; fills the arrays if it fits.   */
+int vro_build_edge_family(int64_t n_rows, const int64_t *source_id, const int64_t *target_id, const int64_t *weight,
+                          int32_t top_n, double beta, int64_t capacity, int64_t *out_n, int64_t *out_source,
+                          int64_t *out_target, double *out_weight)
+{
+    if (n_rows < 0 || top_n <= 0) return VRO_EINVAL;
+    *out_n = 0;
+    if (n_rows == 0) return VRO_OK;
+    visit_t *v = (visit_t *)malloc(sizeof(visit_t) * (size_t)n_rows);
+    int64_t *cnt = (int64_t *)malloc(sizeof(int64_t) * (size_t)n_rows);
+    if (!v || !cnt) { free(v); free(cnt); return VRO_ENOMEM; }
+    for (int64_t i = 0; i < n_rows; ++i) {
+        v[i].person = source_id[i]; v[i].entity = target_id[i]; v[i].weight = weight ? weight[i] : 1;
+    }
+    qsort(v, (size_t)n_rows, sizeof(visit_t), visit_cmp);
+    int64_t m = 0;
+    for (int64_t i = 0; i < n_rows; ++i) {
+        if (m > 0 && v[m - 1].person == v[i].person && v[m - 1].entity == v[i].entity) cnt[m - 1] += v[i].weight;
+        else { v[m] = v[i]; cnt[m] = v[i].weight; m++; }
+    }
+    int64_t ne = 0;
+    for (int64_t s = 0; s < m; ) {
+        int64_t e = s;
+        while (e < m && v[e].person == v[s].person) e++;
+        int64_t total = 0;
+        for (int64_t r = s; r < e; ++r) {                     /* first pass: which rows stay, and their total */
+            int64_t larger = 0;
+            for (int64_t q = s; q < e; ++q) larger += cnt[q] > cnt[r];
+            v[r].weight = larger + 1 <= top_n;                /* reuse the field as the keep flag */
+            if (v[r].weight) total += cnt[r];
+        }
+        for (int64_t r = s; r < e; ++r) {
+            if (!v[r].weight) continue;
+            if (ne < capacity && out_source) {
+                double w = (double)cnt[r] / (double)total;
+                out_source[ne] = v[r].person;
+                out_target[ne] = v[r].entity;
+                out_weight[ne] = w * beta;
+            }
+            ne++;
+        }
+        s = e;
+    }
+    free(v); free(cnt);
+    *out_n = ne;
+    return ne > capacity ? VRO_ENOMEM : VRO_OK;
+}
+
+typedef struct { int64_t person, place, ts; } pvisit_t;
+static int pvisit_cmp(const void *a, const void *b)
+{
+    const pvisit_t *x = (const pvisit_t *)a, *y = (const pvisit_t *)b;
+    return x->person < y->person ? -1 : x->person > y->person;
+}
+
+/* StochasticGraphBuilderMain.generateStochasticGraph (stochastic/StochasticGraphBuilderMain.scala:47-66): the
+ * union, in this order, of PlaceSimilarPlace (the visits self-joined on person_id, different places, timestamps
+ * at most 7 days apart, one row per pair of visits; top 50; stochastic/PlaceSimilarPlace.scala:13-63),
+ * CategorySelectedPlace (top 100), PersonLikesPlace (top 100, beta_person_place) and PersonLikesCategory
+ * (top 100, beta_person_category); the first two have beta = 1 (:8-9).                                      */
+int vro_build_stochastic_graph(int64_t n, const int64_t *person_id, const int64_t *place_id,
+                               const int64_t *category_id, const int64_t *timestamp_ms, double beta_person_place,
+                               double beta_person_category, int64_t capacity, int64_t *out_n, int64_t *out_source,
+                               int64_t *out_target, double *out_weight)
+{
+    if (n < 0) return VRO_EINVAL;
+    *out_n = 0;
+    if (n == 0) return VRO_OK;
+    const int64_t interval = 7LL * 24 * 3600 * 1000;
+    pvisit_t *pv = (pvisit_t *)malloc(sizeof(pvisit_t) * (size_t)n);
+    if (!pv) return VRO_ENOMEM;
+    for (int64_t i = 0; i < n; ++i) { pv[i].person = person_id[i]; pv[i].place = place_id[i]; pv[i].ts = timestamp_ms[i]; }
+    qsort(pv, (size_t)n, sizeof(pvisit_t), pvisit_cmp);
+    int64_t np = 0;
+    for (int64_t s = 0; s < n; ) {
+        int64_t e = s;
+        while (e < n && pv[e].person == pv[s].person) e++;
+        for (int64_t i = s; i < e; ++i)
+            for (int64_t j = s; j < e; ++j) {
+                int64_t dt = pv[i].ts - pv[j].ts; if (dt < 0) dt = -dt;
+                np += pv[i].place != pv[j].place && dt <= interval;
+            }
+        s = e;
+    }
+    int64_t *pa = (int64_t *)malloc(sizeof(int64_t) * (size_t)(np > 0 ? np : 1));
+    int64_t *pb = (int64_t *)malloc(sizeof(int64_t) * (size_t)(np > 0 ? np : 1));
+    if (!pa || !pb) { free(pv); free(pa); free(pb); return VRO_ENOMEM; }
+    int64_t k = 0;
+    for (int64_t s = 0; s < n; ) {
+        int64_t e = s;
+        while (e < n && pv[e].person == pv[s].person) e++;
+        for (int64_t i = s; i < e; ++i)
+            for (int64_t j = s; j < e; ++j) {
+                int64_t dt = pv[i].ts - pv[j].ts; if (dt < 0) dt = -dt;
+                if (pv[i].place != pv[j].place && dt <= interval) { pa[k] = pv[i].place; pb[k] = pv[j].place; k++; }
+            }
+        s = e;
+    }
+    free(pv);
+    int64_t at = 0, got = 0;
+    int rc = VRO_OK, r;
+    const int64_t *fs[4] = {pa, category_id, person_id, person_id};
+    const int64_t *fd[4] = {pb, place_id, place_id, category_id};
+    const int64_t fn[4] = {np, n, n, n};
+    const int32_t ft[4] = {50, 100, 100, 100};
+    const double fb[4] = {1.0, 1.0, beta_person_place, beta_person_category};
+    for (int f = 0; f < 4; ++f) {
+        int64_t room = capacity > at ? capacity - at : 0;
+        r = vro_build_edge_family(fn[f], fs[f], fd[f], 0, ft[f], fb[f], room, &got,
+                                  out_source ? out_source + (at < capacity ? at : 0) : 0,
+                                  out_target ? out_target + (at < capacity ? at : 0) : 0,
+                                  out_weight ? out_weight + (at < capacity ? at : 0) : 0);
+        if (r != VRO_OK && r != VRO_ENOMEM) { rc = r; break; }
+        if (r == VRO_ENOMEM) rc = VRO_ENOMEM;
+        at += got;
+    }
+    free(pa); free(pb);
+    *out_n = at;
+    return rc;
+}

@@ -432,3 +432,32 @@ def test_rating_vectors_builder_bit_exact(vrec, ctx, synth, oracle):
         builders.build_rating_vectors([1], [2 ** 31], 10, ctx=ctx)
     g = builders.build_rating_vectors([], [], 10, ctx=ctx)
     assert len(g[0]) == 0 and g[1].tolist() == [0]
+
+
+# ------------------------------------------------------------------ stochastic graph builder
+def test_stochastic_graph_builder_bit_exact(vrec, ctx, synth, oracle):
+    from vrec import builders
+    v, places = synth.g2_place_visits(5000, 700, seed=13, mean_places=5.0)
+    rng = np.random.default_rng(4)
+    perm = rng.permutation(int(v.count.sum()))
+    pe = np.repeat(v.person_id, v.count)[perm]
+    pl = np.repeat(v.place_id, v.count)[perm]
+    ca = np.repeat(v.category_id, v.count)[perm]
+    ts = 1_546_300_800_000 + rng.integers(0, 20 * 24 * 3600 * 1000, len(pe))      # three weeks: the 7-day window matters
+    rc, ws, wt, ww = oracle.build_stochastic_graph(pe, pl, ca, ts, 0.3, 0.7)
+    assert rc == 0
+    s, t, w = builders.stochastic_graph_builder(pe, pl, ca, ts, 0.3, 0.7, ctx=ctx)
+    assert np.array_equal(s, ws) and np.array_equal(t, wt) and np.array_equal(w, ww)      # same order, same doubles
+    # single families, with and without weights
+    for src, dst, wgt, top_n, beta in ((pe, pl, None, 3, 0.5), (ca, pl, None, 100, 1.0),
+                                       (v.person_id, v.category_id, v.count, 2, 0.25)):
+        rc, ws, wt, ww = oracle.build_edge_family(src, dst, wgt, top_n, beta)
+        s, t, w = builders.build_edge_family(src, dst, top_n, beta, weight=wgt, ctx=ctx)
+        assert rc == 0 and np.array_equal(s, ws) and np.array_equal(t, wt) and np.array_equal(w, ww)
+    # the built graph goes straight into the recommender
+    s, t, w = builders.stochastic_graph_builder(pe, pl, ca, ts, 0.5, 0.5, ctx=ctx)
+    g = vrec.StochasticGraph(s, t, w, ctx=ctx)
+    og = oracle.SgGraph(s, t, w)
+    rec = vrec.StochasticRecommender(g, 0.01, 20)
+    _check_sg_batch(rec, og, np.unique(pe)[:12], places.id, 10, 0.01, 20)
+    assert builders.stochastic_graph_builder([], [], [], [], ctx=ctx)[0].size == 0

@@ -98,3 +98,37 @@ def test_rating_vectors_builder_oracle_vs_numpy_restatement(oracle):
     assert rc == oracle.EINVAL
     rc, persons, rowptr, *_ = oracle.build_rating_vectors([], [], None, 10)
     assert rc == 0 and len(persons) == 0 and rowptr.tolist() == [0]
+
+
+def _expand_visits(v, rng, week_ms=6 * 24 * 3600 * 1000):
+    """One row per visit (PlaceVisitCounts -> place_visits rows), shuffled, timestamps inside one window."""
+    perm = rng.permutation(int(v.count.sum()))
+    pe = np.repeat(v.person_id, v.count)[perm]
+    pl = np.repeat(v.place_id, v.count)[perm]
+    ca = np.repeat(v.category_id, v.count)[perm]
+    ts = 1_546_300_800_000 + rng.integers(0, week_ms, len(pe))
+    return pe, pl, ca, ts
+
+
+def test_stochastic_graph_builder_oracle_vs_numpy_restatement(oracle):
+    """vro_build_stochastic_graph against the numpy restatement of the four edge calculators in vrec/synth.py
+    (every visit inside one 7-day window, so every pair of visits of a person counts)."""
+    v, places = synth.g2_place_visits(400, 60, seed=5, mean_places=4.0)
+    rng = np.random.default_rng(2)
+    pe, pl, ca, ts = _expand_visits(v, rng)
+    rc, s, t, w = oracle.build_stochastic_graph(pe, pl, ca, ts, 0.5, 0.5)
+    assert rc == 0
+    ws, wt, ww = synth.build_stochastic_graph(v, 0.5, 0.5)
+    got = sorted(zip(s.tolist(), t.tolist(), w.tolist()))
+    want = sorted(zip(ws.tolist(), wt.tolist(), ww.tolist()))
+    assert [g[:2] for g in got] == [x[:2] for x in want]
+    assert np.allclose([g[2] for g in got], [x[2] for x in want], rtol=1e-12, atol=0)
+    # one family by hand: counts 3 / 2 / 2 / 1 of source 5, top 2 keeps the tie; weights = count / kept total * beta
+    rc, s, t, w = oracle.build_edge_family([5, 5, 5, 5, 9], [1, 2, 3, 4, 7], [3, 2, 2, 1, 1], 2, 0.5)
+    assert rc == 0 and s.tolist() == [5, 5, 5, 9] and t.tolist() == [1, 2, 3, 7]
+    assert w.tolist() == [3 / 7 * 0.5, 2 / 7 * 0.5, 2 / 7 * 0.5, 1 / 1 * 0.5]
+    # visits more than 7 days apart do not make places similar (PlaceSimilarPlace.scala:29-36)
+    day = 24 * 3600 * 1000
+    rc, s, t, w = oracle.build_stochastic_graph([1, 1, 1], [10, 11, 12], [0, 0, 1], [0, 3 * day, 11 * day], 0.5, 0.5)
+    pairs = [(a, b) for a, b in zip(s.tolist(), t.tolist()) if a >= 10 and b >= 10 and a < 100]
+    assert sorted(pairs) == [(10, 11), (11, 10)]
