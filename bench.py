@@ -594,7 +594,36 @@ def run_builder(args, vrec, ctx, rank):
         cdt = time.perf_counter() - t1
         cpu = {"value": ns / cdt, "unit": "visits/s", "cores": 1, "kind": "port",
                "sample": f"first {ns} visit rows, {cdt:.2f}s, oracle/vrec_oracle.c (qsort, one thread)"}
-    return {"metric": "rating vectors builder, visit rows/s (count per (person, place), rank <= 100, CSR)",
+    # SURVEY 8(f) rank 3, the step in front of the SG path: the four edge families from place visits
+    ng_persons = min(args.knn_persons, 200_000)
+    vg, _ = synth.g2_place_visits(ng_persons, max(1000, args.knn_places // 5), seed=77)
+    permg = rng.permutation(int(vg.count.sum()))
+    gpe = np.repeat(vg.person_id, vg.count)[permg]
+    gpl = np.repeat(vg.place_id, vg.count)[permg]
+    gca = np.repeat(vg.category_id, vg.count)[permg]
+    gts = 1_546_300_800_000 + rng.integers(0, 14 * 24 * 3600 * 1000, len(gpe))
+    builders.stochastic_graph_builder(gpe[:50000], gpl[:50000], gca[:50000], gts[:50000], ctx=ctx)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        gs, gt, gw = builders.stochastic_graph_builder(gpe, gpl, gca, gts, ctx=ctx)
+    gdt = (time.perf_counter() - t0) / reps
+    gcpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        nsamp = min(len(gpe), 400_000)
+        keep = gpe < np.sort(np.unique(gpe))[min(len(np.unique(gpe)) - 1, 25_000)]
+        keep &= np.cumsum(keep) <= nsamp
+        t1 = time.perf_counter()
+        oracle.build_stochastic_graph(gpe[keep], gpl[keep], gca[keep], gts[keep], 0.5, 0.5)
+        gcdt = time.perf_counter() - t1
+        gcpu = {"value": int(keep.sum()) / gcdt, "unit": "visits/s", "cores": 1, "kind": "port",
+                "sample": f"the visits of the first 25000 persons ({int(keep.sum())} rows), {gcdt:.2f}s, "
+                          f"oracle/vrec_oracle.c (qsort, one thread)"}
+    graph = {"metric": "stochastic graph builder, visit rows/s (4 edge families incl. the co-visit self-join)",
+             "value": len(gpe) / gdt, "unit": "visits/s", "ms_per_step": gdt * 1e3,
+             "config": {"workload": f"{len(gpe)} visit rows of {ng_persons} persons over 14 days -> {len(gs)} edges"},
+             "cpu_baseline": gcpu}
+    return {"graph": graph,
+            "metric": "rating vectors builder, visit rows/s (count per (person, place), rank <= 100, CSR)",
             "value": len(pe) / dt, "unit": "visits/s", "ms_per_step": dt * 1e3,
             "config": {"workload": f"{len(pe)} visit rows of {args.knn_persons} persons x {args.knn_places} places "
                                    f"(generator G2, shuffled), {len(out[2])} ratings kept"},
