@@ -194,6 +194,24 @@ int vrec_build_rating_vectors(vrec_ctx *ctx, int64_t n_rows, const int64_t *pers
                               int32_t *out_dim);
 
 /*
+ * PlaceVisits.calcPlaceVisits (PlaceVisits.scala:11-48) with the spatial grid its authors ask for (":30 TODO Very
+ * inefficient almost cross-join"): every location visit of the last `last_days_count` days (counted in whole UTC
+ * days from the latest timestamp, :50-61) becomes a place visit of every place of its region within `accuracy_m`
+ * metres (haversine, Location.scala:30-43; 100 m in the reference, PlaceVisits.scala:127).  Output rows
+ * (person_id, timestamp, place_id, region_id, category_id) in visit order, a visit's places in ascending id --
+ * the input of the two builders above / below.  Distances are fp64 with CUDA's libm: a pair whose distance is
+ * within a few ulps of `accuracy_m` may fall on the other side than with the reference's FastMath.
+ * *out_n = rows; VREC_ENOMEM (after setting *out_n) if capacity is too small or the outputs are NULL.
+ */
+int vrec_build_place_visits(vrec_ctx *ctx, int64_t n_visits, const int64_t *person_id, const double *latitude,
+                            const double *longitude, const int64_t *timestamp_ms, const int64_t *region_id,
+                            int64_t n_places, const int64_t *place_id, const double *place_latitude,
+                            const double *place_longitude, const int64_t *place_category, const int64_t *place_region,
+                            int32_t last_days_count, double accuracy_m, int64_t capacity, int64_t *out_n,
+                            int64_t *out_person, int64_t *out_timestamp_ms, int64_t *out_place, int64_t *out_region,
+                            int64_t *out_category);
+
+/*
  * The step in front of the SG path, on the device.
  *  vrec_build_edge_family        one edge family of the stochastic graph, e.g. PersonLikesPlace
  *      (stochastic/PersonLikesPlace.scala:12-41): count(*) per (source, target) (a row may stand for `weight`

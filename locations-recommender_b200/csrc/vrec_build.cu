@@ -555,3 +555,244 @@ extern "C" int vrec_build_stochastic_graph(vrec_ctx *ctx, int64_t n_visits, cons
     VREC_CUDA(cudaStreamSynchronize(st));
     return VREC_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// PlaceVisits.calcPlaceVisits (PlaceVisits.scala:11-48) with the spatial grid its authors ask for (":30 TODO
+// Very inefficient almost cross-join. Introduce a grid ..."): a location visit becomes a place visit of every
+// place of its region within `accuracy` metres (haversine, Location.scala:30-43), for the visits of the last
+// `last_days_count` days (counted from the latest timestamp, PlaceVisits.scala:50-61).
+// Places are binned on the host into cells at least `accuracy` metres wide in both directions (per region, the
+// longitude step widened by 1 / cos of the region's largest |latitude|), so a visit only looks at the 3 x 3
+// cells around its own.  Distances are fp64 with CUDA's sin / cos / asin / sqrt: a pair whose distance is within
+// a few ulps of `accuracy` can fall on the other side than with the reference's FastMath.
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct PvGrid {
+    int n_regions, n_cells;
+    const long long *region_ids;          // ascending
+    const double *lat0, *lon0, *cell_lon;  // per region
+    double cell_lat;
+    const unsigned long long *cell_key;    // ascending (region index << 42 | iy << 21 | ix)
+    const int *cell_start;                 // [n_cells + 1] into the place arrays (sorted by cell, then place id)
+    const long long *p_id, *p_cat;
+    const double *p_lat, *p_lon;
+};
+
+__device__ __forceinline__ double pv_distance(double lat1d, double lon1d, double lat2d, double lon2d) {
+    const double k = 0.017453292519943295;                 // toRadians
+    const double lat1 = lat1d * k, lat2 = lat2d * k, lon1 = lon1d * k, lon2 = lon2d * k;
+    const double s1 = sin((lat2 - lat1) / 2), s2 = sin((lon2 - lon1) / 2);
+    const double hav = s1 * s1 + cos(lat1) * cos(lat2) * (s2 * s2);
+    return 6371000.0 * 2 * asin(sqrt(hav));
+}
+
+template <bool EMIT>
+__global__ void pv_match_kernel(long long n, const long long *__restrict__ person, const double *__restrict__ lat,
+                                const double *__restrict__ lon, const long long *__restrict__ ts,
+                                const long long *__restrict__ region, long long ts_from, double accuracy, PvGrid g,
+                                int *__restrict__ cnt, const long long *__restrict__ incl, long long *__restrict__ o_person,
+                                long long *__restrict__ o_ts, long long *__restrict__ o_place,
+                                long long *__restrict__ o_region, long long *__restrict__ o_cat) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = 0;
+    long long at = EMIT ? incl[i] - cnt[i] : 0;
+    const long long at0 = at;
+    if (ts[i] >= ts_from) {
+        int lo = 0, hi = g.n_regions;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (g.region_ids[mid] < region[i]) lo = mid + 1; else hi = mid;
+        }
+        if (lo < g.n_regions && g.region_ids[lo] == region[i]) {
+            const int r = lo;
+            const long long iy = (long long)floor((lat[i] - g.lat0[r]) / g.cell_lat);
+            const long long ix = (long long)floor((lon[i] - g.lon0[r]) / g.cell_lon[r]);
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const long long y = iy + dy, x = ix + dx;
+                    if (y < 0 || x < 0 || y >= (1 << 21) || x >= (1 << 21)) continue;
+                    const unsigned long long key = ((unsigned long long)r << 42) | ((unsigned long long)y << 21) | (unsigned long long)x;
+                    int l2 = 0, h2 = g.n_cells;
+                    while (l2 < h2) {
+                        int mid = (l2 + h2) >> 1;
+                        if (g.cell_key[mid] < key) l2 = mid + 1; else h2 = mid;
+                    }
+                    if (l2 >= g.n_cells || g.cell_key[l2] != key) continue;
+                    for (int p = g.cell_start[l2]; p < g.cell_start[l2 + 1]; ++p) {
+                        if (pv_distance(lat[i], lon[i], g.p_lat[p], g.p_lon[p]) <= accuracy) {   // PlaceVisits.scala:22
+                            if (EMIT) {
+                                // keep this visit's rows in ascending place id (insertion into the short run)
+                                long long q = at;
+                                while (q > at0 && o_place[q - 1] > g.p_id[p]) {
+                                    o_place[q] = o_place[q - 1];
+                                    o_cat[q] = o_cat[q - 1];
+                                    --q;
+                                }
+                                o_place[q] = g.p_id[p];
+                                o_cat[q] = g.p_cat[p];
+                                o_person[at] = person[i];
+                                o_ts[at] = ts[i];
+                                o_region[at] = region[i];
+                                ++at;
+                            }
+                            ++c;
+                        }
+                    }
+                }
+        }
+    }
+    if (!EMIT) cnt[i] = c;
+}
+
+}  // namespace
+
+extern "C" int vrec_build_place_visits(vrec_ctx *ctx, int64_t n_visits, const int64_t *person_id, const double *latitude,
+                                       const double *longitude, const int64_t *timestamp_ms, const int64_t *region_id,
+                                       int64_t n_places, const int64_t *place_id, const double *place_latitude,
+                                       const double *place_longitude, const int64_t *place_category,
+                                       const int64_t *place_region, int32_t last_days_count, double accuracy_m,
+                                       int64_t capacity, int64_t *out_n, int64_t *out_person, int64_t *out_timestamp_ms,
+                                       int64_t *out_place, int64_t *out_region, int64_t *out_category) {
+    if (!ctx || !out_n || n_visits < 0 || n_places < 0 || n_visits >= (int64_t)0x7fffffff || n_places >= (int64_t)0x7fffffff ||
+        (n_visits > 0 && (!person_id || !latitude || !longitude || !timestamp_ms || !region_id)) ||
+        (n_places > 0 && (!place_id || !place_latitude || !place_longitude || !place_category || !place_region)) ||
+        !(accuracy_m > 0) || last_days_count < 0) {
+        vrec_set_error("vrec_build_place_visits: bad argument");
+        return VREC_EINVAL;
+    }
+    *out_n = 0;
+    if (n_visits == 0 || n_places == 0) return VREC_OK;
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    VREC_TRY(pool_setup(ctx));
+    cudaStream_t st = ctx->stream;
+    // ---- host: the grid over the places
+    std::vector<long long> regions(place_region, place_region + n_places);
+    std::sort(regions.begin(), regions.end());
+    regions.erase(std::unique(regions.begin(), regions.end()), regions.end());
+    const int nr = (int)regions.size();
+    std::vector<double> lat0((size_t)nr, 1e300), lon0((size_t)nr, 1e300), amax((size_t)nr, 0.0), cell_lon((size_t)nr);
+    std::vector<int> preg((size_t)n_places);
+    for (int64_t p = 0; p < n_places; ++p) {
+        const int r = (int)(std::lower_bound(regions.begin(), regions.end(), (long long)place_region[p]) - regions.begin());
+        preg[p] = r;
+        lat0[r] = std::min(lat0[r], place_latitude[p]);
+        lon0[r] = std::min(lon0[r], place_longitude[p]);
+        amax[r] = std::max(amax[r], std::fabs(place_latitude[p]));
+    }
+    const double deg_per_m = 180.0 / (3.141592653589793 * 6371000.0);
+    const double cell_lat = accuracy_m * deg_per_m * 1.001;
+    for (int r = 0; r < nr; ++r) {
+        // a visit can be `accuracy` metres north / south of the region's outermost place
+        const double a = std::min(89.9, amax[r] + 2 * cell_lat) * 3.141592653589793 / 180.0;
+        cell_lon[r] = cell_lat / std::max(1e-3, std::cos(a));
+        lat0[r] -= cell_lat;                              // one cell of margin: visit cells are never negative by much
+        lon0[r] -= cell_lon[r];
+    }
+    std::vector<unsigned long long> pkey((size_t)n_places);
+    std::vector<int> order((size_t)n_places);
+    bool grid_ok = true;
+    for (int64_t p = 0; p < n_places; ++p) {
+        const int r = preg[p];
+        const long long iy = (long long)std::floor((place_latitude[p] - lat0[r]) / cell_lat);
+        const long long ix = (long long)std::floor((place_longitude[p] - lon0[r]) / cell_lon[r]);
+        if (iy < 0 || ix < 0 || iy >= (1 << 21) || ix >= (1 << 21) || nr >= (1 << 21)) grid_ok = false;
+        pkey[p] = ((unsigned long long)r << 42) | ((unsigned long long)iy << 21) | (unsigned long long)ix;
+        order[p] = (int)p;
+    }
+    if (!grid_ok) {
+        vrec_set_error("vrec_build_place_visits: a region spans more than 2^21 grid cells");
+        return VREC_EINVAL;
+    }
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        return pkey[a] < pkey[b] || (pkey[a] == pkey[b] && place_id[a] < place_id[b]);
+    });
+    std::vector<unsigned long long> cell_key;
+    std::vector<int> cell_start;
+    std::vector<long long> s_id((size_t)n_places), s_cat((size_t)n_places);
+    std::vector<double> s_lat((size_t)n_places), s_lon((size_t)n_places);
+    for (int64_t k = 0; k < n_places; ++k) {
+        const int p = order[k];
+        if (k == 0 || pkey[p] != cell_key.back()) {
+            cell_key.push_back(pkey[p]);
+            cell_start.push_back((int)k);
+        }
+        s_id[k] = place_id[p];
+        s_cat[k] = place_category[p];
+        s_lat[k] = place_latitude[p];
+        s_lon[k] = place_longitude[p];
+    }
+    cell_start.push_back((int)n_places);
+    long long ts_max = timestamp_ms[0];
+    for (int64_t i = 1; i < n_visits; ++i) ts_max = std::max<long long>(ts_max, timestamp_ms[i]);
+    const long long ts_from = ts_max - (long long)last_days_count * 86400000LL;     // PlaceVisits.scala:50-61 (UTC days)
+    // ---- device
+    PoolBuf<long long> d_person, d_ts, d_region, d_rid, d_pid, d_pcat, d_incl;
+    PoolBuf<double> d_lat, d_lon, d_lat0, d_lon0, d_clon, d_plat, d_plon;
+    PoolBuf<unsigned long long> d_ckey;
+    PoolBuf<int> d_cstart, d_cnt;
+    PoolBuf<unsigned char> tmp;
+    const long long n = n_visits;
+    VREC_TRY(d_person.upload((const long long *)person_id, (size_t)n, st));
+    VREC_TRY(d_ts.upload((const long long *)timestamp_ms, (size_t)n, st));
+    VREC_TRY(d_region.upload((const long long *)region_id, (size_t)n, st));
+    VREC_TRY(d_lat.upload(latitude, (size_t)n, st));
+    VREC_TRY(d_lon.upload(longitude, (size_t)n, st));
+    VREC_TRY(d_rid.upload(regions.data(), regions.size(), st));
+    VREC_TRY(d_lat0.upload(lat0.data(), lat0.size(), st));
+    VREC_TRY(d_lon0.upload(lon0.data(), lon0.size(), st));
+    VREC_TRY(d_clon.upload(cell_lon.data(), cell_lon.size(), st));
+    VREC_TRY(d_ckey.upload(cell_key.data(), cell_key.size(), st));
+    VREC_TRY(d_cstart.upload(cell_start.data(), cell_start.size(), st));
+    VREC_TRY(d_pid.upload(s_id.data(), s_id.size(), st));
+    VREC_TRY(d_pcat.upload(s_cat.data(), s_cat.size(), st));
+    VREC_TRY(d_plat.upload(s_lat.data(), s_lat.size(), st));
+    VREC_TRY(d_plon.upload(s_lon.data(), s_lon.size(), st));
+    VREC_TRY(d_cnt.alloc((size_t)n));
+    VREC_TRY(d_incl.alloc((size_t)n));
+    PvGrid g;
+    g.n_regions = nr;
+    g.n_cells = (int)cell_key.size();
+    g.region_ids = d_rid.p;
+    g.lat0 = d_lat0.p;
+    g.lon0 = d_lon0.p;
+    g.cell_lon = d_clon.p;
+    g.cell_lat = cell_lat;
+    g.cell_key = d_ckey.p;
+    g.cell_start = d_cstart.p;
+    g.p_id = d_pid.p;
+    g.p_cat = d_pcat.p;
+    g.p_lat = d_plat.p;
+    g.p_lon = d_plon.p;
+    const int grid = (int)((n + 127) / 128);
+    pv_match_kernel<false><<<grid, 128, 0, st>>>(n, d_person.p, d_lat.p, d_lon.p, d_ts.p, d_region.p, ts_from, accuracy_m, g,
+                                                d_cnt.p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    VREC_LAUNCHED(ctx);
+    VREC_TRY(scan_inclusive_ll(ctx, d_cnt.p, d_incl.p, n, tmp));
+    long long total = 0;
+    VREC_CUDA(cudaMemcpyAsync(&total, d_incl.p + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, st));
+    VREC_CUDA(cudaStreamSynchronize(st));
+    *out_n = total;
+    if (total > capacity || !out_person || !out_timestamp_ms || !out_place || !out_region || !out_category) {
+        vrec_set_error("vrec_build_place_visits: %lld place visits, capacity %lld", total, (long long)capacity);
+        return VREC_ENOMEM;
+    }
+    if (total == 0) return VREC_OK;
+    PoolBuf<long long> o_person, o_ts, o_place, o_region, o_cat;
+    VREC_TRY(o_person.alloc((size_t)total));
+    VREC_TRY(o_ts.alloc((size_t)total));
+    VREC_TRY(o_place.alloc((size_t)total));
+    VREC_TRY(o_region.alloc((size_t)total));
+    VREC_TRY(o_cat.alloc((size_t)total));
+    pv_match_kernel<true><<<grid, 128, 0, st>>>(n, d_person.p, d_lat.p, d_lon.p, d_ts.p, d_region.p, ts_from, accuracy_m, g,
+                                               d_cnt.p, d_incl.p, o_person.p, o_ts.p, o_place.p, o_region.p, o_cat.p);
+    VREC_LAUNCHED(ctx);
+    VREC_CUDA(cudaMemcpyAsync(out_person, o_person.p, sizeof(long long) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    VREC_CUDA(cudaMemcpyAsync(out_timestamp_ms, o_ts.p, sizeof(long long) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    VREC_CUDA(cudaMemcpyAsync(out_place, o_place.p, sizeof(long long) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    VREC_CUDA(cudaMemcpyAsync(out_region, o_region.p, sizeof(long long) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    VREC_CUDA(cudaMemcpyAsync(out_category, o_cat.p, sizeof(long long) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    VREC_CUDA(cudaStreamSynchronize(st));
+    return VREC_OK;
+}

@@ -52,6 +52,9 @@ SIGNATURES = {
     "vrec_knn_last_dense_ms": (C.c_int, [vp, C.POINTER(C.c_double)]),
     "vrec_build_rating_vectors": (C.c_int, [vp, C.c_int64, i64p, i64p, i64p, C.c_int32, C.POINTER(C.c_int64),
                                             C.POINTER(C.c_int64), i64p, i64p, i32p, f64p, C.POINTER(C.c_int32)]),
+    "vrec_build_place_visits": (C.c_int, [vp, C.c_int64, i64p, f64p, f64p, i64p, i64p, C.c_int64, i64p, f64p, f64p, i64p,
+                                          i64p, C.c_int32, C.c_double, C.c_int64, C.POINTER(C.c_int64), i64p, i64p, i64p,
+                                          i64p, i64p]),
     "vrec_build_edge_family": (C.c_int, [vp, C.c_int64, i64p, i64p, i64p, C.c_int32, C.c_double, C.c_int64,
                                          C.POINTER(C.c_int64), i64p, i64p, f64p]),
     "vrec_build_stochastic_graph": (C.c_int, [vp, C.c_int64, i64p, i64p, i64p, i64p, C.c_double, C.c_double, C.c_int64,

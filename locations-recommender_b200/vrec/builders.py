@@ -12,7 +12,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib as L
-from .engine import Context, _check, _i64, _ptr, default_context
+from .engine import Context, _check, _f64, _i64, _ptr, default_context
 from .synth import KnnInputs
 
 
@@ -82,3 +82,27 @@ def stochastic_graph_builder(person_id, place_id, category_id, timestamp_ms, bet
     _check(ctx.lib.vrec_build_stochastic_graph(*args, cap, C.byref(ne), _ptr(os_, L.i64p), _ptr(ot, L.i64p),
                                                _ptr(ow, L.f64p)))
     return os_[:ne.value], ot[:ne.value], ow[:ne.value]
+
+
+def place_visits_builder(person_id, latitude, longitude, timestamp_ms, region_id, place_id, place_latitude,
+                         place_longitude, place_category, place_region, last_days_count: int = 7,
+                         accuracy_m: float = 100.0, ctx: Optional[Context] = None):
+    """Location visits x places -> place visits (person_id, timestamp_ms, place_id, region_id, category_id)
+    (PlaceVisits.calcPlaceVisits, PlaceVisits.scala:11-48; --last-days-count 7, 100 m)."""
+    ctx = ctx or default_context()
+    pe, ts, rg = _i64(person_id), _i64(timestamp_ms), _i64(region_id)
+    la, lo = _f64(latitude), _f64(longitude)
+    pi, pc, pr = _i64(place_id), _i64(place_category), _i64(place_region)
+    pla, plo = _f64(place_latitude), _f64(place_longitude)
+    n, m = len(pe), len(pi)
+    cnt = C.c_int64(0)
+    args = (ctx._h, n, _ptr(pe, L.i64p), _ptr(la, L.f64p), _ptr(lo, L.f64p), _ptr(ts, L.i64p), _ptr(rg, L.i64p), m,
+            _ptr(pi, L.i64p), _ptr(pla, L.f64p), _ptr(plo, L.f64p), _ptr(pc, L.i64p), _ptr(pr, L.i64p),
+            int(last_days_count), float(accuracy_m))
+    rc = ctx.lib.vrec_build_place_visits(*args, 0, C.byref(cnt), None, None, None, None, None)
+    if rc not in (L.OK, L.ENOMEM):
+        _check(rc)
+    cap = max(1, cnt.value)
+    out = [np.zeros(cap, dtype=np.int64) for _ in range(5)]
+    _check(ctx.lib.vrec_build_place_visits(*args, cap, C.byref(cnt), *[_ptr(o, L.i64p) for o in out]))
+    return tuple(o[:cnt.value] for o in out)

@@ -273,3 +273,25 @@ def build_stochastic_graph(person_id, place_id, category_id, timestamp_ms, beta_
     rc = lib().vro_build_stochastic_graph(*args, C.c_int64(cap), C.byref(ne), _p(os_, C.c_int64), _p(ot, C.c_int64),
                                           _p(ow, C.c_double))
     return rc, os_[:ne.value], ot[:ne.value], ow[:ne.value]
+
+
+def build_place_visits(person_id, latitude, longitude, timestamp_ms, region_id, place_id, place_latitude,
+                       place_longitude, place_category, place_region, last_days_count=7, accuracy_m=100.0):
+    """-> rc, (person, timestamp_ms, place, region, category), margins, closest_miss"""
+    pe, ts, rg = _i64(person_id), _i64(timestamp_ms), _i64(region_id)
+    la, lo = _f64(latitude), _f64(longitude)
+    pi, pc, pr = _i64(place_id), _i64(place_category), _i64(place_region)
+    pla, plo = _f64(place_latitude), _f64(place_longitude)
+    n, m = len(pe), len(pi)
+    cnt, miss = C.c_int64(0), C.c_double(0)
+    fn = lib().vro_build_place_visits
+    args = (C.c_int64(n), _p(pe, C.c_int64), _p(la, C.c_double), _p(lo, C.c_double), _p(ts, C.c_int64), _p(rg, C.c_int64),
+            C.c_int64(m), _p(pi, C.c_int64), _p(pla, C.c_double), _p(plo, C.c_double), _p(pc, C.c_int64), _p(pr, C.c_int64),
+            C.c_int32(int(last_days_count)), C.c_double(accuracy_m))
+    fn(*args, C.c_int64(0), C.byref(cnt), None, None, None, None, None, None, C.byref(miss))
+    cap = max(1, cnt.value)
+    out = [np.zeros(cap, dtype=np.int64) for _ in range(5)]
+    margin = np.zeros(cap, dtype=np.float64)
+    rc = fn(*args, C.c_int64(cap), C.byref(cnt), *[_p(o, C.c_int64) for o in out], _p(margin, C.c_double), C.byref(miss))
+    k = cnt.value
+    return rc, tuple(o[:k] for o in out), margin[:k], miss.value

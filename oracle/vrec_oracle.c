@@ -922,3 +922,73 @@ int vro_build_stochastic_graph(int64_t n, const int64_t *person_id, const int64_
     *out_n = at;
     return rc;
 }
+
+/* ------------------------------------------------------------------ */
+/* PlaceVisits.calcPlaceVisits                  */
+/* ------------------------------------------------------------------ */
+
+/* Location.distanceMeters, Location.scala:30-43 (haversine; libm here, FastMath in the reference) */
+double vro_distance_meters(double lat1d, double lon1d, double lat2d, double lon2d)
+{
+    const double k = 0.017453292519943295;
+    double lat1 = lat1d * k, lat2 = lat2d * k, lon1 = lon1d * k, lon2 = lon2d * k;
+    double s1 = sin((lat2 - lat1) / 2), s2 = sin((lon2 - lon1) / 2);
+    double hav = s1 * s1 + cos(lat1) * cos(lat2) * (s2 * s2);
+    return 6371000.0 * 2 * asin(sqrt(hav));
+}
+
+/* PlaceVisits.calcPlaceVisits (PlaceVisits.scala:11-48): the visits with timestamp >= max(timestamp) -
+ * last_days_count days (:50-61, whole UTC days here) joined with the places of the same region (:33), kept where
+ * the distance is <= accuracy_m (:13-22).  This is the reference's "almost cross-join", row by row.  Rows in
+ * visit order, a visit's places in ascending place id; out_margin[k] = |distance - accuracy| of row k and
+ * *out_closest_miss = the smallest such margin among the rejected pairs (so a caller comparing another
+ * implementation can tell boundary cases apart).                                                               */
+int vro_build_place_visits(int64_t n_visits, const int64_t *person_id, const double *latitude, const double *longitude,
+                           const int64_t *timestamp_ms, const int64_t *region_id, int64_t n_places,
+                           const int64_t *place_id, const double *place_latitude, const double *place_longitude,
+                           const int64_t *place_category, const int64_t *place_region, int32_t last_days_count,
+                           double accuracy_m, int64_t capacity, int64_t *out_n, int64_t *out_person,
+                           int64_t *out_timestamp_ms, int64_t *out_place, int64_t *out_region, int64_t *out_category,
+                           double *out_margin, double *out_closest_miss)
+{
+    if (n_visits < 0 || n_places < 0 || !(accuracy_m > 0) || last_days_count < 0) return VRO_EINVAL;
+    *out_n = 0;
+    if (out_closest_miss) *out_closest_miss = 1e300;
+    if (n_visits == 0 || n_places == 0) return VRO_OK;
+    int64_t ts_max = timestamp_ms[0];
+    for (int64_t i = 1; i < n_visits; ++i) if (timestamp_ms[i] > ts_max) ts_max = timestamp_ms[i];
+    const int64_t ts_from = ts_max - (int64_t)last_days_count * 86400000LL;
+    /* places ordered by id so that a visit's rows come out in ascending place id */
+    int64_t *ord = (int64_t *)malloc(sizeof(int64_t) * (size_t)n_places);
+    if (!ord) return VRO_ENOMEM;
+    for (int64_t p = 0; p < n_places; ++p) ord[p] = p;
+    for (int64_t p = 1; p < n_places; ++p) {               /* insertion sort is enough for the oracle's sizes */
+        int64_t v = ord[p], q = p;
+        while (q > 0 && place_id[ord[q - 1]] > place_id[v]) { ord[q] = ord[q - 1]; q--; }
+        ord[q] = v;
+    }
+    int64_t n = 0;
+    double miss = 1e300;
+    for (int64_t i = 0; i < n_visits; ++i) {
+        if (timestamp_ms[i] < ts_from) continue;
+        for (int64_t k = 0; k < n_places; ++k) {
+            int64_t p = ord[k];
+            if (place_region[p] != region_id[i]) continue;
+            double d = vro_distance_meters(latitude[i], longitude[i], place_latitude[p], place_longitude[p]);
+            if (d <= accuracy_m) {
+                if (n < capacity && out_person) {
+                    out_person[n] = person_id[i]; out_timestamp_ms[n] = timestamp_ms[i]; out_place[n] = place_id[p];
+                    out_region[n] = region_id[i]; out_category[n] = place_category[p];
+                    if (out_margin) out_margin[n] = accuracy_m - d;
+                }
+                n++;
+            } else if (d - accuracy_m < miss) {
+                miss = d - accuracy_m;
+            }
+        }
+    }
+    free(ord);
+    *out_n = n;
+    if (out_closest_miss) *out_closest_miss = miss;
+    return n > capacity ? VRO_ENOMEM : VRO_OK;
+}

@@ -461,3 +461,37 @@ def test_stochastic_graph_builder_bit_exact(vrec, ctx, synth, oracle):
     rec = vrec.StochasticRecommender(g, 0.01, 20)
     _check_sg_batch(rec, og, np.unique(pe)[:12], places.id, 10, 0.01, 20)
     assert builders.stochastic_graph_builder([], [], [], [], ctx=ctx)[0].size == 0
+
+
+# ------------------------------------------------------------------ place visits builder
+def test_place_visits_builder_matches_oracle(vrec, ctx, oracle):
+    from tests.test_oracle_selfcheck import _location_visits
+    from vrec import builders
+    rng = np.random.default_rng(8)
+    (person, lat, lon, ts, reg), (pid, plat, plon, pcat, preg) = _location_visits(rng, n_regions=3, places_per_region=900,
+                                                                                  n_visits=20000)
+    reg = reg.copy()
+    reg[:5] = 77                                                        # a region without places: no rows
+    for days, acc in ((7, 100.0), (30, 250.0), (0, 100.0)):
+        rc, want, margin, miss = oracle.build_place_visits(person, lat, lon, ts, reg, pid, plat, plon, pcat, preg, days, acc)
+        got = builders.place_visits_builder(person, lat, lon, ts, reg, pid, plat, plon, pcat, preg, days, acc, ctx=ctx)
+        assert rc == 0
+        # floating point: a pair within 1e-6 m of the radius may legitimately fall on either side (the reference
+        # itself uses FastMath, the oracle libm, the engine CUDA's libm); everything else must agree exactly,
+        # in the same order (visit order, ascending place id)
+        tol = 1e-6
+        if margin.size and margin.min() > tol and miss > tol:
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b)
+        else:
+            gs = set(zip(*[x.tolist() for x in got]))
+            ws = set(zip(*[x.tolist() for x in want]))
+            safe = {r for r, m in zip(zip(*[x.tolist() for x in want]), margin.tolist()) if m > tol}
+            assert safe <= gs and len(gs - ws) <= np.sum(margin <= tol) + 8
+    # straight into the two builders behind it
+    got = builders.place_visits_builder(person, lat, lon, ts, reg, pid, plat, plon, pcat, preg, 30, 100.0, ctx=ctx)
+    inp = builders.rating_vectors_builder(got[0], got[2], got[4], ctx=ctx)
+    assert len(inp.person_id) > 0 and inp.place_rowptr[-1] == len(inp.place_col)
+    s_, t_, w_ = builders.stochastic_graph_builder(got[0], got[2], got[4], got[1], ctx=ctx)
+    assert len(s_) > 0 and np.all(w_ > 0)
+    assert builders.place_visits_builder([], [], [], [], [], pid, plat, plon, pcat, preg, ctx=ctx)[0].size == 0

@@ -132,3 +132,46 @@ def test_stochastic_graph_builder_oracle_vs_numpy_restatement(oracle):
     rc, s, t, w = oracle.build_stochastic_graph([1, 1, 1], [10, 11, 12], [0, 0, 1], [0, 3 * day, 11 * day], 0.5, 0.5)
     pairs = [(a, b) for a, b in zip(s.tolist(), t.tolist()) if a >= 10 and b >= 10 and a < 100]
     assert sorted(pairs) == [(10, 11), (11, 10)]
+
+
+def _location_visits(rng, n_regions=2, places_per_region=400, n_visits=3000):
+    """Places on a jittered grid (~150 m pitch) per region, visits scattered around random places of their region."""
+    centres = [(48.85, 2.35), (59.93, 30.33), (-33.86, 151.2)][:n_regions]
+    pid, plat, plon, pcat, preg = [], [], [], [], []
+    for r, (la, lo) in enumerate(centres):
+        side = int(np.sqrt(places_per_region))
+        gy, gx = np.meshgrid(np.arange(side), np.arange(side), indexing="ij")
+        plat.append(la + gy.ravel() * 0.00135 + rng.normal(0, 0.0002, side * side))
+        plon.append(lo + gx.ravel() * 0.0021 + rng.normal(0, 0.0003, side * side))
+        pid.append(40 + r * 100_000 + np.arange(side * side))
+        pcat.append(rng.integers(0, 20, side * side))
+        preg.append(np.full(side * side, r))
+    pid, plat, plon, pcat, preg = map(np.concatenate, (pid, plat, plon, pcat, preg))
+    pick = rng.integers(0, len(pid), n_visits)
+    lat = plat[pick] + rng.normal(0, 0.0007, n_visits)
+    lon = plon[pick] + rng.normal(0, 0.001, n_visits)
+    person = 1_000_000 + rng.integers(0, 300, n_visits)
+    ts = 1_546_300_800_000 + rng.integers(0, 30 * 24 * 3600 * 1000, n_visits)
+    return (person, lat, lon, ts, preg[pick]), (pid, plat, plon, pcat, preg)
+
+
+def test_place_visits_oracle(oracle):
+    """vro_build_place_visits: the reference's cross-join row by row -- checked against numpy on the same formula."""
+    rng = np.random.default_rng(6)
+    (person, lat, lon, ts, reg), (pid, plat, plon, pcat, preg) = _location_visits(rng)
+    rc, (op, ot, opl, org, oc), margin, miss = oracle.build_place_visits(person, lat, lon, ts, reg, pid, plat, plon, pcat, preg,
+                                                                        7, 100.0)
+    assert rc == 0 and len(op) > 100 and margin.min() >= 0 and miss > 0
+    k = np.pi / 180
+    ts_from = ts.max() - 7 * 86400000
+    want = []
+    for i in np.nonzero(ts >= ts_from)[0]:
+        same = np.nonzero(preg == reg[i])[0]
+        s1 = np.sin((plat[same] * k - lat[i] * k) / 2)
+        s2 = np.sin((plon[same] * k - lon[i] * k) / 2)
+        d = 6371000.0 * 2 * np.arcsin(np.sqrt(s1 * s1 + np.cos(lat[i] * k) * np.cos(plat[same] * k) * (s2 * s2)))
+        for p in same[d <= 100.0]:
+            want.append((int(person[i]), int(ts[i]), int(pid[p]), int(reg[i]), int(pcat[p])))
+    got = list(zip(op.tolist(), ot.tolist(), opl.tolist(), org.tolist(), oc.tolist()))
+    assert sorted(got) == sorted(want)
+    assert oracle.lib().vro_distance_meters  # exported
