@@ -622,7 +622,41 @@ def run_builder(args, vrec, ctx, rank):
              "value": len(gpe) / gdt, "unit": "visits/s", "ms_per_step": gdt * 1e3,
              "config": {"workload": f"{len(gpe)} visit rows of {ng_persons} persons over 14 days -> {len(gs)} edges"},
              "cpu_baseline": gcpu}
-    return {"graph": graph,
+    # location visits x places -> place visits (haversine <= 100 m), spatial grid vs cross-join
+    nlv, side = 2_000_000, 100                                   # 3 regions x 10 000 places (default place count)
+    centres = [(48.85, 2.35), (59.93, 30.33), (-33.86, 151.2)]
+    gy, gx = np.meshgrid(np.arange(side), np.arange(side), indexing="ij")
+    plat = np.concatenate([la + gy.ravel() * 0.00135 for la, lo in centres])
+    plon = np.concatenate([lo + gx.ravel() * 0.0021 for la, lo in centres])
+    pid = 40 + np.arange(len(plat), dtype=np.int64)
+    pcat = rng.integers(0, 20, len(plat))
+    preg = np.repeat(np.arange(3), side * side)
+    pick = rng.integers(0, len(pid), nlv)
+    vlat = plat[pick] + rng.normal(0, 0.0007, nlv)
+    vlon = plon[pick] + rng.normal(0, 0.001, nlv)
+    vper = 1_000_000 + rng.integers(0, 300_000, nlv)
+    vts = 1_546_300_800_000 + rng.integers(0, 7 * 24 * 3600 * 1000, nlv)
+    vreg = preg[pick]
+    builders.place_visits_builder(vper[:10000], vlat[:10000], vlon[:10000], vts[:10000], vreg[:10000], pid, plat, plon, pcat,
+                                  preg, 7, 100.0, ctx=ctx)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        pv = builders.place_visits_builder(vper, vlat, vlon, vts, vreg, pid, plat, plon, pcat, preg, 7, 100.0, ctx=ctx)
+    pdt = (time.perf_counter() - t0) / reps
+    pcpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        ns = 3000
+        t1 = time.perf_counter()
+        oracle.build_place_visits(vper[:ns], vlat[:ns], vlon[:ns], vts[:ns], vreg[:ns], pid, plat, plon, pcat, preg, 7, 100.0)
+        pcdt = (time.perf_counter() - t1) / 2                    # the wrapper runs the join twice (size, then fill)
+        pcpu = {"value": ns / pcdt, "unit": "location visits/s", "cores": 1, "kind": "port",
+                "sample": f"first {ns} location visits x {len(pid)} places, {pcdt:.2f}s, the reference's cross-join "
+                          f"row by row (oracle/vrec_oracle.c, one thread)"}
+    place_visits = {"metric": "place visits builder, location visits/s (haversine <= 100 m against the region's places)",
+                    "value": nlv / pdt, "unit": "location visits/s", "ms_per_step": pdt * 1e3,
+                    "config": {"workload": f"{nlv} location visits x {len(pid)} places in 3 regions -> {len(pv[0])} place visits"},
+                    "cpu_baseline": pcpu}
+    return {"graph": graph, "place_visits": place_visits,
             "metric": "rating vectors builder, visit rows/s (count per (person, place), rank <= 100, CSR)",
             "value": len(pe) / dt, "unit": "visits/s", "ms_per_step": dt * 1e3,
             "config": {"workload": f"{len(pe)} visit rows of {args.knn_persons} persons x {args.knn_places} places "
