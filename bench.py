@@ -402,6 +402,21 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu_baseline:
         cpu_knn_base, _ = cpu_knn(args, inp, places, args.cpu_knn_targets)
         log(f"[bench] knn cpu baseline: {cpu_knn_base['value']:.1f} persons/s on {cpu_knn_base['cores']} threads")
+    # one person at a time (the launchers' REPL, BASELINE configs 1-2): latency of a single query through the ABI
+    single = None
+    if rank == 0:
+        def one(rec_, tgt):
+            t1 = time.perf_counter()
+            rec_.recommend([int(tgt)], flt, m)
+            return (time.perf_counter() - t1) * 1e3
+        rec_k = vrec.KnnRecommender(rs, 0.5, 0.5, args.k_nearest)
+        rec_all = vrec.KnnRecommender(rs, 0.5, 0.5, 2_000_000)        # bin/knn_recommender.sh:32-35 default K
+        pers = inp.person_id
+        one(rec_k, pers[0]); one(rec_all, pers[0])
+        single = {"knn_ms_k50": statistics.median(one(rec_k, pers[7 + 13 * i]) for i in range(9)),
+                  "knn_ms_k2000000": statistics.median(one(rec_all, pers[11 + 17 * i]) for i in range(9)),
+                  "note": "median wall time of vrec_knn_query for ONE person (ids in, top-10 out), region-set resident"}
+        log(f"[bench] single query: K=50 {single['knn_ms_k50']:.2f} ms, K=2000000 {single['knn_ms_k2000000']:.2f} ms")
     rs.close()
     del d_targets
 
@@ -428,6 +443,7 @@ def run_ours(args):
             "cpu_baseline": cpu_knn_base,
             "clocks": clocks_knn,
             "sg": sg,
+            "single_query": single,
             "builder": builder,
         }
         emit(line)
@@ -565,6 +581,17 @@ def run_sg_batch(args, vrec, ctx, world, rank, barrier, max_over_ranks):
         "note": "value == e2e: every step goes through vrec_sg_query with host buffers; kernel_ms_per_step is "
                 "sg_batch_kernel alone (host clock around the launch)",
     }
+    # one person at a time (BASELINE config 2): the per-query kernels, all iterations queued at once
+    lat, its1 = [], 0
+    for i in range(10):
+        t1 = time.perf_counter()
+        oi, op, cnt, its, conv, st = rec.recommend([int(persons[100 + 31 * i])], places, 10)
+        lat.append((time.perf_counter() - t1) * 1e3)
+        its1 = int(its[0])
+    out["single_query"] = {"ms": statistics.median(lat[1:]), "iterations": its1,
+                           "us_per_spmv": 1e3 * statistics.median(lat[1:]) / (its1 + 1),
+                           "note": "median wall time of vrec_sg_query for ONE person on the same graph "
+                                   "(iterations + 1 SpMV launches + ranked top-10), graph resident"}
     g.close()
     return out
 
