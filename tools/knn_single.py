@@ -15,6 +15,8 @@ v, places = synth.g2_place_visits(1_000_000, 100_000)
 inp = synth.build_rating_vectors(v)
 ctx = vrec.Context(0)
 rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
+if len(sys.argv) > 2:
+    rs.set_option("knn_kernel", int(sys.argv[2]))
 rec = vrec.KnnRecommender(rs, 0.5, 0.5, K)
 flt = np.ascontiguousarray(places.id)
 for i in range(6):
