@@ -37,7 +37,7 @@
 
 namespace {
 
-constexpr int BT = 512;             // threads per CTA
+constexpr int BT = 768;             // threads per CTA
 constexpr int BW = BT / 32;
 constexpr int TOPN_FAST = 16;       // max_recs up to this use the warp-local selection
 constexpr size_t SMEM_LIMIT = 227 * 1024 - 12 * 1024;   // dynamic part; ~9 KB of statics + reserve
