@@ -88,6 +88,24 @@ def test_sg_errors_and_corner_cases(vrec, ctx):
     assert cnt[0] == 0
 
 
+def test_sg_degenerate_graphs(vrec, ctx, oracle):
+    # no edges at all, one self-loop, one edge, duplicate edges and a dangling vertex
+    g = vrec.StochasticGraph([], [], [], ctx=ctx)
+    assert g.N == 0
+    oi, op, cnt, its, conv, st = vrec.StochasticRecommender(g, 0.01, 20).recommend([1, 2], None, 5)
+    assert st.tolist() == [-2, -2] and cnt.tolist() == [0, 0]
+    for s, t, w in (([7], [7], [1.0]), ([1], [2], [1.0]), ([1, 1, 1, 2], [2, 2, 3, 3], [0.25, 0.25, 0.5, 1.0])):
+        g = vrec.StochasticGraph(s, t, w, ctx=ctx)
+        og = oracle.SgGraph(s, t, w)
+        for v in sorted(set(s) | set(t)):
+            for eps, mi in ((0.0, 6), (0.01, 20), (0.5, 0)):
+                rec = vrec.StochasticRecommender(g, eps, mi)
+                x = rec.stationary(v)
+                rc, ox, oit, oconv, _ = og.run(v, eps, mi)
+                assert rc == 0 and np.array_equal(x, ox) and (rec.last_iterations, rec.last_converged) == (oit, oconv)
+                _check_sg_batch(rec, og, [v], None, 3, eps, mi)
+
+
 @pytest.mark.parametrize("n,deg,hub,seed", [(50, 3, 0.0, 1), (2000, 6, 0.0, 2), (5000, 5, 0.5, 3),
                                             (30000, 40, 0.3, 4)])
 def test_sg_random_graphs_bit_exact(vrec, ctx, synth, oracle, n, deg, hub, seed):
@@ -311,6 +329,28 @@ def test_knn_tail_places_postings_pass(vrec, ctx, synth, oracle, k):
     rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
     targets = np.concatenate([inp.person_id[:300], inp.person_id[:3], [999999]])
     _check_knn(vrec, oracle, rs, inp, 0.7, 0.3, k, targets, np.arange(0, 900, 3), 10)
+    rs.close()
+
+
+def test_knn_fallback_kernels_for_unusual_data(vrec, ctx, synth, oracle):
+    # data outside the tensor-core path's preconditions must silently take the exact kernels:
+    # (a) negative vector values (the dense-row / signature shortcuts assume non-negative data),
+    # (b) more categories than filter dimensions, (c) long rows (hundreds of places per person), (d) K > 56
+    import dataclasses
+    inp = synth.random_knn_inputs(1500, 400, 9, seed=31)
+    neg = dataclasses.replace(inp, place_val=np.where(np.arange(len(inp.place_val)) % 7 == 0, -inp.place_val,
+                                                      inp.place_val))
+    rs = vrec.KnnRegionSet(*neg.load_args(), ctx=ctx)
+    _check_knn(vrec, oracle, rs, neg, 0.5, 0.5, 20, neg.person_id[:30], np.arange(0, 400, 2), 10)
+    rs.close()
+    wide = synth.random_knn_inputs(1200, 300, 90, seed=32)
+    rs = vrec.KnnRegionSet(*wide.load_args(), ctx=ctx)
+    _check_knn(vrec, oracle, rs, wide, 0.4, 0.6, 20, wide.person_id[:30], None, 10)
+    rs.close()
+    long_rows = synth.random_knn_inputs(600, 2500, 9, seed=33, max_places=300)
+    rs = vrec.KnnRegionSet(*long_rows.load_args(), ctx=ctx)
+    _check_knn(vrec, oracle, rs, long_rows, 0.5, 0.5, 20, long_rows.person_id[:20], np.arange(0, 2500, 5), 10)
+    _check_knn(vrec, oracle, rs, long_rows, 0.5, 0.5, 200, long_rows.person_id[:20], np.arange(0, 2500, 5), 10)
     rs.close()
 
 
