@@ -288,6 +288,7 @@ struct TileAux {
     const unsigned long long *meta;
     const double *rec;
     unsigned tail_bit;          // which flag applies to this kernel's head set
+    bool vals_f32 = false;      // record values stored as floats (see the record layout below)
     // knn_tc_ws_kernel: the targets' category vectors as dense rows [n_targets][cat_dim] (global scratch)
     double *tdense = nullptr;
     int cat_dim = 0;
@@ -297,18 +298,30 @@ constexpr unsigned REC_TAIL_TC = 0x80000000u, REC_TAIL_TILE = 0x40000000u, REC_C
 // Record layout in 8-byte words, every section 16-byte aligned so that it can be fetched with 128-bit loads:
 //   [0..2)  |place|, |cat|
 //   place cols: ints, padded to a multiple of 4   -> rec_cols_words(np) words
-//   place vals: doubles, padded to a multiple of 2 -> rec_vals_words(np) words
+//   place vals: doubles, padded to a multiple of 2 -> rec_vals_words(np) words; or, when every value of the
+//               region-set is exactly representable in fp32 (visit counts always are), floats padded to a
+//               multiple of 4 (TileAux::vals_f32): a third fewer bytes per record on the HBM-bound paths
 //   cat cols, cat vals: same
 __host__ __device__ constexpr int rec_cols_words(int n) { return ((n + 3) / 4) * 2; }
-__host__ __device__ constexpr int rec_vals_words(int n) { return ((n + 1) / 2) * 2; }
+__host__ __device__ constexpr int rec_vals_words(int n, bool f32) { return f32 ? ((n + 3) / 4) * 2 : ((n + 1) / 2) * 2; }
 
 // 4 entries (cols + vals) of a record section with three 128-bit loads
-__device__ __forceinline__ void rec_load4(const int *cols, const double *vals, int k0, unsigned (&c)[4], double (&x)[4]) {
+__device__ __forceinline__ void rec_load4(const int *cols, const double *vals, int k0, unsigned (&c)[4], double (&x)[4],
+                                          bool f32) {
     const int4 ci = __ldg(reinterpret_cast<const int4 *>(cols + k0));
-    const double2 v01 = __ldg(reinterpret_cast<const double2 *>(vals + k0));
-    const double2 v23 = __ldg(reinterpret_cast<const double2 *>(vals + k0 + 2));
     c[0] = (unsigned)ci.x; c[1] = (unsigned)ci.y; c[2] = (unsigned)ci.z; c[3] = (unsigned)ci.w;
-    x[0] = v01.x; x[1] = v01.y; x[2] = v23.x; x[3] = v23.y;
+    if (f32) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(vals) + k0));
+        x[0] = (double)v.x; x[1] = (double)v.y; x[2] = (double)v.z; x[3] = (double)v.w;
+    } else {
+        const double2 v01 = __ldg(reinterpret_cast<const double2 *>(vals + k0));
+        const double2 v23 = __ldg(reinterpret_cast<const double2 *>(vals + k0 + 2));
+        x[0] = v01.x; x[1] = v01.y; x[2] = v23.x; x[3] = v23.y;
+    }
+}
+// one value of a record section
+__device__ __forceinline__ double rec_val(const double *vals, int i, bool f32) {
+    return f32 ? (double)__ldg(reinterpret_cast<const float *>(vals) + i) : __ldg(vals + i);
 }
 
 // Sparse dot of candidate row [s, s+n) with the target row [ts, ts+tn) of one table, in the exact
@@ -350,13 +363,13 @@ __device__ __forceinline__ double bulk_dot(const KnnVec &v, int s, int n, const 
 template <bool TRACK_TAIL>
 __device__ __forceinline__ double packed_dot(const int *__restrict__ pc, const double *__restrict__ pv, int n,
                                              const int *tcol, const double *tval, int tn, unsigned tail_bit,
-                                             int &min_tail) {
+                                             int &min_tail, bool F32) {
     double sum = 0.0;
     int ky = 0;
     for (int k0 = 0; k0 < n && ky < tn; k0 += 4) {
         unsigned c[4];
         double x[4];
-        rec_load4(pc, pv, k0, c, x);
+        rec_load4(pc, pv, k0, c, x, F32);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             if (k0 + e >= n) break;
@@ -380,6 +393,7 @@ __device__ int g_probe_on;
 __device__ __forceinline__ double exact_pair_packed(const TileAux &aux, long long i, const TargetRows &t, double pw,
                                                     double cw, int &min_tail) {
     min_tail = -1;
+    const bool F32 = aux.vals_f32;
     if (i == t.t) return 0.0;
     const bool pr = g_probe_on && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 32;
     long long c0 = clock64();
@@ -393,12 +407,12 @@ __device__ __forceinline__ double exact_pair_packed(const TileAux &aux, long lon
     const double plen = lens.x, clen = lens.y;
     const int *pc = reinterpret_cast<const int *>(r + 2);
     const double *pv = r + 2 + rec_cols_words(np);
-    const int *cc = reinterpret_cast<const int *>(pv + rec_vals_words(np));
-    const double *cvp = pv + rec_vals_words(np) + rec_cols_words(nc);
+    const int *cc = reinterpret_cast<const int *>(pv + rec_vals_words(np, F32));
+    const double *cvp = pv + rec_vals_words(np, F32) + rec_cols_words(nc);
     bool keep = false;
     double ps_sim = 0.0, cs_sim = 0.0;
     if (np > 0) {
-        double sum = packed_dot<true>(pc, pv, np, t.pcol, t.pval, t.pn, aux.tail_bit, min_tail);
+        double sum = packed_dot<true>(pc, pv, np, t.pcol, t.pval, t.pn, aux.tail_bit, min_tail, F32);
         double c = xdiv(sum, xmul(plen, t.plen));
         if (c > 0) {
             keep = true;
@@ -409,7 +423,7 @@ __device__ __forceinline__ double exact_pair_packed(const TileAux &aux, long lon
     long long c2 = clock64();
     if (nc > 0) {
         int dummy = 0;
-        double sum = packed_dot<false>(cc, cvp, nc, t.ccol, t.cval, t.cn, 0u, dummy);
+        double sum = packed_dot<false>(cc, cvp, nc, t.ccol, t.cval, t.cn, 0u, dummy, F32);
         double c = xdiv(sum, xmul(clen, t.clen));
         if (c > 0) {
             keep = true;
@@ -451,6 +465,7 @@ __device__ __forceinline__ unsigned sig_bit(int col) { return ((unsigned)col * 0
 __device__ __forceinline__ double exact_pair_staged(const TileAux &aux, long long i, const StagedTarget &t, double pw,
                                                     double cw, int &min_tail, double thr = 0.0) {
     min_tail = -1;
+    const bool F32 = aux.vals_f32;
     if (i == t.t) return 0.0;
     const unsigned long long m = __ldg(aux.meta + i);
     const int np = (int)((m >> 40) & 0xfffu), nc = (int)(m >> 52);
@@ -459,8 +474,8 @@ __device__ __forceinline__ double exact_pair_staged(const TileAux &aux, long lon
     const double plen = lens.x, clen = lens.y;
     const int *pc = reinterpret_cast<const int *>(r + 2);
     const double *pv = r + 2 + rec_cols_words(np);
-    const int *cc = reinterpret_cast<const int *>(pv + rec_vals_words(np));
-    const double *cvp = pv + rec_vals_words(np) + rec_cols_words(nc);
+    const int *cc = reinterpret_cast<const int *>(pv + rec_vals_words(np, F32));
+    const double *cvp = pv + rec_vals_words(np, F32) + rec_cols_words(nc);
     bool keep = false;
     double ps_sim = 0.0, cs_sim = 0.0;
     if (np > 0) {
@@ -468,7 +483,7 @@ __device__ __forceinline__ double exact_pair_staged(const TileAux &aux, long lon
         for (int k0 = 0; k0 < np; k0 += 4) {
             unsigned c[4];
             double x[4];
-            rec_load4(pc, pv, k0, c, x);
+            rec_load4(pc, pv, k0, c, x, F32);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 if (k0 + e < np) {
@@ -502,7 +517,7 @@ __device__ __forceinline__ double exact_pair_staged(const TileAux &aux, long lon
         for (int k0 = 0; k0 < nc; k0 += 4) {
             unsigned c[4];
             double x[4];
-            rec_load4(cc, cvp, k0, c, x);
+            rec_load4(cc, cvp, k0, c, x, F32);
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if (k0 + e < nc) sum = xadd(sum, xmul(x[e], t.cat_dense[c[e]]));
@@ -523,14 +538,14 @@ __device__ __forceinline__ double exact_pair_staged(const TileAux &aux, long lon
 template <bool TRACK_TAIL>
 __device__ __forceinline__ double records_dot(const int *__restrict__ cc, const double *__restrict__ cv, int nc,
                                               const int *__restrict__ tc_, const double *__restrict__ tv_, int nt,
-                                              unsigned tail_bit, int &min_tail) {
+                                              unsigned tail_bit, int &min_tail, bool F32) {
     unsigned tcol[16];
     double tval[16];
 #pragma unroll
     for (int f0 = 0; f0 < 16; f0 += 4) {
         unsigned c4[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
         double x4[4] = {0.0, 0.0, 0.0, 0.0};
-        if (f0 < nt) rec_load4(tc_, tv_, f0, c4, x4);
+        if (f0 < nt) rec_load4(tc_, tv_, f0, c4, x4, F32);
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
             tcol[f0 + f] = (f0 + f < nt) ? (c4[f] & REC_COL_MASK) : 0xffffffffu;
@@ -541,7 +556,7 @@ __device__ __forceinline__ double records_dot(const int *__restrict__ cc, const 
     for (int k0 = 0; k0 < nc; k0 += 4) {
         unsigned c[4];
         double x[4];
-        rec_load4(cc, cv, k0, c, x);
+        rec_load4(cc, cv, k0, c, x, F32);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             if (k0 + e < nc) {
@@ -571,6 +586,7 @@ __device__ __forceinline__ double records_dot(const int *__restrict__ cc, const 
 __device__ __forceinline__ bool exact_pair_records(const TileAux &aux, int cand, int tix, double pw, double cw,
                                                    int &min_tail, double &out) {
     min_tail = -1;
+    const bool F32 = aux.vals_f32;
     out = 0.0;
     if (cand == tix) return true;
     const bool pr = threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0;
@@ -583,7 +599,7 @@ __device__ __forceinline__ bool exact_pair_records(const TileAux &aux, int cand,
     {
         // the sections are read by dependent loads below: start all of the candidate's 128-byte lines
         // now, so that only the first of those loads pays the HBM latency
-        const int words = 2 + rec_cols_words(npc) + rec_vals_words(npc) + rec_cols_words(ncc) + rec_vals_words(ncc);
+        const int words = 2 + rec_cols_words(npc) + rec_vals_words(npc, F32) + rec_cols_words(ncc) + rec_vals_words(ncc, F32);
         const char *pb = reinterpret_cast<const char *>(rc);
         const int lines = min(8, (int)(((reinterpret_cast<unsigned long long>(pb) & 127ULL) + 8ULL * words + 127ULL) >> 7));
         for (int l = 1; l < lines; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + 128 * l));
@@ -595,16 +611,16 @@ __device__ __forceinline__ bool exact_pair_records(const TileAux &aux, int cand,
     long long z2 = clock64();
     const int *pcc = reinterpret_cast<const int *>(rc + 2);
     const double *pvc = rc + 2 + rec_cols_words(npc);
-    const int *ccc = reinterpret_cast<const int *>(pvc + rec_vals_words(npc));
-    const double *cvc = pvc + rec_vals_words(npc) + rec_cols_words(ncc);
+    const int *ccc = reinterpret_cast<const int *>(pvc + rec_vals_words(npc, F32));
+    const double *cvc = pvc + rec_vals_words(npc, F32) + rec_cols_words(ncc);
     const int *pct = reinterpret_cast<const int *>(rt + 2);
     const double *pvt = rt + 2 + rec_cols_words(npt);
-    const int *cct = reinterpret_cast<const int *>(pvt + rec_vals_words(npt));
-    const double *cvt = pvt + rec_vals_words(npt) + rec_cols_words(nct);
+    const int *cct = reinterpret_cast<const int *>(pvt + rec_vals_words(npt, F32));
+    const double *cvt = pvt + rec_vals_words(npt, F32) + rec_cols_words(nct);
     bool keep = false;
     double ps_sim = 0.0, cs_sim = 0.0;
     if (npc > 0) {
-        double sum = records_dot<true>(pcc, pvc, npc, pct, pvt, npt, aux.tail_bit, min_tail);
+        double sum = records_dot<true>(pcc, pvc, npc, pct, pvt, npt, aux.tail_bit, min_tail, F32);
         double c = xdiv(sum, xmul(lc.x, lt.x));
         if (c > 0) {
             keep = true;
@@ -613,7 +629,7 @@ __device__ __forceinline__ bool exact_pair_records(const TileAux &aux, int cand,
     }
     if (ncc > 0) {
         int dummy = 0;
-        double sum = records_dot<false>(ccc, cvc, ncc, cct, cvt, nct, 0u, dummy);
+        double sum = records_dot<false>(ccc, cvc, ncc, cct, cvt, nct, 0u, dummy, F32);
         double c = xdiv(sum, xmul(lc.y, lt.y));
         if (c > 0) {
             keep = true;
@@ -643,6 +659,7 @@ __device__ __forceinline__ double exact_pair_sig(const TileAux &aux, int cand, i
                                                  const double *__restrict__ tdense, const int *tcols_s, double pw,
                                                  double cw, int &min_tail) {
     min_tail = -1;
+    const bool F32 = aux.vals_f32;
     if (cand == tix) return 0.0;
     const bool pr = threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0;
     long long z0 = clock64();
@@ -652,7 +669,7 @@ __device__ __forceinline__ double exact_pair_sig(const TileAux &aux, int cand, i
     const double *r = aux.rec + (mc & 0xffffffffffULL), *rt = aux.rec + (mt & 0xffffffffffULL);
     {
         // the sections are read by dependent loads below: start all of the candidate's 128-byte lines now
-        const int words = 2 + rec_cols_words(np) + rec_vals_words(np) + rec_cols_words(nc) + rec_vals_words(nc);
+        const int words = 2 + rec_cols_words(np) + rec_vals_words(np, F32) + rec_cols_words(nc) + rec_vals_words(nc, F32);
         const char *pb = reinterpret_cast<const char *>(r);
         const int lines = min(8, (int)(((reinterpret_cast<unsigned long long>(pb) & 127ULL) + 8ULL * words + 127ULL) >> 7));
         for (int l = 1; l < lines; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + 128 * l));
@@ -664,8 +681,8 @@ __device__ __forceinline__ double exact_pair_sig(const TileAux &aux, int cand, i
     const long long zh = z2;
     const int *pc = reinterpret_cast<const int *>(r + 2);
     const double *pv = r + 2 + rec_cols_words(np);
-    const int *cc = reinterpret_cast<const int *>(pv + rec_vals_words(np));
-    const double *cvp = pv + rec_vals_words(np) + rec_cols_words(nc);
+    const int *cc = reinterpret_cast<const int *>(pv + rec_vals_words(np, F32));
+    const double *cvp = pv + rec_vals_words(np, F32) + rec_cols_words(nc);
     const int *tpc = reinterpret_cast<const int *>(rt + 2);
     const double *tpv = rt + 2 + rec_cols_words(npt);
     bool keep = false;
@@ -675,7 +692,7 @@ __device__ __forceinline__ double exact_pair_sig(const TileAux &aux, int cand, i
         for (int k0 = 0; k0 < np; k0 += 4) {
             unsigned c[4];
             double x[4];
-            rec_load4(pc, pv, k0, c, x);
+            rec_load4(pc, pv, k0, c, x, F32);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 if (k0 + e < np) {
@@ -697,7 +714,7 @@ __device__ __forceinline__ double exact_pair_sig(const TileAux &aux, int cand, i
                             match = lo < npt && (int)((unsigned)__ldg(tpc + lo) & REC_COL_MASK) == ix;
                         }
                         if (match) {
-                            sum = xadd(sum, xmul(x[e], __ldg(tpv + lo)));
+                            sum = xadd(sum, xmul(x[e], rec_val(tpv, lo, F32)));
                             if (min_tail < 0 && (c[e] & aux.tail_bit)) min_tail = ix;
                         }
                     }
@@ -720,7 +737,7 @@ __device__ __forceinline__ double exact_pair_sig(const TileAux &aux, int cand, i
         for (int k0 = 0; k0 < nc; k0 += 4) {
             unsigned c[4];
             double x[4];
-            rec_load4(cc, cvp, k0, c, x);
+            rec_load4(cc, cvp, k0, c, x, F32);
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if (k0 + e < nc) sum = xadd(sum, xmul(x[e], __ldg(tdense + c[e])));
@@ -1993,13 +2010,14 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
             const int tix = sm.tid_of[t];
             unsigned long long sig = 0ULL;
             if (tix >= 0) {
+                const bool F32 = aux.vals_f32;
                 const unsigned long long mt = __ldg(aux.meta + tix);
                 const int npt = (int)((mt >> 40) & 0xfffu), nct = (int)(mt >> 52);
                 const double *rt = aux.rec + (mt & 0xffffffffffULL);
                 const int *tpc = reinterpret_cast<const int *>(rt + 2);
                 const double *tpv = rt + 2 + rec_cols_words(npt);
-                const int *tcc = reinterpret_cast<const int *>(tpv + rec_vals_words(npt));
-                const double *tcv = tpv + rec_vals_words(npt) + rec_cols_words(nct);
+                const int *tcc = reinterpret_cast<const int *>(tpv + rec_vals_words(npt, F32));
+                const double *tcv = tpv + rec_vals_words(npt, F32) + rec_cols_words(nct);
                 for (int k = lane; k < npt; k += 32) {
                     const int col = (int)((unsigned)tpc[k] & REC_COL_MASK);
                     sig |= 1ULL << sig_bit(col);
@@ -2010,7 +2028,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                 double *row = aux.tdense + (size_t)(t0 + t) * aux.cat_dim;
                 for (int c = lane; c < aux.cat_dim; c += 32) row[c] = 0.0;
                 __syncwarp();
-                for (int k = lane; k < nct; k += 32) row[tcc[k]] = tcv[k];
+                for (int k = lane; k < nct; k += 32) row[tcc[k]] = rec_val(tcv, k, F32);
             }
             if (lane == 0) sm.tsig[t] = sig;
         }
@@ -2662,6 +2680,7 @@ struct vrec_knn {
     DevBuf<short> d_head_slot;
     DevBuf<int> d_pcp, d_pper;
     DevBuf<double> d_seed_thr;
+    bool rec_f32 = false;                    // packed records hold their values as floats
     DevBuf<int> d_post_bin, d_post_order, d_post_bins;   // longest-first order of the postings kernel's targets
     int64_t opt_post_first = 0;               // 1: postings kernel before the dense kernel, its lists seed the thresholds (measured: 187 instead of 338 dense survivors per target, but the postings kernel loses its cut-off: 18.9 ms vs 17.7 ms per step)
     DevBuf<double> d_tdense;                 // [targets of the batch][cat_dim] dense category rows (knn_tc_ws_kernel)
@@ -2960,6 +2979,11 @@ extern "C" int vrec_knn_load(vrec_ctx *ctx, int64_t P, const int64_t *person_id,
             std::vector<unsigned long long> meta((size_t)P);
             std::vector<double> rec;
             rec.reserve((size_t)(10 * P + 2 * (k->nnz_place + k->nnz_cat)));
+            // values as floats when that loses nothing (visit counts: always)
+            bool F32 = true;
+            for (int64_t e = 0; e < k->nnz_place && F32; ++e) F32 = (double)(float)pv[e] == pv[e];
+            for (int64_t e = 0; e < k->nnz_cat && F32; ++e) F32 = (double)(float)cv[e] == cv[e];
+            k->rec_f32 = F32;
             for (int64_t i = 0; i < P && rc == VREC_OK; ++i) {
                 const int np = prp[i + 1] - prp[i], nc = crp[i + 1] - crp[i];
                 meta[i] = (unsigned long long)rec.size() | ((unsigned long long)np << 40) | ((unsigned long long)nc << 52);
@@ -2973,15 +2997,25 @@ extern "C" int vrec_knn_load(vrec_ctx *ctx, int64_t P, const int64_t *person_id,
                     pc[e] = (unsigned)col | (hs_tc[col] < 0 ? REC_TAIL_TC : 0u) | (head_slot[col] < 0 ? REC_TAIL_TILE : 0u);
                 }
                 at = rec.size();
-                rec.resize(at + (size_t)rec_vals_words(np), 0.0);
-                for (int e = 0; e < np; ++e) rec[at + e] = pv[prp[i] + e];
+                rec.resize(at + (size_t)rec_vals_words(np, F32), 0.0);
+                if (F32) {
+                    float *fv = reinterpret_cast<float *>(rec.data() + at);
+                    for (int e = 0; e < np; ++e) fv[e] = (float)pv[prp[i] + e];
+                } else {
+                    for (int e = 0; e < np; ++e) rec[at + e] = pv[prp[i] + e];
+                }
                 at = rec.size();
                 rec.resize(at + (size_t)rec_cols_words(nc), 0.0);
                 unsigned *cc = reinterpret_cast<unsigned *>(rec.data() + at);
                 for (int e = 0; e < nc; ++e) cc[e] = (unsigned)cci[crp[i] + e];
                 at = rec.size();
-                rec.resize(at + (size_t)rec_vals_words(nc), 0.0);
-                for (int e = 0; e < nc; ++e) rec[at + e] = cv[crp[i] + e];
+                rec.resize(at + (size_t)rec_vals_words(nc, F32), 0.0);
+                if (F32) {
+                    float *fv = reinterpret_cast<float *>(rec.data() + at);
+                    for (int e = 0; e < nc; ++e) fv[e] = (float)cv[crp[i] + e];
+                } else {
+                    for (int e = 0; e < nc; ++e) rec[at + e] = cv[crp[i] + e];
+                }
             }
             rec.resize(rec.size() + 64, 0.0);         // slack: the 128-bit loads may touch the padding of the last record
             if (rc == VREC_OK) rc = k->d_meta.upload(meta.data(), meta.size(), s);
@@ -3278,6 +3312,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                 attr_tc = true;
             }
             aux = TileAux{nullptr, 0, k->d_head_slot_tc.p, k->d_pcp.p, k->d_pper.p, k->d_meta.p, k->d_rec.p, REC_TAIL_TC};
+            aux.vals_f32 = k->rec_f32;
             // No seed pass here: it cost more (heap warm-up on a sample, ~9 ms per 19K targets) than the
             // ~250 extra survivors per target it saves the main pass (~2 ms).  Optional via "tc_seed".
             if (k->opt_tc_seed) {
@@ -3334,6 +3369,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
             }
             aux = TileAux{k->d_feat.p, k->fstride, k->d_head_slot.p, k->d_pcp.p, k->d_pper.p, k->d_meta.p, k->d_rec.p,
                           REC_TAIL_TILE};
+            aux.vals_f32 = k->rec_f32;
             knn_tile_kernel<<<dim3(tiles, 1), TILE_THREADS, smem, ctx->stream>>>(
                 k->dev(), aux, k->d_tidx.p, tn, T, K, 1, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p, stride, sample,
                 1, k->d_seed_thr.p, SP);

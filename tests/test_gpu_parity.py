@@ -343,6 +343,11 @@ def test_knn_fallback_kernels_for_unusual_data(vrec, ctx, synth, oracle):
     rs = vrec.KnnRegionSet(*neg.load_args(), ctx=ctx)
     _check_knn(vrec, oracle, rs, neg, 0.5, 0.5, 20, neg.person_id[:30], np.arange(0, 400, 2), 10)
     rs.close()
+    # values that are not exact in fp32: the packed records must then keep doubles (visit counts pack as floats)
+    frac = dataclasses.replace(inp, place_val=inp.place_val * 0.1 + 1e-9, cat_val=inp.cat_val / 3.0)
+    rs = vrec.KnnRegionSet(*frac.load_args(), ctx=ctx)
+    _check_knn(vrec, oracle, rs, frac, 0.5, 0.5, 20, frac.person_id[:60], np.arange(0, 400, 2), 10)
+    rs.close()
     wide = synth.random_knn_inputs(1200, 300, 90, seed=32)
     rs = vrec.KnnRegionSet(*wide.load_args(), ctx=ctx)
     _check_knn(vrec, oracle, rs, wide, 0.4, 0.6, 20, wide.person_id[:30], None, 10)
