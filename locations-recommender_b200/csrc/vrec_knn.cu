@@ -1874,7 +1874,7 @@ constexpr int WS_NACC = 3;           // TMEM accumulators (3 x 128 columns); the
 constexpr int WS_STAGES = 4;         // B tiles in flight (the A operand lives in tensor memory, not in shared memory)
 constexpr int WS_TMEM_A = WS_NACC * TC_N;   // first TMEM column of the A operand
 constexpr int WS_STAGGER = 1;        // tiles between the starting points of neighbouring CTAs (small: the CTAs share each tile through L2)
-constexpr int WS_BOOT_TILES = 256;   // multiple of 16; 64 groups of 512 candidates per target
+constexpr int WS_BOOT_TILES = 512;   // multiple of 16; 64 groups of 512 candidates per target
 
 __global__ void __launch_bounds__(WS_THREADS, 1)
 knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const int *__restrict__ tidx,
@@ -1934,7 +1934,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
     const int rot = ntiles > 0 ? (int)(((long long)blockIdx.x * WS_STAGGER + (long long)blockIdx.y * 29) % ntiles) : 0;
     // Bootstrap: the first `boot` tiles of the sequence are only scanned for group maxima (below) and
     // are visited again, normally, at the end of the sequence.
-    const int boot = ntiles >= 2 * WS_BOOT_TILES ? WS_BOOT_TILES : 0;
+    const int boot = ntiles >= 64 ? min(WS_BOOT_TILES, (ntiles / 4) / 16 * 16) : 0;   // a quarter of the tiles at most
     const int nseq = ntiles + boot;
     if (tid < 4) s_next_unit[tid] = boot * 4;
     auto tile_index = [&](int i) {
