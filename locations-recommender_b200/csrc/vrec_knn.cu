@@ -2400,44 +2400,66 @@ knn_rate_gather_kernel(const int *__restrict__ rrp, const int *__restrict__ rpl,
     for (int tt = slot; tt < T; tt += nslots) {
         const int n = nb_cnt[tt];
         int ntouched = 0;
-        double l_sim = 0.0;
-        int l_rs = 0, l_rn = 0;
-        for (int k = 0; k < n; ++k) {
-            // the neighbours' (similarity, rating row extent) are fetched 32 at a time, one per lane, and their
-            // rating rows prefetched: the serial loop below then only waits for the rows themselves
-            if ((k & 31) == 0) {
-                const int kk = k + lane;
-                l_sim = 0.0;
-                l_rs = 0;
-                l_rn = 0;
-                if (kk < n) {
-                    const Nb nbl = nb_idx[(size_t)tt * K + kk];
-                    l_sim = nbl.sim;
-                    l_rs = rrp[nbl.idx];
-                    l_rn = rrp[nbl.idx + 1] - l_rs;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rpl + l_rs));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rv + l_rs));
-                }
+        // 32 neighbours at a time: their (similarity, rating row extent) one per lane; then the ratings of those
+        // neighbours as ONE flat list, 32 entries per step whatever the row boundaries are.  Entries of one step
+        // that hit the same place are applied in lane order (= ascending neighbour) in successive rounds
+        // (__match_any_sync), everything else in parallel: the sums keep their left-to-right order.
+        for (int k0 = 0; k0 < n; k0 += 32) {
+            const int kk = k0 + lane;
+            double l_sim = 0.0;
+            int l_rs = 0, l_rn = 0;
+            if (kk < n) {
+                const Nb nbl = nb_idx[(size_t)tt * K + kk];
+                l_sim = nbl.sim;
+                l_rs = rrp[nbl.idx];
+                l_rn = rrp[nbl.idx + 1] - l_rs;
             }
-            Nb nb;
-            nb.sim = __shfl_sync(0xffffffffu, l_sim, k & 31);
-            const int rs = __shfl_sync(0xffffffffu, l_rs, k & 31), rn = __shfl_sync(0xffffffffu, l_rn, k & 31);
-            for (int e0 = 0; e0 < rn; e0 += 32) {
-                int e = e0 + lane;
-                bool valid = e < rn;
-                bool first = false;
-                int pl = 0;
-                if (valid) {
-                    pl = rpl[rs + e];
-                    double w = xmul(rv[rs + e], nb.sim);      // rating * similarity, :60
-                    double dold = myden[pl];
-                    first = dold == 0.0;
-                    mynum[pl] = xadd(mynum[pl], w);           // :63
-                    myden[pl] = xadd(dold, nb.sim);           // :64
+            int incl = l_rn;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int excl = incl - l_rn;
+            for (int j0 = 0; j0 < total; j0 += 32) {
+                const int j = j0 + lane;
+                // neighbour (lane L of this block) that owns flat entry j: largest L with excl_L <= j
+                int L = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int probe = __shfl_sync(0xffffffffu, excl, min(31, L + step));
+                    if (L + step < 32 && probe <= j) L += step;
                 }
-                unsigned m = __ballot_sync(0xffffffffu, first);
+                // rows of length 0 share their offset with the next row: move on to the row that really holds j
+                const int ex_l = __shfl_sync(0xffffffffu, excl, L);
+                const int rs_l = __shfl_sync(0xffffffffu, l_rs, L);
+                const double sim_l = __shfl_sync(0xffffffffu, l_sim, L);
+                const bool valid = j < total;
+                int pl = -1 - lane;                                   // distinct dummies: no match among idle lanes
+                double w = 0.0;
+                if (valid) {
+                    pl = rpl[rs_l + (j - ex_l)];
+                    w = xmul(rv[rs_l + (j - ex_l)], sim_l);           // rating * similarity, :60
+                }
+                const unsigned same = __match_any_sync(0xffffffffu, pl);
+                const int rank = __popc(same & lt_mask);
+                int rounds = __popc(same);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, off));
+                bool first = false;
+                for (int r = 0; r < rounds; ++r) {
+                    if (valid && rank == r) {
+                        const double dold = myden[pl];
+                        first = dold == 0.0;
+                        mynum[pl] = xadd(mynum[pl], w);               // :63
+                        myden[pl] = xadd(dold, sim_l);                // :64
+                    }
+                    __syncwarp();
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, first);
                 if (first) {
-                    int pos = ntouched + __popc(m & lt_mask);
+                    const int pos = ntouched + __popc(m & lt_mask);
                     if (pos < touch_cap) mytouched[pos] = pl;
                 }
                 ntouched += __popc(m);
@@ -2446,11 +2468,38 @@ knn_rate_gather_kernel(const int *__restrict__ rrp, const int *__restrict__ rpl,
         }
         if (ntouched > touch_cap) ntouched = touch_cap;
         __syncwarp();
-        for (int j = lane; j < ntouched; j += 32) {
-            int pl = mytouched[j];
-            double est = xdiv(mynum[pl], myden[pl]);          // :68
-            bool ok = !flag || flag[pl];
-            mynum[pl] = ok ? est : nan;
+        // estimated ratings of the touched places; up to 16 per lane stay in registers for the ranking rounds
+        // (and the scratch rows are cleared in the same pass), more than that go back through the scratch row
+        constexpr int RG = 16;
+        const bool in_regs = ntouched <= 32 * RG;
+        double rv_[RG];
+        int rp_[RG];
+#pragma unroll
+        for (int q = 0; q < RG; ++q) {
+            rv_[q] = nan;
+            rp_[q] = 0;
+        }
+        if (in_regs) {
+#pragma unroll
+            for (int q = 0; q < RG; ++q) {
+                const int j = lane + 32 * q;
+                if (j < ntouched) {
+                    const int pl = mytouched[j];
+                    const double est = xdiv(mynum[pl], myden[pl]);      // :68
+                    const bool ok = !flag || flag[pl];
+                    rv_[q] = ok ? est : nan;
+                    rp_[q] = pl;
+                    mynum[pl] = 0.0;
+                    myden[pl] = 0.0;
+                }
+            }
+        } else {
+            for (int j = lane; j < ntouched; j += 32) {
+                int pl = mytouched[j];
+                double est = xdiv(mynum[pl], myden[pl]);          // :68
+                bool ok = !flag || flag[pl];
+                mynum[pl] = ok ? est : nan;
+            }
         }
         __syncwarp();
         bool have_last = false;
@@ -2461,15 +2510,30 @@ knn_rate_gather_kernel(const int *__restrict__ rrp, const int *__restrict__ rpl,
             bool has = false;
             double bv = 0.0;
             long long bk = 0;
-            for (int j = lane; j < ntouched; j += 32) {
-                int pl = mytouched[j];
-                double x = mynum[pl];
-                if (x != x) continue;
-                if (have_last && !ranks_before(last_val, last_key, x, pl)) continue;
-                if (!has || ranks_before(x, pl, bv, bk)) {
-                    has = true;
-                    bv = x;
-                    bk = pl;
+            if (in_regs) {
+#pragma unroll
+                for (int q = 0; q < RG; ++q) {
+                    const double x = rv_[q];
+                    const int pl = rp_[q];
+                    if (x != x) continue;
+                    if (have_last && !ranks_before(last_val, last_key, x, pl)) continue;
+                    if (!has || ranks_before(x, pl, bv, bk)) {
+                        has = true;
+                        bv = x;
+                        bk = pl;
+                    }
+                }
+            } else {
+                for (int j = lane; j < ntouched; j += 32) {
+                    int pl = mytouched[j];
+                    double x = mynum[pl];
+                    if (x != x) continue;
+                    if (have_last && !ranks_before(last_val, last_key, x, pl)) continue;
+                    if (!has || ranks_before(x, pl, bv, bk)) {
+                        has = true;
+                        bv = x;
+                        bk = pl;
+                    }
                 }
             }
 #pragma unroll
@@ -2494,10 +2558,12 @@ knn_rate_gather_kernel(const int *__restrict__ rrp, const int *__restrict__ rpl,
             count = r + 1;
         }
         if (lane == 0) out_count[tt] = count;
-        for (int j = lane; j < ntouched; j += 32) {
-            int pl = mytouched[j];
-            mynum[pl] = 0.0;
-            myden[pl] = 0.0;
+        if (!in_regs) {
+            for (int j = lane; j < ntouched; j += 32) {
+                int pl = mytouched[j];
+                mynum[pl] = 0.0;
+                myden[pl] = 0.0;
+            }
         }
         __syncwarp();
     }
