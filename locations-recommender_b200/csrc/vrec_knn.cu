@@ -2310,6 +2310,127 @@ __global__ void knn_features_kernel(KnnDev d, const short *__restrict__ head_slo
     }
 }
 
+// Bitonic sort of 32 * NQ (key, payload) pairs held by one warp, element i = q * 32 + lane, "best first" in the
+// (similarity desc, index asc) order: partner distances below 32 are shuffles, the others stay in the thread.
+template <int NQ>
+__device__ __forceinline__ void warp_bitonic_best_first(double (&ks)[NQ], int (&ki)[NQ], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * NQ; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int dq = j >> 5;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    if ((q & dq) == 0) {
+                        const int i = q * 32 + lane;
+                        const bool up = (i & k) == 0;                       // best first inside an "up" block
+                        const bool second_before = ks[q ^ dq] > ks[q] || (ks[q ^ dq] == ks[q] && ki[q ^ dq] < ki[q]);
+                        const bool first_before = ks[q] > ks[q ^ dq] || (ks[q] == ks[q ^ dq] && ki[q] < ki[q ^ dq]);
+                        if (up ? second_before : first_before) {
+                            const double ts = ks[q];
+                            const int ti = ki[q];
+                            ks[q] = ks[q ^ dq];
+                            ki[q] = ki[q ^ dq];
+                            ks[q ^ dq] = ts;
+                            ki[q ^ dq] = ti;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const int i = q * 32 + lane;
+                    const double os = __shfl_xor_sync(0xffffffffu, ks[q], j);
+                    const int oi = __shfl_xor_sync(0xffffffffu, ki[q], j);
+                    const bool up = (i & k) == 0;
+                    const bool lower = (lane & j) == 0;                       // this lane holds the smaller position
+                    const bool other_before = os > ks[q] || (os == ks[q] && oi < ki[q]);
+                    const bool mine_before = ks[q] > os || (ks[q] == os && ki[q] < oi);
+                    // the smaller position of an "up" block keeps the better element, and so on
+                    const bool take = (up == lower) ? other_before : mine_before;
+                    if (take) {
+                        ks[q] = os;
+                        ki[q] = oi;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// knn_merge_kernel for S * K <= 256 (the batch path: 5 lists of 50): one warp per target, everything in
+// registers, no block barriers.  Same outputs.
+constexpr int MERGE_WARP_MAX = 256;
+__global__ void __launch_bounds__(128)
+knn_merge_warp_kernel(const Nb *__restrict__ part, const int *__restrict__ part_cnt, int n_targets, int K, int S,
+                      Nb *__restrict__ nb_rank, Nb *__restrict__ nb_idx, int *__restrict__ nb_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int tt = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (tt >= n_targets) return;
+    constexpr int NQ = MERGE_WARP_MAX / 32;
+    double ks[NQ];
+    int ki[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        ks[q] = -1.0;                                   // sentinels come last
+        ki[q] = 0x7fffffff;
+    }
+    // concatenate the lists: element position p = running offset + index within the list
+    int total = 0;
+    for (int s_ = 0; s_ < S; ++s_) {
+        const int c = part_cnt[tt * S + s_];
+        const Nb *src = part + ((size_t)tt * S + s_) * K;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int p_ = q * 32 + lane - total;
+            if (p_ >= 0 && p_ < c) {
+                const Nb e = src[p_];
+                ks[q] = e.sim;
+                ki[q] = e.idx;
+            }
+        }
+        total += c;
+    }
+    warp_bitonic_best_first<NQ>(ks, ki, lane);
+    const int keep = min(total, K);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const int i = q * 32 + lane;
+        if (i < keep) {
+            Nb e;
+            e.sim = ks[q];
+            e.idx = ki[q];
+            e.pad = 0;
+            nb_rank[(size_t)tt * K + i] = e;
+        }
+    }
+    if (lane == 0) nb_cnt[tt] = keep;
+    __syncwarp();                                       // nb_rank is read back below by other lanes
+    // the kept entries again, in ascending person index: sort (key = -index, payload = rank position)
+    constexpr int NQ2 = 2;                              // keep <= K <= 64 on this path
+    double k2[NQ2];
+    int p2[NQ2];
+#pragma unroll
+    for (int q = 0; q < NQ2; ++q) {
+        const int i = q * 32 + lane;
+        k2[q] = i < keep ? -(double)ki[q] : -4.0e9;      // ascending index == descending -index
+        p2[q] = i;
+    }
+    warp_bitonic_best_first<NQ2>(k2, p2, lane);
+#pragma unroll
+    for (int q = 0; q < NQ2; ++q) {
+        const int i = q * 32 + lane;
+        if (i < keep) {
+            // p2[q] = rank position of the entry with the i-th smallest index; fetch its similarity from its holder
+            const int rp = p2[q];
+            Nb e = nb_rank[(size_t)tt * K + rp];         // written above by this warp
+            e.pad = 0;
+            nb_idx[(size_t)tt * K + i] = e;
+        }
+    }
+}
+
 // Merges the S partial lists of a target (S*K <= TOPK_BUF): final neighbours in
 // (similarity desc, index asc) order -> nb_rank, and the same set in ascending index -> nb_idx.
 __global__ void __launch_bounds__(MERGE_THREADS)
@@ -3452,8 +3573,13 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                                                                k->d_part_cnt.p);
         VREC_LAUNCHED(ctx);
     }
-    knn_merge_kernel<<<tn, MERGE_THREADS, 0, ctx->stream>>>(k->d_part.p, k->d_part_cnt.p, K, SP, k->d_nb_rank.p,
-                                                           k->d_nb_idx.p, k->d_nb_cnt.p);
+    if (SP * K <= MERGE_WARP_MAX && K <= 64) {
+        knn_merge_warp_kernel<<<(int)(((long long)tn * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+            k->d_part.p, k->d_part_cnt.p, tn, K, SP, k->d_nb_rank.p, k->d_nb_idx.p, k->d_nb_cnt.p);
+    } else {
+        knn_merge_kernel<<<tn, MERGE_THREADS, 0, ctx->stream>>>(k->d_part.p, k->d_part_cnt.p, K, SP, k->d_nb_rank.p,
+                                                               k->d_nb_idx.p, k->d_nb_cnt.p);
+    }
     VREC_LAUNCHED(ctx);
     return VREC_OK;
 }
