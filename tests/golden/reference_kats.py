@@ -39,3 +39,20 @@ SG_CASES = [
                        (4, 0.014978183624999999)]),
 ]
 SG_MISSING_VERTEX = 100  # -> IllegalArgumentException("No such vertex in the graph: 100")
+
+# ---------------------------------------------------------------- builders
+# LocationTest.scala:8-29: same location -> 0; two Moscow locations -> 745 +- 5 m; commutative
+LOCATION_SAME = (55.6438965, 37.4433515)
+LOCATION_PAIR = ((55.612652, 37.591753), (55.611152, 37.603366))
+LOCATION_PAIR_DISTANCE, LOCATION_PAIR_TOLERANCE = 745.0, 5.0
+
+# StochasticGraphBuilderTest.scala:11-66: five edge families with weights that sum to 1 per source, betas
+# (0.4, 0.6, 1.0, 0.3, 0.7); after buildWithBalancedWeights the balanced weights of every source sum to 1.0
+# (`===`, exact).  Families as (beta, [(source, target, weight)]); the weights 0.4 / 0.6 are 2/5 and 3/5.
+SGB_FAMILIES = [
+    (0.4, [(1, 2, 1.0)]),
+    (0.6, [(1, 3, 0.4), (1, 5, 0.6)]),
+    (1.0, [(3, 5, 1.0), (5, 3, 1.0)]),
+    (0.3, [(2, 4, 1.0), (4, 2, 1.0)]),
+    (0.7, [(2, 3, 1.0), (4, 5, 1.0)]),
+]

@@ -540,3 +540,29 @@ def test_place_visits_builder_matches_oracle(vrec, ctx, oracle):
     s_, t_, w_ = builders.stochastic_graph_builder(got[0], got[2], got[4], got[1], ctx=ctx)
     assert len(s_) > 0 and np.all(w_ > 0)
     assert builders.place_visits_builder([], [], [], [], [], pid, plat, plon, pcat, preg, ctx=ctx)[0].size == 0
+
+
+def test_builder_reference_kats(vrec, ctx):
+    """The reference's own builder tests through the engine: LocationTest.scala:8-29 (via the place visits
+    builder's radius test) and StochasticGraphBuilderTest.scala:11-66 (balanced weights sum to exactly 1)."""
+    from vrec import builders
+    (a, b) = K.LOCATION_PAIR
+    for radius, n_rows in ((K.LOCATION_PAIR_DISTANCE + K.LOCATION_PAIR_TOLERANCE, 1),
+                           (K.LOCATION_PAIR_DISTANCE - K.LOCATION_PAIR_TOLERANCE, 0)):
+        for (v, p) in ((a, b), (b, a)):                                  # commutative
+            rows = builders.place_visits_builder([1], [v[0]], [v[1]], [0], [0], [40], [p[0]], [p[1]], [3], [0], 7,
+                                                 radius, ctx=ctx)
+            assert len(rows[0]) == n_rows
+    rows = builders.place_visits_builder([1], [K.LOCATION_SAME[0]], [K.LOCATION_SAME[1]], [0], [0], [40],
+                                         [K.LOCATION_SAME[0]], [K.LOCATION_SAME[1]], [3], [0], 7, 1e-9, ctx=ctx)
+    assert rows[2].tolist() == [40]                                      # distance 0
+    sums = {}
+    for beta, edges in K.SGB_FAMILIES:
+        cnt = [int(round(e[2] * 5)) for e in edges]
+        s_, t_, w_ = builders.build_edge_family([e[0] for e in edges], [e[1] for e in edges], 100, beta, weight=cnt,
+                                                ctx=ctx)
+        assert {(x, y): z for x, y, z in zip(s_.tolist(), t_.tolist(), w_.tolist())} == {(e[0], e[1]): e[2] * beta
+                                                                                        for e in edges}
+        for x, z in zip(s_.tolist(), w_.tolist()):
+            sums[x] = sums.get(x, 0.0) + z
+    assert all(v == 1.0 for v in sums.values())

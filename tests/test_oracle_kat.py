@@ -58,3 +58,34 @@ def test_sg_corner_cases(oracle):
     assert rc == 0 and sorted(ids.tolist()) == [2, 4]
     rc, ids, pr, it, conv = g.query(1, 0.01, 20, None, 0)
     assert rc == 0 and len(ids) == 0
+
+
+def test_location_distance_kats(oracle):
+    """LocationTest.scala:8-29 against the oracle's haversine (Location.scala:30-43)."""
+    import ctypes as C
+    f = oracle.lib().vro_distance_meters
+    f.restype = C.c_double
+    f.argtypes = [C.c_double] * 4
+    assert f(*K.LOCATION_SAME, *K.LOCATION_SAME) == 0
+    (a, b) = K.LOCATION_PAIR
+    d = f(*a, *b)
+    assert abs(d - K.LOCATION_PAIR_DISTANCE) <= K.LOCATION_PAIR_TOLERANCE
+    assert d == f(*b, *a)
+
+
+def test_balanced_weights_kat(oracle):
+    """StochasticGraphBuilderTest.scala:11-66 through vro_build_edge_family: every family's weights are
+    reproduced from visit counts (0.4 = 2/5, 0.6 = 3/5, 1.0 = n/n), multiplied by the family's beta, and the
+    balanced weights of every source sum to exactly 1.0."""
+    sums = {}
+    for beta, edges in K.SGB_FAMILIES:
+        src = [e[0] for e in edges]
+        dst = [e[1] for e in edges]
+        cnt = [int(round(e[2] * 5)) for e in edges]                  # 1.0 -> 5, 0.4 -> 2, 0.6 -> 3
+        rc, s, t, w = oracle.build_edge_family(src, dst, cnt, 100, beta)
+        assert rc == 0
+        want = {(e[0], e[1]): e[2] * beta for e in edges}
+        assert {(a, b): x for a, b, x in zip(s.tolist(), t.tolist(), w.tolist())} == want     # exact doubles
+        for a, x in zip(s.tolist(), w.tolist()):
+            sums[a] = sums.get(a, 0.0) + x
+    assert sums and all(v == 1.0 for v in sums.values()), sums
