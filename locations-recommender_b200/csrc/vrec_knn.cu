@@ -480,27 +480,49 @@ __device__ __forceinline__ double exact_pair_staged(const TileAux &aux, long lon
     double ps_sim = 0.0, cs_sim = 0.0;
     if (np > 0) {
         double sum = 0.0;
-        for (int k0 = 0; k0 < np; k0 += 4) {
+        auto place_term = [&](unsigned craw, double x) {
+            const int ix = (int)(craw & REC_COL_MASK);
+            if ((t.sig >> sig_bit(ix)) & 1ULL) {
+                int lo = 0, hi = t.pn;                               // first index with pcol >= ix
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (t.pcol[mid] < ix) lo = mid + 1; else hi = mid;
+                }
+                if (lo < t.pn && t.pcol[lo] == ix) {
+                    sum = xadd(sum, xmul(x, t.pval[lo]));
+                    if (min_tail < 0 && (craw & aux.tail_bit)) min_tail = ix;
+                }
+            }
+        };
+        int k0 = 0;
+        if (F32) {
+            // float records: the first 8 place entries (most rows) with four loads issued together with the
+            // header's, i.e. one memory round trip for header + place section
+            const int4 c0 = __ldg(reinterpret_cast<const int4 *>(pc));
+            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(pv));
+            int4 c1 = make_int4(0, 0, 0, 0);
+            float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (np > 4) {
+                c1 = __ldg(reinterpret_cast<const int4 *>(pc) + 1);
+                v1 = __ldg(reinterpret_cast<const float4 *>(pv) + 1);
+            }
+            place_term((unsigned)c0.x, (double)v0.x);
+            if (np > 1) place_term((unsigned)c0.y, (double)v0.y);
+            if (np > 2) place_term((unsigned)c0.z, (double)v0.z);
+            if (np > 3) place_term((unsigned)c0.w, (double)v0.w);
+            if (np > 4) place_term((unsigned)c1.x, (double)v1.x);
+            if (np > 5) place_term((unsigned)c1.y, (double)v1.y);
+            if (np > 6) place_term((unsigned)c1.z, (double)v1.z);
+            if (np > 7) place_term((unsigned)c1.w, (double)v1.w);
+            k0 = 8;
+        }
+        for (; k0 < np; k0 += 4) {
             unsigned c[4];
             double x[4];
             rec_load4(pc, pv, k0, c, x, F32);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (k0 + e < np) {
-                    const int ix = (int)(c[e] & REC_COL_MASK);
-                    if ((t.sig >> sig_bit(ix)) & 1ULL) {
-                        int lo = 0, hi = t.pn;                       // first index with pcol >= ix
-                        while (lo < hi) {
-                            int mid = (lo + hi) >> 1;
-                            if (t.pcol[mid] < ix) lo = mid + 1; else hi = mid;
-                        }
-                        if (lo < t.pn && t.pcol[lo] == ix) {
-                            sum = xadd(sum, xmul(x[e], t.pval[lo]));
-                            if (min_tail < 0 && (c[e] & aux.tail_bit)) min_tail = ix;
-                        }
-                    }
-                }
-            }
+            for (int e = 0; e < 4; ++e)
+                if (k0 + e < np) place_term(c[e], x[e]);
         }
         double c = xdiv(sum, xmul(plen, t.plen));
         if (c > 0) {
