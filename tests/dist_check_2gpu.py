@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """torchrun-launched check of the row-partitioned SG path: every rank's result must equal the
 single-GPU engine and the CPU oracle bit for bit.  Usage:
-  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/dist_check.py"""
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_check_2gpu.py"""
 import os
 import sys
 
