@@ -163,7 +163,23 @@ def oracle_knn_data(oracle, inp):
                           place_dim=inp.place_dim)
 
 
-def cpu_knn(args, inp, places, n_targets, repeats=1):
+def knn_parity(rec, targets, places, max_recs, answers):
+    """Engine (vrec_knn_query, host buffers) against the oracle's answers for the same targets of the full-size
+    region-set: recommended place ids and their order, estimated ratings bit for bit, counts and statuses."""
+    opl, ort, ocnt, ost = answers[:4]
+    pl, rt, cnt, st = rec.recommend(targets, np.ascontiguousarray(places.id, dtype=np.int64), max_recs)
+    bad = 0
+    for q in range(len(targets)):
+        c = int(ocnt[q])
+        if not (int(cnt[q]) == c and int(st[q]) == int(ost[q]) and np.array_equal(pl[q, :c], opl[q, :c])
+                and np.array_equal(rt[q, :c].view(np.int64), ort[q, :c].view(np.int64))):
+            bad += 1
+    return {"targets": int(len(targets)), "mismatching_targets": bad, "bit_exact": bad == 0,
+            "checked": "place ids + order, estimated_rating bits, counts, statuses against oracle/vrec_oracle.c "
+                       "on the full-size region-set (the cpu_baseline sample)"}
+
+
+def cpu_knn(args, inp, places, n_targets, repeats=1, check=None):
     """CPU oracle (port of the Scala path) on a bounded sample of the same workload."""
     from oracle import oracle
     oracle.build()
@@ -174,11 +190,13 @@ def cpu_knn(args, inp, places, n_targets, repeats=1):
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        rc, *_ = oracle.knn_query_batch(d, targets, 0.5, 0.5, args.k_nearest, places.id, args.max_recs,
-                                        n_threads=threads)
+        rc, *answers = oracle.knn_query_batch(d, targets, 0.5, 0.5, args.k_nearest, places.id, args.max_recs,
+                                              n_threads=threads)
         dt = time.perf_counter() - t0
         assert rc == 0
         best = dt if best is None else min(best, dt)
+    if check is not None:           # the oracle as the checker: same targets through the engine, full size
+        check.update(knn_parity(check.pop("rec"), targets, places, args.max_recs, answers))
     return {"value": n_targets / best, "unit": "persons/s", "cores": threads, "kind": "port",
             "sample": f"{n_targets} random targets of the same region-set, {best:.2f}s, oracle/vrec_oracle.c "
                       f"with OpenMP over targets"}, best
@@ -398,10 +416,13 @@ def run_ours(args):
                         "is paced by its MMA-issue / accumulator hand-over chain and the consumer warps' exact "
                         "evaluations, not by HBM: see DESIGN.md"}
 
-    cpu_knn_base = None
+    cpu_knn_base = knn_par = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu_knn_base, _ = cpu_knn(args, inp, places, args.cpu_knn_targets)
-        log(f"[bench] knn cpu baseline: {cpu_knn_base['value']:.1f} persons/s on {cpu_knn_base['cores']} threads")
+        knn_par = {"rec": rec}
+        cpu_knn_base, _ = cpu_knn(args, inp, places, args.cpu_knn_targets, check=knn_par)
+        log(f"[bench] knn cpu baseline: {cpu_knn_base['value']:.1f} persons/s on {cpu_knn_base['cores']} threads; "
+            f"full-size parity on its {knn_par['targets']} targets: "
+            f"{'bit-exact' if knn_par['bit_exact'] else 'MISMATCH on %d targets' % knn_par['mismatching_targets']}")
     # one person at a time (the launchers' REPL, BASELINE configs 1-2): latency of a single query through the ABI
     single = None
     if rank == 0:
@@ -441,6 +462,7 @@ def run_ours(args):
             "gpu_launches": int(knn_launches),
             "roofline": knn_roof,
             "cpu_baseline": cpu_knn_base,
+            "parity": knn_par,
             "clocks": clocks_knn,
             "sg": sg,
             "single_query": single,
@@ -553,7 +575,7 @@ def run_sg_batch(args, vrec, ctx, world, rank, barrier, max_over_ranks):
     launches = ctx.launch_count - l0
     assert n_done == n_q * args.steps, "batch kernel did not serve the queries"
     value = world * n_q * args.steps / dt
-    cpu = None
+    cpu = parity = None
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import oracle
         oracle.build()
@@ -561,13 +583,25 @@ def run_sg_batch(args, vrec, ctx, world, rank, barrier, max_over_ranks):
         og = oracle.SgGraph(s, t, w)
         sample = persons[:24]
         t1 = time.perf_counter()
-        for v in sample:
-            og.query(int(v), 0.01, 20, places, 10)
+        answers = [og.query(int(v), 0.01, 20, places, 10) for v in sample]
         cdt = time.perf_counter() - t1
+        # the oracle as the checker: the same persons through vrec_sg_query (batch kernel), bit for bit
+        oi, op, cnt, its, conv, st = rec.recommend(sample, places, 10)
+        bad = 0
+        for q, (rc, wi, wp, oit, oconv) in enumerate(answers):
+            c = len(wi)
+            if not (int(st[q]) == rc and int(cnt[q]) == c and (int(its[q]), int(conv[q])) == (oit, oconv)
+                    and np.array_equal(oi[q, :c], wi)
+                    and np.array_equal(op[q, :c].view(np.int64), np.asarray(wp, dtype=np.float64).view(np.int64))):
+                bad += 1
+        parity = {"targets": len(sample), "mismatching_targets": bad, "bit_exact": bad == 0,
+                  "checked": "place ids + order, probability bits, iterations, converged flags against "
+                             "oracle/vrec_oracle.c on the full-size graph (the cpu_baseline sample)"}
         cpu = {"value": len(sample) / cdt, "unit": "persons/s", "cores": os.cpu_count() or 1, "kind": "port",
                "sample": f"{len(sample)} persons of the same graph, one query at a time, {cdt:.2f}s, "
                          f"oracle/vrec_oracle.c with OpenMP over rows"}
-        log(f"[bench] sg batch cpu baseline: {cpu['value']:.1f} persons/s")
+        log(f"[bench] sg batch cpu baseline: {cpu['value']:.1f} persons/s; parity on its {len(sample)} persons: "
+            f"{'bit-exact' if bad == 0 else 'MISMATCH on %d' % bad}")
     out = {
         "metric": "SG recommendations, persons/s (power iteration to eps=0.01 + ranked top-10 per person)",
         "value": value, "unit": "persons/s", "ms_per_step": 1e3 * dt / args.steps, "n_gpus": world, "scaling": "weak",
@@ -577,7 +611,7 @@ def run_sg_batch(args, vrec, ctx, world, rank, barrier, max_over_ranks):
         "e2e": {"value": value, "unit": "persons/s", "h2d_bytes_per_step": 8 * n_q + 8 * len(places),
                 "d2h_bytes_per_step": n_q * (10 * 16 + 12)},
         "kernel_ms_per_step": kernel_us / 1e3 / args.steps, "mean_iterations": its_sum / max(1, n_q * args.steps),
-        "gpu_launches": int(launches), "cpu_baseline": cpu,
+        "gpu_launches": int(launches), "cpu_baseline": cpu, "parity": parity,
         "note": "value == e2e: every step goes through vrec_sg_query with host buffers; kernel_ms_per_step is "
                 "sg_batch_kernel alone (host clock around the launch)",
     }

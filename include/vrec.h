@@ -167,6 +167,10 @@ int vrec_knn_debug_tc_block_cycles(vrec_knn *knn, uint64_t *out, int n);
 /* Duration in milliseconds of the last dense-filter kernel launch (knn_tc_ws_kernel), from CUDA events on
  * vrec_stream(); 0 if that kernel has not run.  bench.py's roofline uses it.                          */
 int vrec_knn_last_dense_ms(vrec_knn *knn, double *out_ms);
+/* Debug: neighbours (person_id ascending, similarity) of target index t of the last vrec_knn_query pass that ran
+ * the fused top-K kernels with this K; what makeRecommendations0 (knn/KnnRecommender.scala:51-70) consumed. */
+int vrec_knn_debug_last_neighbours(vrec_knn *knn, int32_t t, int32_t K, int64_t *out_person_id,
+                                   double *out_similarity, int32_t *out_count);
 /* Debug: exact-evaluation probe of block 0 / thread 0 of the dense kernel, cycles summed over its
  * evaluations: out8 = {meta words, record headers, place matching, evaluations, heap inserts (cycles),
  * heap inserts (count), place section load, category section + dense row}.                            */

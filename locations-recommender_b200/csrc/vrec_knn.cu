@@ -2047,10 +2047,16 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) sig |= __shfl_xor_sync(0xffffffffu, sig, off);
+                // The S CTAs of a tile all fill the same rows, and not at the same time (a grid of more than
+                // one wave starts some of them while others already evaluate): every element is stored ONCE,
+                // with its final value, so a row never passes through a state a concurrent reader must not see.
                 double *row = aux.tdense + (size_t)(t0 + t) * aux.cat_dim;
-                for (int c = lane; c < aux.cat_dim; c += 32) row[c] = 0.0;
-                __syncwarp();
-                for (int k = lane; k < nct; k += 32) row[tcc[k]] = rec_val(tcv, k, F32);
+                for (int c = lane; c < aux.cat_dim; c += 32) {
+                    double v = 0.0;
+                    for (int k = 0; k < nct; ++k)
+                        if (tcc[k] == c) v = rec_val(tcv, k, F32);
+                    row[c] = v;
+                }
             }
             if (lane == 0) sm.tsig[t] = sig;
         }
@@ -3334,6 +3340,28 @@ extern "C" int vrec_knn_debug_stats(vrec_knn *k, uint64_t *out4) {
     unsigned long long z[4] = {0, 0, 0, 0};
     VREC_CUDA(cudaMemcpyFromSymbol(out4, g_tile_stats, sizeof(z)));
     VREC_CUDA(cudaMemcpyToSymbol(g_tile_stats, z, sizeof(z)));
+    return VREC_OK;
+}
+
+// Debug: the neighbour list (ascending person index, as the rating reduction reads it) of target t of the
+// last vrec_knn_query pass over the fused top-K kernels.  capacity >= the K of that query.
+extern "C" int vrec_knn_debug_last_neighbours(vrec_knn *k, int32_t t, int32_t K, int64_t *out_person_id,
+                                              double *out_similarity, int32_t *out_count) {
+    if (!k || !out_person_id || !out_similarity || !out_count || t < 0 || K <= 0) return VREC_EINVAL;
+    if ((size_t)(t + 1) * (size_t)K > k->d_nb_idx.n || (size_t)t >= k->d_nb_cnt.n) return VREC_EINVAL;
+    VREC_CUDA(cudaSetDevice(k->ctx->device));
+    int cnt = 0;
+    std::vector<Nb> h((size_t)K);
+    VREC_CUDA(cudaMemcpyAsync(&cnt, k->d_nb_cnt.p + t, sizeof(int), cudaMemcpyDeviceToHost, k->ctx->stream));
+    VREC_CUDA(cudaMemcpyAsync(h.data(), k->d_nb_idx.p + (size_t)t * K, sizeof(Nb) * (size_t)K, cudaMemcpyDeviceToHost,
+                              k->ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(k->ctx->stream));
+    cnt = std::max(0, std::min(cnt, (int)K));
+    for (int i = 0; i < cnt; ++i) {
+        out_person_id[i] = k->h_person[(size_t)h[i].idx];
+        out_similarity[i] = h[i].sim;
+    }
+    *out_count = cnt;
     return VREC_OK;
 }
 

@@ -45,6 +45,7 @@ SIGNATURES = {
     "vrec_knn_similarities": (C.c_int, [vp, C.c_int64, C.c_double, C.c_double, C.c_int32, f64p]),
     "vrec_knn_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
     "vrec_knn_resident_bytes": (C.c_int64, [vp]),
+    "vrec_knn_debug_last_neighbours": (C.c_int, [vp, C.c_int32, C.c_int32, i64p, f64p, i32p]),
     "vrec_knn_debug_stats": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
     "vrec_knn_debug_tc_cycles": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
     "vrec_knn_debug_tc_block_cycles": (C.c_int, [vp, C.POINTER(C.c_uint64), C.c_int]),

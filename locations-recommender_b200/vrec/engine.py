@@ -209,6 +209,15 @@ class KnnRecommender:
                                          _ptr(out_count, L.i32p), _ptr(out_status, L.i32p)))
         return out_place, out_rating, out_count[:n], out_status[:n]
 
+    def last_neighbours(self, t: int):
+        """Debug: (person ids ascending, similarities) of target index t of the last recommend() pass."""
+        ids = np.zeros(self.k, dtype=np.int64)
+        sims = np.zeros(self.k, dtype=np.float64)
+        cnt = C.c_int32(0)
+        _check(self.rs.ctx.lib.vrec_knn_debug_last_neighbours(self.rs._h, int(t), self.k, _ptr(ids, L.i64p),
+                                                              _ptr(sims, L.f64p), C.byref(cnt)))
+        return ids[:cnt.value], sims[:cnt.value]
+
     def findSimilarPersons(self, personId: int):
         cap = self.k
         ids = np.zeros(cap, dtype=np.int64)

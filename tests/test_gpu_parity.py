@@ -430,6 +430,30 @@ def test_knn_g2_shape(vrec, ctx, synth, oracle):
     rs.close()
 
 
+def test_knn_multi_wave_grid(vrec, ctx, synth, oracle):
+    # 1024 targets = 8 target tiles x 32 candidate splits = 256 CTAs of the dense kernel on 148 SMs: the CTAs of
+    # a tile start at different times (second wave).  Regression: the targets' dense category rows were
+    # zero-filled and re-scattered by every CTA of the tile, so a late CTA wiped rows others were reading
+    # (found by the full-size parity check of bench.py / tools/knn_fullsize_parity.py: ~2 % of the targets).
+    v, places = synth.g2_place_visits(200000, 20000, seed=20181231)
+    inp = synth.build_rating_vectors(v)
+    rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
+    rng = np.random.default_rng(7)
+    targets = inp.person_id[rng.choice(len(inp.person_id), 1024, replace=False)]
+    rc, opl, ort, ocnt, ost = oracle.knn_query_batch(oracle_knn_data(oracle, inp), targets, 0.5, 0.5, 50,
+                                                     places.id, 10)
+    assert rc == 0
+    rec = vrec.KnnRecommender(rs, 0.5, 0.5, 50)
+    for post_first in (0, 0, 0, 1):
+        rs.set_option("post_first", post_first)
+        pl, rt, cnt, st = rec.recommend(targets, places.id, 10)
+        assert st.tolist() == ost.tolist() and cnt.tolist() == ocnt.tolist()
+        assert np.array_equal(pl, opl)
+        assert np.array_equal(rt.view(np.int64), ort.view(np.int64))            # bit-exact
+    rs.set_option("post_first", 0)
+    rs.close()
+
+
 def test_knn_default_sample_data(vrec, ctx, synth, oracle):
     # config 1 shape at reduced size: degenerate diagonal data, huge tie groups
     pl = synth.sample_places(30000, seed=0)

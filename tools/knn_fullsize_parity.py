@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""Full-size (BASELINE config 3) parity probe: the engine against the oracle on random targets of the
+P = 10^6 region-set, with a per-kernel breakdown of any mismatch.  The oracle is the checker here (test tool).
+  python tools/knn_fullsize_parity.py [--targets 1024] [--persons 1000000] [--places 100000]
+Writes gpurun_out/knn_fullsize_parity.json (details of the mismatching targets)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "locations-recommender_b200")):
+    sys.path.insert(0, p)
+import numpy as np  # noqa: E402
+
+import vrec  # noqa: E402
+from oracle import oracle  # noqa: E402
+from vrec import synth  # noqa: E402
+from bench import oracle_knn_data  # noqa: E402
+
+
+def mismatches(got, want, n):
+    pl, rt, cnt, st = got
+    opl, ort, ocnt, ost = want
+    bad = []
+    for q in range(n):
+        c = int(ocnt[q])
+        if not (int(cnt[q]) == c and int(st[q]) == int(ost[q]) and np.array_equal(pl[q, :c], opl[q, :c])
+                and np.array_equal(rt[q, :c].view(np.int64), ort[q, :c].view(np.int64))):
+            bad.append(q)
+    return bad
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--targets", type=int, default=1024)
+    ap.add_argument("--persons", type=int, default=1_000_000)
+    ap.add_argument("--places", type=int, default=100_000)
+    ap.add_argument("--k", type=int, default=50)
+    args = ap.parse_args()
+    t0 = time.time()
+    v, places = synth.g2_place_visits(args.persons, args.places, seed=20181231, region=0)
+    inp = synth.build_rating_vectors(v)
+    print(f"G2 P={len(inp.person_id)} ({time.time() - t0:.1f}s)", flush=True)
+    oracle.build()
+    d = oracle_knn_data(oracle, inp)
+    ctx = vrec.Context(0)
+    rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
+    rng = np.random.default_rng(7)
+    targets = inp.person_id[rng.choice(len(inp.person_id), args.targets, replace=False)]
+    flt = np.ascontiguousarray(places.id, dtype=np.int64)
+    K, m = args.k, 10
+    t0 = time.time()
+    rc, *want = oracle.knn_query_batch(d, targets, 0.5, 0.5, K, flt, m, n_threads=os.cpu_count() or 1)
+    assert rc == 0
+    print(f"oracle: {args.targets} targets in {time.time() - t0:.1f}s", flush=True)
+    rec = vrec.KnnRecommender(rs, 0.5, 0.5, K)
+    n = len(targets)
+    got = rec.recommend(targets, flt, m)
+    bad = mismatches(got, want, n)
+    print(f"default path, batch of {n}: {len(bad)} mismatching targets", flush=True)
+    out = {"targets": int(n), "mismatching": len(bad), "variants": {}, "details": []}
+
+    def neighbour_diff(q, t):
+        ids, sims = rec.last_neighbours(q)
+        rc, oids, osims = oracle.knn_neighbours(d, int(t), 0.5, 0.5, K)
+        o = np.argsort(oids)
+        oids, osims = oids[o], osims[o]
+        e, w = dict(zip(ids.tolist(), sims.tolist())), dict(zip(oids.tolist(), osims.tolist()))
+        return {"n_engine": len(ids), "n_oracle": len(oids),
+                "engine_only": [(i, e[i].hex()) for i in sorted(set(e) - set(w))],
+                "oracle_only": [(i, w[i].hex()) for i in sorted(set(w) - set(e))],
+                "sim_differs": [(i, e[i].hex(), w[i].hex()) for i in sorted(set(e) & set(w)) if e[i] != w[i]],
+                "oracle_kth": min(w.values()).hex() if w else None,
+                "engine_sorted_by_id": bool(np.all(np.diff(ids) > 0))}
+
+    try:
+        # details of the mismatching targets of THIS pass (the neighbour lists are those of the last pass)
+        for q in bad[:10]:
+            c, ce = int(want[2][q]), int(got[2][q])
+            det = {"q": q, "target": int(targets[q]), "tile": q // 128, "row": q % 128,
+                   "places_engine": got[0][q, :ce].tolist(), "places_oracle": want[0][q, :c].tolist(),
+                   "ratings_engine": [float(x).hex() for x in got[1][q, :ce]],
+                   "ratings_oracle": [float(x).hex() for x in want[1][q, :c]]}
+            det.update(neighbour_diff(q, targets[q]))
+            out["details"].append(det)
+            print(json.dumps(det), flush=True)
+        out["bad_positions"] = bad
+        print("bad positions (tile,row):", [(q // 128, q % 128) for q in bad], flush=True)
+        # a matching target's neighbours as a control of the probe itself
+        good = next(q for q in range(n) if q not in set(bad))
+        print("control (matching target):", json.dumps(neighbour_diff(good, targets[good])), flush=True)
+        got2 = rec.recommend(targets, flt, m)
+        bad2 = mismatches(got2, want, n)
+        same = all(np.array_equal(a, b) for a, b in zip(got, got2))
+        print(f"second run: {len(bad2)} mismatching, outputs identical to the first run: {same}, "
+              f"same targets: {bad2 == bad}", flush=True)
+        out["second_run"] = {"mismatching": len(bad2), "identical": bool(same)}
+        for name, opts in [("knn_kernel=1 (exact scan)", {"knn_kernel": 1}),
+                           ("knn_kernel=2 (CUDA-core tile)", {"knn_kernel": 2}),
+                           ("knn_kernel=3 (tensor cores)", {"knn_kernel": 3}),
+                           ("knn_kernel=4 (tensor cores, specialised)", {"knn_kernel": 4}),
+                           ("debug_skip_postings=1 (expect many)", {"debug_skip_postings": 1}),
+                           ("post_first=1", {"post_first": 1}),
+                           ("splits=1", {"splits": 1}), ("splits=2", {"splits": 2}), ("splits=8", {"splits": 8}),
+                           ("tile=128", {"tile": 128}), ("tile=512", {"tile": 512})]:
+            for k_, v_ in opts.items():
+                rs.set_option(k_, v_)
+            b2 = mismatches(rec.recommend(targets, flt, m), want, n)
+            for k_ in opts:
+                rs.set_option(k_, 0)
+            out["variants"][name] = len(b2)
+            print(f"  {name}: {len(b2)} of {n} mismatch", flush=True)
+        for sz in (128, 256, 512):
+            b2 = mismatches(rec.recommend(targets[:sz], flt, m), [w[:sz] for w in want], sz)
+            out["variants"][f"first {sz}"] = len(b2)
+            print(f"  first {sz} targets: {len(b2)} mismatch {b2}", flush=True)
+        # the bench's batch: 18944 targets (148 tiles, one split), the checked ones first
+        rest = np.setdiff1d(inp.person_id, targets)[:18944 - n]
+        big = np.concatenate([targets, rest])
+        for rep in range(2):
+            gb = rec.recommend(big, flt, m)
+            b2 = mismatches([g[:n] for g in gb], want, n)
+            out["variants"][f"batch 18944 run {rep}"] = len(b2)
+            print(f"  batch of {len(big)} (bench shape), first {n} checked: {len(b2)} mismatch", flush=True)
+            for q in b2[:3]:
+                print("   ", json.dumps({"q": q, **neighbour_diff(q, targets[q])}), flush=True)
+    except Exception:
+        import traceback
+        traceback.print_exc()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "knn_fullsize_parity.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    rs.close()
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
