@@ -2158,13 +2158,20 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                 for (int g = 0; g < 16; ++g)
                     if (g == (i & 15)) gmax[g] = fmaxf(gmax[g], m);
             }
-            float *scratch = reinterpret_cast<float *>(sm.hsim);          // heaps are still empty
+            // the minimum of this thread's 16 maxima, then of the row's 4 threads.  Scratch = the survivor
+            // queues (8 KB, not in use before the main sequence; 2 KB needed).  It used to be 64 floats per
+            // row in the heap area, which holds 8 * K bytes per row: K < 32 overran it into the queues, the
+            // heap indices and the target tables (illegal address at K = 7, P = 10^6).
+            static_assert(sizeof(unsigned long long) * TC_QCAP >= sizeof(float) * 4 * TC_M, "bootstrap scratch");
+            float gmin = gmax[0];
 #pragma unroll
-            for (int g = 0; g < 16; ++g) scratch[(size_t)my_t * 64 + cq * 16 + g] = gmax[g];
+            for (int g = 1; g < 16; ++g) gmin = fminf(gmin, gmax[g]);
+            float *scratch = reinterpret_cast<float *>(sm.queue);
+            scratch[my_t * 4 + cq] = gmin;
             tc::bar_sync(1, WS_WORKERS);
             if (tid < TC_M && sm.tid_of[tid] >= 0) {
-                float theta = scratch[(size_t)tid * 64];
-                for (int g = 1; g < 64; ++g) theta = fminf(theta, scratch[(size_t)tid * 64 + g]);
+                float theta = scratch[tid * 4];
+                for (int g = 1; g < 4; ++g) theta = fminf(theta, scratch[tid * 4 + g]);
                 float thr0 = theta / 1.002f - 2e-5f;
                 thr0 = nextafterf(thr0, 0.0f);                             // keep the bound on the safe side
                 if (thr0 > sm.thr[tid]) sm.thr[tid] = thr0;
@@ -3529,10 +3536,13 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
             }
             VREC_CUDA(cudaMemsetAsync(k->d_work.p, 0, sizeof(int), ctx->stream));
             const size_t psmem = (size_t)POST_WARPS * post_warp_bytes(K);
-            static bool attr_post = false;
-            if (!attr_post) {
-                VREC_CUDA(cudaFuncSetAttribute(knn_postings_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                attr_post = true;
+            // 8 warps x (12 K + 1728) bytes: 100 KB covers K <= 922; K up to TOPK_MAX_K = 1024 needs 110 KB
+            // (the launch used to fail with "invalid argument" for 922 < K <= 1024)
+            static size_t attr_post = 0;
+            if (psmem > attr_post) {
+                const size_t want = std::max(psmem, (size_t)100 * 1024);
+                VREC_CUDA(cudaFuncSetAttribute(knn_postings_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+                attr_post = want;
             }
             int pblocks = std::max(1, std::min(ctx->sm_count * 4, (tn + POST_WARPS - 1) / POST_WARPS));
             knn_postings_kernel<<<pblocks, POST_WARPS * 32, psmem, ctx->stream>>>(

@@ -419,7 +419,16 @@ def test_knn_g2_shape(vrec, ctx, synth, oracle):
     _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 50, targets, places.id, 10)
     rs.set_option("splits", 1)
     _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 50, targets[:10], places.id, 10)
+    # one CTA walks all 157 candidate tiles -> the dense kernel bootstraps its thresholds from 32 tiles.
+    # Regression: the bootstrap scratch (64 floats per target) lived in the heap area, 8 K bytes per target,
+    # and overran it for K < 32 (illegal address at K = 7 on the full-size region-set)
+    for k_small in (7, 31):
+        _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, k_small, targets[:10], places.id, 10)
     rs.set_option("splits", 0)
+    # the largest K of the fused top-K kernels: the postings kernel needs 8 x (12 K + 1728) bytes of shared
+    # memory, more than the 100 KB it used to opt in to when K > 922 (launch failed with "invalid argument")
+    for k_large in (923, 1024):
+        _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, k_large, targets[:10], places.id, 10)
     for kern in (1, 2, 3, 4):               # exact scan, CUDA-core tile, tensor-core tiles: same answers
         rs.set_option("knn_kernel", kern)
         _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, 50, targets[:10], places.id, 10)

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--persons", type=int, default=1_000_000)
     ap.add_argument("--places", type=int, default=100_000)
     ap.add_argument("--k", type=int, default=50)
+    ap.add_argument("--skip-variants", action="store_true", help="only the default path and the other K regimes")
     args = ap.parse_args()
     t0 = time.time()
     v, places = synth.g2_place_visits(args.persons, args.places, seed=20181231, region=0)
@@ -75,6 +76,28 @@ def main():
                 "oracle_kth": min(w.values()).hex() if w else None,
                 "engine_sorted_by_id": bool(np.all(np.diff(ids) > 0))}
 
+    def other_k():
+        # the other K regimes at full size: K <= 56 tensor-core filter (above), K <= 1024 fused exact top-K with the
+        # neighbour-row gather, K > 1024 dense similarity rows + radix select + column scan, and the launchers'
+        # K = 2 000 000 (every positive candidate; bin/knn_recommender.sh:32-35)
+        for k_other, nt in ((7, 64), (31, 64), (200, 32), (1000, 32), (3000, 16), (2_000_000, 8)):
+            tg = targets[:nt]
+            rc, *w2 = oracle.knn_query_batch(d, tg, 0.5, 0.5, k_other, flt, m, n_threads=os.cpu_count() or 1)
+            assert rc == 0
+            r2 = vrec.KnnRecommender(rs, 0.5, 0.5, k_other)
+            b2 = mismatches(r2.recommend(tg, flt, m), w2, nt)
+            b1 = mismatches([np.concatenate([r2.recommend([int(t)], flt, m)[i] for t in tg[:4]]) for i in range(4)],
+                            [w[:4] for w in w2], min(4, nt))
+            out["variants"][f"K={k_other}"] = [len(b2), len(b1)]
+            print(f"  K={k_other}: batch of {nt}: {len(b2)} mismatch; one query at a time (4): {len(b1)} mismatch", flush=True)
+
+    if args.skip_variants:
+        other_k()
+        bad_total = len(bad) + sum(sum(v) for k_, v in out["variants"].items() if k_.startswith("K="))
+        with open(os.path.join(ROOT, "gpurun_out", "knn_fullsize_parity.json"), "w") as f:
+            json.dump(out, f, indent=1)
+        rs.close()
+        return 1 if bad_total else 0
     try:
         # details of the mismatching targets of THIS pass (the neighbour lists are those of the last pass)
         for q in bad[:10]:
@@ -126,6 +149,7 @@ def main():
             print(f"  batch of {len(big)} (bench shape), first {n} checked: {len(b2)} mismatch", flush=True)
             for q in b2[:3]:
                 print("   ", json.dumps({"q": q, **neighbour_diff(q, targets[q])}), flush=True)
+        other_k()
     except Exception:
         import traceback
         traceback.print_exc()
