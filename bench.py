@@ -163,17 +163,24 @@ def oracle_knn_data(oracle, inp):
                           place_dim=inp.place_dim)
 
 
+def knn_count_bad(got, answers):
+    """Targets whose recommended place ids / order, estimated-rating bits, count or status differ from the oracle's."""
+    opl, ort, ocnt, ost = answers[:4]
+    pl, rt, cnt, st = got
+    bad = 0
+    for q in range(len(ocnt)):
+        c = int(ocnt[q])
+        if not (int(cnt[q]) == c and int(st[q]) == int(ost[q]) and np.array_equal(pl[q, :c], opl[q, :c])
+                and np.array_equal(np.ascontiguousarray(rt[q, :c]).view(np.int64),
+                                   np.ascontiguousarray(ort[q, :c]).view(np.int64))):
+            bad += 1
+    return bad
+
+
 def knn_parity(rec, targets, places, max_recs, answers):
     """Engine (vrec_knn_query, host buffers) against the oracle's answers for the same targets of the full-size
     region-set: recommended place ids and their order, estimated ratings bit for bit, counts and statuses."""
-    opl, ort, ocnt, ost = answers[:4]
-    pl, rt, cnt, st = rec.recommend(targets, np.ascontiguousarray(places.id, dtype=np.int64), max_recs)
-    bad = 0
-    for q in range(len(targets)):
-        c = int(ocnt[q])
-        if not (int(cnt[q]) == c and int(st[q]) == int(ost[q]) and np.array_equal(pl[q, :c], opl[q, :c])
-                and np.array_equal(rt[q, :c].view(np.int64), ort[q, :c].view(np.int64))):
-            bad += 1
+    bad = knn_count_bad(rec.recommend(targets, np.ascontiguousarray(places.id, dtype=np.int64), max_recs), answers)
     return {"targets": int(len(targets)), "mismatching_targets": bad, "bit_exact": bad == 0,
             "checked": "place ids + order, estimated_rating bits, counts, statuses against oracle/vrec_oracle.c "
                        "on the full-size region-set (the cpu_baseline sample)"}
@@ -196,7 +203,16 @@ def cpu_knn(args, inp, places, n_targets, repeats=1, check=None):
         assert rc == 0
         best = dt if best is None else min(best, dt)
     if check is not None:           # the oracle as the checker: same targets through the engine, full size
+        step = check.pop("step", None)
         check.update(knn_parity(check.pop("rec"), targets, places, args.max_recs, answers))
+        try:        # and targets spread over the last timed end-to-end step (a full batch per call)
+            ids, got = step
+            rc, *ans = oracle.knn_query_batch(d, ids, 0.5, 0.5, args.k_nearest, places.id, args.max_recs,
+                                              n_threads=threads)
+            bad = knn_count_bad(got, ans) if rc == 0 else len(ids)
+            check["timed_step"] = {"targets": int(len(ids)), "mismatching_targets": bad, "bit_exact": bad == 0}
+        except Exception as e:          # the check must never cost the bench line
+            check["timed_step"] = {"error": f"{type(e).__name__}: {e}"}
     return {"value": n_targets / best, "unit": "persons/s", "cores": threads, "kind": "port",
             "sample": f"{n_targets} random targets of the same region-set, {best:.2f}s, oracle/vrec_oracle.c "
                       f"with OpenMP over targets"}, best
@@ -419,10 +435,18 @@ def run_ours(args):
     cpu_knn_base = knn_par = None
     if rank == 0 and not args.no_cpu_baseline:
         knn_par = {"rec": rec}
+        try:        # 128 targets spread over the last end-to-end step, whose answers are still in the host buffers
+            rows = np.arange(0, B, max(1, B // 128))[:128]
+            knn_par["step"] = (tgt_ids[args.warmup + args.steps - 1][rows],
+                               (h_place.numpy()[rows], h_rating.numpy()[rows], h_count.numpy()[rows],
+                                h_status.numpy()[rows]))
+        except Exception as e:
+            log(f"[bench] timed-step parity sample unavailable: {e}")
         cpu_knn_base, _ = cpu_knn(args, inp, places, args.cpu_knn_targets, check=knn_par)
         log(f"[bench] knn cpu baseline: {cpu_knn_base['value']:.1f} persons/s on {cpu_knn_base['cores']} threads; "
             f"full-size parity on its {knn_par['targets']} targets: "
-            f"{'bit-exact' if knn_par['bit_exact'] else 'MISMATCH on %d targets' % knn_par['mismatching_targets']}")
+            f"{'bit-exact' if knn_par['bit_exact'] else 'MISMATCH on %d targets' % knn_par['mismatching_targets']}; "
+            f"timed step: {knn_par.get('timed_step')}")
     # one person at a time (the launchers' REPL, BASELINE configs 1-2): latency of a single query through the ABI
     single = None
     if rank == 0:
@@ -567,6 +591,7 @@ def run_sg_batch(args, vrec, ctx, world, rank, barrier, max_over_ranks):
     for _ in range(args.steps):
         q = rng.choice(persons, n_q, replace=False)
         oi, op, cnt, its, conv, st = rec.recommend(q, places, 10)
+        last_step = (q, (oi, op, cnt, its, conv, st))
         kernel_us += g.batch_info(6)
         its_sum += int(its.sum())
         n_done += g.batch_info(0)
@@ -586,17 +611,29 @@ def run_sg_batch(args, vrec, ctx, world, rank, barrier, max_over_ranks):
         answers = [og.query(int(v), 0.01, 20, places, 10) for v in sample]
         cdt = time.perf_counter() - t1
         # the oracle as the checker: the same persons through vrec_sg_query (batch kernel), bit for bit
-        oi, op, cnt, its, conv, st = rec.recommend(sample, places, 10)
-        bad = 0
-        for q, (rc, wi, wp, oit, oconv) in enumerate(answers):
-            c = len(wi)
-            if not (int(st[q]) == rc and int(cnt[q]) == c and (int(its[q]), int(conv[q])) == (oit, oconv)
-                    and np.array_equal(oi[q, :c], wi)
-                    and np.array_equal(op[q, :c].view(np.int64), np.asarray(wp, dtype=np.float64).view(np.int64))):
-                bad += 1
+        def count_bad(got, rows, wanted):
+            g_id, g_pr, g_cnt, g_its, g_conv, g_st = got
+            n_bad = 0
+            for r, (rc, wi, wp, oit, oconv) in zip(rows, wanted):
+                c = len(wi)
+                if not (int(g_st[r]) == rc and int(g_cnt[r]) == c and (int(g_its[r]), int(g_conv[r])) == (oit, oconv)
+                        and np.array_equal(g_id[r, :c], wi)
+                        and np.array_equal(g_pr[r, :c].view(np.int64),
+                                           np.asarray(wp, dtype=np.float64).view(np.int64))):
+                    n_bad += 1
+            return n_bad
+        bad = count_bad(rec.recommend(sample, places, 10), range(len(sample)), answers)
         parity = {"targets": len(sample), "mismatching_targets": bad, "bit_exact": bad == 0,
                   "checked": "place ids + order, probability bits, iterations, converged flags against "
                              "oracle/vrec_oracle.c on the full-size graph (the cpu_baseline sample)"}
+        try:        # and 24 persons spread over the LAST timed step (a full batch of n_q persons per call)
+            lq, lgot = last_step
+            rows = list(range(0, len(lq), max(1, len(lq) // 24)))[:24]
+            bad_step = count_bad(lgot, rows, [og.query(int(lq[r]), 0.01, 20, places, 10) for r in rows])
+            parity["timed_step"] = {"targets": len(rows), "mismatching_targets": bad_step, "bit_exact": bad_step == 0}
+            bad += bad_step
+        except Exception as e:          # the check must never cost the bench line
+            parity["timed_step"] = {"error": f"{type(e).__name__}: {e}"}
         cpu = {"value": len(sample) / cdt, "unit": "persons/s", "cores": os.cpu_count() or 1, "kind": "port",
                "sample": f"{len(sample)} persons of the same graph, one query at a time, {cdt:.2f}s, "
                          f"oracle/vrec_oracle.c with OpenMP over rows"}
