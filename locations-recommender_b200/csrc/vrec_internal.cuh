@@ -22,6 +22,10 @@ struct vrec_ctx {
     // multi-GPU (vrec_comm.cu): NCCL communicator of the one-process-per-GPU job
     void *comm = nullptr;
     int rank = 0, world = 1;
+    // opt-ins to large dynamic shared memory are per device, so they are remembered per context (a process may
+    // hold contexts on several devices), not in function-local statics
+    size_t attr_knn_post = 0;
+    bool attr_knn_tc = false, attr_knn_ws = false, attr_knn_tile = false;
 };
 
 void vrec_comm_destroy(vrec_ctx *ctx);

@@ -3538,7 +3538,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
             const size_t psmem = (size_t)POST_WARPS * post_warp_bytes(K);
             // 8 warps x (12 K + 1728) bytes: 100 KB covers K <= 922; K up to TOPK_MAX_K = 1024 needs 110 KB
             // (the launch used to fail with "invalid argument" for 922 < K <= 1024)
-            static size_t attr_post = 0;
+            size_t &attr_post = ctx->attr_knn_post;
             if (psmem > attr_post) {
                 const size_t want = std::max(psmem, (size_t)100 * 1024);
                 VREC_CUDA(cudaFuncSetAttribute(knn_postings_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
@@ -3553,7 +3553,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
             return VREC_OK;
         };
         if (use_tc) {
-            static bool attr_tc = false;
+            bool &attr_tc = ctx->attr_knn_tc;
             if (!attr_tc) {
                 VREC_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
                 attr_tc = true;
@@ -3587,7 +3587,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                 VREC_TRY(k->d_tdense.ensure((size_t)tn * (size_t)std::max(1, (int)k->cat_dim)));
                 aux.tdense = k->d_tdense.p;
                 aux.cat_dim = (int)k->cat_dim;
-                static bool attr_ws = false;
+                bool &attr_ws = ctx->attr_knn_ws;
                 if (!attr_ws) {
                     VREC_CUDA(cudaFuncSetAttribute(knn_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
                     attr_ws = true;
@@ -3609,7 +3609,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                 VREC_LAUNCHED(ctx);
             }
         } else {
-            static bool attr_set = false;
+            bool &attr_set = ctx->attr_knn_tile;
             if (!attr_set) {
                 VREC_CUDA(cudaFuncSetAttribute(knn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 attr_set = true;
