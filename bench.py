@@ -62,7 +62,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples SM clocks and throttle reasons during the timed region (nvidia-smi, 200 ms)."""
+    """Samples SM clocks and throttle reasons during the timed region (nvidia-smi, 100 ms)."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -78,7 +78,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -186,11 +186,12 @@ def knn_parity(rec, targets, places, max_recs, answers):
                        "on the full-size region-set (the cpu_baseline sample)"}
 
 
-def cpu_knn(args, inp, places, n_targets, repeats=1, check=None):
+def cpu_knn(args, inp, places, n_targets, repeats=1, check=None, d=None):
     """CPU oracle (port of the Scala path) on a bounded sample of the same workload."""
     from oracle import oracle
     oracle.build()
-    d = oracle_knn_data(oracle, inp)
+    if d is None:
+        d = oracle_knn_data(oracle, inp)
     threads = os.cpu_count() or 1
     rng = np.random.default_rng(7)
     targets = inp.person_id[rng.choice(len(inp.person_id), n_targets, replace=False)]
@@ -252,11 +253,15 @@ def run_reference(args):
     if rank != 0:
         return
     inp, places = build_knn_inputs(args)
-    per_step = args.ref_knn_targets
+    # a step = a bounded sample of the workload, sized so that the whole run ends within a few minutes
+    per_step = min(args.ref_knn_targets, max(64, 8192 // max(1, args.warmup + args.steps)))
+    from oracle import oracle
+    oracle.build()
+    d = oracle_knn_data(oracle, inp)
     times = []
     cb = None
     for i in range(args.warmup + args.steps):
-        cb, dt = cpu_knn(args, inp, places, per_step)
+        cb, dt = cpu_knn(args, inp, places, per_step, d=d)
         if i >= args.warmup:
             times.append(dt)
     total = sum(times)
@@ -768,7 +773,7 @@ def run_builder(args, vrec, ctx, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)     # 20 x 15.6 ms: long enough for several clock samples
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--knn-persons", type=int, default=1_000_000)
