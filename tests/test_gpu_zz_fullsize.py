@@ -60,6 +60,14 @@ def test_knn_full_size_config3(oracle):
             assert rc == 0
             got = vrec.KnnRecommender(rs, 0.5, 0.5, k_small).recommend(targets[:nt], flt, 10)
             assert _bad(got, w2) == [], k_small
+        # large K: K = 1 000 (fused top-K, fp32 tile filter), 3 000 and the launcher's
+        # K = 2 000 000 (bin/knn_recommender.sh:32-36: every positive candidate is a neighbour) go through
+        # the similarity-row / radix-select / column-scan kernels; few targets, the oracle pays ~0.1 s each
+        for k_large, nt in ((1000, 8), (3000, 6), (2_000_000, 6)):
+            rc, *w3 = oracle.knn_query_batch(d, targets[:nt], 0.5, 0.5, k_large, flt, 10, n_threads=threads)
+            assert rc == 0
+            got = vrec.KnnRecommender(rs, 0.5, 0.5, k_large).recommend(targets[:nt], flt, 10)
+            assert _bad(got, w3) == [], k_large
     finally:
         rs.close()
         ctx.close()
