@@ -71,6 +71,131 @@ __device__ __forceinline__ double canon_row_sum(const int *__restrict__ src, con
     return acc[0];
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Flat-window summation (round 2).  A warp owns consecutive rows whose in-edges are one contiguous
+// range [S, E) of src / w.  It walks that range in 128-byte aligned windows of 32 edges -- lane l
+// always holds position p = l (mod 32), so every src load of the warp is one 128-byte line and
+// every w load two: the L1TEX pipe, which retires one wavefront per clock and is what bounds
+// this kernel (one wavefront per scattered gather of x, tools/gather_probe.cu), carries no
+// wasted streaming wavefronts.  Term k of a row that starts at rs sits at position rs + k,
+// i.e. in physical lane (rs + k) mod 32: canonical lane c = k mod 32 is physical lane
+// (c + rs) mod 32, a rotation.  Each physical lane adds its terms in ascending position
+// (= ascending k, step 32), which is exactly the canonical per-lane order, and when a row ends
+// the 32 lane sums are combined by the canonical xor-butterfly over the *rotated* lane numbers.
+// Rows may end anywhere inside a window; the loads and gathers of the next windows are
+// already in flight while a row is being closed (no per-row drain of the memory pipeline).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double rotated_butterfly(double v, int rot, int lane) {
+    const int c = (lane - rot) & 31;                    // canonical lane of this physical lane
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int srcl = ((c ^ off) + rot) & 31;
+        v = xadd(v, __shfl_sync(0xffffffffu, v, srcl));
+    }
+    return v;                                           // fp add commutes: every lane holds lane 0's sum
+}
+
+
+struct FlatRows {                                       // the rows still open in a run (uniform across the warp)
+    unsigned rows;
+    int cur, rs_cur, re_cur;
+    double acc, sigma;
+};
+
+// One batch (FLAT_U windows from wb) of gathered values and weights: adds every lane's products to
+// its open row and closes the rows that end inside a window.
+template <int FLAT_U>
+__device__ __forceinline__ void flat_process(FlatRows &f, const double (&xx)[FLAT_U], const double (&pw)[FLAT_U],
+                                             int wb, int S, int E, int e, int lane) {
+#pragma unroll
+    for (int q = 0; q < FLAT_U; ++q) {
+        const int w0 = wb + 32 * q;
+        if (w0 < E) {                                   // uniform
+            const int P = w0 + lane, wend = w0 + 32;
+            const bool ok = P >= S && P < E;
+            const double prod = xmul(xx[q], pw[q]);
+            while (f.re_cur <= wend) {                  // uniform: row `cur` ends inside this window
+                const bool mine = ok && P >= f.rs_cur && P < f.re_cur;
+                double v = mine ? xadd(f.acc, prod) : f.acc;
+                v = rotated_butterfly(v, f.rs_cur & 31, lane);
+                if (lane == f.cur) f.sigma = v;
+                f.acc = 0.0;
+                f.rs_cur = f.re_cur;                    // rows tile [S, E): the next non-empty row starts here
+                if (f.rows) {
+                    f.cur = __ffs(f.rows) - 1;
+                    f.rows &= f.rows - 1;
+                    f.re_cur = __shfl_sync(0xffffffffu, e, f.cur);
+                } else {
+                    f.cur = -1;
+                    f.rs_cur = f.re_cur = 0x7fffffff;
+                }
+            }
+            if (ok && P >= f.rs_cur) f.acc = xadd(f.acc, prod);   // the row that goes on past this window
+        }
+    }
+}
+
+template <int FLAT_U>
+__device__ __forceinline__ void flat_load_src(int (&c)[FLAT_U], const int *__restrict__ src, int wb, int S, int E,
+                                              int lane, unsigned long long pol) {
+#pragma unroll
+    for (int q = 0; q < FLAT_U; ++q) {
+        const int P = wb + 32 * q + lane;
+        c[q] = (P >= S && P < E) ? ld_stream_i32(src + P, pol) : -1;
+    }
+}
+// gathers of x and the weights of the same batch (both are first needed when the batch is processed)
+template <int FLAT_U>
+__device__ __forceinline__ void flat_gather(double (&xx)[FLAT_U], double (&pw)[FLAT_U], const int (&c)[FLAT_U],
+                                            const double *__restrict__ x, const double *__restrict__ w, int wb,
+                                            int lane, unsigned long long pol_stream, unsigned long long pol_keep) {
+#pragma unroll
+    for (int q = 0; q < FLAT_U; ++q) {
+        const bool ok = c[q] >= 0;
+        xx[q] = ok ? ld_keep_f64(x + c[q], pol_keep) : 0.0;
+        pw[q] = ok ? ld_stream_f64(w + wb + 32 * q + lane, pol_stream) : 0.0;
+    }
+}
+
+// Sums the non-empty rows `rows` (bit i = row of lane i; e = end of that lane's row; rows ascending and
+// contiguous: together they tile [S, E)) and returns this lane's row sum (0.0 for the other lanes).
+// Software pipeline, three batches deep: the columns of batch n+2 and the gathers / weights of batch n+1
+// are in flight while batch n is processed.
+template <int FLAT_U>
+__device__ __forceinline__ double flat_rows_sum(const int *__restrict__ src, const double *__restrict__ w,
+                                                const double *__restrict__ x, int e, unsigned rows,
+                                                int S, int E, int lane, unsigned long long pol_stream,
+                                                unsigned long long pol_keep) {
+    FlatRows f;
+    f.sigma = 0.0;
+    if (rows == 0u || S >= E) return f.sigma;
+    f.cur = __ffs(rows) - 1;
+    f.rows = rows & (rows - 1);
+    f.rs_cur = S;
+    f.re_cur = __shfl_sync(0xffffffffu, e, f.cur);
+    f.acc = 0.0;
+    constexpr int B = 32 * FLAT_U;
+    int cA[FLAT_U], cB[FLAT_U];
+    double xA[FLAT_U], wA[FLAT_U], xB[FLAT_U], wB[FLAT_U];
+    int wb = S & ~31;
+    flat_load_src<FLAT_U>(cA, src, wb, S, E, lane, pol_stream);
+    flat_load_src<FLAT_U>(cB, src, wb + B, S, E, lane, pol_stream);
+    flat_gather<FLAT_U>(xA, wA, cA, x, w, wb, lane, pol_stream, pol_keep);
+    flat_load_src<FLAT_U>(cA, src, wb + 2 * B, S, E, lane, pol_stream);
+    for (; wb < E; wb += 2 * B) {
+        // batch n in (xA, wA); columns of n+1 in cB, of n+2 in cA
+        flat_gather<FLAT_U>(xB, wB, cB, x, w, wb + B, lane, pol_stream, pol_keep);
+        flat_load_src<FLAT_U>(cB, src, wb + 3 * B, S, E, lane, pol_stream);
+        flat_process<FLAT_U>(f, xA, wA, wb, S, E, e, lane);
+        if (wb + B >= E) break;                         // uniform
+        flat_gather<FLAT_U>(xA, wA, cA, x, w, wb + 2 * B, lane, pol_stream, pol_keep);
+        flat_load_src<FLAT_U>(cA, src, wb + 4 * B, S, E, lane, pol_stream);
+        flat_process<FLAT_U>(f, xB, wB, wb + B, S, E, e, lane);
+    }
+    return f.sigma;
+}
+
 // One warp per 1024-term segment of a long row.
 __global__ void __launch_bounds__(SPMV_THREADS)
 sg_long_partials_kernel(const int *__restrict__ row_start, const int *__restrict__ row_end,
@@ -88,14 +213,16 @@ sg_long_partials_kernel(const int *__restrict__ row_start, const int *__restrict
     int j = seg - long_segptr[slot];
     int s = row_start[row] + j * VREC_CANON_SEG;
     int n = min(VREC_CANON_SEG, row_end[row] - s);
-    double v = canon_row_sum<32>(src, w, x, s, n, lane, policy_evict_first(), policy_evict_last(keep_frac));
+    // one row [s, s+n) held by lane 0
+    double v = flat_rows_sum<4>(src, w, x, s + n, 1u, s, s + n, lane, policy_evict_first(), policy_evict_last(keep_frac));
     if (lane == 0) partials[seg] = v;
 }
 
 // Main pass: sigma per row in the canonical order, x' = u*alpha + sigma*(1-alpha)
 // (calcNextX, :108-128), squared-difference residual (isConverged, :130-141) reduced in a
 // fixed order, and the step() control (:92-106) updated by the last block.
-__global__ void __launch_bounds__(SPMV_THREADS, 4)
+template <bool flat, int MINB, int U>
+__global__ void __launch_bounds__(SPMV_THREADS, MINB)
 sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ row_start, const int *__restrict__ row_end,
                const int *__restrict__ src,
                const double *__restrict__ w, const double *__restrict__ x, double *__restrict__ nx,
@@ -112,17 +239,36 @@ sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ row_start, 
     for (long long base = ((long long)blockIdx.x * SPMV_WARPS + warp) * 32; base < n_rows;
          base += total_warps * 32) {
         long long r = base + lane;
-        int s = 0, e = 0;
+        int s, e;
         if (r < n_rows) {
             s = row_start[r];
             e = row_end[r];
+        } else {
+            s = e = row_end[n_rows - 1];                 // keeps the chunk's flat range well-formed
         }
         int n = e - s;
         double sigma = 0.0;
         const unsigned nonempty = __ballot_sync(0xffffffffu, n > 0 && n <= VREC_CANON_SEG);
         unsigned longrows = __ballot_sync(0xffffffffu, n > VREC_CANON_SEG);
-        // two rows at a time: half-warp h sums row 2j+h of this chunk
-        unsigned pairs = (nonempty | (nonempty >> 1)) & 0x55555555u;
+        if (flat) {
+            // rows with contiguous in-edges: one flat sweep per run of rows between two long rows
+            unsigned lm = longrows;
+            int i0 = 0;
+            while (i0 < 32) {
+                const int j = lm ? __ffs(lm) - 1 : 32;
+                if (j > i0) {
+                    const unsigned run = (j == 32 ? 0xffffffffu : ((1u << j) - 1u)) & ~((1u << i0) - 1u);
+                    const int S = __shfl_sync(0xffffffffu, s, i0), E = __shfl_sync(0xffffffffu, e, j - 1);
+                    const double v = flat_rows_sum<U>(src, w, x, e, nonempty & run, S, E, lane, pol_stream, pol_keep);
+                    if ((run >> lane) & 1u) sigma = v;
+                }
+                if (j == 32) break;
+                lm &= lm - 1;
+                i0 = j + 1;
+            }
+        }
+        // (old layout: sub-ranges of a row are not adjacent) two rows at a time: half-warp h sums row 2j+h
+        unsigned pairs = flat ? 0u : (nonempty | (nonempty >> 1)) & 0x55555555u;
         const int half = lane >> 4, sub = lane & 15;
         while (pairs) {
             int l0 = __ffs(pairs) - 1;
@@ -300,6 +446,7 @@ int sg_setup_device(vrec_sg *g, const std::vector<int> &rowptr, const int *h_src
     vrec_ctx *ctx = g->ctx;
     const int64_t rows = g->row_hi - g->row_lo;
     g->nblocks = g->N > SRC_BLOCK ? (int)((g->N + SRC_BLOCK - 1) / SRC_BLOCK) : 1;
+    g->flat = g->nblocks == 1 && !g->force_rows_kernel;
     g->blocks.clear();
     if (g->nblocks == 1) {
         g->blocks.emplace_back(new vrec_sg::Block());
@@ -356,6 +503,7 @@ int sg_setup_generated(vrec_sg *g) {
     vrec_ctx *ctx = g->ctx;
     const int64_t rows = g->row_hi - g->row_lo;
     g->nblocks = g->N > SRC_BLOCK ? (int)((g->N + SRC_BLOCK - 1) / SRC_BLOCK) : 1;
+    g->flat = g->nblocks == 1 && !g->force_rows_kernel;
     g->blocks.clear();
     if (g->nblocks > 1) {
         VREC_TRY(g->d_bptr.alloc((size_t)(g->nblocks + 1) * (size_t)rows));
@@ -413,7 +561,13 @@ int sg_run_device(vrec_sg *g, long long uidx, double epsilon, int max_it, bool c
                     blk.seg_row.p, blk.n_seg, blk.partials.p, g->d_state.p, keep_frac);
                 VREC_LAUNCHED(ctx);
             }
-            sg_spmv_kernel<<<g->grid, SPMV_THREADS, 0, ctx->stream>>>(
+            // measured on 6 M vertices x 100 in-edges (tools/sg_bench.py): (4 CTAs/SM, 2 windows/batch) 2388 us,
+            // (3, 4) 2509 us, (3, 3) 2535 us, (5, 2) 2571 us, (2, 4) 2665 us per iteration
+            auto kern = !g->flat ? sg_spmv_kernel<false, 4, 4>
+                        : g->flat_variant == 1 ? sg_spmv_kernel<true, 3, 4>
+                        : g->flat_variant == 2 ? sg_spmv_kernel<true, 3, 3>
+                                               : sg_spmv_kernel<true, 4, 2>;
+            kern<<<g->grid, SPMV_THREADS, 0, ctx->stream>>>(
                 rows, g->row_lo, blk.row_start, blk.row_end, g->d_src.p, g->d_w.p, x, nx, uidx, blk.long_rows.p,
                 blk.long_segptr.p, blk.n_long, blk.partials.p, g->d_state.p, g->d_block_partials.p, it, max_it, eps2,
                 check_convergence ? (g->partitioned ? 2 : 1) : 0, keep_frac, b > 0 ? 1 : 0,
@@ -761,6 +915,12 @@ extern "C" int vrec_sg_set_option(vrec_sg *sg, const char *name, int32_t value) 
         sg->batch.mode = value;
     } else if (k == "batch_targets_per_cta" && (value >= 0 && value <= 2)) {
         sg->batch.force_t = value;
+    } else if (k == "flat_variant" && value >= 0 && value <= 2) {
+        sg->flat_variant = value;
+    } else if (k == "rows_kernel" && (value == 0 || value == 1)) {
+        // A/B: 1 = the round-1 half-warp-per-row kernel instead of the flat-window kernel
+        sg->force_rows_kernel = value != 0;
+        sg->flat = sg->nblocks == 1 && !sg->force_rows_kernel;
     } else {
         vrec_set_error("vrec_sg_set_option: unknown option or bad value: %s = %d", name, (int)value);
         return VREC_EINVAL;

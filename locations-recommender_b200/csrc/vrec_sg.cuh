@@ -74,6 +74,9 @@ struct vrec_sg {
         DevBuf<double> partials;              // [n_seg]
     };
     int nblocks = 1;
+    int flat_variant = 0;                     // tuning: (CTAs per SM, windows per batch) of the flat kernel, see sg_run_device
+    bool force_rows_kernel = false;           // debug / A-B: keep the round-1 half-warp-per-row kernel
+    bool flat = true;                         // rows of a block are adjacent in src / w: flat-window kernel
     std::vector<std::unique_ptr<Block>> blocks;
     DevBuf<int> d_bptr;                       // [(nblocks+1) x rows] block boundaries per row (nblocks > 1)
     DevBuf<double> d_x[2];

@@ -18,10 +18,16 @@ ap.add_argument("--deg", type=int, default=100)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=1)
+ap.add_argument("--minb", type=int, default=0)
+ap.add_argument("--rows-kernel", type=int, default=0, help="1 = round-1 half-warp-per-row kernel (A/B)")
 a = ap.parse_args()
 ctx = vrec.Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream)
 g = vrec.StochasticGraph.generate(a.n, a.deg, seed=5, ctx=ctx)
+if a.minb:
+    g.set_option("flat_variant", a.minb)
+if a.rows_kernel:
+    g.set_option("rows_kernel", 1)
 ctx.synchronize()
 bytes_it = 12 * g.nnz + 20 * g.N
 for _ in range(a.warmup):
