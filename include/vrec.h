@@ -64,7 +64,9 @@ int vrec_synchronize(vrec_ctx *ctx);
  * ranks by any means (bench.py uses torch.distributed); every rank then calls vrec_comm_init.
  * Region-sharded work (independent region-sets / target ranges) needs no communicator; it is
  * required only for the row-partitioned graph (vrec_sg_load_partitioned / vrec_sg_generate
- * with world > 1), whose per-iteration all-gather of x' runs on NCCL over NVLink.            */
+ * with world > 1): the ranks exchange CUDA IPC handles of their x buffers over it once per graph;
+ * the per-iteration exchange of x' is then fused into the sweep kernel (peer stores over NVLink,
+ * one flag barrier per iteration, csrc/vrec_sg.cu) -- no collective runs inside the iteration.  */
 int vrec_comm_unique_id(void *out128);
 int vrec_comm_init(vrec_ctx *ctx, int rank, int world, const void *unique_id128);
 int vrec_comm_rank(vrec_ctx *ctx);
@@ -249,10 +251,25 @@ int vrec_build_stochastic_graph(vrec_ctx *ctx, int64_t n_visits, const int64_t *
 int vrec_sg_load(vrec_ctx *ctx, int64_t nnz, const int64_t *source_id, const int64_t *target_id,
                  const double *balanced_weight, vrec_sg **out);
 /* Same, for ONE oversized graph on several GPUs: every rank passes the whole edge list and keeps a
- * contiguous block of rows of P^T (vertex_count / world, rounded up); queries must then be issued
- * by all ranks together (same arguments); every rank gets the full result.                      */
+ * contiguous block of rows of P^T, balanced by in-edges (vrec_sg_row_range); queries must then be
+ * issued by all ranks together (same arguments); every rank gets the full result.  The sweep of
+ * calcNextX (stochastic/StochasticRecommender.scala:108-128) stores every rank's rows of x' straight
+ * into the peers' buffers; the residual partials ride in a slot per rank and one flag barrier per
+ * iteration replaces the reference's per-iteration Spark action (:130-141).                      */
 int vrec_sg_load_partitioned(vrec_ctx *ctx, int64_t nnz, const int64_t *source_id, const int64_t *target_id,
                              const double *balanced_weight, vrec_sg **out);
+int vrec_sg_row_range(vrec_sg *sg, int64_t *out_lo, int64_t *out_hi);   /* rows of P^T this process owns */
+/* Single-process group: the `world` parts of one row-partitioned graph held by the calling process
+ * (same kernels, peer stores and residual slots as the one-process-per-GPU path; the exchange
+ * barrier is the stream order).  Serves hosts that drive the parts from one process and is how the
+ * partition logic is verified where a single GPU is visible.  out_parts[world];
+ * vrec_sg_group_stationary: out_x[world x vertex_count] (every part's copy of the result),
+ * out_iterations / out_converged / out_residual [world].  Free every part with vrec_sg_free.     */
+int vrec_sg_group_load(vrec_ctx *ctx, int32_t world, int64_t nnz, const int64_t *source_id,
+                       const int64_t *target_id, const double *balanced_weight, vrec_sg **out_parts);
+int vrec_sg_group_stationary(vrec_sg **parts, int32_t world, int64_t vertex, double epsilon,
+                             int32_t max_iterations, double *out_x, int32_t *out_iterations,
+                             int32_t *out_converged, double *out_residual);
 void vrec_sg_free(vrec_sg *sg);
 int64_t vrec_sg_vertex_count(vrec_sg *sg);
 int64_t vrec_sg_edge_count(vrec_sg *sg);
@@ -281,7 +298,9 @@ int vrec_sg_query(vrec_sg *sg, const int64_t *vertices, int32_t n,
  * person vertex of the reference's graphs; csrc/vrec_sg_batch.cu).  Results are identical either way.
  *  vrec_sg_set_option  "batch": 0 = per-query kernels only, 1 = batch kernel when a call has >= 4
  *                      eligible start vertices (default), 2 = for every eligible start vertex;
- *                      "batch_targets_per_cta": 0 = auto, 1 or 2
+ *                      "batch_targets_per_cta": 0 = auto, 1 or 2;
+ *                      "rows_kernel": 1 = the round-1 half-warp-per-row sweep instead of the flat-window
+ *                      sweep (A/B measurements); "flat_variant": 0..2 = launch shape of the latter
  *  vrec_sg_batch_info  what = 0: start vertices the last vrec_sg_query served with the batch kernel;
  *                      1: batch path available for this graph; 2: vertices with in-edges; 3: edges
  *                      between them; 4: the same with the slice padding;
@@ -315,6 +334,9 @@ int vrec_sg_generate(vrec_ctx *ctx, int64_t n_vertices, int32_t out_degree, uint
 int vrec_host_sg_csr(int64_t nnz, const int64_t *source_id, const int64_t *target_id,
                      const double *balanced_weight, int64_t *out_n, int64_t *out_ids,
                      int32_t *out_rowptr, int32_t *out_src, double *out_w);
+/* Row ranges of a row-partitioned graph for `world` ranks, from the CSR's rowptr [n_rows+1]:
+ * out_bounds[world+1], rank k owns rows [out_bounds[k], out_bounds[k+1]) (balanced by in-edges). */
+int vrec_host_sg_partition(int64_t n_rows, const int32_t *rowptr, int32_t world, int64_t *out_bounds);
 /* Device CSR of P^T (rows owned by this process) copied back: out_rowptr [rows+1], out_src /
  * out_w [edge_count].                                                                        */
 int vrec_sg_export_csr(vrec_sg *sg, int32_t *out_rowptr, int32_t *out_src, double *out_w);

@@ -93,16 +93,20 @@ void vrec_comm_destroy(vrec_ctx *ctx) {
     }
 }
 
-// in-place all-gather of equal slices: buf holds world * count doubles, this rank's slice at rank * count
-int vrec_comm_allgather_f64(vrec_ctx *ctx, double *buf, size_t count) {
-    if (ctx->world <= 1) return VREC_OK;
-    return nccl_check(g_nccl.AllGather(buf + (size_t)ctx->rank * count, buf, count, ncclDouble, (ncclComm_t)ctx->comm,
-                                       ctx->stream),
-                      "ncclAllGather");
-}
-
-int vrec_comm_allreduce_sum_f64(vrec_ctx *ctx, double *buf, size_t count) {
-    if (ctx->world <= 1) return VREC_OK;
-    return nccl_check(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)ctx->comm, ctx->stream),
-                      "ncclAllReduce");
+// all-gather of `bytes` bytes per rank (device buffers); used once per graph to exchange CUDA IPC handles --
+// the iteration itself exchanges x' with peer stores from the sweep kernel, not with a collective
+int vrec_comm_allgather_bytes(vrec_ctx *ctx, const void *send, void *recv, size_t bytes) {
+    if (ctx->world <= 1) {
+        cudaError_t e = cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+            vrec_set_error("cudaMemcpyAsync -> %s", cudaGetErrorString(e));
+            return VREC_ECUDA;
+        }
+        return VREC_OK;
+    }
+    if (!ctx->comm) {
+        vrec_set_error("vrec_comm_init has not been called on this context");
+        return VREC_ENCCL;
+    }
+    return nccl_check(g_nccl.AllGather(send, recv, bytes, ncclChar, (ncclComm_t)ctx->comm, ctx->stream), "ncclAllGather");
 }

@@ -29,8 +29,7 @@ struct vrec_ctx {
 };
 
 void vrec_comm_destroy(vrec_ctx *ctx);
-int vrec_comm_allgather_f64(vrec_ctx *ctx, double *buf, size_t count);
-int vrec_comm_allreduce_sum_f64(vrec_ctx *ctx, double *buf, size_t count);
+int vrec_comm_allgather_bytes(vrec_ctx *ctx, const void *send, void *recv, size_t bytes);
 
 #define VREC_CUDA(call)                                                                   \
     do {                                                                                  \

@@ -5,7 +5,11 @@
 #include <memory>
 #include <numeric>
 
+#include <string.h>
+
 #include "vrec_sg.cuh"
+
+static int sg_check_params(double epsilon, int32_t max_iterations);
 
 namespace {
 
@@ -218,6 +222,20 @@ sg_long_partials_kernel(const int *__restrict__ row_start, const int *__restrict
     if (lane == 0) partials[seg] = v;
 }
 
+// step() control, stochastic/StochasticRecommender.scala:92-106,130-141
+__device__ __forceinline__ void sg_step_decide(SgState *st, double acc, int iteration, int max_it, double eps2) {
+    st->residual = acc;
+    if (acc <= eps2) {                   // :140 `diffSquared <= epsilonSquared`
+        st->converged = 1;
+        st->iterations = iteration;      // :100 "Converged in $iteration iterations"
+        st->done = 1;
+    } else if (iteration + 1 >= max_it) { // :93-95
+        st->converged = 0;
+        st->iterations = max_it;
+        st->done = 1;
+    }
+}
+
 // Main pass: sigma per row in the canonical order, x' = u*alpha + sigma*(1-alpha)
 // (calcNextX, :108-128), squared-difference residual (isConverged, :130-141) reduced in a
 // fixed order, and the step() control (:92-106) updated by the last block.
@@ -229,7 +247,8 @@ sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ row_start, 
                long long uidx, const int *__restrict__ long_rows, const int *__restrict__ long_segptr,
                int n_long, const double *__restrict__ partials, SgState *st,
                double *__restrict__ block_partials, int iteration, int max_it, double eps2,
-               int check_convergence, float keep_frac, int acc_in, int finalize) {
+               int check_convergence, float keep_frac, int acc_in, int finalize,
+               const SgPeers *__restrict__ peers, int out_buf, unsigned long long flag_value) {
     if (st->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long total_warps = (long long)gridDim.x * SPMV_WARPS;
@@ -309,11 +328,19 @@ sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ row_start, 
             double u = (gi == uidx) ? 1.0 : 0.0;
             double v = xadd(xmul(u, kAlpha), xmul(sigma, one_minus));
             st_stream_f64(nx + gi, v, pol_stream);         // the written buffer is the old x: demote it
+            if (peers) {
+                // row-partitioned graph: the exchange step of the path, fused into the sweep -- every rank
+                // needs the whole x' for its gathers, so the owner stores its rows straight into the peers'
+                // buffers over NVLink (32 consecutive rows per warp = 256-byte peer stores)
+                const int world = peers->world, me = peers->rank;
+                for (int p = 0; p < world; ++p)
+                    if (p != me) peers->x[out_buf][p][gi] = v;
+            }
             double d = xsub(v, ld_keep_f64(x + gi, pol_keep));
             dsum = xadd(dsum, xmul(d, d));
         }
     }
-    if (!check_convergence || !finalize) return;
+    if (!finalize || (!check_convergence && !peers)) return;
     // fixed-order reduction of the residual
     __shared__ double s_part[SPMV_WARPS];
     __shared__ int s_last;
@@ -324,7 +351,11 @@ sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ row_start, 
         double t = 0.0;
         for (int i = 0; i < SPMV_WARPS; ++i) t = xadd(t, s_part[i]);
         block_partials[blockIdx.x] = t;
-        __threadfence();
+    }
+    // this CTA's stores (local and peer) are ordered before its ticket
+    if (peers) __threadfence_system(); else __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
         unsigned tk = atomicInc(&st->ticket, gridDim.x - 1);
         s_last = (tk == gridDim.x - 1);
     }
@@ -334,36 +365,66 @@ sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ row_start, 
         double acc = 0.0;
         for (int k = lane; k < (int)gridDim.x; k += 32) acc = xadd(acc, __ldcg(block_partials + k));
         acc = canon_butterfly(acc);
-        if (lane == 0 && check_convergence == 2) {
-            st->residual_partial = acc;          // partitioned: decided after the all-reduce
-        } else if (lane == 0) {
-            st->residual = acc;
-            if (acc <= eps2) {                   // :140 `diffSquared <= epsilonSquared`
-                st->converged = 1;
-                st->iterations = iteration;      // :100 "Converged in $iteration iterations"
-                st->done = 1;
-            } else if (iteration + 1 >= max_it) { // :93-95
-                st->converged = 0;
-                st->iterations = max_it;
-                st->done = 1;
+        if (peers) {
+            // every CTA's ticket has been seen: publish this rank's residual partial and then its step flag to
+            // every rank (itself included); sg_exchange_wait_kernel takes the step() decision on each rank
+            const int world = peers->world, me = peers->rank;
+            if (lane < world) peers->xchg[lane]->res[iteration & 1][me] = acc;
+            __threadfence_system();
+            __syncwarp();
+            if (lane < world) {
+                volatile unsigned long long *f = &peers->xchg[lane]->flag[me];
+                *f = flag_value;
             }
+        } else if (lane == 0) {
+            sg_step_decide(st, acc, iteration, max_it, eps2);
         }
     }
 }
 
-// step() control for a partitioned graph, after the residual partials were all-reduced
-__global__ void sg_control_kernel(SgState *st, int iteration, int max_it, double eps2) {
+// Row-partitioned graphs.  Waits until every rank has published `flag_value` (its x' rows and residual
+// partial have then landed in this rank's memory), adds the partials in rank order -- the same sum on
+// every rank -- and takes the step() decision.  `spin` = 0 when the ranks are driven from one stream
+// (single-process group): stream order already guarantees the flags.
+__global__ void sg_exchange_wait_kernel(SgState *st, SgExchange *xchg, int world, unsigned long long flag_value,
+                                        int iteration, int max_it, double eps2, int decide, int spin) {
     if (st->done) return;
-    double acc = st->residual_partial;
-    st->residual = acc;
-    if (acc <= eps2) {
-        st->converged = 1;
-        st->iterations = iteration;
-        st->done = 1;
-    } else if (iteration + 1 >= max_it) {
-        st->converged = 0;
-        st->iterations = max_it;
-        st->done = 1;
+    const int lane = threadIdx.x;
+    int late = 0;
+    if (spin && lane < world) {
+        volatile unsigned long long *f = &xchg->flag[lane];
+        const long long t0 = clock64();
+        while (*f < flag_value) {
+            if (clock64() - t0 > (1LL << 33)) {     // ~4 s: a peer is gone
+                late = 1;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    late = __any_sync(0xffffffffu, late);
+    __threadfence_system();
+    if (lane == 0) {
+        if (late) {
+            st->converged = -1;                     // reported as VREC_ENCCL by the host
+            st->done = 1;
+        } else if (decide) {
+            volatile double *r = xchg->res[iteration & 1];
+            double acc = 0.0;
+            for (int q = 0; q < world; ++q) acc = xadd(acc, r[q]);
+            sg_step_decide(st, acc, iteration, max_it, eps2);
+        }
+    }
+}
+
+// publishes a step flag without a sweep (start-of-query barrier: nobody may write a peer's buffers while that
+// peer still reads the result of its previous query)
+__global__ void sg_exchange_signal_kernel(const SgPeers *__restrict__ peers, unsigned long long flag_value) {
+    const int lane = threadIdx.x;
+    __threadfence_system();
+    if (lane < peers->world) {
+        volatile unsigned long long *f = &peers->xchg[lane]->flag[peers->rank];
+        *f = flag_value;
     }
 }
 
@@ -403,11 +464,11 @@ __global__ void sg_candidates_kernel(const long long *__restrict__ ids, long lon
     cand_key[i] = id;
 }
 
-// builds the long-(sub-)range tables of one block from host copies of its boundaries
-int sg_fill_block(vrec_sg *g, vrec_sg::Block &blk, const int *h_start, const int *h_end, int64_t rows) {
+// builds the long-(sub-)range tables of one block from a host copy of its rowptr
+int sg_fill_block(vrec_sg *g, vrec_sg::Block &blk, const int *h_rowptr, int64_t rows) {
     std::vector<int> long_rows, long_segptr(1, 0), seg_row;
     for (int64_t r = 0; r < rows; ++r) {
-        int n = h_end[r] - h_start[r];
+        int n = h_rowptr[r + 1] - h_rowptr[r];
         if (n > VREC_CANON_SEG) {
             int m = (n + VREC_CANON_SEG - 1) / VREC_CANON_SEG;
             for (int j = 0; j < m; ++j) seg_row.push_back((int)long_rows.size());
@@ -428,11 +489,14 @@ int sg_fill_block(vrec_sg *g, vrec_sg::Block &blk, const int *h_start, const int
 int sg_alloc_state(vrec_sg *g) {
     vrec_ctx *ctx = g->ctx;
     const int64_t rows = g->row_hi - g->row_lo;
-    const int64_t xlen = g->partitioned ? g->slice * g->ctx->world : g->N;
-    VREC_TRY(g->d_x[0].alloc((size_t)xlen));
-    VREC_TRY(g->d_x[1].alloc((size_t)xlen));
-    VREC_CUDA(cudaMemsetAsync(g->d_x[0].p, 0, sizeof(double) * (size_t)xlen, ctx->stream));
-    VREC_CUDA(cudaMemsetAsync(g->d_x[1].p, 0, sizeof(double) * (size_t)xlen, ctx->stream));
+    // x[0] | x[1] | exchange block in ONE allocation: a peer maps the whole graph state with one IPC handle
+    g->xstride = (g->N + 31) / 32 * 32;
+    const size_t xchg_doubles = (sizeof(SgExchange) + 7) / 8;
+    VREC_TRY(g->d_xbuf.alloc((size_t)(2 * g->xstride) + xchg_doubles));
+    g->d_x[0] = g->d_xbuf.p;
+    g->d_x[1] = g->d_xbuf.p + g->xstride;
+    g->d_xchg = (SgExchange *)(g->d_xbuf.p + 2 * g->xstride);
+    VREC_CUDA(cudaMemsetAsync(g->d_xbuf.p, 0, g->d_xbuf.bytes(), ctx->stream));
     // grid: a fixed function of the row count only, so the residual order is reproducible
     int64_t want = (rows + 32 * SPMV_WARPS - 1) / (32 * SPMV_WARPS);
     g->grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, 148 * 8));
@@ -441,36 +505,52 @@ int sg_alloc_state(vrec_sg *g) {
     return VREC_OK;
 }
 
-// host-built graphs: rowptr / src are host copies of this process's rows
-int sg_setup_device(vrec_sg *g, const std::vector<int> &rowptr, const int *h_src) {
+inline int sg_count_blocks(int64_t N) { return N > SRC_BLOCK ? (int)((N + SRC_BLOCK - 1) / SRC_BLOCK) : 1; }
+
+// host-built graphs: rowptr / src / w are host copies of this process's rows (sources ascending in each
+// row); splits them into the per-source-block CSRs and uploads those
+int sg_setup_device(vrec_sg *g, const std::vector<int> &rowptr, const int *h_src, const double *h_w) {
     vrec_ctx *ctx = g->ctx;
     const int64_t rows = g->row_hi - g->row_lo;
-    g->nblocks = g->N > SRC_BLOCK ? (int)((g->N + SRC_BLOCK - 1) / SRC_BLOCK) : 1;
-    g->flat = g->nblocks == 1 && !g->force_rows_kernel;
+    g->nblocks = sg_count_blocks(g->N);
     g->blocks.clear();
     if (g->nblocks == 1) {
         g->blocks.emplace_back(new vrec_sg::Block());
         vrec_sg::Block &b = *g->blocks[0];
-        b.row_start = g->d_rowptr.p;
-        b.row_end = g->d_rowptr.p + 1;
-        VREC_TRY(sg_fill_block(g, b, rowptr.data(), rowptr.data() + 1, rows));
+        b.nnz = g->nnz;
+        VREC_TRY(b.rowptr.upload(rowptr.data(), rowptr.size(), ctx->stream));
+        VREC_TRY(b.src.upload(h_src, (size_t)g->nnz, ctx->stream));
+        VREC_TRY(b.w.upload(h_w, (size_t)g->nnz, ctx->stream));
+        VREC_TRY(sg_fill_block(g, b, rowptr.data(), rows));
     } else {
-        // boundaries of every source block inside every (source-sorted) row
-        std::vector<int> bptr((size_t)(g->nblocks + 1) * (size_t)rows);
+        std::vector<int> cut((size_t)(g->nblocks + 1) * (size_t)rows);   // boundaries of every block inside every row
         for (int64_t r = 0; r < rows; ++r) {
             const int *lo = h_src + rowptr[r], *hi = h_src + rowptr[r + 1];
-            bptr[r] = rowptr[r];
+            cut[r] = rowptr[r];
             for (int b = 1; b < g->nblocks; ++b)
-                bptr[(size_t)b * rows + r] = (int)(std::lower_bound(lo, hi, (int)((int64_t)b * SRC_BLOCK)) - h_src);
-            bptr[(size_t)g->nblocks * rows + r] = rowptr[r + 1];
+                cut[(size_t)b * rows + r] = (int)(std::lower_bound(lo, hi, (int)((int64_t)b * SRC_BLOCK)) - h_src);
+            cut[(size_t)g->nblocks * rows + r] = rowptr[r + 1];
         }
-        VREC_TRY(g->d_bptr.upload(bptr.data(), bptr.size(), ctx->stream));
+        std::vector<int> brp((size_t)rows + 1), bsrc;
+        std::vector<double> bw;
         for (int b = 0; b < g->nblocks; ++b) {
+            const int *c0 = cut.data() + (size_t)b * rows, *c1 = cut.data() + (size_t)(b + 1) * rows;
+            brp[0] = 0;
+            for (int64_t r = 0; r < rows; ++r) brp[r + 1] = brp[r] + (c1[r] - c0[r]);
+            bsrc.resize((size_t)brp[rows]);
+            bw.resize((size_t)brp[rows]);
+            for (int64_t r = 0; r < rows; ++r) {
+                std::copy(h_src + c0[r], h_src + c1[r], bsrc.begin() + brp[r]);
+                std::copy(h_w + c0[r], h_w + c1[r], bw.begin() + brp[r]);
+            }
             g->blocks.emplace_back(new vrec_sg::Block());
             vrec_sg::Block &blk = *g->blocks[b];
-            blk.row_start = g->d_bptr.p + (size_t)b * rows;
-            blk.row_end = g->d_bptr.p + (size_t)(b + 1) * rows;
-            VREC_TRY(sg_fill_block(g, blk, bptr.data() + (size_t)b * rows, bptr.data() + (size_t)(b + 1) * rows, rows));
+            blk.nnz = brp[rows];
+            VREC_TRY(blk.rowptr.upload(brp.data(), brp.size(), ctx->stream));
+            VREC_TRY(blk.src.upload(bsrc.data(), bsrc.size(), ctx->stream));
+            VREC_TRY(blk.w.upload(bw.data(), bw.size(), ctx->stream));
+            VREC_TRY(sg_fill_block(g, blk, brp.data(), rows));
+            VREC_CUDA(cudaStreamSynchronize(ctx->stream));          // brp / bsrc / bw are reused
         }
     }
     VREC_TRY(sg_alloc_state(g));
@@ -478,111 +558,275 @@ int sg_setup_device(vrec_sg *g, const std::vector<int> &rowptr, const int *h_src
     return VREC_OK;
 }
 
-// block boundaries of device-generated rows (every row has at most VREC_CANON_SEG in-edges: no long tables)
-__global__ void sg_block_ptr_kernel(int n_rows, const int *__restrict__ rowptr, const int *__restrict__ src, int nblocks,
-                                    int *__restrict__ bptr) {
+// ---- device-generated rows (every row has at most VREC_CANON_SEG in-edges: no long tables) ----
+// cut[b * n_rows + r] = first in-edge of row r whose source belongs to block b or later
+__global__ void sg_block_cut_kernel(int n_rows, const int *__restrict__ rowptr, const int *__restrict__ src, int nblocks,
+                                    int *__restrict__ cut) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)n_rows * (nblocks + 1)) return;
     int b = (int)(i / n_rows), r = (int)(i % n_rows);
     int lo = rowptr[r], hi = rowptr[r + 1];
     if (b == 0) {
-        bptr[i] = lo;
+        cut[i] = lo;
     } else if (b == nblocks) {
-        bptr[i] = hi;
+        cut[i] = hi;
     } else {
         const int key = (int)((long long)b * SRC_BLOCK);
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
             if (src[mid] < key) lo = mid + 1; else hi = mid;
         }
-        bptr[i] = lo;
+        cut[i] = lo;
     }
 }
 
-int sg_setup_generated(vrec_sg *g) {
+// one warp per row: copies the row's part [c0, c1) of the row-major arrays to its place in the block's CSR
+__global__ void sg_block_copy_kernel(int n_rows, const int *__restrict__ c0, const int *__restrict__ c1,
+                                     const int *__restrict__ brp, const int *__restrict__ src,
+                                     const double *__restrict__ w, int *__restrict__ bsrc, double *__restrict__ bw) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rows; r += (long long)gridDim.x * wpb) {
+        const int s = c0[r], n = c1[r] - s, d = brp[r];
+        for (int k = lane; k < n; k += 32) {
+            bsrc[d + k] = src[s + k];
+            bw[d + k] = w[s + k];
+        }
+    }
+}
+
+// rm_* = the generated rows in row-major order; they are released once the blocks are built
+int sg_setup_generated(vrec_sg *g, DevBuf<int> &rm_rowptr, DevBuf<int> &rm_src, DevBuf<double> &rm_w) {
     vrec_ctx *ctx = g->ctx;
     const int64_t rows = g->row_hi - g->row_lo;
-    g->nblocks = g->N > SRC_BLOCK ? (int)((g->N + SRC_BLOCK - 1) / SRC_BLOCK) : 1;
-    g->flat = g->nblocks == 1 && !g->force_rows_kernel;
+    g->nblocks = sg_count_blocks(g->N);
     g->blocks.clear();
-    if (g->nblocks > 1) {
-        VREC_TRY(g->d_bptr.alloc((size_t)(g->nblocks + 1) * (size_t)rows));
-        long long n = (long long)rows * (g->nblocks + 1);
-        sg_block_ptr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((int)rows, g->d_rowptr.p, g->d_src.p,
-                                                                               g->nblocks, g->d_bptr.p);
-        VREC_LAUNCHED(ctx);
-    }
-    for (int b = 0; b < g->nblocks; ++b) {
+    if (g->nblocks == 1) {
         g->blocks.emplace_back(new vrec_sg::Block());
-        vrec_sg::Block &blk = *g->blocks[b];
-        if (g->nblocks == 1) {
-            blk.row_start = g->d_rowptr.p;
-            blk.row_end = g->d_rowptr.p + 1;
-        } else {
-            blk.row_start = g->d_bptr.p + (size_t)b * rows;
-            blk.row_end = g->d_bptr.p + (size_t)(b + 1) * rows;
+        vrec_sg::Block &b = *g->blocks[0];
+        b.nnz = g->nnz;
+        std::swap(b.rowptr.p, rm_rowptr.p); std::swap(b.rowptr.n, rm_rowptr.n);
+        std::swap(b.src.p, rm_src.p); std::swap(b.src.n, rm_src.n);
+        std::swap(b.w.p, rm_w.p); std::swap(b.w.n, rm_w.n);
+        VREC_TRY(b.long_rows.alloc(1));
+        VREC_TRY(b.long_segptr.alloc(2));
+        VREC_TRY(b.seg_row.alloc(1));
+        VREC_TRY(b.partials.alloc(1));
+    } else {
+        DevBuf<int> d_cut, d_brp;
+        VREC_TRY(d_cut.alloc((size_t)(g->nblocks + 1) * (size_t)rows));
+        VREC_TRY(d_brp.alloc((size_t)rows + 1));
+        long long n = (long long)rows * (g->nblocks + 1);
+        sg_block_cut_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((int)rows, rm_rowptr.p, rm_src.p,
+                                                                               g->nblocks, d_cut.p);
+        VREC_LAUNCHED(ctx);
+        std::vector<int> cut((size_t)n), brp((size_t)rows + 1);
+        VREC_CUDA(cudaMemcpyAsync(cut.data(), d_cut.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        VREC_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int b = 0; b < g->nblocks; ++b) {
+            const int *c0 = cut.data() + (size_t)b * rows, *c1 = cut.data() + (size_t)(b + 1) * rows;
+            brp[0] = 0;
+            for (int64_t r = 0; r < rows; ++r) brp[r + 1] = brp[r] + (c1[r] - c0[r]);
+            g->blocks.emplace_back(new vrec_sg::Block());
+            vrec_sg::Block &blk = *g->blocks[b];
+            blk.nnz = brp[rows];
+            VREC_TRY(blk.rowptr.upload(brp.data(), brp.size(), ctx->stream));
+            VREC_TRY(blk.src.alloc((size_t)blk.nnz));
+            VREC_TRY(blk.w.alloc((size_t)blk.nnz));
+            sg_block_copy_kernel<<<148 * 8, 256, 0, ctx->stream>>>((int)rows, d_cut.p + (size_t)b * rows,
+                                                                   d_cut.p + (size_t)(b + 1) * rows, blk.rowptr.p,
+                                                                   rm_src.p, rm_w.p, blk.src.p, blk.w.p);
+            VREC_LAUNCHED(ctx);
+            VREC_TRY(blk.long_rows.alloc(1));
+            VREC_TRY(blk.long_segptr.alloc(2));
+            VREC_TRY(blk.seg_row.alloc(1));
+            VREC_TRY(blk.partials.alloc(1));
+            VREC_CUDA(cudaStreamSynchronize(ctx->stream));          // brp is reused
         }
-        VREC_TRY(blk.long_rows.alloc(1));
-        VREC_TRY(blk.long_segptr.alloc(2));
-        VREC_TRY(blk.seg_row.alloc(1));
-        VREC_TRY(blk.partials.alloc(1));
+        rm_rowptr.release();
+        rm_src.release();
+        rm_w.release();
     }
     VREC_TRY(sg_alloc_state(g));
     return VREC_OK;
 }
 
+// ---- peers of a row-partitioned graph ----
+// Offset of a device pointer inside its allocation (an IPC handle always names the allocation's base).
+int sg_alloc_offset(const void *p, size_t *off) {
+    typedef int (*get_range_t)(unsigned long long *, size_t *, unsigned long long);
+    static get_range_t fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &qr);
+        if (e != cudaSuccess || !sym) {
+            vrec_set_error("cuMemGetAddressRange is not available: %s", cudaGetErrorString(e));
+            return VREC_ECUDA;
+        }
+        fn = (get_range_t)sym;
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (fn(&base, &size, (unsigned long long)(uintptr_t)p) != 0) {
+        vrec_set_error("cuMemGetAddressRange failed");
+        return VREC_ECUDA;
+    }
+    *off = (size_t)((unsigned long long)(uintptr_t)p - base);
+    return VREC_OK;
+}
+
+int sg_publish_peers(vrec_sg *g) {
+    VREC_TRY(g->d_peers.upload(&g->peers, 1, g->ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    g->peers_ready = true;
+    return VREC_OK;
+}
+
+// one process per GPU: every rank maps every other rank's state buffer through CUDA IPC; the handles travel
+// over the NCCL communicator the context already owns (vrec_comm_init)
+int sg_setup_peers_ipc(vrec_sg *g) {
+    vrec_ctx *ctx = g->ctx;
+    const int W = ctx->world, me = ctx->rank;
+    if (W > VREC_MAX_WORLD) {
+        vrec_set_error("row-partitioned graphs support at most %d ranks", VREC_MAX_WORLD);
+        return VREC_EINVAL;
+    }
+    struct Wire {
+        cudaIpcMemHandle_t handle;
+        unsigned long long offset;
+    };
+    Wire mine;
+    memset(&mine, 0, sizeof mine);
+    size_t off = 0;
+    VREC_TRY(sg_alloc_offset(g->d_xbuf.p, &off));
+    mine.offset = off;
+    VREC_CUDA(cudaIpcGetMemHandle(&mine.handle, g->d_xbuf.p));
+    DevBuf<unsigned char> d_send, d_recv;
+    VREC_TRY(d_send.upload((const unsigned char *)&mine, sizeof mine, ctx->stream));
+    VREC_TRY(d_recv.alloc(sizeof(Wire) * (size_t)W));
+    VREC_TRY(vrec_comm_allgather_bytes(ctx, d_send.p, d_recv.p, sizeof(Wire)));
+    std::vector<Wire> all((size_t)W);
+    VREC_CUDA(cudaMemcpyAsync(all.data(), d_recv.p, sizeof(Wire) * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
+    VREC_CUDA(cudaStreamSynchronize(ctx->stream));
+    memset(&g->peers, 0, sizeof g->peers);
+    g->peers.world = W;
+    g->peers.rank = me;
+    for (int r = 0; r < W; ++r) {
+        double *base;
+        if (r == me) {
+            base = g->d_xbuf.p;
+        } else {
+            void *m = nullptr;
+            VREC_CUDA(cudaIpcOpenMemHandle(&m, all[r].handle, cudaIpcMemLazyEnablePeerAccess));
+            g->ipc_opened.push_back(m);
+            base = (double *)((char *)m + all[r].offset);
+        }
+        g->peers.x[0][r] = base;
+        g->peers.x[1][r] = base + g->xstride;
+        g->peers.xchg[r] = (SgExchange *)(base + 2 * g->xstride);
+    }
+    return sg_publish_peers(g);
+}
+
 }  // namespace
 
-// launches the whole step() loop for one vertex index; results stay on the device
-int sg_run_device(vrec_sg *g, long long uidx, double epsilon, int max_it, bool check_convergence) {
-    vrec_ctx *ctx = g->ctx;
-    const int rows = (int)(g->row_hi - g->row_lo);
-    const double x0 = 1.0 / (double)g->N;                   // :53-54
-    const double eps2 = epsilon * epsilon;                  // :40
+vrec_sg::~vrec_sg() {
+    for (void *m : ipc_opened) cudaIpcCloseMemHandle(m);
+}
+
+// ---------------------------------------------------------------------------------------
+// The step() loop on the device.  Split in three so that a single-process group of ranks can be
+// driven from one stream (vrec_sg_group_stationary): begin / one sweep / the exchange barrier.
+// ---------------------------------------------------------------------------------------
+static float sg_keep_frac(const vrec_sg *g) {
     // pin at most ~60 MiB of x in L2 (measured: 64 MB of evict_last data stays resident on B200
     // next to the streamed matrix, 80 MB does not)
     const double keep_bytes = 60.0 * 1024 * 1024;
     const double gathered = 8.0 * (double)std::min<int64_t>(std::max<int64_t>(1, g->N), SRC_BLOCK);
-    const float keep_frac = (float)std::min(1.0, keep_bytes / gathered);
+    return (float)std::min(1.0, keep_bytes / gathered);
+}
+
+static unsigned long long sg_flag(const vrec_sg *g, int step) { return (g->epoch << 32) | (unsigned)step; }
+
+int sg_run_begin(vrec_sg *g, int max_it, bool spin) {
+    vrec_ctx *ctx = g->ctx;
+    const double x0 = 1.0 / (double)g->N;                   // :53-54
+    if (g->partitioned) {
+        if (!g->peers_ready) {
+            vrec_set_error("row-partitioned graph: peers are not connected");
+            return VREC_EINVAL;
+        }
+        g->epoch++;
+    }
     sg_reset_state_kernel<<<1, 1, 0, ctx->stream>>>(g->d_state.p, max_it);
     VREC_LAUNCHED(ctx);
     int fill_grid = (int)std::min<int64_t>((g->N + 255) / 256, 148 * 16);
-    sg_fill_kernel<<<std::max(1, fill_grid), 256, 0, ctx->stream>>>(g->d_x[0].p, g->N, x0);
+    sg_fill_kernel<<<std::max(1, fill_grid), 256, 0, ctx->stream>>>(g->d_x[0], g->N, x0);
     VREC_LAUNCHED(ctx);
-    for (int it = 0; it < max_it; ++it) {
-        const double *x = g->d_x[it & 1].p;
-        double *nx = g->d_x[(it + 1) & 1].p;
-        for (int b = 0; b < g->nblocks; ++b) {
-            vrec_sg::Block &blk = *g->blocks[b];
-            if (blk.n_seg > 0) {
-                int pg = (blk.n_seg + SPMV_WARPS - 1) / SPMV_WARPS;
-                sg_long_partials_kernel<<<pg, SPMV_THREADS, 0, ctx->stream>>>(
-                    blk.row_start, blk.row_end, g->d_src.p, g->d_w.p, x, blk.long_rows.p, blk.long_segptr.p,
-                    blk.seg_row.p, blk.n_seg, blk.partials.p, g->d_state.p, keep_frac);
-                VREC_LAUNCHED(ctx);
-            }
-            // measured on 6 M vertices x 100 in-edges (tools/sg_bench.py): (4 CTAs/SM, 2 windows/batch) 2388 us,
-            // (3, 4) 2509 us, (3, 3) 2535 us, (5, 2) 2571 us, (2, 4) 2665 us per iteration
-            auto kern = !g->flat ? sg_spmv_kernel<false, 4, 4>
-                        : g->flat_variant == 1 ? sg_spmv_kernel<true, 3, 4>
-                        : g->flat_variant == 2 ? sg_spmv_kernel<true, 3, 3>
-                                               : sg_spmv_kernel<true, 4, 2>;
-            kern<<<g->grid, SPMV_THREADS, 0, ctx->stream>>>(
-                rows, g->row_lo, blk.row_start, blk.row_end, g->d_src.p, g->d_w.p, x, nx, uidx, blk.long_rows.p,
-                blk.long_segptr.p, blk.n_long, blk.partials.p, g->d_state.p, g->d_block_partials.p, it, max_it, eps2,
-                check_convergence ? (g->partitioned ? 2 : 1) : 0, keep_frac, b > 0 ? 1 : 0,
-                b == g->nblocks - 1 ? 1 : 0);
+    if (g->partitioned && max_it > 0) {
+        // nobody writes x[1] of a peer that may still be reading the result of its previous query
+        sg_exchange_signal_kernel<<<1, 32, 0, ctx->stream>>>(g->d_peers.p, sg_flag(g, 0));
+        VREC_LAUNCHED(ctx);
+        if (spin) {
+            sg_exchange_wait_kernel<<<1, 32, 0, ctx->stream>>>(g->d_state.p, g->d_xchg, g->peers.world, sg_flag(g, 0), 0,
+                                                               max_it, 0.0, 0, 1);
             VREC_LAUNCHED(ctx);
         }
-        if (g->partitioned) {
-            // the one exchange step of the path: every rank needs the whole x' for its gathers
-            VREC_TRY(vrec_comm_allgather_f64(ctx, nx, (size_t)g->slice));
-            if (check_convergence) {
-                VREC_TRY(vrec_comm_allreduce_sum_f64(ctx, &g->d_state.p->residual_partial, 1));
-                sg_control_kernel<<<1, 1, 0, ctx->stream>>>(g->d_state.p, it, max_it, eps2);
-                VREC_LAUNCHED(ctx);
-            }
+    }
+    return VREC_OK;
+}
+
+int sg_run_sweep(vrec_sg *g, long long uidx, int it, int max_it, double eps2, bool check_convergence) {
+    vrec_ctx *ctx = g->ctx;
+    const int rows = (int)(g->row_hi - g->row_lo);
+    const float keep_frac = sg_keep_frac(g);
+    const double *x = g->d_x[it & 1];
+    double *nx = g->d_x[(it + 1) & 1];
+    for (int b = 0; b < g->nblocks; ++b) {
+        vrec_sg::Block &blk = *g->blocks[b];
+        if (blk.n_seg > 0) {
+            int pg = (blk.n_seg + SPMV_WARPS - 1) / SPMV_WARPS;
+            sg_long_partials_kernel<<<pg, SPMV_THREADS, 0, ctx->stream>>>(
+                blk.rowptr.p, blk.rowptr.p + 1, blk.src.p, blk.w.p, x, blk.long_rows.p, blk.long_segptr.p,
+                blk.seg_row.p, blk.n_seg, blk.partials.p, g->d_state.p, keep_frac);
+            VREC_LAUNCHED(ctx);
         }
+        // measured on 6 M vertices x 100 in-edges (tools/sg_bench.py): (4 CTAs/SM, 2 windows/batch) 2388 us,
+        // (3, 4) 2509 us, (3, 3) 2535 us, (5, 2) 2571 us, (2, 4) 2665 us per iteration
+        auto kern = g->rows_kernel ? sg_spmv_kernel<false, 4, 4>
+                    : g->flat_variant == 1 ? sg_spmv_kernel<true, 3, 4>
+                    : g->flat_variant == 2 ? sg_spmv_kernel<true, 3, 3>
+                                           : sg_spmv_kernel<true, 4, 2>;
+        kern<<<g->grid, SPMV_THREADS, 0, ctx->stream>>>(
+            rows, g->row_lo, blk.rowptr.p, blk.rowptr.p + 1, blk.src.p, blk.w.p, x, nx, uidx, blk.long_rows.p,
+            blk.long_segptr.p, blk.n_long, blk.partials.p, g->d_state.p, g->d_block_partials.p, it, max_it, eps2,
+            check_convergence ? 1 : 0, keep_frac, b > 0 ? 1 : 0, b == g->nblocks - 1 ? 1 : 0,
+            g->partitioned ? g->d_peers.p : nullptr, (it + 1) & 1, sg_flag(g, it + 1));
+        VREC_LAUNCHED(ctx);
+    }
+    return VREC_OK;
+}
+
+int sg_run_barrier(vrec_sg *g, int it, int max_it, double eps2, bool check_convergence, bool spin) {
+    if (!g->partitioned) return VREC_OK;
+    vrec_ctx *ctx = g->ctx;
+    sg_exchange_wait_kernel<<<1, 32, 0, ctx->stream>>>(g->d_state.p, g->d_xchg, g->peers.world, sg_flag(g, it + 1), it,
+                                                       max_it, eps2, check_convergence ? 1 : 0, spin ? 1 : 0);
+    VREC_LAUNCHED(ctx);
+    return VREC_OK;
+}
+
+// launches the whole step() loop for one vertex index; results stay on the device
+int sg_run_device(vrec_sg *g, long long uidx, double epsilon, int max_it, bool check_convergence) {
+    const double eps2 = epsilon * epsilon;                  // :40
+    if (g->partitioned && g->peers_local) {
+        vrec_set_error("this graph belongs to a single-process group: use vrec_sg_group_stationary");
+        return VREC_EINVAL;
+    }
+    VREC_TRY(sg_run_begin(g, max_it, true));
+    for (int it = 0; it < max_it; ++it) {
+        VREC_TRY(sg_run_sweep(g, uidx, it, max_it, eps2, check_convergence));
+        VREC_TRY(sg_run_barrier(g, it, max_it, eps2, check_convergence, true));
     }
     return VREC_OK;
 }
@@ -590,6 +834,10 @@ int sg_run_device(vrec_sg *g, long long uidx, double epsilon, int max_it, bool c
 int sg_fetch_state(vrec_sg *g, int max_it, SgState *h, int *result_buf) {
     VREC_CUDA(cudaMemcpyAsync(h, g->d_state.p, sizeof(SgState), cudaMemcpyDeviceToHost, g->ctx->stream));
     VREC_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    if (h->converged < 0) {
+        vrec_set_error("row-partitioned graph: a peer did not reach the exchange barrier in time");
+        return VREC_ENCCL;
+    }
     if (max_it <= 0) {
         h->iterations = 0;
         h->converged = 0;
@@ -688,13 +936,9 @@ extern "C" int vrec_sg_load(vrec_ctx *ctx, int64_t nnz, const int64_t *source_id
         g->nnz = nnz;
         g->row_lo = 0;
         g->row_hi = g->N;
-        g->slice = g->N;
         rc = g->d_ids.upload((const long long *)g->h_ids.data(), g->h_ids.size(), ctx->stream);
     }
-    if (rc == VREC_OK) rc = g->d_rowptr.upload(rowptr.data(), rowptr.size(), ctx->stream);
-    if (rc == VREC_OK) rc = g->d_src.upload(src.data(), src.size(), ctx->stream);
-    if (rc == VREC_OK) rc = g->d_w.upload(w.data(), w.size(), ctx->stream);
-    if (rc == VREC_OK) rc = sg_setup_device(g, rowptr, src.data());
+    if (rc == VREC_OK) rc = sg_setup_device(g, rowptr, src.data(), w.data());
     if (rc == VREC_OK) rc = sg_batch_analyse(g, rowptr, src.data(), w.data());
     if (rc != VREC_OK) {
         delete g;
@@ -704,8 +948,60 @@ extern "C" int vrec_sg_load(vrec_ctx *ctx, int64_t nnz, const int64_t *source_id
     return VREC_OK;
 }
 
-// Row-partitioned load of one oversized graph: every rank passes the whole edge list and keeps
-// the rows [rank*slice, (rank+1)*slice) of P^T; x is all-gathered after every iteration.
+// Row ranges of a row-partitioned graph: contiguous, balanced by in-edges (rank k starts at the first row whose
+// rowptr reaches k * nnz / world), the same on every rank.
+void vrec_sg_partition_bounds(const std::vector<int> &rowptr, int world, std::vector<int64_t> &bounds) {
+    const int64_t N = (int64_t)rowptr.size() - 1, nnz = rowptr[N];
+    bounds.assign((size_t)world + 1, N);
+    bounds[0] = 0;
+    for (int k = 1; k < world; ++k) {
+        const int64_t want = nnz / world * k + (nnz % world) * k / world;
+        int64_t r = std::lower_bound(rowptr.begin(), rowptr.end(), (int)std::min<int64_t>(want, 0x7fffffff)) - rowptr.begin();
+        bounds[k] = std::max(bounds[k - 1], std::min<int64_t>(r, N));
+    }
+}
+
+extern "C" int vrec_host_sg_partition(int64_t n_rows, const int32_t *rowptr, int32_t world, int64_t *out_bounds) {
+    if (!rowptr || !out_bounds || world < 1 || n_rows < 0) return VREC_EINVAL;
+    std::vector<int> rp(rowptr, rowptr + n_rows + 1);
+    std::vector<int64_t> b;
+    vrec_sg_partition_bounds(rp, world, b);
+    std::copy(b.begin(), b.end(), out_bounds);
+    return VREC_OK;
+}
+
+static int sg_load_rows(vrec_ctx *ctx, int rank, int world, int64_t nnz, const int64_t *source_id,
+                        const int64_t *target_id, const double *balanced_weight, vrec_sg **out) {
+    std::vector<int> rowptr, src;
+    std::vector<double> w;
+    vrec_sg *g = new vrec_sg();
+    g->ctx = ctx;
+    int rc = vrec_host_build_sg(nnz, source_id, target_id, balanced_weight, g->h_ids, rowptr, src, w);
+    if (rc == VREC_OK) {
+        g->N = (int64_t)g->h_ids.size();
+        std::vector<int64_t> bounds;
+        vrec_sg_partition_bounds(rowptr, world, bounds);
+        g->row_lo = bounds[rank];
+        g->row_hi = bounds[rank + 1];
+        g->partitioned = world > 1;
+        const int e0 = rowptr[g->row_lo], e1 = rowptr[g->row_hi];
+        g->nnz = e1 - e0;
+        std::vector<int> lrp(rowptr.begin() + g->row_lo, rowptr.begin() + g->row_hi + 1);
+        for (int &v : lrp) v -= e0;
+        rc = g->d_ids.upload((const long long *)g->h_ids.data(), g->h_ids.size(), ctx->stream);
+        if (rc == VREC_OK) rc = sg_setup_device(g, lrp, src.data() + e0, w.data() + e0);
+    }
+    if (rc != VREC_OK) {
+        delete g;
+        return rc;
+    }
+    *out = g;
+    return VREC_OK;
+}
+
+// Row-partitioned load of one oversized graph: every rank passes the whole edge list and keeps a contiguous
+// range of rows of P^T (balanced by in-edges); during a sweep every rank stores its rows of x' straight into
+// the peers' buffers (sg_spmv_kernel), so no separate exchange step exists.
 extern "C" int vrec_sg_load_partitioned(vrec_ctx *ctx, int64_t nnz, const int64_t *source_id,
                                         const int64_t *target_id, const double *balanced_weight, vrec_sg **out) {
     if (!ctx || !out || (nnz > 0 && (!source_id || !target_id || !balanced_weight))) {
@@ -714,33 +1010,97 @@ extern "C" int vrec_sg_load_partitioned(vrec_ctx *ctx, int64_t nnz, const int64_
     }
     *out = nullptr;
     VREC_CUDA(cudaSetDevice(ctx->device));
-    std::vector<int> rowptr, src;
-    std::vector<double> w;
-    vrec_sg *g = new vrec_sg();
-    g->ctx = ctx;
-    int rc = vrec_host_build_sg(nnz, source_id, target_id, balanced_weight, g->h_ids, rowptr, src, w);
-    if (rc == VREC_OK) {
-        g->N = (int64_t)g->h_ids.size();
-        g->slice = (g->N + ctx->world - 1) / ctx->world;
-        g->row_lo = std::min<int64_t>(g->N, g->slice * ctx->rank);
-        g->row_hi = std::min<int64_t>(g->N, g->row_lo + g->slice);
-        g->partitioned = ctx->world > 1;
-        const int e0 = rowptr[g->row_lo], e1 = rowptr[g->row_hi];
-        g->nnz = e1 - e0;
-        std::vector<int> lrp(rowptr.begin() + g->row_lo, rowptr.begin() + g->row_hi + 1);
-        for (int &v : lrp) v -= e0;
-        rowptr.swap(lrp);
-        rc = g->d_ids.upload((const long long *)g->h_ids.data(), g->h_ids.size(), ctx->stream);
-        if (rc == VREC_OK) rc = g->d_rowptr.upload(rowptr.data(), rowptr.size(), ctx->stream);
-        if (rc == VREC_OK) rc = g->d_src.upload(src.data() + e0, (size_t)g->nnz, ctx->stream);
-        if (rc == VREC_OK) rc = g->d_w.upload(w.data() + e0, (size_t)g->nnz, ctx->stream);
-        if (rc == VREC_OK) rc = sg_setup_device(g, rowptr, src.data() + e0);
-    }
-    if (rc != VREC_OK) {
-        delete g;
-        return rc;
+    vrec_sg *g = nullptr;
+    VREC_TRY(sg_load_rows(ctx, ctx->rank, ctx->world, nnz, source_id, target_id, balanced_weight, &g));
+    if (g->partitioned) {
+        int rc = sg_setup_peers_ipc(g);
+        if (rc != VREC_OK) {
+            delete g;
+            return rc;
+        }
     }
     *out = g;
+    return VREC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Single-process group: the `world` parts of one row-partitioned graph held by ONE process (all on the
+// context's device, or on several devices with peer access), driven from the calling thread.  Same kernels,
+// same peer stores, same residual slots as the one-process-per-GPU path; the exchange barrier is the stream
+// order instead of a spin on the peers' flags.  It is how the partition logic is checked where only one GPU
+// is visible (tests), and it serves hosts that drive several GPUs from one process.
+// ---------------------------------------------------------------------------------------
+extern "C" int vrec_sg_group_load(vrec_ctx *ctx, int32_t world, int64_t nnz, const int64_t *source_id,
+                                  const int64_t *target_id, const double *balanced_weight, vrec_sg **out_parts) {
+    if (!ctx || !out_parts || world < 1 || world > VREC_MAX_WORLD ||
+        (nnz > 0 && (!source_id || !target_id || !balanced_weight))) {
+        vrec_set_error("vrec_sg_group_load: bad argument");
+        return VREC_EINVAL;
+    }
+    VREC_CUDA(cudaSetDevice(ctx->device));
+    std::vector<vrec_sg *> parts((size_t)world, nullptr);
+    int rc = VREC_OK;
+    for (int r = 0; r < world && rc == VREC_OK; ++r)
+        rc = sg_load_rows(ctx, r, world, nnz, source_id, target_id, balanced_weight, &parts[r]);
+    for (int r = 0; r < world && rc == VREC_OK; ++r) {
+        vrec_sg *g = parts[r];
+        g->partitioned = true;                      // also for world == 1: exercises the exchange code
+        g->peers_local = true;
+        memset(&g->peers, 0, sizeof g->peers);
+        g->peers.world = world;
+        g->peers.rank = r;
+        for (int q = 0; q < world; ++q) {
+            g->peers.x[0][q] = parts[q]->d_x[0];
+            g->peers.x[1][q] = parts[q]->d_x[1];
+            g->peers.xchg[q] = parts[q]->d_xchg;
+        }
+        rc = sg_publish_peers(g);
+    }
+    if (rc != VREC_OK) {
+        for (vrec_sg *g : parts) delete g;
+        return rc;
+    }
+    std::copy(parts.begin(), parts.end(), out_parts);
+    return VREC_OK;
+}
+
+extern "C" int vrec_sg_group_stationary(vrec_sg **parts, int32_t world, int64_t vertex, double epsilon,
+                                        int32_t max_iterations, double *out_x /* [world x N] */,
+                                        int32_t *out_iterations, int32_t *out_converged, double *out_residual) {
+    if (!parts || world < 1 || !out_x) return VREC_EINVAL;
+    VREC_TRY(sg_check_params(epsilon, max_iterations));
+    vrec_sg *g0 = parts[0];
+    VREC_CUDA(cudaSetDevice(g0->ctx->device));
+    int64_t v = sg_lookup(g0, vertex);
+    if (v < 0) {
+        vrec_set_error("No such vertex in the graph: %lld", (long long)vertex);
+        return VREC_ENOENT;
+    }
+    const double eps2 = epsilon * epsilon;
+    for (int r = 0; r < world; ++r) VREC_TRY(sg_run_begin(parts[r], max_iterations, false));
+    for (int it = 0; it < max_iterations; ++it) {
+        for (int r = 0; r < world; ++r) VREC_TRY(sg_run_sweep(parts[r], v, it, max_iterations, eps2, true));
+        for (int r = 0; r < world; ++r) VREC_TRY(sg_run_barrier(parts[r], it, max_iterations, eps2, true, false));
+    }
+    for (int r = 0; r < world; ++r) {
+        vrec_sg *g = parts[r];
+        SgState st;
+        int buf = 0;
+        VREC_TRY(sg_fetch_state(g, max_iterations, &st, &buf));
+        VREC_CUDA(cudaMemcpyAsync(out_x + (size_t)r * (size_t)g->N, g->d_x[buf], sizeof(double) * (size_t)g->N,
+                                  cudaMemcpyDeviceToHost, g->ctx->stream));
+        VREC_CUDA(cudaStreamSynchronize(g->ctx->stream));
+        if (out_iterations) out_iterations[r] = st.iterations;
+        if (out_converged) out_converged[r] = st.converged;
+        if (out_residual) out_residual[r] = st.residual;
+    }
+    return VREC_OK;
+}
+
+extern "C" int vrec_sg_row_range(vrec_sg *sg, int64_t *out_lo, int64_t *out_hi) {
+    if (!sg || !out_lo || !out_hi) return VREC_EINVAL;
+    *out_lo = sg->row_lo;
+    *out_hi = sg->row_hi;
     return VREC_OK;
 }
 
@@ -766,8 +1126,9 @@ extern "C" int vrec_sg_vertex_ids(vrec_sg *sg, int64_t *out_ids) {
 
 extern "C" int64_t vrec_sg_resident_bytes(vrec_sg *sg) {
     if (!sg) return 0;
-    return (int64_t)(sg->d_rowptr.bytes() + sg->d_src.bytes() + sg->d_w.bytes() + sg->d_x[0].bytes() +
-                     sg->d_x[1].bytes() + sg->d_ids.bytes());
+    size_t b = sg->d_xbuf.bytes() + sg->d_ids.bytes();
+    for (auto &blk : sg->blocks) b += blk->rowptr.bytes() + blk->src.bytes() + blk->w.bytes();
+    return (int64_t)b;
 }
 
 static int sg_check_params(double epsilon, int32_t max_iterations) {
@@ -797,7 +1158,7 @@ extern "C" int vrec_sg_stationary(vrec_sg *sg, int64_t vertex, double epsilon, i
     SgState st;
     int buf = 0;
     VREC_TRY(sg_fetch_state(sg, max_iterations, &st, &buf));
-    VREC_CUDA(cudaMemcpyAsync(out_x, sg->d_x[buf].p, sizeof(double) * (size_t)sg->N, cudaMemcpyDeviceToHost,
+    VREC_CUDA(cudaMemcpyAsync(out_x, sg->d_x[buf], sizeof(double) * (size_t)sg->N, cudaMemcpyDeviceToHost,
                               sg->ctx->stream));
     VREC_CUDA(cudaStreamSynchronize(sg->ctx->stream));
     if (out_iterations) *out_iterations = st.iterations;
@@ -885,7 +1246,7 @@ extern "C" int vrec_sg_query(vrec_sg *sg, const int64_t *vertices, int32_t n, do
         int cg = (int)((n_cand + 255) / 256);
         sg_candidates_kernel<<<cg, 256, 0, ctx->stream>>>(
             sg->h_ids.empty() ? nullptr : sg->d_ids.p, sg->N, use_filter ? sg->d_filter_ids.p : nullptr, n_filter,
-            sg->d_x[buf].p,
+            sg->d_x[buf],
             (long long)vertices[q], sg->d_cand_val.p, sg->d_cand_key.p);
         VREC_LAUNCHED(ctx);
         VREC_TRY(vrec_launch_select_topn(ctx, sg->d_cand_val.p, sg->d_cand_key.p, nullptr, n_cand, 0, 1,
@@ -919,8 +1280,7 @@ extern "C" int vrec_sg_set_option(vrec_sg *sg, const char *name, int32_t value) 
         sg->flat_variant = value;
     } else if (k == "rows_kernel" && (value == 0 || value == 1)) {
         // A/B: 1 = the round-1 half-warp-per-row kernel instead of the flat-window kernel
-        sg->force_rows_kernel = value != 0;
-        sg->flat = sg->nblocks == 1 && !sg->force_rows_kernel;
+        sg->rows_kernel = value != 0;
     } else {
         vrec_set_error("vrec_sg_set_option: unknown option or bad value: %s = %d", name, (int)value);
         return VREC_EINVAL;
@@ -945,16 +1305,44 @@ extern "C" int64_t vrec_sg_batch_info(vrec_sg *sg, int32_t what) {
     }
 }
 
-// Copies the device CSR of P^T (rows owned by this process) back to the host, for tests.
+// Copies the device CSR of P^T (rows owned by this process) back to the host in row-major order, for tests:
+// a row is the concatenation of its parts in the source blocks.
 extern "C" int vrec_sg_export_csr(vrec_sg *sg, int32_t *out_rowptr, int32_t *out_src, double *out_w) {
     if (!sg || !out_rowptr || !out_src || !out_w) return VREC_EINVAL;
     cudaStream_t s = sg->ctx->stream;
     VREC_CUDA(cudaSetDevice(sg->ctx->device));
-    size_t rows = (size_t)(sg->row_hi - sg->row_lo);
-    VREC_CUDA(cudaMemcpyAsync(out_rowptr, sg->d_rowptr.p, sizeof(int) * (rows + 1), cudaMemcpyDeviceToHost, s));
-    VREC_CUDA(cudaMemcpyAsync(out_src, sg->d_src.p, sizeof(int) * (size_t)sg->nnz, cudaMemcpyDeviceToHost, s));
-    VREC_CUDA(cudaMemcpyAsync(out_w, sg->d_w.p, sizeof(double) * (size_t)sg->nnz, cudaMemcpyDeviceToHost, s));
+    const size_t rows = (size_t)(sg->row_hi - sg->row_lo);
+    if (sg->nblocks == 1) {
+        vrec_sg::Block &b = *sg->blocks[0];
+        VREC_CUDA(cudaMemcpyAsync(out_rowptr, b.rowptr.p, sizeof(int) * (rows + 1), cudaMemcpyDeviceToHost, s));
+        VREC_CUDA(cudaMemcpyAsync(out_src, b.src.p, sizeof(int) * (size_t)sg->nnz, cudaMemcpyDeviceToHost, s));
+        VREC_CUDA(cudaMemcpyAsync(out_w, b.w.p, sizeof(double) * (size_t)sg->nnz, cudaMemcpyDeviceToHost, s));
+        VREC_CUDA(cudaStreamSynchronize(s));
+        return VREC_OK;
+    }
+    std::vector<std::vector<int>> rp((size_t)sg->nblocks), bs((size_t)sg->nblocks);
+    std::vector<std::vector<double>> bw((size_t)sg->nblocks);
+    for (int b = 0; b < sg->nblocks; ++b) {
+        vrec_sg::Block &blk = *sg->blocks[b];
+        rp[b].resize(rows + 1);
+        bs[b].resize((size_t)blk.nnz);
+        bw[b].resize((size_t)blk.nnz);
+        VREC_CUDA(cudaMemcpyAsync(rp[b].data(), blk.rowptr.p, sizeof(int) * (rows + 1), cudaMemcpyDeviceToHost, s));
+        VREC_CUDA(cudaMemcpyAsync(bs[b].data(), blk.src.p, sizeof(int) * (size_t)blk.nnz, cudaMemcpyDeviceToHost, s));
+        VREC_CUDA(cudaMemcpyAsync(bw[b].data(), blk.w.p, sizeof(double) * (size_t)blk.nnz, cudaMemcpyDeviceToHost, s));
+    }
     VREC_CUDA(cudaStreamSynchronize(s));
+    size_t pos = 0;
+    for (size_t r = 0; r < rows; ++r) {
+        out_rowptr[r] = (int32_t)pos;
+        for (int b = 0; b < sg->nblocks; ++b) {
+            const int a = rp[b][r], e = rp[b][r + 1];
+            std::copy(bs[b].begin() + a, bs[b].begin() + e, out_src + pos);
+            std::copy(bw[b].begin() + a, bw[b].begin() + e, out_w + pos);
+            pos += (size_t)(e - a);
+        }
+    }
+    out_rowptr[rows] = (int32_t)pos;
     return VREC_OK;
 }
 
@@ -1034,7 +1422,7 @@ extern "C" int vrec_sg_generate(vrec_ctx *ctx, int64_t n_vertices, int32_t out_d
                        ctx->rank, ctx->world);
         return VREC_EINVAL;
     }
-    const int64_t slice = (n_vertices + world - 1) / world;      // equal slices; the last may be short
+    const int64_t slice = (n_vertices + world - 1) / world;      // every row has out_degree in-edges: equal rows = equal nnz
     int64_t lo = std::min<int64_t>(n_vertices, slice * rank), hi = std::min<int64_t>(n_vertices, lo + slice);
     int64_t rows = hi - lo;
     if (rows * out_degree >= (int64_t)0x7fffffff) {
@@ -1047,18 +1435,19 @@ extern "C" int vrec_sg_generate(vrec_ctx *ctx, int64_t n_vertices, int32_t out_d
     g->nnz = rows * out_degree;
     g->row_lo = lo;
     g->row_hi = hi;
-    g->slice = slice;
     g->partitioned = world > 1;
-    int rc = g->d_rowptr.alloc((size_t)rows + 1);
-    if (rc == VREC_OK) rc = g->d_src.alloc((size_t)g->nnz);
-    if (rc == VREC_OK) rc = g->d_w.alloc((size_t)g->nnz);
+    DevBuf<int> rm_rowptr, rm_src;
+    DevBuf<double> rm_w;
+    int rc = rm_rowptr.alloc((size_t)rows + 1);
+    if (rc == VREC_OK) rc = rm_src.alloc((size_t)g->nnz);
+    if (rc == VREC_OK) rc = rm_w.alloc((size_t)g->nnz);
     if (rc == VREC_OK) rc = g->d_ids.alloc(1);
     if (rc == VREC_OK) {
         int wpb = 8;
         size_t smem = (size_t)wpb * out_degree * sizeof(int);
         int grid = (int)std::min<int64_t>((rows + wpb - 1) / wpb, 148 * 16);
         sg_gen_rows_kernel<<<grid, wpb * 32, smem, ctx->stream>>>(n_vertices, out_degree, seed, lo, (int)rows,
-                                                                  g->d_rowptr.p, g->d_src.p, g->d_w.p);
+                                                                  rm_rowptr.p, rm_src.p, rm_w.p);
         ctx->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) {
@@ -1067,9 +1456,10 @@ extern "C" int vrec_sg_generate(vrec_ctx *ctx, int64_t n_vertices, int32_t out_d
         }
     }
     if (rc == VREC_OK) {
-        // every row has out_degree <= 1024 terms: no long (sub-)ranges; block boundaries on the device
-        rc = sg_setup_generated(g);
+        // every row has out_degree <= 1024 terms: no long (sub-)ranges; the source blocks are cut on the device
+        rc = sg_setup_generated(g, rm_rowptr, rm_src, rm_w);
     }
+    if (rc == VREC_OK && g->partitioned) rc = sg_setup_peers_ipc(g);
     if (rc == VREC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         vrec_set_error("vrec_sg_generate: %s", cudaGetErrorString(cudaGetLastError()));
         rc = VREC_ECUDA;

@@ -50,23 +50,38 @@ struct SgBatch {
     int64_t last_batched = 0;                 // queries the last vrec_sg_query served by the batch kernel
 };
 
+// ---- row-partitioned graphs: exchange of x' and of the residual partials over peer memory ----
+constexpr int VREC_MAX_WORLD = 16;
+
+// One per graph and rank, in device memory, written by every peer (NVLink P2P stores).
+struct SgExchange {
+    double res[2][VREC_MAX_WORLD];              // residual partial of rank r for iteration parity p
+    unsigned long long flag[VREC_MAX_WORLD];    // flag[r] = last step rank r has completed: (epoch << 32) | step
+};
+// Where every rank keeps its two x buffers and its exchange block (device copy, one per graph).
+struct SgPeers {
+    double *x[2][VREC_MAX_WORLD];
+    SgExchange *xchg[VREC_MAX_WORLD];
+    int world, rank;
+};
+
 struct vrec_sg {
     vrec_ctx *ctx = nullptr;
     int64_t N = 0, nnz = 0;
-    int64_t row_lo = 0, row_hi = 0;           // rows of P^T owned by this process
-    int64_t slice = 0;                        // rows per rank (equal, padded): x buffers hold slice * world values
+    int64_t row_lo = 0, row_hi = 0;           // rows of P^T owned by this process (balanced by nnz)
     bool partitioned = false;
     std::vector<int64_t> h_ids;               // ascending vertex ids (host copy for lookups)
     DevBuf<long long> d_ids;
-    DevBuf<int> d_rowptr;                     // [rows+1]
-    DevBuf<int> d_src;                        // source vertex index per in-edge
-    DevBuf<double> d_w;
     // Source blocks (canonical order): graphs with more than 3 * 2^21 vertices are
     // swept once per block of 3 * 2^21 sources, so that the gathered part of x (<= 48 MB) stays L2-resident.
-    // Block b of row r is the in-edge range [start[r], end[r]); (sub-)ranges longer than
-    // VREC_CANON_SEG are summed segment-wise through the per-block tables.
+    // Every block is a CSR of its own (block-major layout): the in-edges of a row that come from the block's
+    // sources, rows adjacent in src / w, so that a sweep streams one contiguous array pair.  (Sub-)rows longer
+    // than VREC_CANON_SEG are summed segment-wise through the per-block tables.
     struct Block {
-        const int *row_start = nullptr, *row_end = nullptr;   // device, [rows]
+        int64_t nnz = 0;
+        DevBuf<int> rowptr;                   // [rows+1]
+        DevBuf<int> src;                      // source vertex index per in-edge (global index)
+        DevBuf<double> w;
         int n_long = 0, n_seg = 0;
         DevBuf<int> long_rows;                // [n_long] ascending local row
         DevBuf<int> long_segptr;              // [n_long+1] offsets into partials
@@ -75,11 +90,17 @@ struct vrec_sg {
     };
     int nblocks = 1;
     int flat_variant = 0;                     // tuning: (CTAs per SM, windows per batch) of the flat kernel, see sg_run_device
-    bool force_rows_kernel = false;           // debug / A-B: keep the round-1 half-warp-per-row kernel
-    bool flat = true;                         // rows of a block are adjacent in src / w: flat-window kernel
+    bool rows_kernel = false;                 // debug / A-B: the round-1 half-warp-per-row kernel
     std::vector<std::unique_ptr<Block>> blocks;
-    DevBuf<int> d_bptr;                       // [(nblocks+1) x rows] block boundaries per row (nblocks > 1)
-    DevBuf<double> d_x[2];
+    DevBuf<double> d_xbuf;                    // x[0] | x[1] | SgExchange, one allocation (one IPC handle)
+    double *d_x[2] = {nullptr, nullptr};
+    int64_t xstride = 0;                      // doubles between x[0] and x[1]
+    SgExchange *d_xchg = nullptr;
+    DevBuf<SgPeers> d_peers;                  // device copy of `peers`
+    SgPeers peers;
+    bool peers_ready = false, peers_local = false;
+    std::vector<void *> ipc_opened;           // peer mappings to close
+    unsigned long long epoch = 0;             // query counter of a partitioned graph (same on every rank)
     DevBuf<double> d_block_partials;
     DevBuf<SgState> d_state;
     int grid = 0;
@@ -91,6 +112,7 @@ struct vrec_sg {
     DevBuf<double> d_out_val;
     DevBuf<int> d_out_count;
     SgBatch batch;
+    ~vrec_sg();
 };
 
 int sg_run_device(vrec_sg *g, long long uidx, double epsilon, int max_it, bool check_convergence);

@@ -842,7 +842,7 @@ int sg_batch_prepare(vrec_sg *g) {
     SgState hs;
     int buf = 0;
     VREC_TRY(sg_fetch_state(g, 1, &hs, &buf));
-    sg_gather_active_kernel<<<(n_a + 255) / 256, 256, 0, st>>>(g->d_x[1].p, d_av.p, n_a, b.x1a.p);
+    sg_gather_active_kernel<<<(n_a + 255) / 256, 256, 0, st>>>(g->d_x[1], d_av.p, n_a, b.x1a.p);
     VREC_LAUNCHED(ctx);
     VREC_CUDA(cudaStreamSynchronize(st));
     b.r1_base = hs.residual;

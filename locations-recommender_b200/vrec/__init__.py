@@ -6,4 +6,4 @@ stochastic/StochasticRecommender.scala:28-71); the compute runs in hand-written 
 kernels behind the C ABI of include/vrec.h.
 """
 from .engine import (Context, KnnRecommender, KnnRegionSet, StochasticGraph,  # noqa: F401
-                     StochasticRecommender, VrecError, NoSuchElement)
+                     StochasticGraphGroup, StochasticRecommender, VrecError, NoSuchElement)

@@ -75,6 +75,11 @@ SIGNATURES = {
     "vrec_sg_generate": (C.c_int, [vp, C.c_int64, C.c_int32, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(vp)]),
     "vrec_host_sg_csr": (C.c_int, [C.c_int64, i64p, i64p, f64p, i64p, i64p, i32p, i32p, f64p]),
     "vrec_sg_export_csr": (C.c_int, [vp, i32p, i32p, f64p]),
+    "vrec_sg_row_range": (C.c_int, [vp, i64p, i64p]),
+    "vrec_sg_group_load": (C.c_int, [vp, C.c_int32, C.c_int64, i64p, i64p, f64p, C.POINTER(vp)]),
+    "vrec_sg_group_stationary": (C.c_int, [C.POINTER(vp), C.c_int32, C.c_int64, C.c_double, C.c_int32, f64p, i32p,
+                                           i32p, f64p]),
+    "vrec_host_sg_partition": (C.c_int, [C.c_int64, i32p, C.c_int32, i64p]),
     "vrec_debug_tc_selftest": (C.c_int, [vp, f64p]),
 }
 

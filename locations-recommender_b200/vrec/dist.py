@@ -18,7 +18,9 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def slice_rows(n: int, rank: int, world: int) -> Tuple[int, int]:
-    """Row block of a partitioned graph: equal slices of ceil(n / world) rows (vrec_sg_load_partitioned)."""
+    """Row block of a device-generated partitioned graph (vrec_sg_generate): equal slices of ceil(n / world)
+    rows -- every generated row has the same number of in-edges.  Loaded graphs are cut by in-edges instead
+    (engine.host_sg_partition / vrec_sg_row_range)."""
     s = (int(n) + world - 1) // world
     lo = min(n, s * rank)
     return lo, min(n, lo + s)

@@ -285,6 +285,12 @@ class StochasticGraph:
         _check(self.ctx.lib.vrec_sg_export_csr(self._h, _ptr(rowptr, L.i32p), _ptr(src, L.i32p), _ptr(w, L.f64p)))
         return rowptr, src[:self.nnz], w[:self.nnz]
 
+    def row_range(self):
+        """Rows of P^T this process owns (the whole graph unless row-partitioned)."""
+        lo, hi = C.c_int64(0), C.c_int64(0)
+        _check(self.ctx.lib.vrec_sg_row_range(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def iterate_device(self, iterations: int) -> None:
         _check(self.ctx.lib.vrec_sg_iterate_device(self._h, int(iterations)))
 
@@ -298,6 +304,38 @@ class StochasticGraph:
     @property
     def resident_bytes(self) -> int:
         return int(self.ctx.lib.vrec_sg_resident_bytes(self._h))
+
+
+class StochasticGraphGroup:
+    """The `world` parts of ONE row-partitioned graph held by this process (vrec_sg_group_load): same sweep
+    kernel, peer stores and residual slots as the one-process-per-GPU path, driven from one stream."""
+
+    def __init__(self, source_id, target_id, balanced_weight, world: int, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        s, t, w = _i64(source_id), _i64(target_id), _f64(balanced_weight)
+        self.world = int(world)
+        self._hs = (L.vp * self.world)()
+        _check(self.ctx.lib.vrec_sg_group_load(self.ctx._h, self.world, len(s), _ptr(s, L.i64p), _ptr(t, L.i64p),
+                                               _ptr(w, L.f64p), self._hs))
+        self.parts = [StochasticGraph(None, None, None, ctx=self.ctx, _handle=L.vp(self._hs[r]))
+                      for r in range(self.world)]
+        self.N = self.parts[0].N
+
+    def stationary(self, vertexId: int, epsilon: float, maxIterations: int):
+        """-> (x[world, N], iterations[world], converged[world], residual[world])"""
+        x = np.zeros((self.world, max(1, self.N)), dtype=np.float64)
+        it = np.zeros(self.world, dtype=np.int32)
+        cv = np.zeros(self.world, dtype=np.int32)
+        res = np.zeros(self.world, dtype=np.float64)
+        _check(self.ctx.lib.vrec_sg_group_stationary(self._hs, self.world, int(vertexId), float(epsilon),
+                                                     int(maxIterations), _ptr(x, L.f64p), _ptr(it, L.i32p),
+                                                     _ptr(cv, L.i32p), _ptr(res, L.f64p)))
+        return x[:, :self.N], it, cv, res
+
+    def close(self) -> None:
+        for p in self.parts:
+            p.close()
+        self.parts = []
 
 
 class StochasticRecommender:
@@ -361,6 +399,15 @@ class StochasticRecommender:
                 if status[q] == L.OK:
                     self._message(int(its[q]), int(conv[q]))
         return out_id, out_prob, cnt[:n], its[:n], conv[:n], status[:n]
+
+
+def host_sg_partition(rowptr, world: int) -> np.ndarray:
+    """Row ranges of a row-partitioned graph (balanced by in-edges): bounds[world + 1]."""
+    lib = L.load()
+    rp = _i32(rowptr)
+    out = np.zeros(world + 1, dtype=np.int64)
+    _check(lib.vrec_host_sg_partition(len(rp) - 1, _ptr(rp, L.i32p), int(world), _ptr(out, L.i64p)))
+    return out
 
 
 def host_sg_csr(source_id, target_id, balanced_weight):

@@ -38,15 +38,24 @@ for (n, deg, hub, seed) in [(5000, 5, 0.5, 3), (30001, 20, 0.2, 4)]:
         print(f"[rank {rank}] N={n} vertex={vertex} eps={eps}: {'ok' if good else 'MISMATCH'} "
               f"(iterations {rec.last_iterations}, converged {rec.last_converged})", flush=True)
         ok = ok and good
+    lo, hi = g.row_range()
+    print(f"[rank {rank}] N={n}: rows [{lo}, {hi}) with {g.nnz} of {len(s)} in-edges", flush=True)
     g.close()
-# generated graph: partitioned result equals the oracle on the exported slices
-gg = vrec.StochasticGraph.generate(40000, 16, seed=5, rank=rank, world=world, ctx=ctx)
-x = vrec.StochasticRecommender(gg, 0.0, 5).stationary(0)
-xs = [None] * world
-dist.all_gather_object(xs, x.tobytes())
-same = all(b == xs[0] for b in xs)
-print(f"[rank {rank}] generated graph: ranks agree = {same}, sum = {x.sum():.12f}", flush=True)
-ok = ok and same
+# generated graphs (one and two source blocks): every rank's partitioned result equals the unpartitioned
+# engine on the same device, which the GPU suite checks against the oracle
+for (n, deg, its) in [(40000, 16, 5), (7_000_000, 8, 3)]:
+    gg = vrec.StochasticGraph.generate(n, deg, seed=5, rank=rank, world=world, ctx=ctx)
+    rec = vrec.StochasticRecommender(gg, 1e-7, its)
+    x = rec.stationary(0)
+    g1 = vrec.StochasticGraph.generate(n, deg, seed=5, ctx=ctx)
+    rec1 = vrec.StochasticRecommender(g1, 1e-7, its)
+    x1 = rec1.stationary(0)
+    same = np.array_equal(x, x1) and (rec.last_iterations, rec.last_converged) == (rec1.last_iterations,
+                                                                                  rec1.last_converged)
+    print(f"[rank {rank}] generated graph N={n}: partitioned == unpartitioned: {same}", flush=True)
+    ok = ok and same
+    gg.close()
+    g1.close()
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()

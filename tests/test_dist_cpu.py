@@ -25,6 +25,26 @@ def test_shard_ranges_cover():
     assert abs(sum([5, 1, 1, 1, 4, 4][i] for i in units[0]) - 8) <= 1
 
 
+def test_partition_bounds_balance_in_edges():
+    """Row ranges of a row-partitioned graph: contiguous, covering, balanced by in-edges."""
+    import numpy as np
+    from vrec.engine import host_sg_partition
+    rng = np.random.default_rng(11)
+    for n, world in ((1, 2), (10, 3), (5000, 2), (5000, 8), (40000, 7)):
+        deg = rng.integers(0, 40, size=n)
+        deg[rng.integers(0, n, size=max(1, n // 100))] += 2000          # hubs
+        rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+        b = host_sg_partition(rowptr, world)
+        assert b[0] == 0 and b[-1] == n and np.all(np.diff(b) >= 0)
+        nnz = int(rowptr[-1])
+        per = np.diff(rowptr[b].astype(np.int64))
+        if nnz and n >= 50 * world:
+            assert per.max() <= nnz / world + deg.max() + 1                # no rank exceeds its share by a row
+    # no in-edges at all: every rank still gets a well-formed (possibly empty) range
+    b = host_sg_partition(np.zeros(6, dtype=np.int32), 4)
+    assert b[0] == 0 and b[-1] == 5 and np.all(np.diff(b) >= 0)
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"

@@ -184,6 +184,43 @@ def test_sg_source_blocked_order(vrec, ctx, synth, oracle):
     assert (rec.last_iterations, rec.last_converged) == (oit, oconv)
     assert np.array_equal(x, ox)
     g.close()
+    # the same graph row-partitioned over 3 parts: two source blocks per part, peer stores, residual slots
+    grp = vrec.StochasticGraphGroup(s, t, w, 3, ctx=ctx)
+    xs, its, conv, _ = grp.stationary(v, 1e-4, 6)
+    for r in range(3):
+        assert (int(its[r]), int(conv[r])) == (oit, oconv), r
+        assert np.array_equal(xs[r], ox), r
+    grp.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5])
+def test_sg_row_partitioned_group_bit_exact(vrec, ctx, synth, oracle, world):
+    """SURVEY 8(e) row 3 on one GPU: the parts of a row-partitioned graph (rows balanced by in-edges), every
+    part's sweep storing its rows of x' into all parts' buffers, the residual partials added in rank order --
+    every part's copy of the result equals the oracle bit for bit, with the same iteration count."""
+    from vrec.engine import host_sg_csr, host_sg_partition
+    for (n, deg, hub, seed) in [(5000, 5, 0.5, 3), (30001, 20, 0.2, 4), (64, 2, 0.0, 9)]:
+        s, t, w = synth.random_stochastic_graph(n, deg, seed=seed, hub_fraction=hub)
+        og = oracle.SgGraph(s, t, w)
+        grp = vrec.StochasticGraphGroup(s, t, w, world, ctx=ctx)
+        ids, rowptr, _, _ = host_sg_csr(s, t, w)
+        bounds = host_sg_partition(rowptr, world)
+        assert [p.row_range() for p in grp.parts] == [(int(bounds[r]), int(bounds[r + 1])) for r in range(world)]
+        assert sum(p.nnz for p in grp.parts) == len(s)
+        for vertex, eps, max_it in [(int(og.ids[0]), 0.0, 6), (int(og.ids[n // 2]), 1e-3, 20),
+                                    (int(og.ids[-1]), 0.05, 0)]:
+            xs, its, conv, res = grp.stationary(vertex, eps, max_it)
+            rc, ox, oit, oconv, ores = og.run(vertex, eps, max_it)
+            assert rc == 0
+            for r in range(world):
+                assert (int(its[r]), int(conv[r])) == (oit, oconv), (world, r, vertex)
+                assert np.array_equal(xs[r], ox), (world, r, vertex)
+            if max_it > 0:
+                assert np.all(res == res[0])                                  # the same sum on every rank
+                assert abs(res[0] - ores) <= 1e-12 * max(ores, 1e-300)
+        with pytest.raises(vrec.NoSuchElement):
+            grp.stationary(-12345, 0.01, 5)
+        grp.close()
 
 
 def _check_sg_batch(rec, og, vertices, flt, max_recs, eps, max_it):
