@@ -292,6 +292,11 @@ struct TileAux {
     // knn_tc_ws_kernel: the targets' category vectors as dense rows [n_targets][cat_dim] (global scratch)
     double *tdense = nullptr;
     int cat_dim = 0;
+    // compact records (round 2): the candidate side of the two hot evaluators (exact_pair_sig, exact_pair_staged)
+    // when every value of the region-set is a small integer -- see the layout below.  nullptr: not available.
+    const unsigned long long *cmeta = nullptr;
+    const unsigned long long *crec = nullptr;
+    const double *plen = nullptr, *clen = nullptr;   // |place| / |cat| per person (the targets' lengths)
 };
 
 constexpr unsigned REC_TAIL_TC = 0x80000000u, REC_TAIL_TILE = 0x40000000u, REC_COL_MASK = 0x3fffffffu;
@@ -323,6 +328,46 @@ __device__ __forceinline__ void rec_load4(const int *cols, const double *vals, i
 __device__ __forceinline__ double rec_val(const double *vals, int i, bool f32) {
     return f32 ? (double)__ldg(reinterpret_cast<const float *>(vals) + i) : __ldg(vals + i);
 }
+
+// ---- compact records -------------------------------------------------------------------------------
+// Visit counts are small integers.  When every place value of a region-set is an integer in [0, 255], every
+// category value an integer in [0, 1023], place_dim <= 2^22 and cat_dim <= 64, a person's record shrinks to
+//   place entries, 4 bytes each:  col (bits 0..21) | value (22..29) | tail flags (30: tile head set, 31: tc head set)
+//   category entries, 2 bytes each: col (bits 0..5) | value (6..15)
+// both sections padded to 8 bytes, no header: 10^6 persons of BASELINE config 3 take ~50 MB instead of ~160 MB,
+// which is what lets the ~3 K exact evaluations per target hit the L2 instead of HBM.  cmeta[i] has the layout
+// of meta[i] (offset in 8-byte words | place count << 40 | category count << 52).  The vector lengths are not
+// stored: sum(v^2) is an exact integer, so sqrt((double)sum) is bit for bit the length knn_norms_kernel
+// computed (Distance.vectorLength, knn/Distance.scala:11-16).
+constexpr unsigned CREC_COL_MASK = 0x3fffffu;
+constexpr int CREC_PW = 6, CREC_CW = 3;            // words fetched up front: 12 place + 12 category entries
+__host__ __device__ constexpr int crec_place_words(int n) { return (n + 1) >> 1; }
+__host__ __device__ constexpr int crec_cat_words(int n) { return (n + 3) >> 2; }
+__device__ __forceinline__ unsigned long long ld_rec_u64(const unsigned long long *p, unsigned long long pol) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+// The candidate's record, fetched with one round trip: all words of a typical record are requested before
+// the first is used.  place(e) / cat(e) return entry e (any e; entries beyond the prefetched words are
+// loaded on demand).
+struct CRec {
+    const unsigned long long *r;
+    int np, nc, pwords;
+    unsigned long long pw[CREC_PW], cw[CREC_CW];
+    __device__ __forceinline__ void open(const TileAux &aux, unsigned long long m, unsigned long long pol) {
+        np = (int)((m >> 40) & 0xfffu);
+        nc = (int)(m >> 52);
+        r = aux.crec + (m & 0xffffffffffULL);
+        pwords = crec_place_words(np);
+        const int cwords = crec_cat_words(nc);
+#pragma unroll
+        for (int j = 0; j < CREC_PW; ++j) pw[j] = j < pwords ? ld_rec_u64(r + j, pol) : 0ULL;
+#pragma unroll
+        for (int j = 0; j < CREC_CW; ++j) cw[j] = j < cwords ? ld_rec_u64(r + pwords + j, pol) : 0ULL;
+    }
+};
 
 // Sparse dot of candidate row [s, s+n) with the target row [ts, ts+tn) of one table, in the exact
 // order of the mllib merge (matches visited in ascending index), but with the candidate's entries
@@ -456,6 +501,83 @@ struct StagedTarget {
 
 __device__ __forceinline__ unsigned sig_bit(int col) { return ((unsigned)col * 0x9E3779B1u) >> 26; }
 
+// exact_pair_staged on the candidate's compact record (same operations in the same order, so the same bits).
+__device__ __forceinline__ double exact_pair_staged_compact(const TileAux &aux, long long i, const StagedTarget &t,
+                                                            double pw, double cw, int &min_tail, double thr) {
+    min_tail = -1;
+    if (i == t.t) return 0.0;
+    const unsigned long long pol = policy_evict_last();
+    CRec rc;
+    rc.open(aux, __ldg(aux.cmeta + i), pol);
+    const int np = rc.np, nc = rc.nc;
+    bool keep = false;
+    double ps_sim = 0.0, cs_sim = 0.0;
+    if (np > 0) {
+        double sum = 0.0;
+        unsigned sq = 0u;
+        auto place_term = [&](unsigned craw) {
+            const int ix = (int)(craw & CREC_COL_MASK);
+            const unsigned v = (craw >> 22) & 0xffu;
+            sq += v * v;
+            if ((t.sig >> sig_bit(ix)) & 1ULL) {
+                int lo = 0, hi = t.pn;                               // first index with pcol >= ix
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (t.pcol[mid] < ix) lo = mid + 1; else hi = mid;
+                }
+                if (lo < t.pn && t.pcol[lo] == ix) {
+                    sum = xadd(sum, xmul((double)v, t.pval[lo]));
+                    if (min_tail < 0 && (craw & aux.tail_bit)) min_tail = ix;
+                }
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < CREC_PW; ++j) {
+            if (2 * j < np) place_term((unsigned)rc.pw[j]);
+            if (2 * j + 1 < np) place_term((unsigned)(rc.pw[j] >> 32));
+        }
+        for (int j = CREC_PW; j < rc.pwords; ++j) {
+            const unsigned long long wd = ld_rec_u64(rc.r + j, pol);
+            place_term((unsigned)wd);
+            if (2 * j + 1 < np) place_term((unsigned)(wd >> 32));
+        }
+        const double c = xdiv(sum, xmul(sqrt((double)sq), t.plen));
+        if (c > 0) {
+            keep = true;
+            ps_sim = c;
+        }
+    }
+    // see exact_pair_staged: the category section cannot lift the pair over `thr` any more
+    if (xadd(xmul(ps_sim, pw), xmul(1.0000001, cw)) < thr) return 0.0;
+    if (nc > 0) {
+        double sum = 0.0;
+        unsigned sq = 0u;
+        auto cat_term = [&](unsigned h) {
+            const unsigned v = (h >> 6) & 0x3ffu;
+            sq += v * v;
+            sum = xadd(sum, xmul((double)v, t.cat_dense[h & 63u]));
+        };
+#pragma unroll
+        for (int j = 0; j < CREC_CW; ++j) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (4 * j + q < nc) cat_term((unsigned)(rc.cw[j] >> (16 * q)) & 0xffffu);
+        }
+        for (int j = CREC_CW; j < crec_cat_words(nc); ++j) {
+            const unsigned long long wd = ld_rec_u64(rc.r + rc.pwords + j, pol);
+            for (int q = 0; q < 4; ++q)
+                if (4 * j + q < nc) cat_term((unsigned)(wd >> (16 * q)) & 0xffffu);
+        }
+        const double c = xdiv(sum, xmul(sqrt((double)sq), t.clen));
+        if (c > 0) {
+            keep = true;
+            cs_sim = c;
+        }
+    }
+    if (!keep) return 0.0;
+    return xadd(xmul(ps_sim, pw), xmul(cs_sim, cw));
+}
+
 // Same value as exact_pair_packed, without data-dependent merge loops:
 //  * category dot: sum over the candidate's entries (ascending) of x * dense[col]; entries the target
 //    lacks contribute x * 0.0 = +0.0, and s + 0.0 == s, so the sum equals the merge's bit for bit
@@ -464,6 +586,7 @@ __device__ __forceinline__ unsigned sig_bit(int col) { return ((unsigned)col * 0
 //    set, and then a fixed-depth binary search over the target row finds it.
 __device__ __forceinline__ double exact_pair_staged(const TileAux &aux, long long i, const StagedTarget &t, double pw,
                                                     double cw, int &min_tail, double thr = 0.0) {
+    if (aux.cmeta) return exact_pair_staged_compact(aux, i, t, pw, cw, min_tail, thr);
     min_tail = -1;
     const bool F32 = aux.vals_f32;
     if (i == t.t) return 0.0;
@@ -669,6 +792,101 @@ __device__ __forceinline__ bool exact_pair_records(const TileAux &aux, int cand,
     return true;
 }
 
+// exact_pair_sig on the candidate's compact record; the target side (its own record: columns for the binary
+// search when they are not in shared memory, values) stays on the full-size records, which the 128 targets of a
+// CTA keep L1/L2-resident.
+__device__ __forceinline__ double exact_pair_sig_compact(const TileAux &aux, int cand, int tix, unsigned long long tsig,
+                                                         const double *__restrict__ tdense, const int *tcols_s,
+                                                         double pw, double cw, int &min_tail) {
+    min_tail = -1;
+    const bool F32 = aux.vals_f32;
+    if (cand == tix) return 0.0;
+    const unsigned long long pol = policy_evict_last();
+    CRec rc;
+    rc.open(aux, __ldg(aux.cmeta + cand), pol);
+    const unsigned long long mt = __ldg(aux.meta + tix);
+    const int npt = (int)((mt >> 40) & 0xfffu);
+    const double *rt = aux.rec + (mt & 0xffffffffffULL);
+    const double tplen = __ldg(aux.plen + tix), tclen = __ldg(aux.clen + tix);
+    const int *tpc = reinterpret_cast<const int *>(rt + 2);
+    const double *tpv = rt + 2 + rec_cols_words(npt);
+    const int np = rc.np, nc = rc.nc;
+    bool keep = false;
+    double ps_sim = 0.0, cs_sim = 0.0;
+    if (np > 0) {
+        double sum = 0.0;
+        unsigned sq = 0u;
+        auto place_term = [&](unsigned craw) {
+            const int ix = (int)(craw & CREC_COL_MASK);
+            const unsigned v = (craw >> 22) & 0xffu;
+            sq += v * v;
+            if ((tsig >> sig_bit(ix)) & 1ULL) {
+                int lo = 0, hi = npt;                                // first index with target col >= ix
+                bool match;
+                if (tcols_s) {                                       // the target's columns are in shared memory
+                    while (lo < hi) {
+                        int mid = (lo + hi) >> 1;
+                        if (tcols_s[mid] < ix) lo = mid + 1; else hi = mid;
+                    }
+                    match = lo < npt && tcols_s[lo] == ix;
+                } else {
+                    while (lo < hi) {
+                        int mid = (lo + hi) >> 1;
+                        if ((int)((unsigned)__ldg(tpc + mid) & REC_COL_MASK) < ix) lo = mid + 1; else hi = mid;
+                    }
+                    match = lo < npt && (int)((unsigned)__ldg(tpc + lo) & REC_COL_MASK) == ix;
+                }
+                if (match) {
+                    sum = xadd(sum, xmul((double)v, rec_val(tpv, lo, F32)));
+                    if (min_tail < 0 && (craw & aux.tail_bit)) min_tail = ix;
+                }
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < CREC_PW; ++j) {
+            if (2 * j < np) place_term((unsigned)rc.pw[j]);
+            if (2 * j + 1 < np) place_term((unsigned)(rc.pw[j] >> 32));
+        }
+        for (int j = CREC_PW; j < rc.pwords; ++j) {
+            const unsigned long long wd = ld_rec_u64(rc.r + j, pol);
+            place_term((unsigned)wd);
+            if (2 * j + 1 < np) place_term((unsigned)(wd >> 32));
+        }
+        const double c = xdiv(sum, xmul(sqrt((double)sq), tplen));
+        if (c > 0) {
+            keep = true;
+            ps_sim = c;
+        }
+    }
+    if (nc > 0) {
+        double sum = 0.0;
+        unsigned sq = 0u;
+        auto cat_term = [&](unsigned h) {
+            const unsigned v = (h >> 6) & 0x3ffu;
+            sq += v * v;
+            sum = xadd(sum, xmul((double)v, __ldg(tdense + (h & 63u))));
+        };
+#pragma unroll
+        for (int j = 0; j < CREC_CW; ++j) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (4 * j + q < nc) cat_term((unsigned)(rc.cw[j] >> (16 * q)) & 0xffffu);
+        }
+        for (int j = CREC_CW; j < crec_cat_words(nc); ++j) {
+            const unsigned long long wd = ld_rec_u64(rc.r + rc.pwords + j, pol);
+            for (int q = 0; q < 4; ++q)
+                if (4 * j + q < nc) cat_term((unsigned)(wd >> (16 * q)) & 0xffffu);
+        }
+        const double c = xdiv(sum, xmul(sqrt((double)sq), tclen));
+        if (c > 0) {
+            keep = true;
+            cs_sim = c;
+        }
+    }
+    if (!keep) return 0.0;
+    return xadd(xmul(ps_sim, pw), xmul(cs_sim, cw));
+}
+
 // exact_pair for two persons with packed records, the target described by a 64-bit signature of its
 // places and its category vector as a dense row (both prepared once per CTA): the same operations in the
 // same order as exact_pair_staged, i.e. as the mllib merge, with ~10x fewer instructions than matching
@@ -680,6 +898,7 @@ __device__ __forceinline__ bool exact_pair_records(const TileAux &aux, int cand,
 __device__ __forceinline__ double exact_pair_sig(const TileAux &aux, int cand, int tix, unsigned long long tsig,
                                                  const double *__restrict__ tdense, const int *tcols_s, double pw,
                                                  double cw, int &min_tail) {
+    if (aux.cmeta) return exact_pair_sig_compact(aux, cand, tix, tsig, tdense, tcols_s, pw, cw, min_tail);
     min_tail = -1;
     const bool F32 = aux.vals_f32;
     if (cand == tix) return 0.0;
@@ -1829,10 +2048,14 @@ knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_t
                 auto fetch = [&](int j, int &cand_out, unsigned long long &meta_out, int &pl_out) {
                     int at = locate(j, pl_out);
                     cand_out = at >= 0 ? __ldg(aux.pper + at) : -1;
-                    meta_out = (cand_out >= 0 && aux.meta) ? __ldg(aux.meta + cand_out) : 0ULL;
+                    const unsigned long long *mp = aux.cmeta ? aux.cmeta : aux.meta;
+                    meta_out = (cand_out >= 0 && mp) ? __ldg(mp + cand_out) : 0ULL;
                 };
                 auto prefetch_record = [&](int cand_, unsigned long long m_) {
-                    if (cand_ >= 0 && aux.meta) {
+                    if (cand_ >= 0 && aux.cmeta) {
+                        const char *r = reinterpret_cast<const char *>(aux.crec + (m_ & 0xffffffffffULL));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
+                    } else if (cand_ >= 0 && aux.meta) {
                         const char *r = reinterpret_cast<const char *>(aux.rec + (m_ & 0xffffffffffULL));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128));
@@ -2257,7 +2480,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                         const int jj = __ffs(pass) - 1;
                         pass &= pass - 1;
                         wq[pos++] = ((unsigned long long)ut << 32) | (unsigned long long)(unsigned)(tile + c0 + jj);
-                        if (aux.meta) asm volatile("prefetch.global.L2 [%0];" ::"l"(aux.meta + tile + c0 + jj));
+                        if (aux.meta) asm volatile("prefetch.global.L2 [%0];" ::"l"((aux.cmeta ? aux.cmeta : aux.meta) + tile + c0 + jj));
                     }
                     __syncwarp();
                     wn += total;
@@ -2909,6 +3132,16 @@ struct vrec_knn {
     DevBuf<int> d_work;
     DevBuf<unsigned long long> d_meta;     // packed records for the exact evaluation
     DevBuf<double> d_rec;
+    DevBuf<unsigned long long> d_cmeta, d_crec;   // compact records (small-integer region-sets), see CRec
+    int64_t opt_compact = 1;               // 0: evaluate on the full-size records even when compact ones exist (A/B)
+    void attach_compact(TileAux &aux) const {
+        aux.plen = d_plen.p;
+        aux.clen = d_clen.p;
+        if (opt_compact && d_cmeta.p && d_crec.p && d_meta.p) {
+            aux.cmeta = d_cmeta.p;
+            aux.crec = d_crec.p;
+        }
+    }
     // tensor-core variant: fp16 row-major features over TC_D dims, its own (larger) head set
     bool tc_ok = false;
     DevBuf<__half> d_feat16;
@@ -3247,6 +3480,41 @@ extern "C" int vrec_knn_load(vrec_ctx *ctx, int64_t P, const int64_t *person_id,
                 k->d_meta.release();
                 k->d_rec.release();
             }
+            // compact records: small-integer values only (visit counts), see CRec
+            bool compact = rc == VREC_OK && place_dim <= (1 << 22) && cat_dim <= 64;
+            for (int64_t e = 0; e < k->nnz_place && compact; ++e)
+                compact = pv[e] >= 0.0 && pv[e] <= 255.0 && pv[e] == (double)(int)pv[e];
+            for (int64_t e = 0; e < k->nnz_cat && compact; ++e)
+                compact = cv[e] >= 0.0 && cv[e] <= 1023.0 && cv[e] == (double)(int)cv[e];
+            if (compact) {
+                std::vector<unsigned long long> cmeta((size_t)P), crec;
+                crec.reserve((size_t)(k->nnz_place / 2 + k->nnz_cat / 4 + 2 * P + 16));
+                for (int64_t i = 0; i < P; ++i) {
+                    const int np = prp[i + 1] - prp[i], nc = crp[i + 1] - crp[i];
+                    cmeta[i] = (unsigned long long)crec.size() | ((unsigned long long)np << 40) |
+                               ((unsigned long long)nc << 52);
+                    size_t at = crec.size();
+                    crec.resize(at + (size_t)crec_place_words(np), 0ULL);
+                    unsigned *pe = reinterpret_cast<unsigned *>(crec.data() + at);
+                    for (int e = 0; e < np; ++e) {
+                        const int col = pci[prp[i] + e];
+                        pe[e] = (unsigned)col | ((unsigned)(int)pv[prp[i] + e] << 22) | (hs_tc[col] < 0 ? REC_TAIL_TC : 0u) |
+                                (head_slot[col] < 0 ? REC_TAIL_TILE : 0u);
+                    }
+                    at = crec.size();
+                    crec.resize(at + (size_t)crec_cat_words(nc), 0ULL);
+                    unsigned short *ce = reinterpret_cast<unsigned short *>(crec.data() + at);
+                    for (int e = 0; e < nc; ++e)
+                        ce[e] = (unsigned short)((unsigned)cci[crp[i] + e] | ((unsigned)(int)cv[crp[i] + e] << 6));
+                }
+                crec.resize(crec.size() + 16, 0ULL);
+                int rc2 = k->d_cmeta.upload(cmeta.data(), cmeta.size(), s);
+                if (rc2 == VREC_OK) rc2 = k->d_crec.upload(crec.data(), crec.size(), s);
+                if (rc2 != VREC_OK || cudaStreamSynchronize(s) != cudaSuccess) {
+                    k->d_cmeta.release();
+                    k->d_crec.release();
+                }
+            }
         }
     }
     if (rc == VREC_OK && cudaStreamSynchronize(s) != cudaSuccess) {
@@ -3315,6 +3583,10 @@ extern "C" int vrec_knn_set_option(vrec_knn *k, const char *name, int64_t value)
     }
     if (!strcmp(name, "debug_skip_postings")) {
         k->opt_debug_skip_postings = value;
+        return VREC_OK;
+    }
+    if (!strcmp(name, "compact_records") && (value == 0 || value == 1)) {
+        k->opt_compact = value;            // 0: exact evaluations on the full-size records (A/B of the compact ones)
         return VREC_OK;
     }
     if (!strcmp(name, "splits") && value >= 0 && value <= 32) {
@@ -3560,6 +3832,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
             }
             aux = TileAux{nullptr, 0, k->d_head_slot_tc.p, k->d_pcp.p, k->d_pper.p, k->d_meta.p, k->d_rec.p, REC_TAIL_TC};
             aux.vals_f32 = k->rec_f32;
+            k->attach_compact(aux);
             // No seed pass here: it cost more (heap warm-up on a sample, ~9 ms per 19K targets) than the
             // ~250 extra survivors per target it saves the main pass (~2 ms).  Optional via "tc_seed".
             if (k->opt_tc_seed) {
@@ -3617,6 +3890,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
             aux = TileAux{k->d_feat.p, k->fstride, k->d_head_slot.p, k->d_pcp.p, k->d_pper.p, k->d_meta.p, k->d_rec.p,
                           REC_TAIL_TILE};
             aux.vals_f32 = k->rec_f32;
+            k->attach_compact(aux);
             knn_tile_kernel<<<dim3(tiles, 1), TILE_THREADS, smem, ctx->stream>>>(
                 k->dev(), aux, k->d_tidx.p, tn, T, K, 1, k->cat_dim, pw, cw, k->d_part.p, k->d_part_cnt.p, stride, sample,
                 1, k->d_seed_thr.p, SP);

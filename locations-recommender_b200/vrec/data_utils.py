@@ -56,6 +56,29 @@ def load_places(data_dir: str) -> pa.Table:
     return _read(f"{data_dir}/places_sample")
 
 
+class Places:
+    """places_sample as plain columns (Arrow buffers -> numpy, no pandas hop): the region filter and the
+    final join of printRecommendations (knn/KnnRecommenderMain.scala:96-102)."""
+
+    COLUMNS = ("id", "latitude", "longitude", "category_id", "name", "description", "region_id")
+
+    def __init__(self, table: pa.Table):
+        self.id = table["id"].to_numpy().astype(np.int64)
+        self.region_id = table["region_id"].to_numpy().astype(np.int64)
+        self._cols = {c: table[c] for c in self.COLUMNS if c not in ("id", "region_id")}
+        self._order = np.argsort(self.id, kind="stable")
+        self._sorted = self.id[self._order]
+
+    def of_region(self, region: int) -> np.ndarray:
+        return np.ascontiguousarray(self.id[self.region_id == int(region)])
+
+    def row(self, place_id: int) -> list:
+        k = int(np.searchsorted(self._sorted, place_id))
+        i = int(self._order[k])
+        assert self._sorted[k] == place_id
+        return [int(place_id)] + [self._cols[c][i].as_py() for c in self.COLUMNS[1:-1]] + [int(self.region_id[i])]
+
+
 def write_partitioned(table: pa.Table, path: str, partition_cols) -> None:
     pq.write_to_dataset(table, path, partition_cols=list(partition_cols))
 
@@ -73,9 +96,15 @@ def vectors_to_table(person_id, rowptr, col, val, size: int) -> pa.Table:
 
 
 def table_to_vectors(t: pa.Table):
-    """-> person_id, rowptr, col, val, size.  Dense vectors (type == 1) are not produced by the builders."""
+    """-> person_id, rowptr, col, val, size.  The Arrow list offsets / values of the VectorUDT column ARE the CSR.
+    Dense vectors (type == 1: `values` only, no `indices`) are never written by RatingVectorsBuilder
+    (knn/RatingVectorsBuilder.scala:74-83 builds SparseVectors) and are rejected rather than misread."""
     pid = t["person_id"].to_numpy().astype(np.int64)
     vec = t["rating_vector"].combine_chunks()
+    kinds = vec.field("type").to_numpy(zero_copy_only=False)
+    if len(kinds) and np.any(kinds != 0):
+        raise ValueError(f"rating_vector holds {int(np.count_nonzero(kinds != 0))} dense vectors (VectorUDT type 1); "
+                         "the recommender inputs are sparse vectors")
     idx, vals = vec.field("indices"), vec.field("values")
     rowptr = idx.offsets.to_numpy().astype(np.int64)
     rowptr = rowptr - rowptr[0]
@@ -128,14 +157,15 @@ def load_knn_inputs(region_ids, data_dir: str, verbose: bool = True):
     persons = np.union1d(ppid, cpid)
 
     def align(pid, rowptr, col, val):
+        # rows of one table -> rows of the union of persons (persons missing from a table get an empty row);
+        # vectorised: no per-person Python work at 10^6 persons
         order = np.argsort(pid, kind="stable")
+        src_len = np.diff(rowptr)[order]
         lens = np.zeros(len(persons), dtype=np.int64)
-        where = np.searchsorted(persons, pid[order])
-        lens[where] = np.diff(rowptr)[order]
+        lens[np.searchsorted(persons, pid[order])] = src_len
         out_rp = np.concatenate([[0], np.cumsum(lens)])
-        starts = rowptr[:-1][order]
-        take = np.concatenate([np.arange(s, s + n) for s, n in zip(starts, np.diff(rowptr)[order])]) \
-            if len(order) else np.zeros(0, dtype=np.int64)
+        dst_start = np.concatenate([[0], np.cumsum(src_len)[:-1]]) if len(order) else np.zeros(0, dtype=np.int64)
+        take = np.repeat(rowptr[:-1][order] - dst_start, src_len) + np.arange(int(src_len.sum()), dtype=np.int64)
         return out_rp, col[take], val[take]
 
     prp2, pc2, pv2 = align(ppid, prp, pc, pv)

@@ -6,8 +6,6 @@ import argparse
 import sys
 import time
 
-import numpy as np
-
 from . import data_utils as du
 from .engine import Context, KnnRecommender, KnnRegionSet
 from .main_common import calc_recommender_target, parse_input, repl, show
@@ -44,8 +42,7 @@ def main(argv=None) -> None:
     print(f"Loading persons from {cfg.data_dir}/persons_sample")
     persons = du.load_persons(cfg.data_dir)
     print(f"Loading places from {cfg.data_dir}/places_sample")
-    places = du.load_places(cfg.data_dir).to_pandas()
-    places["region_id"] = places["region_id"].astype(np.int64)
+    places = du.Places(du.load_places(cfg.data_dir))
     cache = {}          # region-sets stay resident on the device between queries
 
     def query(line: str) -> None:
@@ -55,20 +52,15 @@ def main(argv=None) -> None:
         if key not in cache:
             cache[key] = KnnRegionSet(*du.load_knn_inputs(key, cfg.data_dir), ctx=ctx)
         rec = KnnRecommender(cache[key], cfg.place_weight, cfg.category_weight, cfg.k_nearest)
-        region_places = places[places["region_id"] == tgt.targetRegionId]
+        region_places = places.of_region(tgt.targetRegionId)
         print(f"Person {tgt.personId} might want to visit in region {tgt.targetRegionId}:")
         t0 = time.time()
-        pl, rt, cnt, st = rec.recommend([tgt.personId], region_places["id"].to_numpy(), cfg.max_recommendations)
+        pl, rt, cnt, st = rec.recommend([tgt.personId], region_places, cfg.max_recommendations)
         if st[0] != 0:
             raise ValueError(f"No such person: {tgt.personId}")
-        by_id = region_places.set_index("id")
         cols = ["id", "latitude", "longitude", "category_id", "name", "description", "region_id", "place_id",
                 "estimated_rating"]
-        rows = []
-        for p, r in zip(pl[0, :cnt[0]], rt[0, :cnt[0]]):
-            row = by_id.loc[int(p)]
-            rows.append([int(p), row["latitude"], row["longitude"], row["category_id"], row["name"],
-                         row["description"], row["region_id"], int(p), r])
+        rows = [places.row(int(p)) + [int(p), r] for p, r in zip(pl[0, :cnt[0]], rt[0, :cnt[0]])]
         show(rows, cols)
         print(f"Done in {int((time.time() - t0) * 1000)} milliseconds")
 
