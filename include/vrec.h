@@ -300,7 +300,10 @@ int vrec_sg_query(vrec_sg *sg, const int64_t *vertices, int32_t n,
  *                      eligible start vertices (default), 2 = for every eligible start vertex;
  *                      "batch_targets_per_cta": 0 = auto, 1 or 2;
  *                      "rows_kernel": 1 = the round-1 half-warp-per-row sweep instead of the flat-window
- *                      sweep (A/B measurements); "flat_variant": 0..2 = launch shape of the latter
+ *                      sweep (A/B measurements); "flat_variant": 0..2 = launch shape of the latter;
+ *                      "graph": 0 = queue all maxIterations sweeps instead of replaying one sweep from a
+ *                      CUDA-graph `while` node until step() returns (default 1; row-partitioned graphs always
+ *                      queue: their exchange barrier waits on peers)
  *  vrec_sg_batch_info  what = 0: start vertices the last vrec_sg_query served with the batch kernel;
  *                      1: batch path available for this graph; 2: vertices with in-edges; 3: edges
  *                      between them; 4: the same with the slice padding;

@@ -519,6 +519,10 @@ __device__ __forceinline__ double exact_pair_staged_compact(const TileAux &aux, 
             const int ix = (int)(craw & CREC_COL_MASK);
             const unsigned v = (craw >> 22) & 0xffu;
             sq += v * v;
+            // signature test (registers only), then a binary search over the target's sorted places.  (Measured
+            // alternative: a direct-mapped table over the 64 signature slots in shared memory instead of the
+            // search -- 10 % fewer instructions but 7.8 ms instead of 4.2 ms per 18 944 targets: the heavy targets
+            // that dominate this pass have 30-64 places, their slots collide, and the collision path serialises.)
             if ((t.sig >> sig_bit(ix)) & 1ULL) {
                 int lo = 0, hi = t.pn;                               // first index with pcol >= ix
                 while (lo < hi) {

@@ -19,12 +19,19 @@ __global__ void sg_fill_kernel(double *x, long long n, double v) {
     for (; i < n; i += stride) x[i] = v;
 }
 
-__global__ void sg_reset_state_kernel(SgState *st, int max_it) {
+__global__ void sg_reset_state_kernel(SgState *st, int max_it, long long uidx, double eps2, int check,
+                                      unsigned long long flag_base) {
     st->done = max_it <= 0 ? 1 : 0;          // maxIterations == 0 returns x0 (:93-95)
     st->iterations = 0;
     st->converged = 0;
     st->ticket = 0;
     st->residual = -1.0;
+    st->cur = 0;
+    st->max_it = max_it;
+    st->check = check;
+    st->uidx = uidx;
+    st->eps2 = eps2;
+    st->flag_base = flag_base;
 }
 
 // Canonical sum of terms x[src[k]] * w[k], k in [s, s+n), n <= VREC_CANON_SEG, computed by a
@@ -204,11 +211,12 @@ __device__ __forceinline__ double flat_rows_sum(const int *__restrict__ src, con
 __global__ void __launch_bounds__(SPMV_THREADS)
 sg_long_partials_kernel(const int *__restrict__ row_start, const int *__restrict__ row_end,
                         const int *__restrict__ src,
-                        const double *__restrict__ w, const double *__restrict__ x,
+                        const double *__restrict__ w, const double *x0, const double *x1,
                         const int *__restrict__ long_rows, const int *__restrict__ long_segptr,
                         const int *__restrict__ seg_row, int n_seg, double *__restrict__ partials,
-                        const SgState *__restrict__ st, float keep_frac) {
+                        const SgState *st, float keep_frac) {
     if (st->done) return;
+    const double *__restrict__ x = (st->cur & 1) ? x1 : x0;
     const int lane = threadIdx.x & 31;
     int seg = blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5);
     if (seg >= n_seg) return;
@@ -223,9 +231,10 @@ sg_long_partials_kernel(const int *__restrict__ row_start, const int *__restrict
 }
 
 // step() control, stochastic/StochasticRecommender.scala:92-106,130-141
-__device__ __forceinline__ void sg_step_decide(SgState *st, double acc, int iteration, int max_it, double eps2) {
-    st->residual = acc;
-    if (acc <= eps2) {                   // :140 `diffSquared <= epsilonSquared`
+__device__ __forceinline__ void sg_step_decide(SgState *st, double acc, int iteration) {
+    const int max_it = st->max_it;
+    if (st->check) st->residual = acc;
+    if (st->check && acc <= st->eps2) {  // :140 `diffSquared <= epsilonSquared`
         st->converged = 1;
         st->iterations = iteration;      // :100 "Converged in $iteration iterations"
         st->done = 1;
@@ -234,6 +243,7 @@ __device__ __forceinline__ void sg_step_decide(SgState *st, double acc, int iter
         st->iterations = max_it;
         st->done = 1;
     }
+    st->cur = iteration + 1;             // every CTA of this sweep has read `cur` (it took its ticket at its end)
 }
 
 // Main pass: sigma per row in the canonical order, x' = u*alpha + sigma*(1-alpha)
@@ -243,13 +253,22 @@ template <bool flat, int MINB, int U>
 __global__ void __launch_bounds__(SPMV_THREADS, MINB)
 sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ row_start, const int *__restrict__ row_end,
                const int *__restrict__ src,
-               const double *__restrict__ w, const double *__restrict__ x, double *__restrict__ nx,
-               long long uidx, const int *__restrict__ long_rows, const int *__restrict__ long_segptr,
+               const double *__restrict__ w, double *x0, double *x1,
+               const int *__restrict__ long_rows, const int *__restrict__ long_segptr,
                int n_long, const double *__restrict__ partials, SgState *st,
-               double *__restrict__ block_partials, int iteration, int max_it, double eps2,
-               int check_convergence, float keep_frac, int acc_in, int finalize,
-               const SgPeers *__restrict__ peers, int out_buf, unsigned long long flag_value) {
-    if (st->done) return;
+               double *__restrict__ block_partials, float keep_frac, int acc_in, int finalize,
+               const SgPeers *__restrict__ peers, cudaGraphConditionalHandle loop_cond) {
+    if (st->done) {
+        // replayed by the CUDA-graph `while` node (loop_cond != 0): make sure the loop ends
+        if (loop_cond && finalize && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional(loop_cond, 0u);
+        return;
+    }
+    // the sweep's parameters (device-resident loop state): iteration `cur` reads x[cur & 1] and writes the other
+    const int iteration = st->cur, check_convergence = st->check;
+    const long long uidx = st->uidx;
+    const double *__restrict__ x = (iteration & 1) ? x1 : x0;
+    double *__restrict__ nx = (iteration & 1) ? x0 : x1;
+    const int out_buf = (iteration + 1) & 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long total_warps = (long long)gridDim.x * SPMV_WARPS;
     const double one_minus = 1 - kAlpha;                     // :121, evaluates to 0.85
@@ -340,8 +359,8 @@ sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ row_start, 
             dsum = xadd(dsum, xmul(d, d));
         }
     }
-    if (!finalize || (!check_convergence && !peers)) return;
-    // fixed-order reduction of the residual
+    if (!finalize) return;
+    // fixed-order reduction of the residual; the last CTA also advances the loop state
     __shared__ double s_part[SPMV_WARPS];
     __shared__ int s_last;
     dsum = canon_butterfly(dsum);
@@ -374,10 +393,12 @@ sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ row_start, 
             __syncwarp();
             if (lane < world) {
                 volatile unsigned long long *f = &peers->xchg[lane]->flag[me];
-                *f = flag_value;
+                *f = st->flag_base + (unsigned long long)(iteration + 1);
             }
         } else if (lane == 0) {
-            sg_step_decide(st, acc, iteration, max_it, eps2);
+            sg_step_decide(st, acc, iteration);
+            // body of the CUDA-graph `while` node: go on while step() has not returned
+            if (loop_cond) cudaGraphSetConditional(loop_cond, st->done ? 0u : 1u);
         }
     }
 }
@@ -386,10 +407,11 @@ sg_spmv_kernel(int n_rows, long long row_lo, const int *__restrict__ row_start, 
 // partial have then landed in this rank's memory), adds the partials in rank order -- the same sum on
 // every rank -- and takes the step() decision.  `spin` = 0 when the ranks are driven from one stream
 // (single-process group): stream order already guarantees the flags.
-__global__ void sg_exchange_wait_kernel(SgState *st, SgExchange *xchg, int world, unsigned long long flag_value,
-                                        int iteration, int max_it, double eps2, int decide, int spin) {
+__global__ void sg_exchange_wait_kernel(SgState *st, SgExchange *xchg, int world, int step, int decide, int spin) {
     if (st->done) return;
     const int lane = threadIdx.x;
+    const int iteration = st->cur;
+    const unsigned long long flag_value = st->flag_base + (unsigned long long)step;
     int late = 0;
     if (spin && lane < world) {
         volatile unsigned long long *f = &xchg->flag[lane];
@@ -412,7 +434,7 @@ __global__ void sg_exchange_wait_kernel(SgState *st, SgExchange *xchg, int world
             volatile double *r = xchg->res[iteration & 1];
             double acc = 0.0;
             for (int q = 0; q < world; ++q) acc = xadd(acc, r[q]);
-            sg_step_decide(st, acc, iteration, max_it, eps2);
+            sg_step_decide(st, acc, iteration);
         }
     }
 }
@@ -431,8 +453,11 @@ __global__ void sg_exchange_signal_kernel(const SgPeers *__restrict__ peers, uns
 // candidate values for the ranked top-N: filter ids -> vertex index by binary search
 __global__ void sg_candidates_kernel(const long long *__restrict__ ids, long long N,
                                      const long long *__restrict__ filter, long long n_filter,
-                                     const double *__restrict__ x, long long target_id,
+                                     const double *x0, const double *x1, const SgState *st, long long target_id,
                                      double *__restrict__ cand_val, long long *__restrict__ cand_key) {
+    // which buffer step() returned: nextX when it converged (:101), x when the limit was reached (:95)
+    const int buf = st->max_it <= 0 ? 0 : st->converged ? ((st->iterations + 1) & 1) : (st->max_it & 1);
+    const double *__restrict__ x = buf ? x1 : x0;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long n = filter ? n_filter : N;
     if (i >= n) return;
@@ -732,6 +757,8 @@ int sg_setup_peers_ipc(vrec_sg *g) {
 
 vrec_sg::~vrec_sg() {
     for (void *m : ipc_opened) cudaIpcCloseMemHandle(m);
+    if (loop_exec) cudaGraphExecDestroy((cudaGraphExec_t)loop_exec);
+    if (loop_graph) cudaGraphDestroy((cudaGraph_t)loop_graph);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -748,7 +775,7 @@ static float sg_keep_frac(const vrec_sg *g) {
 
 static unsigned long long sg_flag(const vrec_sg *g, int step) { return (g->epoch << 32) | (unsigned)step; }
 
-int sg_run_begin(vrec_sg *g, int max_it, bool spin) {
+int sg_run_begin(vrec_sg *g, long long uidx, double eps2, int max_it, bool check_convergence, bool spin) {
     vrec_ctx *ctx = g->ctx;
     const double x0 = 1.0 / (double)g->N;                   // :53-54
     if (g->partitioned) {
@@ -758,7 +785,8 @@ int sg_run_begin(vrec_sg *g, int max_it, bool spin) {
         }
         g->epoch++;
     }
-    sg_reset_state_kernel<<<1, 1, 0, ctx->stream>>>(g->d_state.p, max_it);
+    sg_reset_state_kernel<<<1, 1, 0, ctx->stream>>>(g->d_state.p, max_it, uidx, eps2, check_convergence ? 1 : 0,
+                                                    sg_flag(g, 0));
     VREC_LAUNCHED(ctx);
     int fill_grid = (int)std::min<int64_t>((g->N + 255) / 256, 148 * 16);
     sg_fill_kernel<<<std::max(1, fill_grid), 256, 0, ctx->stream>>>(g->d_x[0], g->N, x0);
@@ -768,27 +796,26 @@ int sg_run_begin(vrec_sg *g, int max_it, bool spin) {
         sg_exchange_signal_kernel<<<1, 32, 0, ctx->stream>>>(g->d_peers.p, sg_flag(g, 0));
         VREC_LAUNCHED(ctx);
         if (spin) {
-            sg_exchange_wait_kernel<<<1, 32, 0, ctx->stream>>>(g->d_state.p, g->d_xchg, g->peers.world, sg_flag(g, 0), 0,
-                                                               max_it, 0.0, 0, 1);
+            sg_exchange_wait_kernel<<<1, 32, 0, ctx->stream>>>(g->d_state.p, g->d_xchg, g->peers.world, 0, 0, 1);
             VREC_LAUNCHED(ctx);
         }
     }
     return VREC_OK;
 }
 
-int sg_run_sweep(vrec_sg *g, long long uidx, int it, int max_it, double eps2, bool check_convergence) {
+// one sweep x -> x' over all source blocks; which iteration it is, the start vertex, epsilon and the buffers'
+// roles come from the device-resident SgState, so the same launches can be replayed
+int sg_run_sweep(vrec_sg *g, cudaGraphConditionalHandle loop_cond = 0) {
     vrec_ctx *ctx = g->ctx;
     const int rows = (int)(g->row_hi - g->row_lo);
     const float keep_frac = sg_keep_frac(g);
-    const double *x = g->d_x[it & 1];
-    double *nx = g->d_x[(it + 1) & 1];
     for (int b = 0; b < g->nblocks; ++b) {
         vrec_sg::Block &blk = *g->blocks[b];
         if (blk.n_seg > 0) {
             int pg = (blk.n_seg + SPMV_WARPS - 1) / SPMV_WARPS;
             sg_long_partials_kernel<<<pg, SPMV_THREADS, 0, ctx->stream>>>(
-                blk.rowptr.p, blk.rowptr.p + 1, blk.src.p, blk.w.p, x, blk.long_rows.p, blk.long_segptr.p,
-                blk.seg_row.p, blk.n_seg, blk.partials.p, g->d_state.p, keep_frac);
+                blk.rowptr.p, blk.rowptr.p + 1, blk.src.p, blk.w.p, g->d_x[0], g->d_x[1], blk.long_rows.p,
+                blk.long_segptr.p, blk.seg_row.p, blk.n_seg, blk.partials.p, g->d_state.p, keep_frac);
             VREC_LAUNCHED(ctx);
         }
         // measured on 6 M vertices x 100 in-edges (tools/sg_bench.py): (4 CTAs/SM, 2 windows/batch) 2388 us,
@@ -798,21 +825,58 @@ int sg_run_sweep(vrec_sg *g, long long uidx, int it, int max_it, double eps2, bo
                     : g->flat_variant == 2 ? sg_spmv_kernel<true, 3, 3>
                                            : sg_spmv_kernel<true, 4, 2>;
         kern<<<g->grid, SPMV_THREADS, 0, ctx->stream>>>(
-            rows, g->row_lo, blk.rowptr.p, blk.rowptr.p + 1, blk.src.p, blk.w.p, x, nx, uidx, blk.long_rows.p,
-            blk.long_segptr.p, blk.n_long, blk.partials.p, g->d_state.p, g->d_block_partials.p, it, max_it, eps2,
-            check_convergence ? 1 : 0, keep_frac, b > 0 ? 1 : 0, b == g->nblocks - 1 ? 1 : 0,
-            g->partitioned ? g->d_peers.p : nullptr, (it + 1) & 1, sg_flag(g, it + 1));
+            rows, g->row_lo, blk.rowptr.p, blk.rowptr.p + 1, blk.src.p, blk.w.p, g->d_x[0], g->d_x[1], blk.long_rows.p,
+            blk.long_segptr.p, blk.n_long, blk.partials.p, g->d_state.p, g->d_block_partials.p, keep_frac,
+            b > 0 ? 1 : 0, b == g->nblocks - 1 ? 1 : 0, g->partitioned ? g->d_peers.p : nullptr, loop_cond);
         VREC_LAUNCHED(ctx);
     }
     return VREC_OK;
 }
 
-int sg_run_barrier(vrec_sg *g, int it, int max_it, double eps2, bool check_convergence, bool spin) {
+int sg_run_barrier(vrec_sg *g, int it, bool check_convergence, bool spin) {
     if (!g->partitioned) return VREC_OK;
     vrec_ctx *ctx = g->ctx;
-    sg_exchange_wait_kernel<<<1, 32, 0, ctx->stream>>>(g->d_state.p, g->d_xchg, g->peers.world, sg_flag(g, it + 1), it,
-                                                       max_it, eps2, check_convergence ? 1 : 0, spin ? 1 : 0);
+    sg_exchange_wait_kernel<<<1, 32, 0, ctx->stream>>>(g->d_state.p, g->d_xchg, g->peers.world, it + 1, 1,
+                                                       spin ? 1 : 0);
+    (void)check_convergence;      // the decision reads SgState::check
     VREC_LAUNCHED(ctx);
+    return VREC_OK;
+}
+
+// The step() loop of one graph as a CUDA graph: a conditional `while` node whose body is one sweep (its last CTA
+// sets the loop condition from SgState::done).  A query then costs one graph launch whatever maxIterations is, and nothing runs after the
+// iteration that converged (the reference pays one Spark action per iteration, :130-141; the round-1 engine
+// queued all maxIterations sweeps and let the late ones exit on `done`).
+static int sg_build_loop_graph(vrec_sg *g) {
+    vrec_ctx *ctx = g->ctx;
+    cudaGraph_t graph = nullptr;
+    VREC_CUDA(cudaGraphCreate(&graph, 0));
+    cudaGraphConditionalHandle handle;
+    VREC_CUDA(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = handle;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    VREC_CUDA(cudaGraphAddNode(&node, graph, nullptr, 0, &np));
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    const int64_t l0 = ctx->launches;
+    VREC_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    int rc = sg_run_sweep(g, handle);            // the last CTA of the sweep sets the loop condition
+    cudaGraph_t captured = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &captured);
+    g->loop_launches = (int)(ctx->launches - l0);
+    ctx->launches = l0;                                     // captured, not launched
+    if (rc != VREC_OK || e != cudaSuccess) {
+        if (e != cudaSuccess) vrec_set_error("cudaStreamEndCapture -> %s", cudaGetErrorString(e));
+        cudaGraphDestroy(graph);
+        return rc != VREC_OK ? rc : VREC_ECUDA;
+    }
+    cudaGraphExec_t exec = nullptr;
+    VREC_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    g->loop_graph = graph;
+    g->loop_exec = exec;
     return VREC_OK;
 }
 
@@ -823,10 +887,18 @@ int sg_run_device(vrec_sg *g, long long uidx, double epsilon, int max_it, bool c
         vrec_set_error("this graph belongs to a single-process group: use vrec_sg_group_stationary");
         return VREC_EINVAL;
     }
-    VREC_TRY(sg_run_begin(g, max_it, true));
+    VREC_TRY(sg_run_begin(g, uidx, eps2, max_it, check_convergence, true));
+    if (max_it <= 0) return VREC_OK;
+    if (!g->partitioned && g->use_graph) {
+        if (!g->loop_exec) VREC_TRY(sg_build_loop_graph(g));
+        VREC_CUDA(cudaGraphLaunch((cudaGraphExec_t)g->loop_exec, g->ctx->stream));
+        g->ctx->launches += g->loop_launches;               // at least one pass; sg_fetch_state adds the rest
+        g->graph_pending = true;
+        return VREC_OK;
+    }
     for (int it = 0; it < max_it; ++it) {
-        VREC_TRY(sg_run_sweep(g, uidx, it, max_it, eps2, check_convergence));
-        VREC_TRY(sg_run_barrier(g, it, max_it, eps2, check_convergence, true));
+        VREC_TRY(sg_run_sweep(g));
+        VREC_TRY(sg_run_barrier(g, it, check_convergence, true));
     }
     return VREC_OK;
 }
@@ -837,6 +909,10 @@ int sg_fetch_state(vrec_sg *g, int max_it, SgState *h, int *result_buf) {
     if (h->converged < 0) {
         vrec_set_error("row-partitioned graph: a peer did not reach the exchange barrier in time");
         return VREC_ENCCL;
+    }
+    if (g->graph_pending) {                                 // passes of the graph's body beyond the first
+        g->ctx->launches += (int64_t)g->loop_launches * std::max(0, h->cur - 1);
+        g->graph_pending = false;
     }
     if (max_it <= 0) {
         h->iterations = 0;
@@ -1077,10 +1153,10 @@ extern "C" int vrec_sg_group_stationary(vrec_sg **parts, int32_t world, int64_t 
         return VREC_ENOENT;
     }
     const double eps2 = epsilon * epsilon;
-    for (int r = 0; r < world; ++r) VREC_TRY(sg_run_begin(parts[r], max_iterations, false));
+    for (int r = 0; r < world; ++r) VREC_TRY(sg_run_begin(parts[r], v, eps2, max_iterations, true, false));
     for (int it = 0; it < max_iterations; ++it) {
-        for (int r = 0; r < world; ++r) VREC_TRY(sg_run_sweep(parts[r], v, it, max_iterations, eps2, true));
-        for (int r = 0; r < world; ++r) VREC_TRY(sg_run_barrier(parts[r], it, max_iterations, eps2, true, false));
+        for (int r = 0; r < world; ++r) VREC_TRY(sg_run_sweep(parts[r]));
+        for (int r = 0; r < world; ++r) VREC_TRY(sg_run_barrier(parts[r], it, true, false));
     }
     for (int r = 0; r < world; ++r) {
         vrec_sg *g = parts[r];
@@ -1237,27 +1313,29 @@ extern "C" int vrec_sg_query(vrec_sg *sg, const int64_t *vertices, int32_t n, do
         }
         out_status[q] = VREC_OK;
         VREC_TRY(sg_run_device(sg, v, epsilon, max_iterations, true));
+        // everything below is queued behind the loop: one synchronisation per query
+        const bool want_recs = max_recs > 0 && n_cand > 0;
+        int cnt = 0;
+        if (want_recs) {
+            int cg = (int)((n_cand + 255) / 256);
+            sg_candidates_kernel<<<cg, 256, 0, ctx->stream>>>(
+                sg->h_ids.empty() ? nullptr : sg->d_ids.p, sg->N, use_filter ? sg->d_filter_ids.p : nullptr, n_filter,
+                sg->d_x[0], sg->d_x[1], sg->d_state.p, (long long)vertices[q], sg->d_cand_val.p, sg->d_cand_key.p);
+            VREC_LAUNCHED(ctx);
+            VREC_TRY(vrec_launch_select_topn(ctx, sg->d_cand_val.p, sg->d_cand_key.p, nullptr, n_cand, 0, 1,
+                                             max_recs, sg->d_out_key.p, sg->d_out_val.p, sg->d_out_count.p));
+            VREC_CUDA(cudaMemcpyAsync(&cnt, sg->d_out_count.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            VREC_CUDA(cudaMemcpyAsync(h_key.data(), sg->d_out_key.p, sizeof(long long) * m, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+            VREC_CUDA(cudaMemcpyAsync(h_val.data(), sg->d_out_val.p, sizeof(double) * m, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        }
         SgState st;
         int buf = 0;
-        VREC_TRY(sg_fetch_state(sg, max_iterations, &st, &buf));
+        VREC_TRY(sg_fetch_state(sg, max_iterations, &st, &buf));          // synchronises
         if (out_iterations) out_iterations[q] = st.iterations;
         if (out_converged) out_converged[q] = st.converged;
-        if (max_recs == 0 || n_cand == 0) continue;
-        int cg = (int)((n_cand + 255) / 256);
-        sg_candidates_kernel<<<cg, 256, 0, ctx->stream>>>(
-            sg->h_ids.empty() ? nullptr : sg->d_ids.p, sg->N, use_filter ? sg->d_filter_ids.p : nullptr, n_filter,
-            sg->d_x[buf],
-            (long long)vertices[q], sg->d_cand_val.p, sg->d_cand_key.p);
-        VREC_LAUNCHED(ctx);
-        VREC_TRY(vrec_launch_select_topn(ctx, sg->d_cand_val.p, sg->d_cand_key.p, nullptr, n_cand, 0, 1,
-                                         max_recs, sg->d_out_key.p, sg->d_out_val.p, sg->d_out_count.p));
-        int cnt = 0;
-        VREC_CUDA(cudaMemcpyAsync(&cnt, sg->d_out_count.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        VREC_CUDA(cudaMemcpyAsync(h_key.data(), sg->d_out_key.p, sizeof(long long) * m, cudaMemcpyDeviceToHost,
-                                  ctx->stream));
-        VREC_CUDA(cudaMemcpyAsync(h_val.data(), sg->d_out_val.p, sizeof(double) * m, cudaMemcpyDeviceToHost,
-                                  ctx->stream));
-        VREC_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (!want_recs) continue;
         out_count[q] = cnt;
         for (int k = 0; k < cnt; ++k) {
             out_id[(size_t)q * max_recs + k] = h_key[k];
@@ -1278,6 +1356,9 @@ extern "C" int vrec_sg_set_option(vrec_sg *sg, const char *name, int32_t value) 
         sg->batch.force_t = value;
     } else if (k == "flat_variant" && value >= 0 && value <= 2) {
         sg->flat_variant = value;
+    } else if (k == "graph" && (value == 0 || value == 1)) {
+        // 0 = queue all maxIterations sweeps (late ones exit on `done`) instead of the CUDA-graph while loop
+        sg->use_graph = value;
     } else if (k == "rows_kernel" && (value == 0 || value == 1)) {
         // A/B: 1 = the round-1 half-warp-per-row kernel instead of the flat-window kernel
         sg->rows_kernel = value != 0;

@@ -16,7 +16,15 @@ struct SgState {
     int converged;     // 1 = "Converged in ...", 0 = "... reached the maximum ..."
     unsigned int ticket;
     double residual;   // last sum of squared differences (:131-139)
-    double residual_partial;   // this rank's share before the all-reduce (partitioned graphs)
+    // the query's parameters and the loop counter live on the device: every sweep reads them here, so the same
+    // launch can be replayed by a CUDA-graph `while` node until `done` (no host round trip per iteration)
+    int cur;           // `iteration` of the sweep that runs next (step()'s argument, :92)
+    int max_it;
+    int check;         // 1: isConverged after every sweep; 0: fixed number of sweeps (vrec_sg_iterate_device)
+    int pad;
+    long long uidx;    // index of the start vertex (u = 1 there), -1: none
+    double eps2;       // epsilon * epsilon (:40)
+    unsigned long long flag_base;   // row-partitioned graphs: epoch << 32 (see SgExchange)
 };
 
 // Batch path (vrec_sg_batch.cu): many personalised queries whose start vertex has no in-edge
@@ -104,6 +112,12 @@ struct vrec_sg {
     DevBuf<double> d_block_partials;
     DevBuf<SgState> d_state;
     int grid = 0;
+    // the step() loop as a CUDA graph: one conditional `while` node whose body is one sweep (all source blocks)
+    // plus the kernel that sets the loop condition from SgState::done.  Built at the first query.
+    void *loop_graph = nullptr, *loop_exec = nullptr;     // cudaGraph_t / cudaGraphExec_t
+    int loop_launches = 0;                                // kernel launches of one pass of the body
+    int use_graph = 1;                                    // option "graph": 0 = queue all maxIterations sweeps
+    bool graph_pending = false;                           // a graph launch whose pass count is not yet in ctx->launches
     // top-N scratch
     DevBuf<long long> d_filter_ids;
     DevBuf<double> d_cand_val;

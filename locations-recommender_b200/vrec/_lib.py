@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libvrec.so")
+# VREC_LIB_PATH: an alternative build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("VREC_LIB_PATH") or os.path.join(_PKG, "libvrec.so")
 
 OK, ENOENT, ENOMEM, ENODEV, EINVAL, ECUDA, ENCCL = 0, -2, -12, -19, -22, -100, -101
 
