@@ -339,6 +339,9 @@ __device__ __forceinline__ double rec_val(const double *vals, int i, bool f32) {
 // of meta[i] (offset in 8-byte words | place count << 40 | category count << 52).  The vector lengths are not
 // stored: sum(v^2) is an exact integer, so sqrt((double)sum) is bit for bit the length knn_norms_kernel
 // computed (Distance.vectorLength, knn/Distance.scala:11-16).
+#ifndef VREC_POST_SEARCH
+#define VREC_POST_SEARCH 1        // 1: two-pass place matching in the postings evaluator (see exact_pair_staged_compact)
+#endif
 constexpr unsigned CREC_COL_MASK = 0x3fffffu;
 constexpr int CREC_PW = 6, CREC_CW = 3;            // words fetched up front: 12 place + 12 category entries
 __host__ __device__ constexpr int crec_place_words(int n) { return (n + 1) >> 1; }
@@ -515,35 +518,69 @@ __device__ __forceinline__ double exact_pair_staged_compact(const TileAux &aux, 
     if (np > 0) {
         double sum = 0.0;
         unsigned sq = 0u;
-        auto place_term = [&](unsigned craw) {
+        // the target's entry for column ix, if any: binary search over its sorted places (shared memory)
+        auto place_match = [&](unsigned craw) {
             const int ix = (int)(craw & CREC_COL_MASK);
-            const unsigned v = (craw >> 22) & 0xffu;
-            sq += v * v;
-            // signature test (registers only), then a binary search over the target's sorted places.  (Measured
-            // alternative: a direct-mapped table over the 64 signature slots in shared memory instead of the
-            // search -- 10 % fewer instructions but 7.8 ms instead of 4.2 ms per 18 944 targets: the heavy targets
-            // that dominate this pass have 30-64 places, their slots collide, and the collision path serialises.)
-            if ((t.sig >> sig_bit(ix)) & 1ULL) {
-                int lo = 0, hi = t.pn;                               // first index with pcol >= ix
-                while (lo < hi) {
-                    int mid = (lo + hi) >> 1;
-                    if (t.pcol[mid] < ix) lo = mid + 1; else hi = mid;
-                }
-                if (lo < t.pn && t.pcol[lo] == ix) {
-                    sum = xadd(sum, xmul((double)v, t.pval[lo]));
-                    if (min_tail < 0 && (craw & aux.tail_bit)) min_tail = ix;
-                }
+            int lo = 0, hi = t.pn;                                   // first index with pcol >= ix
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (t.pcol[mid] < ix) lo = mid + 1; else hi = mid;
+            }
+            if (lo < t.pn && t.pcol[lo] == ix) {
+                sum = xadd(sum, xmul((double)((craw >> 22) & 0xffu), t.pval[lo]));
+                if (min_tail < 0 && (craw & aux.tail_bit)) min_tail = ix;
             }
         };
+#if VREC_POST_SEARCH == 1
+        // Pass 1 (all lanes, no memory): squares and the signature test of the prefetched entries -> a bit mask.
+        // Pass 2: each lane searches only ITS entries that passed, in ascending order (the order the products are
+        // added in), re-reading the entry word from the L1.  The search used to sit inside the 12 unrolled entry
+        // slots and ran in nearly every slot for ~5 of 32 lanes: 47 % of the kernel's instructions
+        // (profiles/r2_knn_hot_lines.txt); now the warp runs as many search rounds as its busiest lane has hits.
+        unsigned pend = 0u;
 #pragma unroll
         for (int j = 0; j < CREC_PW; ++j) {
-            if (2 * j < np) place_term((unsigned)rc.pw[j]);
-            if (2 * j + 1 < np) place_term((unsigned)(rc.pw[j] >> 32));
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                if (2 * j + hf < np) {
+                    const unsigned craw = hf ? (unsigned)(rc.pw[j] >> 32) : (unsigned)rc.pw[j];
+                    const unsigned v = (craw >> 22) & 0xffu;
+                    sq += v * v;
+                    if ((t.sig >> sig_bit((int)(craw & CREC_COL_MASK))) & 1ULL) pend |= 1u << (2 * j + hf);
+                }
+            }
         }
-        for (int j = CREC_PW; j < rc.pwords; ++j) {
+        while (pend) {
+            const int e = __ffs(pend) - 1;
+            pend &= pend - 1;
+            const unsigned long long wd = ld_rec_u64(rc.r + (e >> 1), pol);
+            place_match((e & 1) ? (unsigned)(wd >> 32) : (unsigned)wd);
+        }
+#else
+#pragma unroll
+        for (int j = 0; j < CREC_PW; ++j) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                if (2 * j + hf < np) {
+                    const unsigned craw = hf ? (unsigned)(rc.pw[j] >> 32) : (unsigned)rc.pw[j];
+                    const unsigned v = (craw >> 22) & 0xffu;
+                    sq += v * v;
+                    if ((t.sig >> sig_bit((int)(craw & CREC_COL_MASK))) & 1ULL) place_match(craw);
+                }
+            }
+        }
+#endif
+        for (int j = CREC_PW; j < rc.pwords; ++j) {                  // long records: the rest, entry by entry
             const unsigned long long wd = ld_rec_u64(rc.r + j, pol);
-            place_term((unsigned)wd);
-            if (2 * j + 1 < np) place_term((unsigned)(wd >> 32));
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                if (2 * j + hf < np) {
+                    const unsigned craw = hf ? (unsigned)(wd >> 32) : (unsigned)wd;
+                    const unsigned v = (craw >> 22) & 0xffu;
+                    sq += v * v;
+                    if ((t.sig >> sig_bit((int)(craw & CREC_COL_MASK))) & 1ULL) place_match(craw);
+                }
+            }
         }
         const double c = xdiv(sum, xmul(sqrt((double)sq), t.plen));
         if (c > 0) {
@@ -2123,6 +2160,14 @@ constexpr int WS_NACC = 3;           // TMEM accumulators (3 x 128 columns); the
 constexpr int WS_STAGES = 4;         // B tiles in flight (the A operand lives in tensor memory, not in shared memory)
 constexpr int WS_TMEM_A = WS_NACC * TC_N;   // first TMEM column of the A operand
 constexpr int WS_STAGGER = 1;        // tiles between the starting points of neighbouring CTAs (small: the CTAs share each tile through L2)
+#ifndef VREC_WS_EVAL_WARPS
+#define VREC_WS_EVAL_WARPS 8     // consumer warps that only evaluate survivors (0: every consumer warp filters AND evaluates, round 1)
+#endif
+constexpr int WS_EVAL_WARPS = VREC_WS_EVAL_WARPS;
+constexpr int WS_FILTER_WARPS = WS_WORKERS / 32 - WS_EVAL_WARPS;     // a multiple of 4: TMEM lane quarters
+static_assert(WS_FILTER_WARPS >= 4 && WS_FILTER_WARPS % 4 == 0, "filter warps must cover the four TMEM lane quarters");
+constexpr unsigned long long WS_Q_FREE = 0xffffffffffffULL;          // payload of a free ring slot (48 bits)
+constexpr unsigned long long WS_Q_NONE = 0xffffffffffffffffULL;      // "this lane holds no survivor"
 constexpr int WS_BOOT_TILES = 512;   // multiple of 16; 64 groups of 512 candidates per target
 
 __global__ void __launch_bounds__(WS_THREADS, 1)
@@ -2137,6 +2182,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
     __shared__ uint32_t tmem_base_s;
     __shared__ unsigned int s_stats[4];
     __shared__ int s_next_unit[4];
+    __shared__ int s_q_res, s_q_take, s_q_done;     // survivor ring (WS_EVAL_WARPS > 0): reserved / claimed entries, finished filter warps
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool worker = tid < WS_WORKERS;
     const int tile_m = blockIdx.x, sp = blockIdx.y;
@@ -2406,7 +2452,120 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
             tc::bar_sync(1, WS_WORKERS);
         }
         // ---- main sequence.  The unit of consumer work is (tile, lane quarter, column quarter) = 32 target
-        // rows x 32 candidates; the warps claim units in order from shared counters, so a warp that is busy
+        // rows x 32 candidates; the warps of a lane quarter claim units in order from a shared counter.
+#if VREC_WS_EVAL_WARPS > 0
+        // Round 2: the consumer warps are split.  FILTER warps (2 per TMEM lane quarter) only drain accumulators,
+        // test thresholds and push survivors into a ring in shared memory; EVALUATOR warps only pull survivors
+        // (32 at a time, one per lane) and evaluate them exactly.  An exact evaluation is a chain of dependent
+        // memory reads (a drain of 32 took ~25 K cycles = 13 tile periods): with every warp doing both, a lane
+        // quarter whose warps happened to be evaluating held up its accumulator, and the MMA thread waited 737
+        // cycles per tile for one (measured, tools/knn_bench.py) -- now no warp that touches TMEM ever blocks.
+        // Ring slot = lap (16 bits) | payload (48): FREE(L) -> entry of lap L (target << 32 | candidate) -> FREE(L+1).
+        // A writer of lap L waits for FREE(L), a reader of lap L for an entry tagged L: writers of different laps
+        // can never race for a slot (with a plain "empty" marker a lap-L+1 entry could overtake the lap-L one,
+        // and with every evaluator waiting for a lap-L entry nobody would claim it -- a deadlock the reduced-size
+        // tests, whose loose thresholds flood the ring, ran into at once).
+        for (int q = tid; q < TC_QCAP; q += WS_WORKERS) sm.queue[q] = WS_Q_FREE;                 // FREE(0)
+        if (tid == 0) {
+            s_q_res = 0;
+            s_q_take = 0;
+            s_q_done = 0;
+        }
+        tc::bar_sync(1, WS_WORKERS);
+        volatile unsigned long long *ring = sm.queue;
+        if (warp >= WS_FILTER_WARPS) {
+            // ================= evaluator warps =================
+            for (;;) {
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(&s_q_take, 32);
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                const int my = pos + lane;
+                const unsigned long long lap = (unsigned long long)((my / TC_QCAP) & 0xffff);
+                unsigned long long e = WS_Q_NONE;
+                for (;;) {
+                    const unsigned long long v = ring[my & (TC_QCAP - 1)];
+                    if ((v >> 48) == lap && (v & WS_Q_FREE) != WS_Q_FREE) {
+                        e = v;
+                        ring[my & (TC_QCAP - 1)] = (((lap + 1) & 0xffff) << 48) | WS_Q_FREE;     // FREE(lap + 1)
+                        break;
+                    }
+                    if (*(volatile int *)&s_q_done == WS_FILTER_WARPS && my >= *(volatile int *)&s_q_res) break;
+                    __nanosleep(256);
+                }
+                __syncwarp();
+                if (!__any_sync(0xffffffffu, e != WS_Q_NONE)) break;           // nothing left for this warp
+                const int tt = e != WS_Q_NONE ? (int)((e >> 32) & 0xffu) : -1;
+                tile_process_sig(aux, sm, tt, (int)(unsigned)(e & 0xffffffffu), K, pw, cw);
+            }
+        } else {
+            // ================= filter warps =================
+            const int n_units = nseq * 4;
+            const int ulq = lq;
+            for (;;) {
+                int u = 0;
+                if (lane == 0) u = atomicAdd(&s_next_unit[ulq], 1);
+                u = __shfl_sync(0xffffffffu, u, 0);
+                if (u >= n_units) break;
+                const int i = u >> 2, ucq = u & 3;
+                const int a = i % WS_NACC;
+                tc::mbar_wait(&tfull[a], (uint32_t)((i / WS_NACC) & 1));
+                tc::fence_after_sync();
+                WS_CTICK(1)                                       // claim + wait for the accumulator
+                const int ut = ulq * 32 + lane;
+                const float thr = *(volatile float *)(sm.thr + ut);
+                const long long tile = (long long)tile_index(i) * TC_N;
+                const int c0 = ucq * 32;
+                float v[32];
+                tc::tmem_ld32(tbase + ((uint32_t)(ulq * 32) << 16) + (uint32_t)(a * TC_N + c0), v);
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tempty[a]);            // this unit is out of the accumulator
+                float vmax = v[0];
+#pragma unroll
+                for (int jj = 1; jj < 32; ++jj) vmax = fmaxf(vmax, v[jj]);
+                unsigned pass = 0;
+                if (vmax * 1.002f + 2e-5f >= thr) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) pass |= (v[jj] * 1.002f + 2e-5f >= thr ? 1u : 0u) << jj;
+                }
+                if (tile + c0 + 32 > d.P) {                            // last tile: columns past the last person
+                    const long long over = tile + c0 + 32 - d.P;
+                    pass = over >= 32 ? 0u : (pass & (0xffffffffu >> over));
+                }
+                const unsigned any = __ballot_sync(0xffffffffu, pass != 0u);
+                WS_CTICK(2)                                       // epilogue
+                if (any) {
+                    int cnt = __popc(pass), incl = cnt;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        int o = __shfl_up_sync(0xffffffffu, incl, off);
+                        if (lane >= off) incl += o;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_q_res, total);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    int pos = base + incl - cnt;
+                    while (pass) {
+                        const int jj = __ffs(pass) - 1;
+                        pass &= pass - 1;
+                        const unsigned long long tag = (unsigned long long)((pos / TC_QCAP) & 0xffff) << 48;
+                        while (ring[pos & (TC_QCAP - 1)] != (tag | WS_Q_FREE)) __nanosleep(128);   // previous lap not taken yet
+                        ring[pos & (TC_QCAP - 1)] = tag | ((unsigned long long)ut << 32) |
+                                                    (unsigned long long)(unsigned)(tile + c0 + jj);
+                        ++pos;
+                        if (aux.meta) asm volatile("prefetch.global.L2 [%0];" ::"l"((aux.cmeta ? aux.cmeta : aux.meta) + tile + c0 + jj));
+                    }
+                    __syncwarp();
+                    WS_CTICK(10)                                  // queueing
+                }
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) atomicAdd(&s_q_done, 1);
+        }
+#else
+        // (round 1) the warps claim units in order from shared counters, so a warp that is busy
         // with exact evaluations (a chain of dependent HBM reads, tens of thousands of cycles) never holds up
         // an accumulator: the others take over its units and the tensor pipe keeps running.  Survivors go
         // to a per-warp queue that the warp drains by itself once it holds one candidate per lane.
@@ -2494,6 +2653,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
             }
         }
         drain_own();
+#endif
         if (cprof) {
             g_tc_cycles[1] += cacc1;
             g_tc_cycles[2] += cacc2;
