@@ -11,6 +11,10 @@
 
 namespace {
 
+#ifndef VREC_WS_ABLATE
+#define VREC_WS_ABLATE 0          // > 0: timing experiments that break the results (never in a shipped build)
+#endif
+
 // ------------------------------------------------------------------ device views
 struct KnnVec {                 // one rating-vector table in CSR form
     const int *rowptr;          // [P+1]
@@ -1135,7 +1139,7 @@ __device__ __forceinline__ void tile_heap_insert(const TileSmem &sm, int t, int 
                 hs[pos] = sim;
                 hi[pos] = idx;
                 *cntp = n + 1;
-                if (n + 1 == K) *thr = fmaxf(*thr, __double2float_rd(hs[0]));
+                if (VREC_WS_ABLATE != 3 && n + 1 == K) *thr = fmaxf(*thr, __double2float_rd(hs[0]));
             } else if (nb_worse(hs[0], hi[0], sim, idx)) {
                 int pos = 0;
                 for (;;) {                              // sift down from the root
@@ -1159,7 +1163,7 @@ __device__ __forceinline__ void tile_heap_insert(const TileSmem &sm, int t, int 
                 }
                 hs[pos] = sim;
                 hi[pos] = idx;
-                *thr = fmaxf(*thr, __double2float_rd(hs[0]));
+                if (VREC_WS_ABLATE != 3) *thr = fmaxf(*thr, __double2float_rd(hs[0]));
             }
             __threadfence_block();
             atomicExch(sm.lock + t, 0);
@@ -2160,6 +2164,9 @@ constexpr int WS_NACC = 3;           // TMEM accumulators (3 x 128 columns); the
 constexpr int WS_STAGES = 4;         // B tiles in flight (the A operand lives in tensor memory, not in shared memory)
 constexpr int WS_TMEM_A = WS_NACC * TC_N;   // first TMEM column of the A operand
 constexpr int WS_STAGGER = 1;        // tiles between the starting points of neighbouring CTAs (small: the CTAs share each tile through L2)
+#ifndef VREC_WS_STATIC_UNITS
+#define VREC_WS_STATIC_UNITS 1   // 1: a lane quarter's units go round robin over its filter warps; 0: claimed with an atomic
+#endif
 #ifndef VREC_WS_EVAL_WARPS
 #define VREC_WS_EVAL_WARPS 8     // consumer warps that only evaluate survivors (0: every consumer warp filters AND evaluates, round 1)
 #endif
@@ -2501,11 +2508,17 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
             // ================= filter warps =================
             const int n_units = nseq * 4;
             const int ulq = lq;
+#if VREC_WS_STATIC_UNITS
+            // a lane quarter's units go round robin over its filter warps (they never block, so a dynamic claim --
+            // an atomic on shared memory plus a shuffle per unit -- buys nothing)
+            for (int u = boot * 4 + (warp >> 2); u < n_units; u += WS_FILTER_WARPS / 4) {
+#else
             for (;;) {
                 int u = 0;
                 if (lane == 0) u = atomicAdd(&s_next_unit[ulq], 1);
                 u = __shfl_sync(0xffffffffu, u, 0);
                 if (u >= n_units) break;
+#endif
                 const int i = u >> 2, ucq = u & 3;
                 const int a = i % WS_NACC;
                 tc::mbar_wait(&tfull[a], (uint32_t)((i / WS_NACC) & 1));
@@ -2520,11 +2533,13 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                 tc::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&tempty[a]);            // this unit is out of the accumulator
-                float vmax = v[0];
+                float m8[8];                                           // maximum by a tree: depth 5 instead of 31
 #pragma unroll
-                for (int jj = 1; jj < 32; ++jj) vmax = fmaxf(vmax, v[jj]);
+                for (int jj = 0; jj < 8; ++jj) m8[jj] = fmaxf(fmaxf(v[jj], v[jj + 8]), fmaxf(v[jj + 16], v[jj + 24]));
+                const float vmax = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
+                                         fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
                 unsigned pass = 0;
-                if (vmax * 1.002f + 2e-5f >= thr) {
+                if (VREC_WS_ABLATE != 2 && vmax * 1.002f + 2e-5f >= thr) {
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) pass |= (v[jj] * 1.002f + 2e-5f >= thr ? 1u : 0u) << jj;
                 }
@@ -2532,6 +2547,9 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                     const long long over = tile + c0 + 32 - d.P;
                     pass = over >= 32 ? 0u : (pass & (0xffffffffu >> over));
                 }
+#if VREC_WS_ABLATE == 1 || VREC_WS_ABLATE == 2
+                pass = 0;                                          // timing experiment only: drop every survivor
+#endif
                 const unsigned any = __ballot_sync(0xffffffffu, pass != 0u);
                 WS_CTICK(2)                                       // epilogue
                 if (any) {

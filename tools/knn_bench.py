@@ -88,5 +88,8 @@ for s in range(a.warmup + a.steps):
     if cy[5] and a.kernel == 3:
         print(f"   tc block0 cycles/tile: load-wait {cy[0] / cy[5]:.0f}, mma {cy[1] / cy[5]:.0f}, epilogue {cy[2] / cy[5]:.0f}, "
               f"mma issue {cy[8] / cy[5]:.0f}, load issue {cy[3] / cy[5]:.0f} [cp.async wait {cy[6] / cy[5]:.0f}, barrier {cy[7] / cy[5]:.0f}]; postings pass total {cy[4] / 1e6:.2f} Mcycles; tiles {cy[5]}")
+    dms = C.c_double(0.0)
+    lib.vrec_knn_last_dense_ms(rs._h, C.byref(dms))
+    print(f"   dense filter kernel {dms.value:.2f} ms")
     print(f"kernel={a.kernel} step {s}: {ms:.1f} ms  {B / ms * 1e3:,.0f} persons/s   per target: postings evals {st[0] / B:.0f}, "
           f"filter survivors {st[1] / B:.0f}, heap inserts {st[2] / B:.0f}, queue overflow {st[3] / B:.0f}", flush=True)
