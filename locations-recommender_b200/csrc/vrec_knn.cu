@@ -2156,7 +2156,10 @@ knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_t
 // Synchronisation is mbarrier-only on the data path: full[stage] (TMA transaction bytes),
 // tfull[acc] / sempty[stage] (tcgen05.commit), tempty[acc] (one arrival per consumer warp).
 // ---------------------------------------------------------------------------------------
-constexpr int WS_WORKERS = 512;
+#ifndef VREC_WS_WORKERS
+#define VREC_WS_WORKERS 512
+#endif
+constexpr int WS_WORKERS = VREC_WS_WORKERS;   // consumer threads: filter warps + evaluator warps
 constexpr int WS_THREADS = WS_WORKERS + 64;           // + MMA warp + loader warp
 constexpr int WS_VOTE_EVERY = 4;
 constexpr int WS_WQ = TC_QCAP / (WS_WORKERS / 32);   // survivor queue entries per consumer warp
@@ -2166,6 +2169,9 @@ constexpr int WS_TMEM_A = WS_NACC * TC_N;   // first TMEM column of the A operan
 constexpr int WS_STAGGER = 1;        // tiles between the starting points of neighbouring CTAs (small: the CTAs share each tile through L2)
 #ifndef VREC_WS_STATIC_UNITS
 #define VREC_WS_STATIC_UNITS 1   // 1: a lane quarter's units go round robin over its filter warps; 0: claimed with an atomic
+#endif
+#ifndef VREC_WS_POLL_NS
+#define VREC_WS_POLL_NS 256      // pause of an evaluator lane between two looks at its ring slot
 #endif
 #ifndef VREC_WS_EVAL_WARPS
 #define VREC_WS_EVAL_WARPS 8     // consumer warps that only evaluate survivors (0: every consumer warp filters AND evaluates, round 1)
@@ -2225,7 +2231,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
         }
         for (int a = 0; a < WS_NACC; ++a) {
             tc::mbar_init(&tfull[a], 1);
-            tc::mbar_init(&tempty[a], WS_WORKERS / 32);
+            tc::mbar_init(&tempty[a], 16);              // one arrival per unit: 4 lane quarters x 4 column quarters
         }
         tc::mbar_init_fence();
         *sm.qn = 0;
@@ -2422,7 +2428,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
             float gmax[16];
 #pragma unroll
             for (int g = 0; g < 16; ++g) gmax[g] = 0.0f;
-            for (int i = 0; i < boot; ++i) {
+            for (int i = 0; i < (warp < 16 ? boot : 0); ++i) {     // 16 warps = the 16 units of a tile
                 const int a = i % WS_NACC;
                 tc::mbar_wait(&tfull[a], (uint32_t)((i / WS_NACC) & 1));
                 tc::fence_after_sync();
@@ -2447,7 +2453,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
 #pragma unroll
             for (int g = 1; g < 16; ++g) gmin = fminf(gmin, gmax[g]);
             float *scratch = reinterpret_cast<float *>(sm.queue);
-            scratch[my_t * 4 + cq] = gmin;
+            if (warp < 16) scratch[my_t * 4 + cq] = gmin;
             tc::bar_sync(1, WS_WORKERS);
             if (tid < TC_M && sm.tid_of[tid] >= 0) {
                 float theta = scratch[tid * 4];
@@ -2497,7 +2503,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                         break;
                     }
                     if (*(volatile int *)&s_q_done == WS_FILTER_WARPS && my >= *(volatile int *)&s_q_res) break;
-                    __nanosleep(256);
+                    __nanosleep(VREC_WS_POLL_NS);
                 }
                 __syncwarp();
                 if (!__any_sync(0xffffffffu, e != WS_Q_NONE)) break;           // nothing left for this warp
