@@ -2951,6 +2951,13 @@ knn_merge_kernel(const Nb *__restrict__ part, const int *__restrict__ part_cnt, 
 // target: neighbours in ascending person index, num/den accumulated in the same pass in a
 // dense per-warp scratch row; then the region filter + ranked top-N
 // (knn/KnnRecommenderMain.scala:96-100).
+// The scratch rows (2 x 8 bytes per place and warp: 3.8 GB for 2 368 warps x 100 000 places) are far larger than
+// L2, so every num/den update of a dense row is a DRAM round trip (2.8 GB read per 18 944 targets, 1.1 ms).  A
+// target whose neighbours hold at most RATE_HASH_MAX ratings (K = 50: ~400) instead maps place -> slot through a
+// RATE_HASH-entry open-addressing table in shared memory and keeps num/den in the first RATE_HASH entries of its
+// rows (38 MB over all warps: L2-resident).  Same additions in the same order; the rows are zero again afterwards.
+constexpr int RATE_HASH = 1024;          // table entries per warp (power of two)
+constexpr int RATE_HASH_MAX = 512;       // ratings of a target's neighbours up to which the table is used (= 32 lanes x RG below)
 __global__ void __launch_bounds__(RATE_WARPS * 32)
 knn_rate_gather_kernel(const int *__restrict__ rrp, const int *__restrict__ rpl, const double *__restrict__ rv,
                        const Nb *__restrict__ nb_idx, const int *__restrict__ nb_cnt, int T, int K, int rdim,
@@ -2964,9 +2971,28 @@ knn_rate_gather_kernel(const int *__restrict__ rrp, const int *__restrict__ rpl,
     int *mytouched = touched + (size_t)slot * touch_cap;
     const unsigned lt_mask = (1u << lane) - 1u;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    __shared__ int s_keys[RATE_WARPS][RATE_HASH];
+    volatile int *keys = s_keys[warp];
+    for (int q = lane; q < RATE_HASH; q += 32) keys[q] = -1;
+    __syncwarp();
     for (int tt = slot; tt < T; tt += nslots) {
         const int n = nb_cnt[tt];
         int ntouched = 0;
+        bool use_hash = false;
+        if (rdim > 4 * RATE_HASH) {                                    // small rows stay in L2 anyway
+            int total_all = 0;
+            for (int k0 = 0; k0 < n && total_all <= RATE_HASH_MAX; k0 += 32) {
+                int c = 0;
+                if (k0 + lane < n) {
+                    const int pi = nb_idx[(size_t)tt * K + k0 + lane].idx;
+                    c = rrp[pi + 1] - rrp[pi];
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+                total_all += c;
+            }
+            use_hash = total_all <= RATE_HASH_MAX;
+        }
         // 32 neighbours at a time: their (similarity, rating row extent) one per lane; then the ratings of those
         // neighbours as ONE flat list, 32 entries per step whatever the row boundaries are.  Entries of one step
         // that hit the same place are applied in lane order (= ascending neighbour) in successive rounds
@@ -3015,19 +3041,39 @@ knn_rate_gather_kernel(const int *__restrict__ rrp, const int *__restrict__ rpl,
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, off));
                 bool first = false;
+                int slot_at = 0;                                      // index of this entry's num / den
                 for (int r = 0; r < rounds; ++r) {
                     if (valid && rank == r) {
-                        const double dold = myden[pl];
-                        first = dold == 0.0;
-                        mynum[pl] = xadd(mynum[pl], w);               // :63
-                        myden[pl] = xadd(dold, sim_l);                // :64
+                        int at = pl;
+                        bool fresh = false;
+                        if (use_hash) {
+                            // find or insert (the lanes of one round hold different places)
+                            at = (int)(((unsigned)pl * 2654435761u) >> 22) & (RATE_HASH - 1);
+                            for (;;) {
+                                int kq = keys[at];
+                                if (kq == -1) {
+                                    kq = atomicCAS((int *)&keys[at], -1, pl);
+                                    if (kq == -1) {
+                                        fresh = true;
+                                        break;
+                                    }
+                                }
+                                if (kq == pl) break;
+                                at = (at + 1) & (RATE_HASH - 1);
+                            }
+                        }
+                        const double dold = myden[at];
+                        first = use_hash ? fresh : dold == 0.0;
+                        mynum[at] = xadd(mynum[at], w);               // :63
+                        myden[at] = xadd(dold, sim_l);                // :64
+                        slot_at = at;
                     }
                     __syncwarp();
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, first);
                 if (first) {
                     const int pos = ntouched + __popc(m & lt_mask);
-                    if (pos < touch_cap) mytouched[pos] = pl;
+                    if (pos < touch_cap) mytouched[pos] = slot_at;
                 }
                 ntouched += __popc(m);
             }
@@ -3051,13 +3097,15 @@ knn_rate_gather_kernel(const int *__restrict__ rrp, const int *__restrict__ rpl,
             for (int q = 0; q < RG; ++q) {
                 const int j = lane + 32 * q;
                 if (j < ntouched) {
-                    const int pl = mytouched[j];
-                    const double est = xdiv(mynum[pl], myden[pl]);      // :68
+                    const int at = mytouched[j];
+                    const int pl = use_hash ? keys[at] : at;
+                    const double est = xdiv(mynum[at], myden[at]);      // :68
                     const bool ok = !flag || flag[pl];
                     rv_[q] = ok ? est : nan;
                     rp_[q] = pl;
-                    mynum[pl] = 0.0;
-                    myden[pl] = 0.0;
+                    mynum[at] = 0.0;
+                    myden[at] = 0.0;
+                    if (use_hash) keys[at] = -1;
                 }
             }
         } else {

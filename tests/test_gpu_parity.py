@@ -500,6 +500,21 @@ def test_knn_multi_wave_grid(vrec, ctx, synth, oracle):
     rs.close()
 
 
+@pytest.mark.parametrize("k", [5, 50, 300])
+def test_knn_rating_scratch_paths(vrec, ctx, synth, oracle, k):
+    # more than 4096 places: the rating reduction of a target whose neighbours hold <= 512 ratings goes through the
+    # shared-memory place table (K = 5, most of K = 50), the others through the dense scratch rows (K = 300, the
+    # heavy tail of K = 50) -- in one launch, the same warp alternating between the two
+    v, places = synth.g2_place_visits(50000, 8000, seed=11)
+    inp = synth.build_rating_vectors(v)
+    rs = vrec.KnnRegionSet(*inp.load_args(), ctx=ctx)
+    rng = np.random.default_rng(k)
+    targets = inp.person_id[rng.choice(len(inp.person_id), 600, replace=False)]
+    _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, k, targets, places.id[::2], 10)
+    _check_knn(vrec, oracle, rs, inp, 0.5, 0.5, k, targets[:50], None, 25)
+    rs.close()
+
+
 def test_knn_default_sample_data(vrec, ctx, synth, oracle):
     # config 1 shape at reduced size: degenerate diagonal data, huge tie groups
     pl = synth.sample_places(30000, seed=0)
