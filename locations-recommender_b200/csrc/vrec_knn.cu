@@ -2157,18 +2157,28 @@ knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_t
 // tfull[acc] / sempty[stage] (tcgen05.commit), tempty[acc] (one arrival per consumer warp).
 // ---------------------------------------------------------------------------------------
 #ifndef VREC_WS_WORKERS
-#define VREC_WS_WORKERS 512
+#define VREC_WS_WORKERS 640
 #endif
 constexpr int WS_WORKERS = VREC_WS_WORKERS;   // consumer threads: filter warps + evaluator warps
 constexpr int WS_THREADS = WS_WORKERS + 64;           // + MMA warp + loader warp
 constexpr int WS_VOTE_EVERY = 4;
-constexpr int WS_WQ = TC_QCAP / (WS_WORKERS / 32);   // survivor queue entries per consumer warp
+#ifndef VREC_WS_QCAP
+#define VREC_WS_QCAP 1024
+#endif
+constexpr int WS_QCAP = VREC_WS_QCAP;      // survivor ring entries (power of two)
+constexpr int WS_WQ = WS_QCAP / (WS_WORKERS / 32);   // survivor queue entries per consumer warp
 constexpr int WS_NACC = 3;           // TMEM accumulators (3 x 128 columns); the A operand (128 targets x 128 halves) takes 64 more
-constexpr int WS_STAGES = 4;         // B tiles in flight (the A operand lives in tensor memory, not in shared memory)
+#ifndef VREC_WS_STAGES
+#define VREC_WS_STAGES 4
+#endif
+constexpr int WS_STAGES = VREC_WS_STAGES;         // B tiles in flight (the A operand lives in tensor memory, not in shared memory)
 constexpr int WS_TMEM_A = WS_NACC * TC_N;   // first TMEM column of the A operand
 constexpr int WS_STAGGER = 1;        // tiles between the starting points of neighbouring CTAs (small: the CTAs share each tile through L2)
 #ifndef VREC_WS_STATIC_UNITS
 #define VREC_WS_STATIC_UNITS 1   // 1: a lane quarter's units go round robin over its filter warps; 0: claimed with an atomic
+#endif
+#ifndef VREC_WS_PUSH_BALLOT
+#define VREC_WS_PUSH_BALLOT 1   // survivor ring positions from a ballot per round (0: prefix scan over the lanes' counts)
 #endif
 #ifndef VREC_WS_POLL_NS
 #define VREC_WS_POLL_NS 256      // pause of an evaluator lane between two looks at its ring slot
@@ -2207,7 +2217,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
     {
         unsigned char *p = base + WS_STAGES * TC_TILE_BYTES;
         sm.hsim = (double *)p;                      p += sizeof(double) * (size_t)TC_M * K;
-        sm.queue = (unsigned long long *)p;         p += sizeof(unsigned long long) * TC_QCAP;
+        sm.queue = (unsigned long long *)p;         p += sizeof(unsigned long long) * WS_QCAP;
         sm.hidx = (int *)p;                         p += sizeof(int) * (size_t)TC_M * K;
         sm.thr = (float *)p;                        p += sizeof(float) * TC_M;
         sm.thr_stride = 1;
@@ -2369,9 +2379,12 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                                       TC_TILE_BYTES, &full[st]);
                 }
             }
-        } else if (lane == 0) {
-            // ================= MMA warp: one thread issues every tile's chain =================
-            const bool pprof = blockIdx.x == 0 && blockIdx.y == 0;
+        } else {
+            // ================= MMA warp: the whole warp walks the tiles, one elected lane issues =================
+            // (warp-uniform control flow and operands: the descriptors live in uniform registers; with the loop
+            // under `if (lane == 0)` every tcgen05.mma was wrapped in an ELECT / R2UR loop and the issue of a
+            // tile's 8 MMAs took ~850 cycles of dependent instructions -- more than their 542 cycles of math)
+            const bool pprof = lane == 0 && blockIdx.x == 0 && blockIdx.y == 0;
             long long pk0 = clock64(), pk1;
             unsigned long long pacc0 = 0, pacc7 = 0, pacc8 = 0;      // phase cycles, in registers until the end
 #define WS_PTICK(slot)                                                 \
@@ -2380,6 +2393,8 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
         pacc##slot += (unsigned long long)(pk1 - pk0);                 \
         pk0 = pk1;                                                     \
     }
+            const uint32_t tbase_u = __shfl_sync(0xffffffffu, tbase, 0);
+            const uint32_t b_addr_u = __shfl_sync(0xffffffffu, b_addr0, 0);
             for (int i = 0; i < nseq; ++i) {
                 const int st = i % WS_STAGES, a = i % WS_NACC;
                 tc::mbar_wait(&full[st], (uint32_t)((i / WS_STAGES) & 1));                 // B(i) landed
@@ -2387,15 +2402,18 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                 if (i >= WS_NACC) tc::mbar_wait(&tempty[a], (uint32_t)((i / WS_NACC - 1) & 1));   // accumulator drained
                 WS_PTICK(7)
                 tc::fence_after_sync();
-                const uint32_t b_addr = b_addr0 + (uint32_t)st * TC_TILE_BYTES;
-                const uint32_t acc = tbase + (uint32_t)a * TC_N;
+                const uint32_t b_addr = b_addr_u + (uint32_t)st * TC_TILE_BYTES;
+                const uint32_t acc = tbase_u + (uint32_t)a * TC_N;
+                if (tc::elect_one()) {
 #pragma unroll
-                for (int k = 0; k < TC_D / 16; ++k) {
-                    uint64_t db = tc::make_desc_sw128(tc::sw128_kstep_addr(b_addr, TC_N, k));
-                    tc::mma_f16_ts(acc, tbase + WS_TMEM_A + (uint32_t)(k * 8), db, idesc, k > 0);
+                    for (int k = 0; k < TC_D / 16; ++k) {
+                        uint64_t db = tc::make_desc_sw128(tc::sw128_kstep_addr(b_addr, TC_N, k));
+                        tc::mma_f16_ts(acc, tbase_u + WS_TMEM_A + (uint32_t)(k * 8), db, idesc, k > 0);
+                    }
+                    tc::mma_commit(&tfull[a]);        // accumulator ready for the consumers
+                    tc::mma_commit(&sempty[st]);      // B stage reusable
                 }
-                tc::mma_commit(&tfull[a]);        // accumulator ready for the consumers
-                tc::mma_commit(&sempty[st]);      // B stage reusable
+                __syncwarp();
                 WS_PTICK(8)
             }
             if (pprof) {
@@ -2448,7 +2466,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
             // queues (8 KB, not in use before the main sequence; 2 KB needed).  It used to be 64 floats per
             // row in the heap area, which holds 8 * K bytes per row: K < 32 overran it into the queues, the
             // heap indices and the target tables (illegal address at K = 7, P = 10^6).
-            static_assert(sizeof(unsigned long long) * TC_QCAP >= sizeof(float) * 4 * TC_M, "bootstrap scratch");
+            static_assert(sizeof(unsigned long long) * WS_QCAP >= sizeof(float) * 4 * TC_M, "bootstrap scratch");
             float gmin = gmax[0];
 #pragma unroll
             for (int g = 1; g < 16; ++g) gmin = fminf(gmin, gmax[g]);
@@ -2478,7 +2496,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
         // can never race for a slot (with a plain "empty" marker a lap-L+1 entry could overtake the lap-L one,
         // and with every evaluator waiting for a lap-L entry nobody would claim it -- a deadlock the reduced-size
         // tests, whose loose thresholds flood the ring, ran into at once).
-        for (int q = tid; q < TC_QCAP; q += WS_WORKERS) sm.queue[q] = WS_Q_FREE;                 // FREE(0)
+        for (int q = tid; q < WS_QCAP; q += WS_WORKERS) sm.queue[q] = WS_Q_FREE;                 // FREE(0)
         if (tid == 0) {
             s_q_res = 0;
             s_q_take = 0;
@@ -2493,13 +2511,13 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                 if (lane == 0) pos = atomicAdd(&s_q_take, 32);
                 pos = __shfl_sync(0xffffffffu, pos, 0);
                 const int my = pos + lane;
-                const unsigned long long lap = (unsigned long long)((my / TC_QCAP) & 0xffff);
+                const unsigned long long lap = (unsigned long long)((my / WS_QCAP) & 0xffff);
                 unsigned long long e = WS_Q_NONE;
                 for (;;) {
-                    const unsigned long long v = ring[my & (TC_QCAP - 1)];
+                    const unsigned long long v = ring[my & (WS_QCAP - 1)];
                     if ((v >> 48) == lap && (v & WS_Q_FREE) != WS_Q_FREE) {
                         e = v;
-                        ring[my & (TC_QCAP - 1)] = (((lap + 1) & 0xffff) << 48) | WS_Q_FREE;     // FREE(lap + 1)
+                        ring[my & (WS_QCAP - 1)] = (((lap + 1) & 0xffff) << 48) | WS_Q_FREE;     // FREE(lap + 1)
                         break;
                     }
                     if (*(volatile int *)&s_q_done == WS_FILTER_WARPS && my >= *(volatile int *)&s_q_res) break;
@@ -2559,6 +2577,26 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                 const unsigned any = __ballot_sync(0xffffffffu, pass != 0u);
                 WS_CTICK(2)                                       // epilogue
                 if (any) {
+#if VREC_WS_PUSH_BALLOT
+                    // one round per survivor of the busiest lane (nearly always one): positions from a ballot
+                    unsigned has = any;
+                    while (has) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&s_q_res, __popc(has));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (pass) {
+                            const int pos = base + __popc(has & ((1u << lane) - 1u));
+                            const int jj = __ffs(pass) - 1;
+                            pass &= pass - 1;
+                            const unsigned long long tag = (unsigned long long)((pos / WS_QCAP) & 0xffff) << 48;
+                            while (ring[pos & (WS_QCAP - 1)] != (tag | WS_Q_FREE)) __nanosleep(128);   // previous lap not taken yet
+                            ring[pos & (WS_QCAP - 1)] = tag | ((unsigned long long)ut << 32) |
+                                                        (unsigned long long)(unsigned)(tile + c0 + jj);
+                            if (aux.meta) asm volatile("prefetch.global.L2 [%0];" ::"l"((aux.cmeta ? aux.cmeta : aux.meta) + tile + c0 + jj));
+                        }
+                        has = __ballot_sync(0xffffffffu, pass != 0u);
+                    }
+#else
                     int cnt = __popc(pass), incl = cnt;
 #pragma unroll
                     for (int off = 1; off < 32; off <<= 1) {
@@ -2573,13 +2611,14 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                     while (pass) {
                         const int jj = __ffs(pass) - 1;
                         pass &= pass - 1;
-                        const unsigned long long tag = (unsigned long long)((pos / TC_QCAP) & 0xffff) << 48;
-                        while (ring[pos & (TC_QCAP - 1)] != (tag | WS_Q_FREE)) __nanosleep(128);   // previous lap not taken yet
-                        ring[pos & (TC_QCAP - 1)] = tag | ((unsigned long long)ut << 32) |
+                        const unsigned long long tag = (unsigned long long)((pos / WS_QCAP) & 0xffff) << 48;
+                        while (ring[pos & (WS_QCAP - 1)] != (tag | WS_Q_FREE)) __nanosleep(128);   // previous lap not taken yet
+                        ring[pos & (WS_QCAP - 1)] = tag | ((unsigned long long)ut << 32) |
                                                     (unsigned long long)(unsigned)(tile + c0 + jj);
                         ++pos;
                         if (aux.meta) asm volatile("prefetch.global.L2 [%0];" ::"l"((aux.cmeta ? aux.cmeta : aux.meta) + tile + c0 + jj));
                     }
+#endif
                     __syncwarp();
                     WS_CTICK(10)                                  // queueing
                 }
@@ -3979,9 +4018,9 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     int ws_pool_ints = 0;
     if (use_tc) {
         T = TC_M;
-        smem = 1024 + (1 + TC_STAGES) * (size_t)TC_TILE_BYTES + 12 * (size_t)TC_M * K +
-               sizeof(unsigned long long) * TC_QCAP + sizeof(float) * TC_M + sizeof(int) * 3 * TC_M + 16 +
-               sizeof(unsigned long long) * TC_M;
+        smem = 1024 + (use_ws ? WS_STAGES : 1 + TC_STAGES) * (size_t)TC_TILE_BYTES + 12 * (size_t)TC_M * K +
+               sizeof(unsigned long long) * (use_ws ? WS_QCAP : TC_QCAP) + sizeof(float) * TC_M +
+               sizeof(int) * 3 * TC_M + 16 + sizeof(unsigned long long) * TC_M;
         if (use_ws) {
             // what is left of the 227 KB holds the targets' place columns (knn_tc_ws_kernel)
             const size_t limit = 227 * 1024 - 2048;

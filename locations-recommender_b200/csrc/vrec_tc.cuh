@@ -111,6 +111,20 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+// one lane of a converged warp (elect.sync): the caller's operands stay warp-uniform, so the compiler keeps them in
+// uniform registers and issues tcgen05.mma / commit directly.  Under `if (lane == 0)` it cannot prove that and wraps
+// every UTCHMMA in an ELECT / R2UR loop: ~15 dependent instructions per MMA, 850 cycles per 8-MMA tile for one thread.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
