@@ -26,6 +26,7 @@ ap.add_argument("--splits", type=int, default=0)
 ap.add_argument("--skip-postings", type=int, default=0)
 ap.add_argument("--tc-seed", type=int, default=0)
 ap.add_argument("--compact", type=int, default=1, help="0 = exact evaluations on the full-size records (A/B)")
+ap.add_argument("--post-first", type=int, default=0, help="1 = postings kernel before the dense filter (its K-th best seeds the thresholds)")
 a = ap.parse_args()
 v, places = synth.g2_place_visits(a.persons, a.places)
 inp = synth.build_rating_vectors(v)
@@ -37,6 +38,7 @@ rs.set_option("splits", a.splits)
 rs.set_option("debug_skip_postings", a.skip_postings)
 rs.set_option("tc_seed", a.tc_seed)
 rs.set_option("compact_records", a.compact)
+rs.set_option("post_first", a.post_first)
 lib = ctx.lib
 flt = np.ascontiguousarray(places.id)
 lib.vrec_knn_set_filter(rs._h, flt.ctypes.data_as(L.i64p), len(flt))
