@@ -1945,7 +1945,10 @@ __global__ void knn_seed_from_post_kernel(int n_targets, int K, int S, int parts
     if (lane == 0) seed_thr[tt] = v;
 }
 
-__global__ void __launch_bounds__(POST_WARPS * 32, 4)
+#ifndef VREC_POST_MINB
+#define VREC_POST_MINB 4
+#endif
+__global__ void __launch_bounds__(POST_WARPS * 32, VREC_POST_MINB)
 knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_targets, int K, int S, int part_stride,
                     int cat_dim, double pw, double cw, Nb *__restrict__ part, int *__restrict__ part_cnt,
                     const double *__restrict__ seed_thr, int *__restrict__ work_counter,
@@ -2191,6 +2194,11 @@ constexpr int WS_FILTER_WARPS = WS_WORKERS / 32 - WS_EVAL_WARPS;     // a multip
 static_assert(WS_FILTER_WARPS >= 4 && WS_FILTER_WARPS % 4 == 0, "filter warps must cover the four TMEM lane quarters");
 constexpr unsigned long long WS_Q_FREE = 0xffffffffffffULL;          // payload of a free ring slot (48 bits)
 constexpr unsigned long long WS_Q_NONE = 0xffffffffffffffffULL;      // "this lane holds no survivor"
+#ifndef VREC_WS_MARGIN_MUL
+#define VREC_WS_MARGIN_MUL 1.002f
+#define VREC_WS_MARGIN_ADD 2e-5f
+#endif
+constexpr float WS_MARGIN_MUL = VREC_WS_MARGIN_MUL, WS_MARGIN_ADD = VREC_WS_MARGIN_ADD;   // filter: U * MUL + ADD >= threshold
 constexpr int WS_BOOT_TILES = 512;   // multiple of 16; 64 groups of 512 candidates per target
 
 __global__ void __launch_bounds__(WS_THREADS, 1)
@@ -2563,9 +2571,9 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                 const float vmax = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
                                          fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
                 unsigned pass = 0;
-                if (VREC_WS_ABLATE != 2 && vmax * 1.002f + 2e-5f >= thr) {
+                if (VREC_WS_ABLATE != 2 && vmax * WS_MARGIN_MUL + WS_MARGIN_ADD >= thr) {
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) pass |= (v[jj] * 1.002f + 2e-5f >= thr ? 1u : 0u) << jj;
+                    for (int jj = 0; jj < 32; ++jj) pass |= (v[jj] * WS_MARGIN_MUL + WS_MARGIN_ADD >= thr ? 1u : 0u) << jj;
                 }
                 if (tile + c0 + 32 > d.P) {                            // last tile: columns past the last person
                     const long long over = tile + c0 + 32 - d.P;
