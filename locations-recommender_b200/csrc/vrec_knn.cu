@@ -1485,6 +1485,14 @@ constexpr int TC_SBO = 128;                              // next 8 rows
 constexpr int TC_STAGES = 3;                             // B tiles in flight
 constexpr int TC_QCAP = 1024;                            // survivor queue entries (fits next to 3 B stages)
 
+// The first tcgen05 filter kernel (no warp specialisation, cp.async loads, row-major fp16 features) is superseded
+// by knn_tc_ws_kernel and compiled only on request (-DVREC_WITH_TC_BASELINE=1, A/B measurements): without it the
+// region-set does not carry the 256 B / person row-major feature copy either, and knn_kernel = 3 and the
+// "tc_seed" option select the warp-specialised kernel / nothing.
+#ifndef VREC_WITH_TC_BASELINE
+#define VREC_WITH_TC_BASELINE 0
+#endif
+#if VREC_WITH_TC_BASELINE
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool valid) {
     unsigned bytes = valid ? 16u : 0u;                   // src-size 0 -> zero fill
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes)
@@ -1856,6 +1864,7 @@ knn_tc_kernel(KnnDev d, TileAux aux, const __half *__restrict__ feat16, const in
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tbase, 2 * TC_N);
 }
+#endif   // VREC_WITH_TC_BASELINE
 
 
 // ---------------------------------------------------------------------------------------
@@ -2772,6 +2781,7 @@ __global__ void knn_features16sw_kernel(KnnDev d, const short *__restrict__ head
         *reinterpret_cast<uint4 *>(img + tc::sw128_offset(TC_N, (int)(i & 127), c)) = *reinterpret_cast<const uint4 *>(row + c * 8);
 }
 
+#if VREC_WITH_TC_BASELINE
 // fp16 features, row-major [P][TC_D]: category vector / length, then the head places' values / length
 __global__ void knn_features16_kernel(KnnDev d, const short *__restrict__ head_slot, int cat_dim,
                                       __half *__restrict__ feat16) {
@@ -2786,6 +2796,7 @@ __global__ void knn_features16_kernel(KnnDev d, const short *__restrict__ head_s
         if (slot >= 0) row[cat_dim + slot] = __double2half(d.place.val[k] / pl);
     }
 }
+#endif
 
 // Dense fp32 features, dim-major: F[d][i] = cat[i][d] / |cat_i| for d < cat_dim, then the head
 // places' values / |place_i|.  `wscale` (host) is applied per target in knn_tile_kernel.
@@ -3681,6 +3692,7 @@ extern "C" int vrec_knn_load(vrec_ctx *ctx, int64_t P, const int64_t *person_id,
             std::vector<short> &hs = hs_tc;
             for (int h = 0; h < n_head_tc; ++h) hs[byc[h]] = (short)h;
             rc = k->d_head_slot_tc.upload(hs.data(), hs.size(), s);
+#if VREC_WITH_TC_BASELINE
             if (rc == VREC_OK) rc = k->d_feat16.alloc((size_t)TC_D * (size_t)P);
             if (rc == VREC_OK) {
                 knn_features16_kernel<<<(int)((P + 127) / 128), 128, 0, s>>>(k->dev(), k->d_head_slot_tc.p, cat_dim,
@@ -3688,6 +3700,7 @@ extern "C" int vrec_knn_load(vrec_ctx *ctx, int64_t P, const int64_t *person_id,
                 ctx->launches++;
                 if (cudaGetLastError() != cudaSuccess) rc = VREC_ECUDA;
             }
+#endif
             if (rc == VREC_OK) {
                 k->tc_tiles = (int)((P + TC_N - 1) / TC_N);
                 rc = k->d_featsw.alloc((size_t)k->tc_tiles * TC_TILE_BYTES);
@@ -4013,7 +4026,7 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
     // 0 = automatic (tensor cores > CUDA-core tile > exact scan), 1 = exact scan, 2 = tile,
     // 3 = tensor cores (all warps do everything), 4 = tensor cores, warp-specialised (the automatic choice)
     const bool use_tc = k->tc_ok && K <= TC_MAX_K && (k->opt_kernel == 0 || k->opt_kernel >= 3);
-    const bool use_ws = use_tc && k->opt_kernel != 3;
+    const bool use_ws = use_tc && (k->opt_kernel != 3 || !VREC_WITH_TC_BASELINE);
     const bool tiled = !use_tc && k->tile_ok && k->opt_kernel != 1;
     const bool filtered = use_tc || tiled;
     // filtered kernels: slot S of every target's partial lists belongs to the postings kernel
@@ -4108,16 +4121,19 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
             return VREC_OK;
         };
         if (use_tc) {
+#if VREC_WITH_TC_BASELINE
             bool &attr_tc = ctx->attr_knn_tc;
             if (!attr_tc) {
                 VREC_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
                 attr_tc = true;
             }
+#endif
             aux = TileAux{nullptr, 0, k->d_head_slot_tc.p, k->d_pcp.p, k->d_pper.p, k->d_meta.p, k->d_rec.p, REC_TAIL_TC};
             aux.vals_f32 = k->rec_f32;
             k->attach_compact(aux);
             // No seed pass here: it cost more (heap warm-up on a sample, ~9 ms per 19K targets) than the
             // ~250 extra survivors per target it saves the main pass (~2 ms).  Optional via "tc_seed".
+#if VREC_WITH_TC_BASELINE
             if (k->opt_tc_seed) {
                 long long smp = std::min<long long>(k->P, std::max<long long>(TC_N, k->opt_tc_seed));
                 long long str = std::max<long long>(1, k->P / smp);
@@ -4126,7 +4142,9 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                     k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, 1, k->cat_dim, pw, cw, k->d_part.p,
                     k->d_part_cnt.p, str, smp, 1, k->d_seed_thr.p, SP);
                 VREC_LAUNCHED(ctx);
-            } else {
+            } else
+#endif
+            {
                 VREC_CUDA(cudaMemsetAsync(k->d_seed_thr.p, 0, sizeof(double) * (size_t)tn, ctx->stream));
             }
             if (post_first) {
@@ -4159,10 +4177,12 @@ int knn_run_topk(vrec_knn *k, int tn, double pw, double cw, int K) {
                 VREC_LAUNCHED(ctx);
                 VREC_CUDA(cudaEventRecord(k->ev_dense[1], ctx->stream));
             } else {
+#if VREC_WITH_TC_BASELINE
                 knn_tc_kernel<<<dim3(tiles, S), TC_THREADS, smem, ctx->stream>>>(
                     k->dev(), aux, k->d_feat16.p, k->d_tidx.p, tn, K, S, k->cat_dim, pw, cw, k->d_part.p,
                     k->d_part_cnt.p, 1, k->P, main_mode, k->d_seed_thr.p, SP);
                 VREC_LAUNCHED(ctx);
+#endif
             }
         } else {
             bool &attr_set = ctx->attr_knn_tile;

@@ -79,6 +79,12 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __half *__restri
     if (warp == 0) tc::tmem_dealloc(tbase, 256);
 }
 
+// Micro-benchmarks behind tools/tc_stream.py (MMA issue rate, L2 -> shared-memory streaming): not part of the
+// shipped library; build with -DVREC_WITH_MICROBENCH=1 (make CUDAFLAGS_EXTRA=-DVREC_WITH_MICROBENCH=1) to use them.
+#ifndef VREC_WITH_MICROBENCH
+#define VREC_WITH_MICROBENCH 0
+#endif
+#if VREC_WITH_MICROBENCH
 // issue `reps` chains of 8 MMAs (128x128x128) back to back and time them with clock64
 __global__ void __launch_bounds__(128) tc_rate_kernel(int swizzled, int reps, long long *out_cycles) {
     extern __shared__ unsigned char smem_raw[];
@@ -155,9 +161,11 @@ __global__ void __launch_bounds__(128) tc_stream_kernel(const unsigned char *__r
     }
     __syncthreads();
 }
+#endif   // VREC_WITH_MICROBENCH
 
 }  // namespace
 
+#if VREC_WITH_MICROBENCH
 // Debug: milliseconds for `ctas` CTAs to stream ntiles x 32 KB each from a common buffer through `stages`
 // bulk copies in flight (start points `stagger` tiles apart).
 extern "C" int vrec_debug_tc_stream(vrec_ctx *ctx, int ctas, int ntiles, int stages, int stagger, double *out_ms) {
@@ -200,6 +208,7 @@ extern "C" int vrec_debug_tc_mma_rate(vrec_ctx *ctx, int swizzled, int reps, int
     VREC_CUDA(cudaStreamSynchronize(ctx->stream));
     return VREC_OK;
 }
+#endif   // VREC_WITH_MICROBENCH
 
 // Debug: C[128x128] = A[128x128] * B[128x128]^T for caller-supplied fp16 bit patterns (row-major).
 extern "C" int vrec_debug_tc_matmul(vrec_ctx *ctx, const uint16_t *A, const uint16_t *B, float *C, int swizzled) {

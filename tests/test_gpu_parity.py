@@ -330,7 +330,8 @@ def _check_knn(vrec, oracle, rs, inp, pw, cw, k, targets, flt, max_recs):
 def test_knn_random_bit_exact(vrec, ctx, synth, oracle, seed, k, path, kernel):
     # path: rating reduction (0 auto, 1 neighbour-row gather, 2 column scan)
     # kernel: similarity + top-K (0 auto, 1 per-target exact scan, 2 tiled fp32 filter + exact survivors,
-    #         3 tcgen05 fp16 filter + exact survivors, 4 the same, warp-specialised with TMA bulk copies)
+    #         3 the first tcgen05 filter kernel when the library was built with -DVREC_WITH_TC_BASELINE=1, else
+    #         the same as 4: tcgen05 fp16 filter, warp-specialised with TMA bulk copies, + exact survivors)
     if path == 1 and k > 1024:
         pytest.skip("gather path needs k <= 1024")
     inp = synth.random_knn_inputs(700, 60, 9, seed=seed, separate_ratings=(seed == 2))

@@ -1,4 +1,5 @@
-"""L2 -> shared memory streaming bandwidth of 148 CTAs reading one common 256 MB buffer with bulk copies."""
+"""L2 -> shared memory streaming bandwidth of 148 CTAs reading one common 256 MB buffer with bulk copies.
+Needs a library built with the micro-benchmarks: make -C locations-recommender_b200/csrc EXTRA=-DVREC_WITH_MICROBENCH=1"""
 import ctypes as C
 import os
 import sys
