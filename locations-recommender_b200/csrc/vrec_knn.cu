@@ -861,11 +861,11 @@ __device__ __forceinline__ double exact_pair_sig_compact(const TileAux &aux, int
     if (np > 0) {
         double sum = 0.0;
         unsigned sq = 0u;
-        auto place_term = [&](unsigned craw) {
+        // the target's entry for a candidate entry that passed the signature test (binary search), and its product
+        auto place_match = [&](unsigned craw) {
             const int ix = (int)(craw & CREC_COL_MASK);
             const unsigned v = (craw >> 22) & 0xffu;
-            sq += v * v;
-            if ((tsig >> sig_bit(ix)) & 1ULL) {
+            {
                 int lo = 0, hi = npt;                                // first index with target col >= ix
                 bool match;
                 if (tcols_s) {                                       // the target's columns are in shared memory
@@ -887,12 +887,35 @@ __device__ __forceinline__ double exact_pair_sig_compact(const TileAux &aux, int
                 }
             }
         };
+        auto place_term = [&](unsigned craw) {
+            const unsigned v = (craw >> 22) & 0xffu;
+            sq += v * v;
+            if ((tsig >> sig_bit((int)(craw & CREC_COL_MASK))) & 1ULL) place_match(craw);
+        };
+        // Pass 1 (no memory): squares and the signature test of the prefetched entries -> a bit mask.  Pass 2: each
+        // lane searches only ITS entries that passed, in ascending order (the order the products are added in).
+        // With the search inside the unrolled entry slots the warp ran it in nearly every slot for a few lanes
+        // (as in the postings evaluator, profiles/r2_knn_hot_lines.txt); now as many rounds as its busiest lane has hits.
+        unsigned pend = 0u;
 #pragma unroll
         for (int j = 0; j < CREC_PW; ++j) {
-            if (2 * j < np) place_term((unsigned)rc.pw[j]);
-            if (2 * j + 1 < np) place_term((unsigned)(rc.pw[j] >> 32));
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                if (2 * j + hf < np) {
+                    const unsigned craw = hf ? (unsigned)(rc.pw[j] >> 32) : (unsigned)rc.pw[j];
+                    const unsigned v = (craw >> 22) & 0xffu;
+                    sq += v * v;
+                    if ((tsig >> sig_bit((int)(craw & CREC_COL_MASK))) & 1ULL) pend |= 1u << (2 * j + hf);
+                }
+            }
         }
-        for (int j = CREC_PW; j < rc.pwords; ++j) {
+        while (pend) {
+            const int e = __ffs(pend) - 1;
+            pend &= pend - 1;
+            const unsigned long long wd = ld_rec_u64(rc.r + (e >> 1), pol);
+            place_match((e & 1) ? (unsigned)(wd >> 32) : (unsigned)wd);
+        }
+        for (int j = CREC_PW; j < rc.pwords; ++j) {                  // long records: the rest, entry by entry
             const unsigned long long wd = ld_rec_u64(rc.r + j, pol);
             place_term((unsigned)wd);
             if (2 * j + 1 < np) place_term((unsigned)(wd >> 32));
@@ -1113,8 +1136,11 @@ __device__ __forceinline__ bool nb_worse(double sa, int ia, double sb, int ib) {
 
 // insert (sim, idx) into the heap of target slot t (under its lock)
 __device__ __forceinline__ void tile_heap_insert(const TileSmem &sm, int t, int K, double sim, int idx) {
-    volatile double *hs = sm.hsim + (size_t)t * K;
-    volatile int *hi = sm.hidx + (size_t)t * K;
+    // inside the lock the heap is read and written with plain accesses (the fences after the acquire and before the
+    // release order them against the other holders; `volatile` generic pointers made every access a strong
+    // system-scope load and every child was read twice)
+    double *hs = sm.hsim + (size_t)t * K;
+    int *hi = sm.hidx + (size_t)t * K;
     volatile int *cntp = sm.hcnt + t;
     volatile float *thr = sm.thr + (size_t)t * sm.thr_stride;
     bool done = false;
@@ -1143,18 +1169,27 @@ __device__ __forceinline__ void tile_heap_insert(const TileSmem &sm, int t, int 
             } else if (nb_worse(hs[0], hi[0], sim, idx)) {
                 int pos = 0;
                 for (;;) {                              // sift down from the root
-                    int l = 2 * pos + 1, r = l + 1, w = -1;
+                    const int l = 2 * pos + 1, r = l + 1;
+                    int w = -1;
                     double ws = sim;
                     int wi = idx;
-                    if (l < K && nb_worse(hs[l], hi[l], ws, wi)) {
-                        w = l;
-                        ws = hs[l];
-                        wi = hi[l];
+                    if (l < K) {
+                        const double ls = hs[l];
+                        const int li = hi[l];
+                        if (nb_worse(ls, li, ws, wi)) {
+                            w = l;
+                            ws = ls;
+                            wi = li;
+                        }
                     }
-                    if (r < K && nb_worse(hs[r], hi[r], ws, wi)) {
-                        w = r;
-                        ws = hs[r];
-                        wi = hi[r];
+                    if (r < K) {
+                        const double rs = hs[r];
+                        const int ri = hi[r];
+                        if (nb_worse(rs, ri, ws, wi)) {
+                            w = r;
+                            ws = rs;
+                            wi = ri;
+                        }
                     }
                     if (w < 0) break;
                     hs[pos] = ws;
@@ -1163,7 +1198,7 @@ __device__ __forceinline__ void tile_heap_insert(const TileSmem &sm, int t, int 
                 }
                 hs[pos] = sim;
                 hi[pos] = idx;
-                if (VREC_WS_ABLATE != 3) *thr = fmaxf(*thr, __double2float_rd(hs[0]));
+                if (VREC_WS_ABLATE != 3) *thr = fmaxf(*thr, __double2float_rd(pos == 0 ? sim : hs[0]));
             }
             __threadfence_block();
             atomicExch(sm.lock + t, 0);
@@ -1219,7 +1254,7 @@ __device__ __forceinline__ void tile_process_staged(const TileAux &aux, const Ti
 __device__ __noinline__ void tile_process_sig(const TileAux &aux, const TileSmem &sm, int t, int c, int K, double pw,
                                               double cw) {
     double sim = 0.0;
-    bool pending = false;
+    bool pending = false, evaluated = false;
     if (t >= 0) {
         const int tix = sm.tid_of[t];
         if (tix >= 0) {
@@ -1227,11 +1262,18 @@ __device__ __noinline__ void tile_process_sig(const TileAux &aux, const TileSmem
             const unsigned short off = sm.toff[t];
             sim = exact_pair_sig(aux, c, tix, sm.tsig[t], aux.tdense + (size_t)(sm.t_base + t) * aux.cat_dim,
                                  off == 0xffffu ? nullptr : sm.tpool + off, pw, cw, min_tail);
-            atomicAdd(sm.stats + 1, 1u);
+            evaluated = true;
             pending = sim > 0 && min_tail < 0;      // pairs sharing a tail place belong to the postings kernel
         }
     }
     __syncwarp();
+    // debug counters, one atomic per warp (32 atomics on one shared-memory word were ~250 cycles of every batch)
+    const unsigned n_eval = __popc(__ballot_sync(0xffffffffu, evaluated));
+    const unsigned n_ins = __popc(__ballot_sync(0xffffffffu, pending));      // an upper bound: some find the heap moved on
+    if ((threadIdx.x & 31) == 0) {
+        if (n_eval) atomicAdd(sm.stats + 1, n_eval);
+        if (n_ins) atomicAdd(sm.stats + 2, n_ins);
+    }
     for (;;) {
         if (pending) {
             volatile double *hs = sm.hsim + (size_t)t * K;
@@ -1242,13 +1284,7 @@ __device__ __noinline__ void tile_process_sig(const TileAux &aux, const TileSmem
         if (pending) {
             const unsigned same = __match_any_sync(todo, t);
             if ((int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) {
-                atomicAdd(sm.stats + 2, 1u);
-                long long h0 = clock64();
                 tile_heap_insert(sm, t, K, sim, c);
-                if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
-                    g_probe[4] += (unsigned long long)(clock64() - h0);
-                    g_probe[5] += 1;
-                }
                 pending = false;
             }
         }
@@ -2192,6 +2228,10 @@ constexpr int WS_STAGGER = 1;        // tiles between the starting points of nei
 #ifndef VREC_WS_PUSH_BALLOT
 #define VREC_WS_PUSH_BALLOT 1   // survivor ring positions from a ballot per round (0: prefix scan over the lanes' counts)
 #endif
+#ifndef VREC_WS_EBATCH
+#define VREC_WS_EBATCH 32        // ring entries an evaluator warp takes at a time (one per lane)
+#endif
+constexpr int WS_EBATCH = VREC_WS_EBATCH;
 #ifndef VREC_WS_POLL_NS
 #define VREC_WS_POLL_NS 256      // pause of an evaluator lane between two looks at its ring slot
 #endif
@@ -2523,14 +2563,17 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
         volatile unsigned long long *ring = sm.queue;
         if (warp >= WS_FILTER_WARPS) {
             // ================= evaluator warps =================
+            const bool eprof = warp == WS_FILTER_WARPS && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+            unsigned long long e_wait = 0, e_eval = 0, e_n = 0;     // first evaluator warp of block 0: cycles waiting / evaluating, batches
             for (;;) {
+                const long long ek0 = clock64();
                 int pos = 0;
-                if (lane == 0) pos = atomicAdd(&s_q_take, 32);
+                if (lane == 0) pos = atomicAdd(&s_q_take, WS_EBATCH);
                 pos = __shfl_sync(0xffffffffu, pos, 0);
                 const int my = pos + lane;
                 const unsigned long long lap = (unsigned long long)((my / WS_QCAP) & 0xffff);
                 unsigned long long e = WS_Q_NONE;
-                for (;;) {
+                for (; lane < WS_EBATCH;) {
                     const unsigned long long v = ring[my & (WS_QCAP - 1)];
                     if ((v >> 48) == lap && (v & WS_Q_FREE) != WS_Q_FREE) {
                         e = v;
@@ -2543,7 +2586,18 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
                 __syncwarp();
                 if (!__any_sync(0xffffffffu, e != WS_Q_NONE)) break;           // nothing left for this warp
                 const int tt = e != WS_Q_NONE ? (int)((e >> 32) & 0xffu) : -1;
+                const long long ek1 = clock64();
                 tile_process_sig(aux, sm, tt, (int)(unsigned)(e & 0xffffffffu), K, pw, cw);
+                if (eprof) {
+                    e_wait += (unsigned long long)(ek1 - ek0);
+                    e_eval += (unsigned long long)(clock64() - ek1);
+                    e_n += 1;
+                }
+            }
+            if (eprof) {
+                g_tc_cycles[3] += e_wait;
+                g_tc_cycles[4] += e_eval;
+                g_tc_cycles[6] += e_n;
             }
         } else {
             // ================= filter warps =================

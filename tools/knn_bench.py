@@ -90,6 +90,8 @@ for s in range(a.warmup + a.steps):
     if cy[5] and a.kernel == 3:
         print(f"   tc block0 cycles/tile: load-wait {cy[0] / cy[5]:.0f}, mma {cy[1] / cy[5]:.0f}, epilogue {cy[2] / cy[5]:.0f}, "
               f"mma issue {cy[8] / cy[5]:.0f}, load issue {cy[3] / cy[5]:.0f} [cp.async wait {cy[6] / cy[5]:.0f}, barrier {cy[7] / cy[5]:.0f}]; postings pass total {cy[4] / 1e6:.2f} Mcycles; tiles {cy[5]}")
+    if cy[6] and a.kernel in (0, 4):
+        print(f"   ws block0 first evaluator warp: {cy[6]} batches, {cy[4] / cy[6]:.0f} cycles evaluating and {cy[3] / cy[6]:.0f} waiting per batch")
     dms = C.c_double(0.0)
     lib.vrec_knn_last_dense_ms(rs._h, C.byref(dms))
     print(f"   dense filter kernel {dms.value:.2f} ms")
