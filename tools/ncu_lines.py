@@ -59,3 +59,9 @@ print(f"{kernel}: {tot} warp instructions, {ts} stall samples; lines by instruct
 for line, c in by.most_common(30):
     print(f"  {line[0]}:{line[1]:<5} {c / tot * 100:5.1f}% instr  {bys[line] / ts * 100:5.1f}% samples  "
           f"{byt[line] / max(1, c):4.1f} of 32 lanes active")
+if os.environ.get("NCU_LINES_BY_SAMPLES"):          # second list: where the warps wait
+    print("lines by stall samples")
+    for line, s_ in bys.most_common(int(os.environ["NCU_LINES_BY_SAMPLES"])):
+        c = by[line]
+        print(f"  {line[0]}:{line[1]:<5} {c / tot * 100:5.1f}% instr  {s_ / ts * 100:5.1f}% samples  "
+              f"{byt[line] / max(1, c):4.1f} of 32 lanes active")
