@@ -2194,18 +2194,20 @@ knn_postings_kernel(KnnDev d, TileAux aux, const int *__restrict__ tidx, int n_t
 
 
 // ---------------------------------------------------------------------------------------
-// Warp-specialised tensor-core kernel (the default batch path).
-//   warp 16 (one elected thread) = producer: streams B tiles with TMA bulk copies -- the fp16
-//       features are stored in HBM as ready-made 32 KB shared-memory images (128 persons, K-major,
-//       SWIZZLE_128B), so one cp.async.bulk per tile lands them in place -- and issues the MMA
-//       chains into WS_NACC rotating TMEM accumulators;
-//   warps 0..15 = consumers: pull a tile's accumulator out of TMEM, apply the threshold filter,
-//       queue the survivors and (every few tiles, by a named-barrier vote) evaluate them exactly.
-// Synchronisation is mbarrier-only on the data path: full[stage] (TMA transaction bytes),
-// tfull[acc] / sempty[stage] (tcgen05.commit), tempty[acc] (one arrival per consumer warp).
+// Warp-specialised tensor-core kernel (the default batch path).  Roles by warp:
+//   loader warp (one thread): streams B tiles with TMA bulk copies -- the fp16 features are stored in HBM as
+//       ready-made 32 KB shared-memory images (128 persons, K-major, SWIZZLE_128B), so one cp.async.bulk per tile
+//       lands them in place -- WS_STAGES tiles ahead;
+//   MMA warp (warp-uniform loop, one elected lane issues): a tile's 8 tcgen05.mma into one of WS_NACC rotating
+//       TMEM accumulators, A operand in tensor memory;
+//   filter warps (WS_FILTER_WARPS, a multiple of 4: one group per TMEM lane quarter): pull 32 x 32 units of an
+//       accumulator out of TMEM, apply the threshold filter, push the survivors into a ring in shared memory;
+//   evaluator warps (WS_EVAL_WARPS): take 32 survivors at a time and evaluate them exactly (heaps, thresholds).
+// Synchronisation is mbarrier-only on the data path: full[stage] (TMA transaction bytes), tfull[acc] /
+// sempty[stage] (tcgen05.commit), tempty[acc] (one arrival per unit = 16 per tile).
 // ---------------------------------------------------------------------------------------
 #ifndef VREC_WS_WORKERS
-#define VREC_WS_WORKERS 640
+#define VREC_WS_WORKERS 640     // 12 filter + 8 evaluator warps (measured: profiles/r2_knn_dense_variants.log)
 #endif
 constexpr int WS_WORKERS = VREC_WS_WORKERS;   // consumer threads: filter warps + evaluator warps
 constexpr int WS_THREADS = WS_WORKERS + 64;           // + MMA warp + loader warp
@@ -2542,7 +2544,7 @@ knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const
         // ---- main sequence.  The unit of consumer work is (tile, lane quarter, column quarter) = 32 target
         // rows x 32 candidates; the warps of a lane quarter claim units in order from a shared counter.
 #if VREC_WS_EVAL_WARPS > 0
-        // Round 2: the consumer warps are split.  FILTER warps (2 per TMEM lane quarter) only drain accumulators,
+        // Round 2: the consumer warps are split.  FILTER warps (WS_FILTER_WARPS / 4 per TMEM lane quarter) only drain accumulators,
         // test thresholds and push survivors into a ring in shared memory; EVALUATOR warps only pull survivors
         // (32 at a time, one per lane) and evaluate them exactly.  An exact evaluation is a chain of dependent
         // memory reads (a drain of 32 took ~25 K cycles = 13 tile periods): with every warp doing both, a lane
