@@ -2250,7 +2250,10 @@ constexpr unsigned long long WS_Q_NONE = 0xffffffffffffffffULL;      // "this la
 #define VREC_WS_MARGIN_ADD 2e-5f
 #endif
 constexpr float WS_MARGIN_MUL = VREC_WS_MARGIN_MUL, WS_MARGIN_ADD = VREC_WS_MARGIN_ADD;   // filter: U * MUL + ADD >= threshold
-constexpr int WS_BOOT_TILES = 512;   // multiple of 16; 64 groups of 512 candidates per target
+#ifndef VREC_WS_BOOT_TILES
+#define VREC_WS_BOOT_TILES 1024    // measured at P = 10^6, K = 50: 256 / 512 / 1024 / 1536 / 2048 tiles -> 6.67 / 6.49 / 6.36 / 6.40 / 6.47 ms
+#endif
+constexpr int WS_BOOT_TILES = VREC_WS_BOOT_TILES;   // multiple of 16; 64 groups of 2 048 candidates per target
 
 __global__ void __launch_bounds__(WS_THREADS, 1)
 knn_tc_ws_kernel(KnnDev d, TileAux aux, const __half *__restrict__ featsw, const int *__restrict__ tidx,
